@@ -1,0 +1,831 @@
+/*
+ * mhm_oracle.c -- CPU restatement of the mHM L1 cell cascade, meteo prologue and
+ * mRM Muskingum routing.  TEST INFRASTRUCTURE ONLY (see mhm_oracle.h).
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared (oracle/Makefile).
+ * -ffp-contract=off: gfortran -O3 on generic x86-64 emits no FMA, so neither may we.
+ * exp/log/pow are glibc's, the same libm a gfortran build of the reference calls.
+ */
+#include "mhm_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ============================================================================
+ *  Cell processes
+ * ==========================================================================*/
+
+/* mHM/mo_canopy_interc.f90:75-133 */
+void orc_canopy_interc(double pet, double interc_max, double precip, double *interc,
+                       double *throughfall, double *evap_canopy) {
+  double aux_help = *interc + precip; /* :105 */
+  if (aux_help >= interc_max) {
+    *throughfall = aux_help - interc_max;
+    *interc = interc_max;
+  } else {
+    *throughfall = 0.0;
+    *interc = aux_help;
+  }
+  if (interc_max > ORC_EPS_DP) { /* :116-121 */
+    *evap_canopy = pet * pow(*interc / interc_max, ORC_TWOTHIRD);
+  } else {
+    *evap_canopy = 0.0;
+  }
+  if (*evap_canopy < 0.0) *evap_canopy = 0.0; /* :124 */
+  if (*interc > *evap_canopy) {               /* :126-131 */
+    *interc = *interc - *evap_canopy;
+  } else {
+    *evap_canopy = *interc;
+    *interc = 0.0;
+  }
+}
+
+/* mHM/mo_snow_accum_melt.f90:70-158 */
+void orc_snow_accum_melt(double deg_day_incr, double deg_day_max, double deg_day_noprec,
+                         double prec, double temperature, double temperature_thresh,
+                         double thrfall, double *snow_pack, double *deg_day, double *melt,
+                         double *prec_effect, double *rain, double *snow) {
+  double aux_help;
+  if (temperature > temperature_thresh) { /* :118-124 */
+    *snow = 0.0;
+    *rain = thrfall;
+  } else {
+    *snow = thrfall;
+    *rain = 0.0;
+  }
+  if (prec <= (deg_day_max - deg_day_noprec) / deg_day_incr) { /* :127-131 */
+    *deg_day = deg_day_noprec + deg_day_incr * prec;
+  } else {
+    *deg_day = deg_day_max;
+  }
+  if (temperature > temperature_thresh) { /* :134-153 */
+    if (*snow_pack > 0.0) {
+      aux_help = *deg_day * (temperature - temperature_thresh);
+      if (aux_help > *snow_pack) {
+        *melt = *snow_pack;
+        *snow_pack = 0.0;
+      } else {
+        *melt = aux_help;
+        *snow_pack = *snow_pack - aux_help;
+      }
+    } else {
+      *melt = 0.0;
+      *snow_pack = 0.0;
+    }
+  } else {
+    *melt = 0.0;
+    *snow_pack = *snow_pack + *snow;
+  }
+  *prec_effect = *melt + *rain; /* :156 */
+}
+
+/* mHM/mo_soil_moisture.f90:333-363 */
+double orc_feddes_et_reduction(double soil_moist, double soil_moist_FC, double wilting_point,
+                               double frac_roots) {
+  if (soil_moist >= soil_moist_FC) {
+    return frac_roots;
+  } else if (soil_moist > wilting_point) {
+    return frac_roots * (soil_moist - wilting_point) / (soil_moist_FC - wilting_point);
+  }
+  return 0.0;
+}
+
+/* mHM/mo_soil_moisture.f90:405-446 */
+double orc_jarvis_et_reduction(double soil_moist, double soil_moist_sat, double wilting_point,
+                               double frac_roots, double jarvis_thresh_c1) {
+  double theta_inorm = (soil_moist - wilting_point) / (soil_moist_sat - wilting_point);
+  double r = 0.0; /* the reference leaves the result undefined for NaN input */
+  if (theta_inorm < 0.0) theta_inorm = 0.0;
+  if (theta_inorm > 1.0) theta_inorm = 1.0;
+  if (theta_inorm >= jarvis_thresh_c1) {
+    r = frac_roots;
+  } else if (theta_inorm < jarvis_thresh_c1) {
+    r = frac_roots * (theta_inorm / jarvis_thresh_c1);
+  }
+  return r;
+}
+
+/* mHM/mo_soil_moisture.f90:94-290 */
+void orc_soil_moisture(int32_t processCase, double frac_sealed, double water_thresh_sealed,
+                       double pet, double evap_coeff, int32_t nH, int64_t st,
+                       const double *soil_moist_sat, const double *frac_roots,
+                       const double *soil_moist_FC, const double *wilting_point,
+                       const double *soil_moist_exponen, double jarvis_thresh_c1,
+                       double aet_canopy, double prec_effec, double *runoff_sealed,
+                       double *storage_sealed, double *infiltration, double *soil_moist,
+                       double *aet, double *aet_sealed) {
+  int32_t hh, j;
+  double prec_effec_soil, frac_runoff, soil_stress_factor = 0.0, tmp;
+
+  *runoff_sealed = 0.0; /* :179-180 */
+  *aet_sealed = 0.0;
+  if (frac_sealed > 0.0) { /* :183-213 */
+    tmp = *storage_sealed + prec_effec;
+    if (tmp > water_thresh_sealed) {
+      *runoff_sealed = tmp - water_thresh_sealed;
+      *storage_sealed = water_thresh_sealed;
+    } else {
+      *runoff_sealed = 0.0;
+      *storage_sealed = tmp;
+    }
+    if (water_thresh_sealed > ORC_EPS_DP) {
+      *aet_sealed = (pet / evap_coeff - aet_canopy) * (*storage_sealed / water_thresh_sealed);
+      if (*aet_sealed < 0.0) *aet_sealed = 0.0;
+    } else {
+      *aet_sealed = DBL_MAX; /* huge(1.0_dp) :199 */
+    }
+    if (*storage_sealed > *aet_sealed) {
+      *storage_sealed = *storage_sealed - *aet_sealed;
+    } else {
+      *aet_sealed = *storage_sealed;
+      *storage_sealed = 0.0;
+    }
+  }
+
+  for (hh = 0; hh < nH; hh++) { /* :216-217 */
+    aet[hh * st] = 0.0;
+    infiltration[hh * st] = 0.0;
+  }
+  prec_effec_soil = prec_effec; /* :220 */
+
+  for (hh = 0; hh < nH; hh++) { /* :222-286 */
+    double sm = soil_moist[hh * st], sat = soil_moist_sat[hh * st], inf, a;
+    if (hh != 0) prec_effec_soil = infiltration[(hh - 1) * st];
+    if (sm > sat) { /* :227 */
+      inf = prec_effec_soil;
+    } else {
+      if (sm > ORC_EPS_DP) { /* :232-236 */
+        frac_runoff = exp(soil_moist_exponen[hh * st] * log(sm / sat));
+      } else {
+        frac_runoff = 0.0;
+      }
+      tmp = prec_effec_soil * (1.0 - frac_runoff); /* :238 */
+      if ((sm + tmp) > sat) {                      /* :240-246 */
+        inf = prec_effec_soil + (sm - sat);
+        sm = sat;
+      } else {
+        inf = prec_effec_soil - tmp;
+        sm = sm + tmp;
+      }
+    }
+    infiltration[hh * st] = inf;
+
+    a = pet - aet_canopy; /* :252 */
+    if (hh != 0) {        /* :253: sum(aet(1:hh-1), mask = aet > 0) in index order */
+      double s = 0.0;
+      for (j = 0; j < hh; j++)
+        if (aet[j * st] > 0.0) s = s + aet[j * st];
+      a = a - s;
+    }
+    switch (processCase) { /* :256-268 */
+      case 1:
+      case 4:
+        soil_stress_factor = orc_feddes_et_reduction(sm, soil_moist_FC[hh * st],
+                                                     wilting_point[hh * st], frac_roots[hh * st]);
+        break;
+      case 2:
+      case 3:
+        soil_stress_factor = orc_jarvis_et_reduction(sm, sat, wilting_point[hh * st],
+                                                     frac_roots[hh * st], jarvis_thresh_c1);
+        break;
+      default:
+        break;
+    }
+    a = a * soil_stress_factor; /* :270 */
+    if (a < 0.0) a = 0.0;       /* :273 */
+    if (sm > a) {               /* :276-281 */
+      sm = sm - a;
+    } else {
+      a = sm - ORC_EPS_DP;
+      sm = ORC_EPS_DP;
+    }
+    if (sm < ORC_EPS_DP) sm = ORC_EPS_DP; /* :284 */
+    aet[hh * st] = a;
+    soil_moist[hh * st] = sm;
+  }
+}
+
+/* mHM/mo_runoff.f90:74-154 */
+void orc_runoff_unsat_zone(double k1, double kp, double k0, double alpha, double karst_loss,
+                           double pefec_soil, double unsat_thresh, double *sat_storage,
+                           double *unsat_storage, double *slow_interflow,
+                           double *fast_interflow, double *perc) {
+  double a, b;
+  *unsat_storage = *unsat_storage + pefec_soil; /* :120 */
+  *fast_interflow = 0.0;
+  if (*unsat_storage > unsat_thresh) { /* :124-127 */
+    a = k0 * (*unsat_storage - unsat_thresh);
+    b = *unsat_storage - ORC_EPS_DP;
+    *fast_interflow = (a < b) ? a : b;
+  }
+  *unsat_storage = *unsat_storage - *fast_interflow;
+  *slow_interflow = 0.0;
+  if (*unsat_storage > ORC_EPS_DP) { /* :133-136 */
+    a = k1 * pow(*unsat_storage, 1.0 + alpha);
+    b = *unsat_storage - ORC_EPS_DP;
+    *slow_interflow = (a < b) ? a : b;
+  }
+  *unsat_storage = *unsat_storage - *slow_interflow;
+  *perc = kp * *unsat_storage; /* :143 */
+  if (*unsat_storage > *perc) {
+    *unsat_storage = *unsat_storage - *perc;
+    *sat_storage = *sat_storage + *perc * karst_loss;
+  } else {
+    *sat_storage = *sat_storage + *unsat_storage * karst_loss;
+    *unsat_storage = 0.0;
+  }
+}
+
+/* mHM/mo_runoff.f90:191-212 */
+void orc_runoff_sat_zone(double k2, double *sat_storage, double *baseflow) {
+  if (*sat_storage > 0.0) {
+    *baseflow = k2 * *sat_storage;
+    *sat_storage = *sat_storage - *baseflow;
+  } else {
+    *baseflow = 0.0;
+    *sat_storage = 0.0;
+  }
+}
+
+/* mHM/mo_runoff.f90:248-274 */
+void orc_L1_total_runoff(double fSealed, double fast_interflow, double slow_interflow,
+                         double baseflow, double direct_runoff, double *total_runoff) {
+  *total_runoff = ((baseflow + slow_interflow + fast_interflow) * (1.0 - fSealed)) +
+                  (direct_runoff * fSealed);
+}
+
+/* ============================================================================
+ *  PET (mHM/mo_pet.f90) and temporal disaggregation (meteo/mo_meteo_temporal_tools.f90)
+ * ==========================================================================*/
+
+/* FORCES mo_utils::le (un-vendored): a <= b with an epsilon*|b| equality band */
+static int orc_le(double a, double b) {
+  if ((ORC_EPS_DP * fabs(b) - fabs(a - b)) < 0.0) return a < b;
+  return 1;
+}
+
+/* mo_pet.f90:426-441 */
+double orc_sat_vap_pressure(double tavg) {
+  return ORC_TETENS_C1 * exp(ORC_TETENS_C2 * tavg / (tavg + ORC_TETENS_C3));
+}
+
+/* mo_pet.f90:384-399 */
+double orc_slope_satpressure(double tavg) {
+  return ORC_SATPRESSURESLOPE1 * orc_sat_vap_pressure(tavg) /
+         exp(2.0 * log(tavg + ORC_TETENS_C3));
+}
+
+/* mo_pet.f90:314-355 */
+double orc_extraterr_rad_approx(int32_t doy, double latitude) {
+  double dr, delta, omega, arg;
+  dr = 1.0 + ORC_DUFFIEDR * cos(ORC_TWOPI * doy / ORC_YEARDAYS);
+  delta = ORC_DUFFIEDELTA1 * sin(ORC_TWOPI * doy / ORC_YEARDAYS - ORC_DUFFIEDELTA2);
+  arg = -tan(latitude) * tan(delta);
+  if (arg < -1.0) arg = -1.0;
+  if (arg > 1.0) arg = 1.0;
+  omega = acos(arg);
+  return ORC_DAYSECS / ORC_PI / ORC_SPECHEATET * ORC_SOLARCONST * dr *
+         (omega * sin(latitude) * sin(delta) + cos(latitude) * cos(delta) * sin(omega));
+}
+
+/* mo_pet.f90:73-116 */
+double orc_pet_hargreaves(double HarSamCoeff, double HarSamConst, double tavg, double tmax,
+                          double tmin, double latitude, int32_t doy) {
+  double delta_temp = tmax - tmin;
+  if (orc_le(delta_temp, 0.0) || orc_le(tavg, -HarSamConst)) return 0.0;
+  return HarSamCoeff * orc_extraterr_rad_approx(doy, ORC_DEG2RAD * latitude) *
+         (tavg + HarSamConst) * sqrt(delta_temp);
+}
+
+/* mo_pet.f90:149-174 */
+double orc_pet_priestly(double PrieTayParam, double Rn, double tavg) {
+  double delta = orc_slope_satpressure(tavg);
+  return PrieTayParam * delta / (ORC_PSYCHRO + delta) * (Rn * ORC_DAYSECS / ORC_SPECHEATET);
+}
+
+/* mo_pet.f90:235-272 */
+double orc_pet_penman(double net_rad, double tavg, double act_vap_pressure,
+                      double aerodyn_resistance, double bulksurface_resistance, double a_s,
+                      double a_sh) {
+  return ORC_DAYSECS / ORC_SPECHEATET *
+         (orc_slope_satpressure(tavg) * net_rad +
+          ORC_RHO0 * ORC_CP0 * (orc_sat_vap_pressure(tavg) - act_vap_pressure) * a_sh /
+              aerodyn_resistance) /
+         (orc_slope_satpressure(tavg) +
+          ORC_PSYCHRO * a_sh / a_s * (1.0 + bulksurface_resistance / aerodyn_resistance));
+}
+
+/* mo_meteo_temporal_tools.f90:32-59 */
+double orc_temporal_disagg_meteo_weights(double v, double w, double c) {
+  return (v + c) * w - c;
+}
+
+/* mo_meteo_temporal_tools.f90:66-101 */
+double orc_temporal_disagg_flux_daynight(int32_t isday, double ntimesteps_day, double v,
+                                         double fday, double fnight) {
+  if (ntimesteps_day > 1.0) {
+    if (isday) return 2.0 * v * fday / ntimesteps_day;
+    return 2.0 * v * fnight / ntimesteps_day;
+  }
+  return v;
+}
+
+/* mo_meteo_temporal_tools.f90:108-161 */
+double orc_temporal_disagg_state_daynight(int32_t isday, double ntimesteps_day, double v,
+                                          double fday, double fnight, int32_t add_correction) {
+  if (ntimesteps_day > 1.0) {
+    if (add_correction) return isday ? v + fday : v + fnight;
+    return isday ? 2.0 * v * fday : 2.0 * v * fnight;
+  }
+  return v;
+}
+
+/* ============================================================================
+ *  Calendar.  FORCES mo_julian (un-vendored) julday/caldat are the Numerical
+ *  Recipes routines with the Gregorian switch of 15 Oct 1582; restated here.
+ * ==========================================================================*/
+int32_t orc_julday(int32_t dd, int32_t mm, int32_t yy) {
+  const int32_t IGREG = 15 + 31 * (10 + 12 * 1582);
+  int32_t jy = yy, jm, ja, jul;
+  if (jy < 0) jy = jy + 1;
+  if (mm > 2) {
+    jm = mm + 1;
+  } else {
+    jy = jy - 1;
+    jm = mm + 13;
+  }
+  jul = (int32_t)floor(365.25 * jy) + (int32_t)floor(30.6001 * jm) + dd + 1720995;
+  if (dd + 31 * (mm + 12 * yy) >= IGREG) {
+    ja = (int32_t)(0.01 * jy);
+    jul = jul + 2 - ja + (int32_t)(0.25 * ja);
+  }
+  return jul;
+}
+
+void orc_caldat(int32_t julian, int32_t *dd, int32_t *mm, int32_t *yy) {
+  const int32_t IGREG = 2299161;
+  int32_t ja, jalpha, jb, jc, jd, je;
+  if (julian >= IGREG) {
+    jalpha = (int32_t)(((julian - 1867216) - 0.25) / 36524.25);
+    ja = julian + 1 + jalpha - (int32_t)(0.25 * jalpha);
+  } else {
+    ja = julian;
+  }
+  jb = ja + 1524;
+  jc = (int32_t)(6680.0 + ((jb - 2439870) - 122.1) / 365.25);
+  jd = 365 * jc + (int32_t)(0.25 * jc);
+  je = (int32_t)((jb - jd) / 30.6001);
+  *dd = jb - jd - (int32_t)(30.6001 * je);
+  *mm = je - 1;
+  if (*mm > 12) *mm = *mm - 12;
+  *yy = jc - 4715;
+  if (*mm > 2) *yy = *yy - 1;
+  if (*yy <= 0) *yy = *yy - 1;
+}
+
+int32_t orc_doy(int32_t dd, int32_t mm, int32_t yy) {
+  return orc_julday(dd, mm, yy) - orc_julday(1, 1, yy) + 1;
+}
+
+/* ============================================================================
+ *  Routing
+ * ==========================================================================*/
+
+/* mRM/mo_mrm_pre_routing.f90:77-143 */
+void orc_L11_runoff_acc(int32_t nCells1, int32_t nNodes, const double *qAll,
+                        const double *efecArea, const int32_t *L1_L11_Id,
+                        const double *L11_areaCell, const int32_t *L11_L1_Id, int32_t TS,
+                        int32_t map_flag, double *qAcc) {
+  int32_t k;
+  double TST = ORC_HOURSECS * TS; /* :110 */
+  if (map_flag) {                 /* :112-130 */
+    for (k = 0; k < nNodes; k++) qAcc[k] = 0.0;
+    for (k = 0; k < nCells1; k++)
+      qAcc[L1_L11_Id[k] - 1] = qAcc[L1_L11_Id[k] - 1] + qAll[k] * efecArea[k];
+    for (k = 0; k < nNodes; k++) qAcc[k] = qAcc[k] * 1000.0 / TST;
+  } else { /* :132-141 */
+    for (k = 0; k < nNodes; k++) qAcc[k] = qAll[L11_L1_Id[k] - 1];
+    for (k = 0; k < nNodes; k++) qAcc[k] = qAcc[k] * L11_areaCell[k] * 1000.0 / TST;
+  }
+}
+
+/* mRM/mo_mrm_pre_routing.f90:179-214 */
+void orc_add_inflow(int32_t nInflowGauges, const int32_t *InflowIndexList,
+                    const int32_t *InflowHeadwater, const int32_t *InflowNodeList,
+                    const double *QInflow, double *qOut) {
+  int32_t ii;
+  for (ii = 0; ii < nInflowGauges; ii++) {
+    if (InflowHeadwater[ii]) {
+      qOut[InflowNodeList[ii] - 1] = qOut[InflowNodeList[ii] - 1] + QInflow[InflowIndexList[ii] - 1];
+    } else {
+      qOut[InflowNodeList[ii] - 1] = QInflow[InflowIndexList[ii] - 1];
+    }
+  }
+}
+
+/* mRM/mo_mrm_routing.f90:380-481.  qTIN/qTR are Fortran (nNodes, 2): [0]=IT1 (past), [1]=IT */
+void orc_L11_routing(int32_t nNodes, int32_t nLinks, const int32_t *netPerm,
+                     const int32_t *fromN, const int32_t *toN, const double *C1,
+                     const double *C2, const double *qOUT, int32_t nInflowGauges,
+                     const int32_t *InflowHeadwater, const int32_t *InflowNodeList,
+                     double *qTIN, double *qTR, double *Qmod) {
+  double *qTIN1 = qTIN, *qTIN2 = qTIN + nNodes, *qTR1 = qTR, *qTR2 = qTR + nNodes;
+  int32_t g, i, k, iNode, tNode;
+  for (k = 0; k < nNodes; k++) qTIN2[k] = 0.0; /* :428 */
+  for (k = 0; k < nLinks; k++) {               /* :435-459 */
+    i = netPerm[k] - 1;
+    iNode = fromN[i] - 1;
+    tNode = toN[i] - 1;
+    qTIN2[iNode] = qTIN2[iNode] + qOUT[iNode];
+    qTR2[iNode] = qTR1[iNode] + C1[i] * (qTIN1[iNode] - qTR1[iNode]) +
+                  C2[i] * (qTIN2[iNode] - qTIN1[iNode]);
+    if (nInflowGauges > 0) {
+      for (g = 0; g < nInflowGauges; g++)
+        if ((tNode + 1 == InflowNodeList[g]) && (!InflowHeadwater[g])) qTR2[iNode] = 0.0;
+    }
+    qTIN2[tNode] = qTIN2[tNode] + qTR2[iNode];
+  }
+  tNode = toN[netPerm[nLinks - 1] - 1] - 1; /* :466-467: ONLY the last link's sink */
+  qTIN2[tNode] = qTIN2[tNode] + qOUT[tNode];
+  for (k = 0; k < nNodes; k++) { /* :474-478 */
+    Qmod[k] = qTIN2[k];
+    qTR1[k] = qTR2[k];
+    qTIN1[k] = qTIN2[k];
+  }
+}
+
+/* mRM/mo_mrm_mpr.f90:61-119.  length/slope carry nSlope (= nNodes-1) entries at the
+ * call site (mo_mhm_interface_run.f90:577-578); ssMax is the maxval over all of them. */
+void orc_reg_rout(const double *param, int32_t nLinks, int32_t nSlope, const double *length,
+                  const double *slope, const double *fFPimp, double TS, double *C1, double *C2) {
+  int32_t i;
+  double ssMax = slope[0], K, xi;
+  for (i = 1; i < nSlope; i++)
+    if (slope[i] > ssMax) ssMax = slope[i];
+  for (i = 0; i < nLinks; i++) {
+    K = param[0] + param[1] * (length[i] * 0.001) + param[2] * slope[i] + param[3] * fFPimp[i];
+    xi = param[4] * (1.0 + slope[i] / ssMax);
+    if (xi > 0.5) xi = 0.5;
+    if (xi < 0.005) xi = 0.005;
+    if (K > 0.5 * TS / xi) K = 0.5 * TS / xi;
+    if (K < 0.5 * TS / (1.0 - xi)) K = 0.5 * TS / (1.0 - xi);
+    C1[i] = TS / (K * (1.0 - xi) + 0.5 * TS);
+    C2[i] = 1.0 - C1[i] * K / TS;
+  }
+}
+
+/* mRM/mo_mrm_constants.F90:42-46 */
+static const double given_TS[19] = {60.,   120.,  180.,  240.,   300.,   360.,   600.,
+                                    720.,  900.,  1200., 1800.,  3600.,  7200.,  10800.,
+                                    14400., 21600., 28800., 43200., 86400.};
+
+/* FORCES mo_utils::locate (un-vendored): j with xx(j) <= x < xx(j+1); 0 / n outside */
+static int32_t orc_locate(const double *xx, int32_t n, double x) {
+  int32_t jl = 0, ju = n + 1, jm;
+  while (ju - jl > 1) {
+    jm = (ju + jl) / 2;
+    if (x >= xx[jm - 1]) jl = jm; else ju = jm;
+  }
+  if (x == xx[0]) return 1;
+  if (x == xx[n - 1]) return n - 1;
+  return jl;
+}
+
+/* mRM/mo_mrm_mpr.f90:241-329, processCase(8)=2: K = length / celerity */
+double orc_mrm_update_param_case2(int32_t nNodes, int32_t nOutlets, const double *length,
+                                  double celerity, double *C1, double *C2) {
+  int32_t i, ind;
+  double xi = fabs(0.0), kmin, TSrout; /* rout_space_weight = 0 */
+  double *K = (double *)malloc(sizeof(double) * (size_t)nNodes);
+  for (i = 0; i < nNodes; i++) K[i] = length[i] / celerity;
+  kmin = K[0];
+  for (i = 1; i < nNodes - nOutlets; i++)
+    if (K[i] < kmin) kmin = K[i];
+  ind = orc_locate(given_TS, 19, kmin);
+  if (ind < 1) ind = 1;
+  TSrout = given_TS[ind - 1];
+  for (i = 0; i < nNodes; i++) {
+    C1[i] = TSrout / (K[i] * (1.0 - xi) + 0.5 * TSrout);
+    C2[i] = 1.0 - C1[i] * K[i] / TSrout;
+  }
+  free(K);
+  return TSrout;
+}
+
+/* mRM/mo_mrm_routing.f90:104-303 for one call; GaugeDischarge = mRM_runoff(tt, :) with
+ * Fortran (nTimeSteps, nGaugesTotal) layout -> element (tt, g) at [ (g-1)*nTimeSteps + tt-1 ] */
+static void orc_mRM_routing(orc_domain *d, int32_t tt, const double *RunToRout,
+                            int32_t timestep_rout, double tsRoutFactor, int32_t yId,
+                            const double *InflowDischarge, double *qAcc) {
+  int32_t nNodes = d->nNodes, nLinks = d->nNodes - d->nOutlets, k, gg, t, rout_loop;
+  if (d->pc_rout == 1 && !d->read_states) { /* :211-218 */
+    if (nNodes > 1)
+      orc_reg_rout(d->rout_param, nLinks, nNodes - 1, d->L11_length, d->L11_slope,
+                   d->L11_nLinkFracFPimp + (size_t)(yId - 1) * nNodes, (double)timestep_rout,
+                   d->L11_C1, d->L11_C2);
+  }
+  rout_loop = (int32_t)lround(1.0 / tsRoutFactor); /* :224 nint */
+  if (rout_loop < 1) rout_loop = 1;
+  orc_L11_runoff_acc(d->nCells, nNodes, RunToRout, d->L1_areaCell, d->L1_L11_Id,
+                     d->L11_areaCell, d->L11_L1_Id, timestep_rout, d->map_flag, d->L11_qOUT);
+  orc_add_inflow(d->nInflowGauges, d->InflowGaugeIndexList, d->InflowGaugeHeadwater,
+                 d->InflowGaugeNodeList, InflowDischarge, d->L11_qOUT);
+  if (nNodes > 1) { /* :243-282 */
+    for (k = 0; k < nNodes; k++) qAcc[k] = 0.0;
+    for (t = 0; t < rout_loop; t++) {
+      orc_L11_routing(nNodes, nLinks, d->netPerm, d->fromN, d->toN, d->L11_C1, d->L11_C2,
+                      d->L11_qOUT, d->nInflowGauges, d->InflowGaugeHeadwater,
+                      d->InflowGaugeNodeList, d->L11_qTIN, d->L11_qTR, d->L11_qMod);
+      for (k = 0; k < nNodes; k++) qAcc[k] = qAcc[k] + d->L11_qMod[k];
+    }
+    for (k = 0; k < nNodes; k++) d->L11_qMod[k] = qAcc[k] / (double)rout_loop;
+  } else {
+    for (k = 0; k < nNodes; k++) d->L11_qMod[k] = d->L11_qOUT[k];
+  }
+  for (gg = 0; gg < d->nGauges; gg++) /* :299-301 */
+    d->mRM_runoff[(size_t)(d->gaugeIndexList[gg] - 1) * d->nTimeSteps + (tt - 1)] =
+        d->L11_qMod[d->gaugeNodeList[gg] - 1];
+}
+
+/* ============================================================================
+ *  Time loop
+ * ==========================================================================*/
+
+/* common/mo_common_datetime_type.f90:28-155: date state carried through the loop */
+typedef struct {
+  int32_t year, month, day, hour, iLAI, yId;
+  int32_t is_new_day, is_new_month, is_new_year;
+} orc_dt;
+
+static int32_t lc_yid(const orc_domain *d, int32_t year) {
+  int32_t i = year - d->lc_year_start;
+  if (i < 0) i = 0;
+  if (i >= d->lc_nyears) i = d->lc_nyears - 1;
+  return d->LCyearId[i];
+}
+
+static void dt_init(const orc_domain *d, orc_dt *s) { /* :71-108 */
+  orc_caldat(d->jul_start, &s->day, &s->month, &s->year);
+  s->is_new_day = s->is_new_month = s->is_new_year = 1;
+  s->yId = lc_yid(d, s->year);
+  s->hour = 0;
+  s->iLAI = 0;
+}
+
+static void dt_update_LAI(const orc_domain *d, orc_dt *s) { /* :135-155 */
+  switch (d->timeStep_LAI_input) {
+    case 0:
+    case 1: s->iLAI = s->month; break;
+    case -1: if (s->is_new_day) s->iLAI++; break;
+    case -2: if (s->is_new_month) s->iLAI++; break;
+    case -3: if (s->is_new_year) s->iLAI++; break;
+    default: break;
+  }
+}
+
+static void dt_increment(const orc_domain *d, orc_dt *s) { /* :110-133 */
+  int32_t pd = s->day, pm = s->month, py = s->year, jul;
+  s->is_new_day = s->is_new_month = s->is_new_year = 0;
+  s->hour = s->hour + d->timestep_h;
+  /* newTime = julday + hour/24; int(newTime) = julday + hour/24 (integer division) */
+  jul = orc_julday(s->day, s->month, s->year) + s->hour / 24;
+  s->hour = s->hour % 24;
+  orc_caldat(jul, &s->day, &s->month, &s->year);
+  if (pd != s->day) s->is_new_day = 1;
+  if (pm != s->month) s->is_new_month = 1;
+  if (py != s->year) s->is_new_year = 1;
+}
+
+void orc_time_indices(const orc_domain *d, int32_t n, int32_t *month, int32_t *hour,
+                      int32_t *yId, int32_t *iLAI, int32_t *iMeteoTS, int32_t *isday,
+                      int32_t *doy, int32_t *year) {
+  orc_dt s;
+  int32_t tt, per = (int32_t)lround(24.0 / (double)d->nTstepForcingDay);
+  dt_init(d, &s);
+  for (tt = 1; tt <= n; tt++) {
+    dt_update_LAI(d, &s);
+    month[tt - 1] = s.month;
+    hour[tt - 1] = s.hour;
+    yId[tt - 1] = s.yId;
+    iLAI[tt - 1] = s.iLAI;
+    iMeteoTS[tt - 1] = (int32_t)ceil((double)tt / (double)per); /* mo_meteo_handler.f90:607 */
+    isday[tt - 1] = (s.hour > 6) && (s.hour <= 18);               /* :1048 */
+    doy[tt - 1] = orc_doy(s.day, s.month, s.year);
+    year[tt - 1] = s.year;
+    dt_increment(d, &s);
+    if (s.is_new_year && tt < d->nTimeSteps) s.yId = lc_yid(d, s.year);
+  }
+}
+
+#define P3(base, n, dim2, j, y) ((base) + ((size_t)(y) * (dim2) + (j)) * (size_t)(n))
+
+int32_t orc_flux_record_size(int32_t nH) { return 22 + 3 * nH; }
+
+/* one model step for all cells: meteo/mo_meteo_handler.f90:915-1285 (get_corrected_pet,
+ * get_temp, get_prec) followed by mHM/mo_mhm.f90:229-521 */
+static void orc_step_cells(orc_domain *d, int32_t tt, const orc_dt *s, int32_t iMeteoTS) {
+  const int32_t n = d->nCells, nH = d->nH;
+  const int32_t month = s->month, hour = s->hour, y = s->yId - 1, il = s->iLAI - 1;
+  const int32_t isday = (hour > 6) && (hour <= 18);
+  const int32_t doy = orc_doy(s->day, s->month, s->year);
+  const size_t mo = (size_t)(iMeteoTS - 1) * n;
+  const double nts = (double)d->nTstepDay;
+  const double c2TSTu = d->c2TSTu;
+  const double *fSealed = P3(d->fSealed, n, 1, 0, y), *alpha = P3(d->alpha, n, 1, 0, y);
+  const double *ddinc = P3(d->degDayInc, n, 1, 0, y), *ddmax = P3(d->degDayMax, n, 1, 0, y);
+  const double *ddnop = P3(d->degDayNoPre, n, 1, 0, y);
+  const double *fRoots = P3(d->fRoots, n, nH, 0, y);
+  const double *maxInter = P3(d->maxInter, n, d->nLAI, il, 0);
+  const double *k0 = P3(d->kFastFlow, n, 1, 0, y), *k1 = P3(d->kSlowFlow, n, 1, 0, y);
+  const double *k2 = P3(d->kBaseFlow, n, 1, 0, y), *kp = P3(d->kPerco, n, 1, 0, y);
+  const double *FC = P3(d->soilMoistFC, n, nH, 0, y), *SAT = P3(d->soilMoistSat, n, nH, 0, y);
+  const double *EXPN = P3(d->soilMoistExp, n, nH, 0, y), *WP = P3(d->wiltingPoint, n, nH, 0, y);
+  const double *tthr = P3(d->tempThresh, n, 1, 0, y);
+  const double *petLAI = d->petLAIcorFactor ? P3(d->petLAIcorFactor, n, d->nLAI, il, y) : 0;
+  const double *PTa = d->PrieTayAlpha ? P3(d->PrieTayAlpha, n, d->nLAI, il, 0) : 0;
+  const double *aeroR = d->aeroResist ? P3(d->aeroResist, n, d->nLAI, il, y) : 0;
+  const double *surfR = d->surfResist ? P3(d->surfResist, n, d->nLAI, il, 0) : 0;
+  int32_t k;
+
+  if (tt == 1 && !d->read_states) { /* mo_mhm.f90:448-450 */
+    size_t i;
+    for (i = 0; i < (size_t)n * nH; i++) d->soilMoist[i] = 0.5 * FC[i];
+  }
+
+#pragma omp parallel for schedule(static) num_threads(d->num_threads)
+  for (k = 0; k < n; k++) {
+    double pet = 0.0, v;
+    /* ---- get_corrected_pet, mo_meteo_handler.f90:1053-1119 ---- */
+    switch (d->pc_pet) {
+      case -1: pet = petLAI[k] * d->pet[mo + k]; break;
+      case 0: pet = d->fAsp[k] * d->pet[mo + k]; break;
+      case 1:
+        pet = d->fAsp[k] * orc_pet_hargreaves(d->HarSamCoeff[k], ORC_HARSAMCONST,
+                                              d->temp[mo + k], d->tmax[mo + k],
+                                              d->tmin[mo + k], d->latitude[k], doy);
+        break;
+      case 2:
+        v = d->netrad[mo + k];
+        pet = orc_pet_priestly(PTa[k], v > 0.0 ? v : 0.0, d->temp[mo + k]);
+        break;
+      case 3:
+        v = d->netrad[mo + k];
+        pet = orc_pet_penman(v > 0.0 ? v : 0.0, d->temp[mo + k],
+                             d->absvappress[mo + k] / 1000.0,
+                             aeroR[k] / d->windspeed[mo + k], surfR[k], 1.0, 1.0);
+        break;
+      default: break;
+    }
+    if (d->is_hourly_forcing) {
+      d->pet_calc[k] = pet;
+    } else if (d->read_meteo_weights) {
+      d->pet_calc[k] = orc_temporal_disagg_meteo_weights(
+          pet, d->pet_weights[((size_t)hour * 12 + (month - 1)) * n + k], 0.0);
+    } else {
+      d->pet_calc[k] = orc_temporal_disagg_flux_daynight(
+          isday, nts, pet, d->fday_pet[month - 1], d->fnight_pet[month - 1]);
+    }
+    /* ---- get_temp :1166-1201 ---- */
+    if (d->is_hourly_forcing) {
+      d->temp_calc[k] = d->temp[mo + k];
+    } else if (d->read_meteo_weights) {
+      d->temp_calc[k] = orc_temporal_disagg_meteo_weights(
+          d->temp[mo + k], d->temp_weights[((size_t)hour * 12 + (month - 1)) * n + k], ORC_T0);
+    } else {
+      d->temp_calc[k] = orc_temporal_disagg_state_daynight(
+          isday, nts, d->temp[mo + k], d->fday_temp[month - 1], d->fnight_temp[month - 1], 1);
+    }
+    /* ---- get_prec :1247-1281 ---- */
+    if (d->is_hourly_forcing) {
+      d->prec_calc[k] = d->pre[mo + k];
+    } else if (d->read_meteo_weights) {
+      d->prec_calc[k] = orc_temporal_disagg_meteo_weights(
+          d->pre[mo + k], d->pre_weights[((size_t)hour * 12 + (month - 1)) * n + k], 0.0);
+    } else {
+      d->prec_calc[k] = orc_temporal_disagg_flux_daynight(
+          isday, nts, d->pre[mo + k], d->fday_prec[month - 1], d->fnight_prec[month - 1]);
+    }
+
+    /* ---- mo_mhm.f90:458-499 ---- */
+    orc_canopy_interc(d->pet_calc[k], maxInter[k], d->prec_calc[k], &d->inter[k],
+                      &d->throughfall[k], &d->aETCanopy[k]);
+    orc_snow_accum_melt(ddinc[k], ddmax[k] * c2TSTu, ddnop[k] * c2TSTu, d->prec_calc[k],
+                        d->temp_calc[k], tthr[k], d->throughfall[k], &d->snowPack[k],
+                        &d->degDay[k], &d->melt[k], &d->preEffect[k], &d->rain[k], &d->snow[k]);
+    orc_soil_moisture(d->pc_soil, fSealed[k], d->sealedThresh[k], d->pet_calc[k],
+                      d->evap_coeff[month - 1], nH, n, SAT + k, fRoots + k, FC + k, WP + k,
+                      EXPN + k, d->jarvis_thresh_c1[k], d->aETCanopy[k], d->preEffect[k],
+                      &d->runoffSeal[k], &d->sealSTW[k], d->infilSoil + k, d->soilMoist + k,
+                      d->aETSoil + k, &d->aETSealed[k]);
+    orc_runoff_unsat_zone(c2TSTu / k1[k], c2TSTu / kp[k], c2TSTu / k0[k], alpha[k],
+                          d->karstLoss[k], d->infilSoil[(size_t)(nH - 1) * n + k],
+                          d->unsatThresh[k], &d->satSTW[k], &d->unsatSTW[k],
+                          &d->slowRunoff[k], &d->fastRunoff[k], &d->percol[k]);
+    orc_runoff_sat_zone(c2TSTu / k2[k], &d->satSTW[k], &d->baseflow[k]);
+    orc_L1_total_runoff(fSealed[k], d->fastRunoff[k], d->slowRunoff[k], d->baseflow[k],
+                        d->runoffSeal[k], &d->total_runoff[k]);
+  }
+
+  if (d->flux_history) {
+    const size_t rs = (size_t)orc_flux_record_size(nH);
+    double *H = d->flux_history + (size_t)(tt - 1) * rs * n;
+    const double *src[22] = {d->pet_calc,  d->temp_calc,  d->prec_calc,  d->aETCanopy,
+                             d->aETSealed, d->baseflow,   d->fastRunoff, d->melt,
+                             d->percol,    d->preEffect,  d->rain,       d->runoffSeal,
+                             d->slowRunoff, d->snow,      d->throughfall, d->total_runoff,
+                             d->degDay,    d->inter,      d->snowPack,   d->sealSTW,
+                             d->unsatSTW,  d->satSTW};
+    int32_t r, h;
+    for (r = 0; r < 22; r++) memcpy(H + (size_t)r * n, src[r], sizeof(double) * n);
+    for (h = 0; h < nH; h++) {
+      memcpy(H + (size_t)(22 + h) * n, d->aETSoil + (size_t)h * n, sizeof(double) * n);
+      memcpy(H + (size_t)(22 + nH + h) * n, d->infilSoil + (size_t)h * n, sizeof(double) * n);
+      memcpy(H + (size_t)(22 + 2 * nH + h) * n, d->soilMoist + (size_t)h * n, sizeof(double) * n);
+    }
+  }
+}
+
+/* mo_mhm_eval.f90:136-150 + mo_mhm_interface_run.f90:341-638 */
+int32_t orc_run(orc_domain *d, int32_t tt_first, int32_t tt_last) {
+  orc_dt s;
+  int32_t tt, k, g, jj;
+  const int32_t per = (int32_t)lround(24.0 / (double)d->nTstepForcingDay);
+  double tsRoutFactor = 1.0, tsRoutFactorIn = 1.0;
+  int32_t timestep_rout = d->timestep_h, doRoute;
+  double *qAcc = 0;
+
+  if (d->do_routing) qAcc = (double *)malloc(sizeof(double) * (size_t)d->nNodes);
+  dt_init(d, &s);
+  for (tt = 1; tt <= tt_last; tt++) {
+    int32_t iMeteoTS;
+    dt_update_LAI(d, &s); /* mo_mhm_interface_run.f90:355 */
+    if (tt >= tt_first) {
+      iMeteoTS = (int32_t)ceil((double)tt / (double)per); /* mo_meteo_handler.f90:607 */
+      orc_step_cells(d, tt, &s, iMeteoTS);
+
+      /* ---- routing scheduling, mo_mhm_interface_run.f90:460-608 ---- */
+      doRoute = 0;
+      if (d->do_routing) {
+        int32_t iDischargeTS = (int32_t)ceil((double)tt / (double)d->nTstepDay); /* :463 */
+        if (d->pc_rout == 1) {                                                     /* :465-474 */
+          doRoute = 1;
+          tsRoutFactorIn = 1.0;
+          timestep_rout = d->timestep_h;
+          for (k = 0; k < d->nCells; k++) d->RunToRout[k] = d->total_runoff[k];
+          for (g = 0; g < d->nInflowTotal; g++)
+            d->InflowDischarge[g] = d->InflowQ[(size_t)g * d->nDays + iDischargeTS - 1];
+        } else if (d->pc_rout == 2 || d->pc_rout == 3) { /* :476-513 */
+          tsRoutFactor = d->L11_TSrout / (d->timestep_h * ORC_HOURSECS);
+          if (tsRoutFactor < 1.0) {
+            tsRoutFactorIn = tsRoutFactor;
+            for (k = 0; k < d->nCells; k++) d->RunToRout[k] = d->total_runoff[k];
+            for (g = 0; g < d->nInflowTotal; g++)
+              d->InflowDischarge[g] = d->InflowQ[(size_t)g * d->nDays + iDischargeTS - 1];
+            timestep_rout = d->timestep_h;
+            doRoute = 1;
+          } else {
+            tsRoutFactorIn = tsRoutFactor;
+            for (k = 0; k < d->nCells; k++)
+              d->RunToRout[k] = d->RunToRout[k] + d->total_runoff[k];
+            for (g = 0; g < d->nInflowTotal; g++)
+              d->InflowDischarge[g] =
+                  d->InflowDischarge[g] + d->InflowQ[(size_t)g * d->nDays + iDischargeTS - 1];
+            if (tt == d->nTimeSteps && (tt % (int32_t)lround(tsRoutFactorIn)) != 0)
+              tsRoutFactorIn = (double)(tt % (int32_t)lround(tsRoutFactorIn));
+            if ((tt % (int32_t)lround(tsRoutFactorIn)) == 0 || tt == d->nTimeSteps) {
+              for (g = 0; g < d->nInflowTotal; g++)
+                d->InflowDischarge[g] = d->InflowDischarge[g] / tsRoutFactorIn;
+              timestep_rout = d->timestep_h * (int32_t)lround(tsRoutFactorIn);
+              doRoute = 1;
+            }
+          }
+        }
+        if (doRoute)
+          orc_mRM_routing(d, tt, d->RunToRout, timestep_rout, tsRoutFactorIn, s.yId,
+                          d->InflowDischarge, qAcc);
+        if (d->pc_rout == 1) { /* :595-598 */
+          for (g = 0; g < d->nInflowTotal; g++) d->InflowDischarge[g] = 0.0;
+          for (k = 0; k < d->nCells; k++) d->RunToRout[k] = 0.0;
+        } else if (d->pc_rout == 2 || d->pc_rout == 3) { /* :599-612 */
+          if (!(tsRoutFactorIn < 1.0) && doRoute) {
+            for (jj = 1; jj <= (int32_t)lround(tsRoutFactorIn); jj++)
+              for (g = 0; g < d->nGaugesTotal; g++)
+                d->mRM_runoff[(size_t)g * d->nTimeSteps + (tt - jj)] =
+                    d->mRM_runoff[(size_t)g * d->nTimeSteps + (tt - 1)];
+            for (g = 0; g < d->nInflowTotal; g++) d->InflowDischarge[g] = 0.0;
+            for (k = 0; k < d->nCells; k++) d->RunToRout[k] = 0.0;
+          }
+        }
+      }
+    }
+    dt_increment(d, &s); /* :623 */
+    if (s.is_new_year && tt < d->nTimeSteps) s.yId = lc_yid(d, s.year); /* :626-628 */
+  }
+  free(qAcc);
+  return 0;
+}
