@@ -1,0 +1,345 @@
+/*
+ * mhm_cuda.h -- C ABI of libmhm_cuda.so, the B200 (sm_100a) implementation of mHM's
+ * L1 hot path: meteo prologue + cell process cascade, mRM Muskingum routing and the
+ * MPR upscaling operators.
+ *
+ * Who binds this: the reference's Fortran driver through ISO_C_BINDING
+ * (mhm_b200/fortran/mo_mhm_cuda.F90 holds the `interface ... bind(C)` blocks and
+ * INTEGRATION.md shows the four patched call sites).  Every entry point names the
+ * reference routine / call site it replaces (paths relative to /root/reference/src).
+ *
+ * Conventions
+ *  - plain C types only; all arrays are caller-owned host memory unless the name ends
+ *    in `_device`; the library never frees or keeps a host pointer after the call
+ *    returns (except mhm_cuda_bind_*: kept until mhm_cuda_unregister_domain / finalize).
+ *  - every function returns 0 on success, non-zero on failure; the message is available
+ *    from mhm_cuda_last_error().  The Fortran shim turns non-zero into
+ *    `call error_message('mhm_cuda: ', ...)` like every other fatal path of the reference.
+ *  - Fortran array sections are passed as (base pointer of the whole module-global array,
+ *    leading dimension ld = size(array,1), offset = s1-1 of the domain's first cell).
+ *    Element (k, j, y) (1-based) of a (nCellsTot, dim2, dim3) array is
+ *    base[(offset + k-1) + ld*((j-1) + dim2*(y-1))].
+ *  - all ids that index Fortran arrays (yId, iLAI, node ids, netPerm ...) stay 1-based.
+ *  - `member`: index (0-based) of an ensemble member = one parameter set / one
+ *    mhm_eval(parameterset) evaluation (mHM/mo_mhm_eval.f90:94).  A plain run has
+ *    nMembers = 1 and passes member = 0.
+ *  - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef MHM_CUDA_H
+#define MHM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mhm_cuda_context mhm_cuda_context; /* opaque; Fortran: type(c_ptr) */
+
+/* ---------------------------------------------------------------------------------
+ * B0  lifecycle.  Call sites: after mhm_initialize/mrm_init
+ * (mHM/mo_mhm_interface.F90:169-174) and before restart writing (:462-476).
+ * --------------------------------------------------------------------------------- */
+int mhm_cuda_init(int device, mhm_cuda_context **ctx);      /* device < 0: current device */
+int mhm_cuda_finalize(mhm_cuda_context *ctx);
+const char *mhm_cuda_last_error(void);
+const char *mhm_cuda_version(void);
+
+/* sizes and process switches of one domain (common/mo_common_types.F90:52-88 Grid;
+ * processMatrix as filled by MPR/mo_mpr_read_config.f90:390-988, passed verbatim,
+ * column-major (nProcesses, 3)) */
+typedef struct mhm_domain_config {
+  int32_t nCells;        /* level1(iDomain)%nCells */
+  int32_t nHorizons;     /* nSoilHorizons_mHM (1..8) */
+  int32_t nLAI;          /* nLAI: 2nd dim of L1_maxInter */
+  int32_t nLCscenes;     /* nLCoverScene */
+  int32_t nMembers;      /* parameter sets evaluated side by side (>= 1) */
+  int32_t nProcesses;    /* rows of processMatrix (11) */
+  int32_t timestep_h;    /* timeStep [h] */
+  int32_t read_states;   /* read_restart: skip the 0.5*FC soil moisture start */
+  double c2TSTu;         /* mHM/mo_startup.f90:168, timeStep/24 */
+  const int32_t *processMatrix;
+} mhm_domain_config;
+
+int mhm_cuda_register_domain(mhm_cuda_context *ctx, int32_t iDomain,
+                             const mhm_domain_config *cfg);
+int mhm_cuda_unregister_domain(mhm_cuda_context *ctx, int32_t iDomain);
+
+/* effective parameters (MPR/mo_mpr_global_variables.f90:128-170).  Layout in the
+ * reference: (nCellsTot, dim2, dim3). */
+enum mhm_param_id {
+  MHM_P_FSEALED = 0,      /* L1_fSealed        (:,1,nLC)    */
+  MHM_P_ALPHA,            /* L1_alpha          (:,1,nLC)    */
+  MHM_P_DEGDAYINC,        /* L1_degDayInc      (:,1,nLC)    */
+  MHM_P_DEGDAYMAX,        /* L1_degDayMax      (:,1,nLC)    */
+  MHM_P_DEGDAYNOPRE,      /* L1_degDayNoPre    (:,1,nLC)    */
+  MHM_P_FROOTS,           /* L1_fRoots         (:,nH,nLC)   */
+  MHM_P_MAXINTER,         /* L1_maxInter       (:,nLAI,1)   */
+  MHM_P_KARSTLOSS,        /* L1_karstLoss      (:,1,1)      */
+  MHM_P_KFASTFLOW,        /* L1_kFastFlow      (:,1,nLC)    */
+  MHM_P_KSLOWFLOW,        /* L1_kSlowFlow      (:,1,nLC)    */
+  MHM_P_KBASEFLOW,        /* L1_kBaseFlow      (:,1,nLC)    */
+  MHM_P_KPERCO,           /* L1_kPerco         (:,1,nLC)    */
+  MHM_P_SOILMOISTFC,      /* L1_soilMoistFC    (:,nH,nLC)   */
+  MHM_P_SOILMOISTSAT,     /* L1_soilMoistSat   (:,nH,nLC)   */
+  MHM_P_SOILMOISTEXP,     /* L1_soilMoistExp   (:,nH,nLC)   */
+  MHM_P_JARVIS_C1,        /* L1_jarvis_thresh_c1 (:,1,1)    */
+  MHM_P_TEMPTHRESH,       /* L1_tempThresh     (:,1,nLC)    */
+  MHM_P_UNSATTHRESH,      /* L1_unsatThresh    (:,1,1)      */
+  MHM_P_SEALEDTHRESH,     /* L1_sealedThresh   (:,1,1)      */
+  MHM_P_WILTINGPOINT,     /* L1_wiltingPoint   (:,nH,nLC)   */
+  MHM_P_PETLAICORFACTOR,  /* L1_petLAIcorFactor(:,nLAI,nLC) */
+  MHM_P_FASP,             /* L1_fAsp           (:,1,1)      */
+  MHM_P_HARSAMCOEFF,      /* L1_HarSamCoeff    (:,1,1)      */
+  MHM_P_PRIETAYALPHA,     /* L1_PrieTayAlpha   (:,nLAI,1)   */
+  MHM_P_AERORESIST,       /* L1_aeroResist     (:,nLAI,nLC) */
+  MHM_P_SURFRESIST,       /* L1_surfResist     (:,nLAI,1)   */
+  MHM_P_LATITUDE,         /* pack(level1%y, mask) (:,1,1)   */
+  MHM_P_COUNT
+};
+
+/* upload one parameter array of one member: replaces the array-section arguments of
+ * `call mhm(...)` (mHM/mo_mhm_interface_run.f90:394-457) and of get_corrected_pet
+ * (:366-374).  Called after mpr_eval (:234) or read_restart_states (:224). */
+int mhm_cuda_set_param(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                       int32_t param_id, const double *base, int64_t ld, int64_t offset,
+                       int32_t dim2, int32_t dim3);
+
+/* states (mHM/mo_global_variables.f90:130-136) */
+enum mhm_state_id {
+  MHM_S_INTER = 0,  /* L1_inter     */
+  MHM_S_SNOWPACK,   /* L1_snowPack  */
+  MHM_S_SEALSTW,    /* L1_sealSTW   */
+  MHM_S_UNSATSTW,   /* L1_unsatSTW  */
+  MHM_S_SATSTW,     /* L1_satSTW    */
+  MHM_S_SOILMOIST,  /* L1_soilMoist (:, nH) */
+  MHM_S_COUNT
+};
+int mhm_cuda_set_state(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                       int32_t state_id, const double *base, int64_t ld, int64_t offset);
+int mhm_cuda_get_state(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                       int32_t state_id, double *base, int64_t ld, int64_t offset);
+/* mHM/mo_init_states.f90:280-300 (fluxes_states_default_init) for all members, on device */
+int mhm_cuda_states_default_init(mhm_cuda_context *ctx, int32_t iDomain,
+                                 const double *HorizonDepth_mHM);
+
+/* fluxes of the last executed step (mHM/mo_global_variables.f90:141-160) */
+enum mhm_flux_id {
+  MHM_F_PET_CALC = 0, MHM_F_TEMP_CALC, MHM_F_PREC_CALC, MHM_F_AETCANOPY, MHM_F_AETSEALED,
+  MHM_F_BASEFLOW, MHM_F_FASTRUNOFF, MHM_F_MELT, MHM_F_PERCOL, MHM_F_PREEFFECT, MHM_F_RAIN,
+  MHM_F_RUNOFFSEAL, MHM_F_SLOWRUNOFF, MHM_F_SNOW, MHM_F_THROUGHFALL, MHM_F_TOTAL_RUNOFF,
+  MHM_F_DEGDAY,       /* L1_degDay(:,1,1), intent(out) of snow_accum_melt */
+  MHM_F_AETSOIL,      /* L1_aETSoil  (:, nH) */
+  MHM_F_INFILSOIL,    /* L1_infilSoil(:, nH) */
+  MHM_F_COUNT
+};
+int mhm_cuda_get_flux(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                      int32_t flux_id, double *base, int64_t ld, int64_t offset);
+
+/* ---------------------------------------------------------------------------------
+ * meteo (meteo/mo_meteo_handler.f90).  Forcing arrays are L1_pre/L1_temp/... of shape
+ * (nCellsTot, nMeteoSteps): cell-contiguous per meteo step.
+ * --------------------------------------------------------------------------------- */
+typedef struct mhm_meteo_config {
+  int32_t pet_case;            /* processMatrix(5,1): -1, 0, 1, 2, 3 */
+  int32_t nTstepForcingDay;    /* 1 = daily forcing, 24 = hourly */
+  int32_t is_hourly_forcing;   /* self%is_hourly_forcing */
+  int32_t read_meteo_weights;  /* self%read_meteo_weights */
+  double fday_prec[12];
+  double fnight_prec[12];
+  double fday_pet[12];
+  double fnight_pet[12];
+  double fday_temp[12];
+  double fnight_temp[12];
+  double evap_coeff[12];       /* mhm.nml panEvapo */
+} mhm_meteo_config;
+int mhm_cuda_set_meteo_config(mhm_cuda_context *ctx, int32_t iDomain,
+                              const mhm_meteo_config *cfg);
+
+enum mhm_meteo_var {
+  MHM_M_PRE = 0, MHM_M_TEMP, MHM_M_PET, MHM_M_TMIN, MHM_M_TMAX, MHM_M_NETRAD,
+  MHM_M_ABSVAPPRESS, MHM_M_WINDSPEED, MHM_M_COUNT
+};
+/* upload meteo steps [first_step, first_step + n_steps) (1-based meteo time index
+ * iMeteoTS, mo_meteo_handler.f90:607) of one variable; replaces what prepare_data
+ * (:645-912) leaves in L1_<var>(s_meteo:e_meteo, :).  A chunk stays resident until
+ * the next call for the same variable; run calls must stay inside the resident chunk. */
+int mhm_cuda_set_meteo(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,
+                       const double *base, int64_t ld, int64_t offset, int64_t first_step,
+                       int64_t n_steps);
+/* same, but `dev` is a device pointer to a dense [n_steps][nCells] array that the
+ * caller keeps alive (zero copy; used when forcing is already resident in HBM) */
+int mhm_cuda_set_meteo_device(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,
+                              const double *dev, int64_t first_step, int64_t n_steps);
+/* L1_pre_weights / L1_temp_weights / L1_pet_weights (nCellsTot, 12, 24); var = PRE/TEMP/PET */
+int mhm_cuda_set_meteo_weights(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,
+                               const double *base, int64_t ld, int64_t offset);
+
+/* ---------------------------------------------------------------------------------
+ * time axis: common/mo_common_datetime_type.f90:71-155 restated inside the library so
+ * that a block of steps can run without returning to the host.
+ * --------------------------------------------------------------------------------- */
+typedef struct mhm_time_config {
+  int32_t jul_start;            /* simPer(iDomain)%julStart (Julian day number) */
+  int32_t nTimeSteps;           /* domainDateTime%nTimeSteps */
+  int32_t warming_days;         /* warmingDays(iDomain) */
+  int32_t timeStep_LAI_input;   /* 0/1: iLAI = month; -1/-2/-3: running counter */
+  int32_t lc_year_start;        /* first year covered by LCyearId */
+  int32_t lc_nyears;
+  const int32_t *LCyearId;      /* LCyearId(year, iDomain), 1-based scene ids */
+} mhm_time_config;
+int mhm_cuda_set_time(mhm_cuda_context *ctx, int32_t iDomain, const mhm_time_config *cfg);
+
+/* per-step indices as the reference derives them; host helper (no GPU needed) so the
+ * Fortran side / tests can cross-check the library's calendar */
+typedef struct mhm_step_index {
+  int32_t iMeteoTS;   /* 1-based */
+  int32_t year;
+  int16_t yId;        /* 1-based land-cover scene */
+  int16_t iLAI;       /* 1-based */
+  int16_t doy;
+  int8_t month;       /* 1..12 */
+  int8_t hour;        /* 0..23 */
+  int8_t isday;       /* hour > 6 .and. hour <= 18 */
+  int8_t pad_[3];
+} mhm_step_index;
+int mhm_time_indices(const mhm_time_config *cfg, int32_t timestep_h, int32_t nTstepForcingDay,
+                     int32_t tt_first, int32_t n_steps, mhm_step_index *out);
+
+/* ---------------------------------------------------------------------------------
+ * B1  one model step (per-step parity seam).  Replaces get_corrected_pet + get_temp +
+ * get_prec + `call mhm(...)` (mHM/mo_mhm_interface_run.f90:366-457).  All fluxes of the
+ * step are left on the device (mhm_cuda_get_flux / mhm_cuda_sync_to_host).
+ * --------------------------------------------------------------------------------- */
+int mhm_cuda_cell_step(mhm_cuda_context *ctx, int32_t iDomain, int32_t tt,
+                       const mhm_step_index *idx);
+
+/* B2  a block of model steps tt_first .. tt_first+n_steps-1 (performance seam; replaces
+ * the TimeLoop body mHM/mo_mhm_eval.f90:136-150 for those steps, including the routing
+ * schedule mo_mhm_interface_run.f90:460-612 when a network is set).  Fluxes of the
+ * block's last step are left on the device, the gauge series in the runoff buffer. */
+int mhm_cuda_run_steps(mhm_cuda_context *ctx, int32_t iDomain, int32_t tt_first,
+                       int32_t n_steps);
+/* variant selection: 0 = strict (no FMA contraction, IEEE division, literal formulas;
+ * default), 1 = fast (same algorithm, FMA + hoisted reciprocals; <= 1e-9 relative) */
+int mhm_cuda_set_math_mode(mhm_cuda_context *ctx, int32_t mode);
+
+/* keep host module globals coherent (pybind get%L1_variable, restart writing): bind once,
+ * then mhm_cuda_sync_to_host copies every bound state/flux of every member 0 array back */
+int mhm_cuda_bind_host_state(mhm_cuda_context *ctx, int32_t iDomain, int32_t state_id,
+                             double *base, int64_t ld, int64_t offset);
+int mhm_cuda_bind_host_flux(mhm_cuda_context *ctx, int32_t iDomain, int32_t flux_id,
+                            double *base, int64_t ld, int64_t offset);
+int mhm_cuda_sync_to_host(mhm_cuda_context *ctx, int32_t iDomain);
+
+/* total runoff history of the last run_steps block, Fortran (nCells, n_steps) per member
+ * (what `RunToRout = L1_total_runoff(s1:e1)` saw at each step) */
+int mhm_cuda_get_runoff_history(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                                double *out, int64_t ld);
+
+/* ---------------------------------------------------------------------------------
+ * B3  routing (mRM/mo_mrm_routing.f90:104-303, mo_mrm_pre_routing.f90:77-214,
+ * mo_mrm_mpr.f90:61-119,241-329)
+ * --------------------------------------------------------------------------------- */
+typedef struct mrm_network {
+  int32_t nNodes;               /* level11(iDomain)%nCells */
+  int32_t nOutlets;             /* L11_nOutlets(iDomain) */
+  int32_t map_flag;             /* ge(resolutionRouting, resolutionHydrology) */
+  int32_t nGauges;              /* domain_mrm%nGauges */
+  int32_t nInflowGauges;        /* domain_mrm%nInflowGauges */
+  int32_t nGaugesTotal;         /* size(mRM_runoff, 2) */
+  int32_t nInflowTotal;         /* size(InflowGauge%Q, 2) */
+  int32_t processCase;          /* processMatrix(8,1): 1, 2 or 3 */
+  const int32_t *L1_L11_Id;     /* (nCells1) */
+  const int32_t *L11_L1_Id;     /* (nNodes) */
+  const int32_t *netPerm;       /* (nNodes) valid 1..nLinks */
+  const int32_t *fromN;         /* (nNodes) valid 1..nLinks */
+  const int32_t *toN;           /* (nNodes) valid 1..nLinks */
+  const double *L1_areaCell;    /* level1%CellArea * 1e-6 [km2] (nCells1) */
+  const double *L11_areaCell;   /* level11%CellArea * 1e-6 [km2] (nNodes) */
+  const int32_t *gaugeIndexList;        /* (nGauges) */
+  const int32_t *gaugeNodeList;         /* (nGauges) */
+  const int32_t *InflowGaugeIndexList;  /* (nInflowGauges) */
+  const int32_t *InflowGaugeHeadwater;  /* (nInflowGauges) 0/1 */
+  const int32_t *InflowGaugeNodeList;   /* (nInflowGauges) */
+} mrm_network;
+int mrm_cuda_set_network(mhm_cuda_context *ctx, int32_t iDomain, const mrm_network *net);
+
+/* L11_routing_order (mRM/mo_mrm_net_startup.f90:728-859) in O(nLinks): host helper that
+ * yields the identical rOrder/netPerm as the reference's O(nLinks^2) sweeps */
+int mrm_routing_order(int32_t nNodes, int32_t nLinks, const int32_t *fromN,
+                      const int32_t *toN, int32_t *rOrder, int32_t *netPerm);
+
+/* Muskingum parameters of one member.
+ * case 1: reg_rout (mo_mrm_mpr.f90:61-119) is evaluated on the device whenever the land
+ *         cover scene changes: pass the 5 routing gammas, L11_length(s11:e11-1),
+ *         L11_slope(s11:e11-1) and L11_nLinkFracFPimp(s11:e11, 1:nLC).
+ * case 2/3: pass C1/C2 as left by mrm_update_param (:241-329) and L11_TSrout. */
+int mrm_cuda_set_reg_rout(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                          const double *param5, const double *L11_length,
+                          const double *L11_slope, const double *L11_nLinkFracFPimp);
+int mrm_cuda_set_c1c2(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                      const double *C1, const double *C2, double L11_TSrout);
+
+enum mrm_state_id { MRM_S_QOUT = 0, MRM_S_QTIN, MRM_S_QTR, MRM_S_QMOD, MRM_S_C1, MRM_S_C2,
+                    MRM_S_COUNT };
+/* L11_qOUT, L11_qMod, L11_C1, L11_C2: (nNodes); L11_qTIN, L11_qTR: (nNodes, 2) */
+int mrm_cuda_set_state(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                       int32_t state_id, const double *base, int64_t ld, int64_t offset);
+int mrm_cuda_get_state(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                       int32_t state_id, double *base, int64_t ld, int64_t offset);
+/* InflowGauge%Q (nDays, nInflowTotal) */
+int mrm_cuda_set_inflow(mhm_cuda_context *ctx, int32_t iDomain, const double *Q,
+                        int64_t nDays);
+
+/* one call of mRM_routing for step tt (per-step seam, mo_mhm_interface_run.f90:552-590).
+ * RunToRout: host (nCells1) or NULL to take the device's L1_total_runoff of the last
+ * cell step; InflowDischarge: host (nInflowTotal) or NULL; yId selects nLinkFracFPimp. */
+int mrm_cuda_route(mhm_cuda_context *ctx, int32_t iDomain, int32_t member, int32_t tt,
+                   int32_t yId, const double *RunToRout, int32_t timestep_rout,
+                   double tsRoutFactorIn, const double *InflowDischarge);
+/* gauge series mRM_runoff(tt_first : tt_first+n_steps-1, :) of one member into the
+ * Fortran (nTimeSteps, nGaugesTotal) array `out` with leading dimension ld */
+int mrm_cuda_get_runoff(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                        double *out, int64_t ld, int32_t tt_first, int32_t n_steps);
+
+/* ---------------------------------------------------------------------------------
+ * B4  MPR upscaling operators (MPR/mo_upscaling_operators.f90:152-227, 266-329, 369-432).
+ * L0 data is the packed vector (nL0_cells); the remap is given by the L1 cell bounds
+ * in the 2-D L0 grid (common/mo_grid.f90:97-175): upper/lower = first-index (row) range,
+ * left/right = second-index (column) range, 1-based inclusive; mask0/cellId0 describe
+ * the unpacking (mask0 is the nrows0 x ncols0 logical mask, Fortran order, as int32 0/1).
+ * --------------------------------------------------------------------------------- */
+typedef struct mpr_l0_grid mpr_l0_grid; /* opaque: device copy of mask/ids/bounds */
+int mpr_cuda_grid_create(mhm_cuda_context *ctx, int32_t nrows0, int32_t ncols0,
+                         const int32_t *mask0, int32_t nL1_cells,
+                         const int32_t *upper_bound, const int32_t *lower_bound,
+                         const int32_t *left_bound, const int32_t *right_bound,
+                         const int32_t *n_subcells, mpr_l0_grid **grid);
+int mpr_cuda_grid_destroy(mhm_cuda_context *ctx, mpr_l0_grid *grid);
+int mpr_cuda_upscale_arithmetic_mean(mhm_cuda_context *ctx, const mpr_l0_grid *grid,
+                                     double nodata, const double *L0_data, double *L1_out);
+int mpr_cuda_upscale_harmonic_mean(mhm_cuda_context *ctx, const mpr_l0_grid *grid,
+                                   double nodata, const double *L0_data, double *L1_out);
+int mpr_cuda_upscale_geometric_mean(mhm_cuda_context *ctx, const mpr_l0_grid *grid,
+                                    double nodata, const double *L0_data, double *L1_out);
+int mpr_cuda_l0_fractional_cover(mhm_cuda_context *ctx, const mpr_l0_grid *grid,
+                                 const int32_t *dataIn0, int32_t class_id, double *L1_out);
+
+/* ---------------------------------------------------------------------------------
+ * measurement hooks (bench.py): CUDA events on the library's own stream
+ * --------------------------------------------------------------------------------- */
+int mhm_cuda_event_record(mhm_cuda_context *ctx, int32_t slot);            /* slot 0..15 */
+int mhm_cuda_event_elapsed_ms(mhm_cuda_context *ctx, int32_t a, int32_t b, double *ms);
+int mhm_cuda_synchronize(mhm_cuda_context *ctx);
+/* accumulated device time [ms] and launch count of kernel class `which` since the last
+ * reset (0 = fused cell kernel, 1 = routing kernels, 2 = upscaling kernels) */
+int mhm_cuda_kernel_stats(mhm_cuda_context *ctx, int32_t which, double *ms, int64_t *launches);
+int mhm_cuda_kernel_stats_reset(mhm_cuda_context *ctx, int32_t enable_timing);
+/* fp64 FMA peak micro-benchmark on this device: returns DFMA/s (x2 = FLOP/s) */
+int mhm_cuda_measure_dfma_peak(mhm_cuda_context *ctx, double *dfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHM_CUDA_H */

@@ -1,0 +1,770 @@
+// api.cu -- C ABI (include/mhm_cuda.h): lifecycle, parameter/state/flux/meteo transfer,
+// calendar, and the drivers of the fused cell kernel (per-step seam and time blocks).
+#include <cstring>
+#include <mutex>
+
+#include "context.h"
+
+namespace mhm {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+Domain* find_domain(mhm_cuda_context* ctx, int32_t iDomain) {
+  if (!ctx) {
+    set_error("null context");
+    return nullptr;
+  }
+  auto it = ctx->domains.find(iDomain);
+  if (it == ctx->domains.end()) {
+    set_error("domain %d is not registered", iDomain);
+    return nullptr;
+  }
+  return it->second;
+}
+
+static size_t state_rows(const Domain* d, int id) {
+  return id == MHM_S_SOILMOIST ? (size_t)d->cfg.nHorizons : 1;
+}
+static size_t flux_rows(const Domain* d, int id) {
+  return (id == MHM_F_AETSOIL || id == MHM_F_INFILSOIL) ? (size_t)d->cfg.nHorizons : 1;
+}
+
+// copy a Fortran section (rows x nCells, row stride ld) host -> dense device rows
+static int h2d_rows(mhm_cuda_context* ctx, double* dst, const double* base, int64_t ld,
+                    int64_t offset, size_t n, size_t rows) {
+  MHM_CUDA_OK(cudaMemcpy2DAsync(dst, n * sizeof(double), base + offset, (size_t)ld * sizeof(double),
+                                n * sizeof(double), rows, cudaMemcpyHostToDevice, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+static int d2h_rows(mhm_cuda_context* ctx, double* base, int64_t ld, int64_t offset,
+                    const double* src, size_t n, size_t rows) {
+  MHM_CUDA_OK(cudaMemcpy2DAsync(base + offset, (size_t)ld * sizeof(double), src, n * sizeof(double),
+                                n * sizeof(double), rows, cudaMemcpyDeviceToHost, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static void free_domain(Domain* d) {
+  for (auto& p : d->P) cudaFree(p);
+  for (auto& p : d->S) cudaFree(p);
+  for (auto& p : d->F) cudaFree(p);
+  for (int v = 0; v < MHM_M_COUNT; ++v)
+    if (d->met_owned[v]) cudaFree(d->met[v]);
+  for (auto& p : d->weights) cudaFree(p);
+  cudaFree(d->d_idx);
+  cudaFree(d->d_idx_one);
+  cudaFree(d->runoff_hist);
+  if (d->rt) routing_free(d->rt);
+  delete d;
+}
+
+}  // namespace mhm
+
+using namespace mhm;
+
+void mhm_cuda_context::stat_begin(int which) {
+  if (!timing) return;
+  TimedLaunch t;
+  t.which = which;
+  for (cudaEvent_t* e : {&t.a, &t.b}) {
+    if (!ev_pool.empty()) {
+      *e = ev_pool.back();
+      ev_pool.pop_back();
+    } else {
+      cudaEventCreate(e);
+    }
+  }
+  cudaEventRecord(t.a, stream);
+  pending.push_back(t);
+}
+void mhm_cuda_context::stat_end(int which) {
+  stat_launches[which] += 1;
+  if (!timing) return;
+  cudaEventRecord(pending.back().b, stream);
+}
+int mhm_cuda_context::stat_flush() {
+  if (pending.empty()) return 0;
+  MHM_CUDA_OK(cudaStreamSynchronize(stream));
+  for (auto& t : pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.a, t.b);
+    stat_ms[t.which] += ms;
+    ev_pool.push_back(t.a);
+    ev_pool.push_back(t.b);
+  }
+  pending.clear();
+  return 0;
+}
+
+extern "C" {
+
+const char* mhm_cuda_last_error(void) { return g_err.c_str(); }
+const char* mhm_cuda_version(void) { return "mhm_cuda 0.1 (sm_100a)"; }
+
+int mhm_cuda_init(int device, mhm_cuda_context** out) {
+  MHM_REQUIRE(out, "mhm_cuda_init: null output handle");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("mhm_cuda_init: no CUDA device available (%s); there is no CPU fallback",
+              cudaGetErrorString(e));
+    return 3;
+  }
+  if (device < 0) MHM_CUDA_OK(cudaGetDevice(&device));
+  MHM_REQUIRE(device < count, "mhm_cuda_init: device %d out of range (%d devices)", device, count);
+  MHM_CUDA_OK(cudaSetDevice(device));
+  auto* ctx = new mhm_cuda_context();
+  ctx->device = device;
+  MHM_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->ev) MHM_CUDA_OK(cudaEventCreate(&ev));
+  if (const char* s = getenv("MHM_CUDA_BLOCK_BYTES")) ctx->block_bytes = (size_t)atoll(s);
+  *out = ctx;
+  return 0;
+}
+
+int mhm_cuda_finalize(mhm_cuda_context* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->domains) free_domain(kv.second);
+  for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+  for (auto& t : ctx->pending) {
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+int mhm_cuda_register_domain(mhm_cuda_context* ctx, int32_t iDomain, const mhm_domain_config* cfg) {
+  MHM_REQUIRE(ctx && cfg, "register_domain: null argument");
+  MHM_REQUIRE(ctx->domains.find(iDomain) == ctx->domains.end(), "domain %d already registered",
+              iDomain);
+  MHM_REQUIRE(cfg->nCells > 0, "register_domain: nCells = %d", cfg->nCells);
+  MHM_REQUIRE(cfg->nHorizons >= 1 && cfg->nHorizons <= kMaxHorizons,
+              "register_domain: nHorizons = %d outside 1..%d", cfg->nHorizons, kMaxHorizons);
+  MHM_REQUIRE(cfg->nLAI >= 1 && cfg->nLCscenes >= 1 && cfg->nMembers >= 1,
+              "register_domain: nLAI/nLCscenes/nMembers must be >= 1");
+  MHM_REQUIRE(cfg->processMatrix && cfg->nProcesses >= 8,
+              "register_domain: processMatrix with >= 8 rows required");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  auto* d = new Domain();
+  d->id = iDomain;
+  d->cfg = *cfg;
+  d->processMatrix.assign(cfg->processMatrix, cfg->processMatrix + (size_t)cfg->nProcesses * 3);
+  d->cfg.processMatrix = d->processMatrix.data();
+  d->soil_case = d->processMatrix[2];  // processMatrix(3,1)
+  d->pet_case = d->processMatrix[4];   // processMatrix(5,1)
+  d->rout_case = d->processMatrix[7];  // processMatrix(8,1)
+  MHM_REQUIRE(d->soil_case >= 1 && d->soil_case <= 4, "soil moisture processCase %d unsupported",
+              d->soil_case);
+  MHM_REQUIRE(d->pet_case >= -1 && d->pet_case <= 3, "PET processCase %d unsupported", d->pet_case);
+  const size_t n = (size_t)cfg->nCells, M = (size_t)cfg->nMembers;
+  for (int s = 0; s < MHM_S_COUNT; ++s) {
+    const size_t sz = M * state_rows(d, s) * n * sizeof(double);
+    MHM_CUDA_OK(cudaMalloc(&d->S[s], sz));
+    MHM_CUDA_OK(cudaMemsetAsync(d->S[s], 0, sz, ctx->stream));
+  }
+  for (int f = 0; f < MHM_F_COUNT; ++f) {
+    const size_t sz = M * flux_rows(d, f) * n * sizeof(double);
+    MHM_CUDA_OK(cudaMalloc(&d->F[f], sz));
+    MHM_CUDA_OK(cudaMemsetAsync(d->F[f], 0, sz, ctx->stream));
+  }
+  MHM_CUDA_OK(cudaMalloc(&d->d_idx_one, sizeof(StepIdx)));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->domains[iDomain] = d;
+  return 0;
+}
+
+int mhm_cuda_unregister_domain(mhm_cuda_context* ctx, int32_t iDomain) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_domain(d);
+  ctx->domains.erase(iDomain);
+  return 0;
+}
+
+int mhm_cuda_set_param(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, int32_t id,
+                       const double* base, int64_t ld, int64_t offset, int32_t dim2, int32_t dim3) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(id >= 0 && id < MHM_P_COUNT, "set_param: bad param id %d", id);
+  MHM_REQUIRE(member >= 0 && member < d->cfg.nMembers, "set_param: bad member %d", member);
+  MHM_REQUIRE(base && ld >= d->cfg.nCells && offset >= 0, "set_param: bad base/ld/offset");
+  // expected shape per the reference's allocation (mo_mpr_global_variables.f90:128-170)
+  const int nH = d->cfg.nHorizons, nLAI = d->cfg.nLAI, nLC = d->cfg.nLCscenes;
+  int e2 = 1, e3 = 1;
+  switch (id) {
+    case MHM_P_FSEALED: case MHM_P_ALPHA: case MHM_P_DEGDAYINC: case MHM_P_DEGDAYMAX:
+    case MHM_P_DEGDAYNOPRE: case MHM_P_KFASTFLOW: case MHM_P_KSLOWFLOW: case MHM_P_KBASEFLOW:
+    case MHM_P_KPERCO: case MHM_P_TEMPTHRESH: e3 = nLC; break;
+    case MHM_P_FROOTS: case MHM_P_SOILMOISTFC: case MHM_P_SOILMOISTSAT: case MHM_P_SOILMOISTEXP:
+    case MHM_P_WILTINGPOINT: e2 = nH; e3 = nLC; break;
+    case MHM_P_MAXINTER: case MHM_P_PRIETAYALPHA: case MHM_P_SURFRESIST: e2 = nLAI; break;
+    case MHM_P_PETLAICORFACTOR: case MHM_P_AERORESIST: e2 = nLAI; e3 = nLC; break;
+    default: break;
+  }
+  MHM_REQUIRE(dim2 == e2 && dim3 == e3, "set_param(%d): shape (:,%d,%d) given, (:,%d,%d) expected",
+              id, dim2, dim3, e2, e3);
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->cfg.nCells, rows = (size_t)dim2 * dim3;
+  if (!d->P[id]) {
+    MHM_CUDA_OK(cudaMalloc(&d->P[id], (size_t)d->cfg.nMembers * rows * n * sizeof(double)));
+    d->P_dim2[id] = dim2;
+    d->P_dim3[id] = dim3;
+  }
+  return h2d_rows(ctx, d->P[id] + (size_t)member * rows * n, base, ld, offset, n, rows);
+}
+
+int mhm_cuda_set_state(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, int32_t id,
+                       const double* base, int64_t ld, int64_t offset) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(id >= 0 && id < MHM_S_COUNT, "set_state: bad state id %d", id);
+  MHM_REQUIRE(member >= 0 && member < d->cfg.nMembers, "set_state: bad member %d", member);
+  MHM_REQUIRE(base && ld >= d->cfg.nCells && offset >= 0, "set_state: bad base/ld/offset");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->cfg.nCells, rows = state_rows(d, id);
+  return h2d_rows(ctx, d->S[id] + (size_t)member * rows * n, base, ld, offset, n, rows);
+}
+
+int mhm_cuda_get_state(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, int32_t id,
+                       double* base, int64_t ld, int64_t offset) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(id >= 0 && id < MHM_S_COUNT, "get_state: bad state id %d", id);
+  MHM_REQUIRE(member >= 0 && member < d->cfg.nMembers, "get_state: bad member %d", member);
+  MHM_REQUIRE(base && ld >= d->cfg.nCells && offset >= 0, "get_state: bad base/ld/offset");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->cfg.nCells, rows = state_rows(d, id);
+  return d2h_rows(ctx, base, ld, offset, d->S[id] + (size_t)member * rows * n, n, rows);
+}
+
+int mhm_cuda_get_flux(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, int32_t id,
+                      double* base, int64_t ld, int64_t offset) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(id >= 0 && id < MHM_F_COUNT, "get_flux: bad flux id %d", id);
+  MHM_REQUIRE(member >= 0 && member < d->cfg.nMembers, "get_flux: bad member %d", member);
+  MHM_REQUIRE(base && ld >= d->cfg.nCells && offset >= 0, "get_flux: bad base/ld/offset");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->cfg.nCells, rows = flux_rows(d, id);
+  return d2h_rows(ctx, base, ld, offset, d->F[id] + (size_t)member * rows * n, n, rows);
+}
+
+__global__ void fill_kernel(double* p, size_t n, double v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// mHM/mo_init_states.f90:280-300; constants MPR/mo_mpr_constants.f90:26-30
+int mhm_cuda_states_default_init(mhm_cuda_context* ctx, int32_t iDomain, const double* depth) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const int nH = d->cfg.nHorizons;
+  MHM_REQUIRE(nH == 1 || depth, "states_default_init: HorizonDepth_mHM required");
+  const size_t n = (size_t)d->cfg.nCells, M = (size_t)d->cfg.nMembers;
+  auto fill = [&](double* p, size_t cnt, double v) {
+    fill_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(p, cnt, v);
+  };
+  const double P1 = 0.0, P2 = 15.0, P3 = 10.0, P4 = 75.0, P5 = 1500.0, C1 = 0.25;
+  fill(d->S[MHM_S_INTER], M * n, P1);
+  fill(d->S[MHM_S_SNOWPACK], M * n, P2);
+  fill(d->S[MHM_S_SEALSTW], M * n, P1);
+  fill(d->S[MHM_S_UNSATSTW], M * n, P3);
+  fill(d->S[MHM_S_SATSTW], M * n, P4);
+  for (size_t m = 0; m < M; ++m) {
+    for (int i = 0; i < nH; ++i) {
+      double v;
+      if (i == nH - 1) {
+        v = (P5 - (nH > 1 ? depth[nH - 2] : 0.0)) * C1;
+      } else if (i == 0) {
+        v = depth[0] * C1;
+      } else {
+        v = (depth[i] - depth[i - 1]) * C1;
+      }
+      fill(d->S[MHM_S_SOILMOIST] + (m * nH + i) * n, n, v);
+    }
+  }
+  for (int f = 0; f < MHM_F_COUNT; ++f)
+    MHM_CUDA_OK(cudaMemsetAsync(d->F[f], 0, M * flux_rows(d, f) * n * sizeof(double), ctx->stream));
+  MHM_CUDA_OK(cudaGetLastError());
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- meteo
+int mhm_cuda_set_meteo_config(mhm_cuda_context* ctx, int32_t iDomain, const mhm_meteo_config* cfg) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(cfg, "set_meteo_config: null config");
+  MHM_REQUIRE(cfg->pet_case == d->pet_case,
+              "set_meteo_config: pet_case %d differs from processMatrix(5,1) = %d", cfg->pet_case,
+              d->pet_case);
+  MHM_REQUIRE(cfg->nTstepForcingDay >= 1 && cfg->nTstepForcingDay <= 24,
+              "set_meteo_config: nTstepForcingDay = %d", cfg->nTstepForcingDay);
+  // the reference rejects PET cases 1-3 with hourly forcing (mo_meteo_handler.f90:879-909)
+  MHM_REQUIRE(!(cfg->is_hourly_forcing && cfg->pet_case > 0),
+              "set_meteo_config: PET processCase %d needs daily forcing", cfg->pet_case);
+  d->mcfg = *cfg;
+  d->has_meteo_cfg = true;
+  d->h_idx.clear();  // calendar depends on nTstepForcingDay
+  return 0;
+}
+
+static int meteo_store(mhm_cuda_context* ctx, Domain* d, int var, size_t rows) {
+  const size_t need = rows * (size_t)d->cfg.nCells;
+  if (!d->met_owned[var] || d->met_cap[var] < need) {
+    if (d->met_owned[var]) cudaFree(d->met[var]);
+    d->met[var] = nullptr;
+    MHM_CUDA_OK(cudaMalloc(&d->met[var], need * sizeof(double)));
+    d->met_owned[var] = true;
+    d->met_cap[var] = need;
+  }
+  (void)ctx;
+  return 0;
+}
+
+int mhm_cuda_set_meteo(mhm_cuda_context* ctx, int32_t iDomain, int32_t var, const double* base,
+                       int64_t ld, int64_t offset, int64_t first_step, int64_t n_steps) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(var >= 0 && var < MHM_M_COUNT, "set_meteo: bad variable %d", var);
+  MHM_REQUIRE(base && ld >= d->cfg.nCells && offset >= 0 && first_step >= 1 && n_steps >= 1,
+              "set_meteo: bad base/ld/offset/steps");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  // the running block may still read the old chunk
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (int rc = meteo_store(ctx, d, var, (size_t)n_steps)) return rc;
+  d->met_first[var] = first_step;
+  d->met_n[var] = n_steps;
+  return h2d_rows(ctx, d->met[var], base, ld, offset, (size_t)d->cfg.nCells, (size_t)n_steps);
+}
+
+int mhm_cuda_set_meteo_device(mhm_cuda_context* ctx, int32_t iDomain, int32_t var,
+                              const double* dev, int64_t first_step, int64_t n_steps) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(var >= 0 && var < MHM_M_COUNT, "set_meteo_device: bad variable %d", var);
+  MHM_REQUIRE(dev && first_step >= 1 && n_steps >= 1, "set_meteo_device: bad arguments");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (d->met_owned[var]) cudaFree(d->met[var]);
+  d->met_owned[var] = false;
+  d->met_cap[var] = 0;
+  d->met[var] = const_cast<double*>(dev);
+  d->met_first[var] = first_step;
+  d->met_n[var] = n_steps;
+  return 0;
+}
+
+int mhm_cuda_set_meteo_weights(mhm_cuda_context* ctx, int32_t iDomain, int32_t var,
+                               const double* base, int64_t ld, int64_t offset) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(var == MHM_M_PRE || var == MHM_M_TEMP || var == MHM_M_PET,
+              "set_meteo_weights: variable %d has no weights", var);
+  MHM_REQUIRE(base && ld >= d->cfg.nCells && offset >= 0, "set_meteo_weights: bad base/ld/offset");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->cfg.nCells;
+  if (!d->weights[var]) MHM_CUDA_OK(cudaMalloc(&d->weights[var], 24 * 12 * n * sizeof(double)));
+  return h2d_rows(ctx, d->weights[var], base, ld, offset, n, 24 * 12);
+}
+
+// ---------------------------------------------------------------------------------- time
+int mhm_cuda_set_time(mhm_cuda_context* ctx, int32_t iDomain, const mhm_time_config* cfg) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(cfg && cfg->nTimeSteps >= 1, "set_time: bad config");
+  d->axis.jul_start = cfg->jul_start;
+  d->axis.nTimeSteps = cfg->nTimeSteps;
+  d->axis.warming_days = cfg->warming_days;
+  d->axis.timeStep_LAI_input = cfg->timeStep_LAI_input;
+  d->axis.lc_year_start = cfg->lc_year_start;
+  d->axis.LCyearId.clear();
+  if (cfg->LCyearId && cfg->lc_nyears > 0)
+    d->axis.LCyearId.assign(cfg->LCyearId, cfg->LCyearId + cfg->lc_nyears);
+  d->has_time = true;
+  d->h_idx.clear();
+  return 0;
+}
+
+int mhm_time_indices(const mhm_time_config* cfg, int32_t timestep_h, int32_t nTstepForcingDay,
+                     int32_t tt_first, int32_t n_steps, mhm_step_index* out) {
+  MHM_REQUIRE(cfg && out && tt_first >= 1 && n_steps >= 0 && timestep_h >= 1 &&
+                  nTstepForcingDay >= 1,
+              "mhm_time_indices: bad arguments");
+  TimeAxis ax;
+  ax.jul_start = cfg->jul_start;
+  ax.nTimeSteps = cfg->nTimeSteps;
+  ax.warming_days = cfg->warming_days;
+  ax.timeStep_LAI_input = cfg->timeStep_LAI_input;
+  ax.lc_year_start = cfg->lc_year_start;
+  if (cfg->LCyearId && cfg->lc_nyears > 0)
+    ax.LCyearId.assign(cfg->LCyearId, cfg->LCyearId + cfg->lc_nyears);
+  std::vector<StepIdx> v;
+  fill_step_indices(ax, timestep_h, nTstepForcingDay, tt_first + n_steps - 1, v);
+  for (int i = 0; i < n_steps; ++i) {
+    const StepIdx& s = v[(size_t)tt_first - 1 + i];
+    mhm_step_index& o = out[i];
+    memset(&o, 0, sizeof(o));
+    o.iMeteoTS = s.iMeteoTS;
+    o.year = s.year;
+    o.yId = s.yId;
+    o.iLAI = s.iLAI;
+    o.doy = s.doy;
+    o.month = s.month;
+    o.hour = s.hour;
+    o.isday = s.isday;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------- cell kernel
+static int ensure_calendar(mhm_cuda_context* ctx, Domain* d) {
+  if (!d->h_idx.empty()) return 0;
+  MHM_REQUIRE(d->has_time, "domain %d: mhm_cuda_set_time has not been called", d->id);
+  MHM_REQUIRE(d->has_meteo_cfg, "domain %d: mhm_cuda_set_meteo_config has not been called", d->id);
+  fill_step_indices(d->axis, d->cfg.timestep_h, d->mcfg.nTstepForcingDay, d->axis.nTimeSteps,
+                    d->h_idx);
+  cudaFree(d->d_idx);
+  d->d_idx = nullptr;
+  MHM_CUDA_OK(cudaMalloc(&d->d_idx, d->h_idx.size() * sizeof(StepIdx)));
+  MHM_CUDA_OK(cudaMemcpyAsync(d->d_idx, d->h_idx.data(), d->h_idx.size() * sizeof(StepIdx),
+                              cudaMemcpyHostToDevice, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int check_inputs(Domain* d, const StepIdx* idx, int n_steps) {
+  MHM_REQUIRE(d->has_meteo_cfg, "domain %d: meteo config missing", d->id);
+  static const int always[] = {MHM_P_FSEALED,     MHM_P_ALPHA,        MHM_P_DEGDAYINC,
+                               MHM_P_DEGDAYMAX,   MHM_P_DEGDAYNOPRE,  MHM_P_FROOTS,
+                               MHM_P_MAXINTER,    MHM_P_KARSTLOSS,    MHM_P_KFASTFLOW,
+                               MHM_P_KSLOWFLOW,   MHM_P_KBASEFLOW,    MHM_P_KPERCO,
+                               MHM_P_SOILMOISTFC, MHM_P_SOILMOISTSAT, MHM_P_SOILMOISTEXP,
+                               MHM_P_JARVIS_C1,   MHM_P_TEMPTHRESH,   MHM_P_UNSATTHRESH,
+                               MHM_P_SEALEDTHRESH, MHM_P_WILTINGPOINT};
+  for (int id : always) MHM_REQUIRE(d->P[id], "domain %d: parameter %d has not been set", d->id, id);
+  std::vector<int> needP, needM = {MHM_M_PRE, MHM_M_TEMP};
+  switch (d->pet_case) {
+    case -1: needP = {MHM_P_PETLAICORFACTOR}; needM.push_back(MHM_M_PET); break;
+    case 0: needP = {MHM_P_FASP}; needM.push_back(MHM_M_PET); break;
+    case 1:
+      needP = {MHM_P_FASP, MHM_P_HARSAMCOEFF, MHM_P_LATITUDE};
+      needM.push_back(MHM_M_TMIN);
+      needM.push_back(MHM_M_TMAX);
+      break;
+    case 2: needP = {MHM_P_PRIETAYALPHA}; needM.push_back(MHM_M_NETRAD); break;
+    case 3:
+      needP = {MHM_P_AERORESIST, MHM_P_SURFRESIST};
+      needM.push_back(MHM_M_NETRAD);
+      needM.push_back(MHM_M_ABSVAPPRESS);
+      needM.push_back(MHM_M_WINDSPEED);
+      break;
+  }
+  for (int id : needP) MHM_REQUIRE(d->P[id], "domain %d: parameter %d has not been set", d->id, id);
+  int64_t lo = idx[0].iMeteoTS, hi = idx[0].iMeteoTS;
+  int ymax = 1, lmax = 1;
+  for (int i = 0; i < n_steps; ++i) {
+    lo = idx[i].iMeteoTS < lo ? idx[i].iMeteoTS : lo;
+    hi = idx[i].iMeteoTS > hi ? idx[i].iMeteoTS : hi;
+    ymax = idx[i].yId > ymax ? idx[i].yId : ymax;
+    lmax = idx[i].iLAI > lmax ? idx[i].iLAI : lmax;
+    MHM_REQUIRE(idx[i].yId >= 1 && idx[i].iLAI >= 1 && idx[i].month >= 1 && idx[i].month <= 12,
+                "step index %d: yId/iLAI/month out of range", i);
+  }
+  MHM_REQUIRE(ymax <= d->cfg.nLCscenes, "yId %d exceeds nLCscenes %d", ymax, d->cfg.nLCscenes);
+  MHM_REQUIRE(lmax <= d->cfg.nLAI, "iLAI %d exceeds nLAI %d", lmax, d->cfg.nLAI);
+  for (int v : needM) {
+    MHM_REQUIRE(d->met[v], "domain %d: meteo variable %d has not been set", d->id, v);
+    MHM_REQUIRE(lo >= d->met_first[v] && hi < d->met_first[v] + d->met_n[v],
+                "domain %d: meteo variable %d holds steps %lld..%lld, steps %lld..%lld needed",
+                d->id, v, (long long)d->met_first[v], (long long)(d->met_first[v] + d->met_n[v] - 1),
+                (long long)lo, (long long)hi);
+  }
+  if (!d->mcfg.is_hourly_forcing && d->mcfg.read_meteo_weights)
+    MHM_REQUIRE(d->weights[MHM_M_PRE] && d->weights[MHM_M_TEMP] && d->weights[MHM_M_PET],
+                "domain %d: meteo weights have not been set", d->id);
+  return 0;
+}
+
+static void fill_args(mhm_cuda_context* ctx, Domain* d, CellArgs& a) {
+  (void)ctx;
+  memset(&a, 0, sizeof(a));
+  a.nCells = d->cfg.nCells;
+  a.nMembers = d->cfg.nMembers;
+  a.nLC = d->cfg.nLCscenes;
+  a.nLAI = d->cfg.nLAI;
+  a.soil_case = d->soil_case;
+  a.pet_case = d->pet_case;
+  a.is_hourly = d->mcfg.is_hourly_forcing;
+  a.read_weights = d->mcfg.read_meteo_weights;
+  a.read_states = d->cfg.read_states;
+  a.nTstepDay_dp = (double)(24 / d->cfg.timestep_h);
+  a.c2TSTu = d->cfg.c2TSTu;
+  for (int v = 0; v < MHM_M_COUNT; ++v) {
+    a.met[v] = d->met[v];
+    a.met_first[v] = d->met_first[v];
+  }
+  a.w_pre = d->weights[MHM_M_PRE];
+  a.w_temp = d->weights[MHM_M_TEMP];
+  a.w_pet = d->weights[MHM_M_PET];
+  for (int p = 0; p < MHM_P_COUNT; ++p) a.P[p] = d->P[p];
+  for (int s = 0; s < MHM_S_COUNT; ++s) a.S[s] = d->S[s];
+  for (int f = 0; f < MHM_F_COUNT; ++f) a.F[f] = d->F[f];
+  for (int m = 0; m < 12; ++m) {
+    a.tab.fday_prec[m] = d->mcfg.fday_prec[m];
+    a.tab.fnight_prec[m] = d->mcfg.fnight_prec[m];
+    a.tab.fday_pet[m] = d->mcfg.fday_pet[m];
+    a.tab.fnight_pet[m] = d->mcfg.fnight_pet[m];
+    a.tab.fday_temp[m] = d->mcfg.fday_temp[m];
+    a.tab.fnight_temp[m] = d->mcfg.fnight_temp[m];
+    a.tab.evap_coeff[m] = d->mcfg.evap_coeff[m];
+    a.tab.inv_evap_coeff[m] = 1.0 / d->mcfg.evap_coeff[m];
+  }
+}
+
+static int launch_cells(mhm_cuda_context* ctx, Domain* d, const CellArgs& a) {
+  ctx->stat_begin(kStatCell);
+  int rc = ctx->math_mode == 1 ? launch_cell_block_fast(a, d->cfg.nHorizons, ctx->stream)
+                               : launch_cell_block_strict(a, d->cfg.nHorizons, ctx->stream);
+  ctx->stat_end(kStatCell);
+  MHM_REQUIRE(rc == 0, "cell kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}
+
+int mhm_cuda_set_math_mode(mhm_cuda_context* ctx, int32_t mode) {
+  MHM_REQUIRE(ctx && (mode == 0 || mode == 1), "set_math_mode: mode must be 0 or 1");
+  ctx->math_mode = mode;
+  return 0;
+}
+
+int mhm_cuda_cell_step(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt,
+                       const mhm_step_index* idx) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(idx && tt >= 1, "cell_step: bad arguments");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  StepIdx s{};
+  s.iMeteoTS = idx->iMeteoTS;
+  s.yId = idx->yId;
+  s.iLAI = idx->iLAI;
+  s.doy = idx->doy;
+  s.year = (int16_t)idx->year;
+  s.month = idx->month;
+  s.hour = idx->hour;
+  s.isday = idx->isday;
+  if (int rc = check_inputs(d, &s, 1)) return rc;
+  MHM_CUDA_OK(cudaMemcpyAsync(d->d_idx_one, &s, sizeof(s), cudaMemcpyHostToDevice, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // &s is a stack object
+  CellArgs a;
+  fill_args(ctx, d, a);
+  a.nSteps = 1;
+  a.tt_first = tt;
+  a.idx = d->d_idx_one;
+  a.write_fluxes = 1;
+  a.runoff_hist = nullptr;
+  d->last_yId = s.yId;
+  d->hist_steps = 0;
+  return launch_cells(ctx, d, a);
+}
+
+int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first, int32_t n_steps) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  if (int rc = ensure_calendar(ctx, d)) return rc;
+  MHM_REQUIRE(tt_first >= 1 && n_steps >= 1 && tt_first + n_steps - 1 <= d->axis.nTimeSteps,
+              "run_steps: steps %d..%d outside 1..%d", tt_first, tt_first + n_steps - 1,
+              d->axis.nTimeSteps);
+  if (int rc = check_inputs(d, d->h_idx.data() + (tt_first - 1), n_steps)) return rc;
+  const size_t n = (size_t)d->cfg.nCells, M = (size_t)d->cfg.nMembers;
+  // time blocks sized by the history-buffer budget (runoff + routing histories)
+  size_t per_step = 3 * M * n * sizeof(double);
+  int32_t tb = (int32_t)(ctx->block_bytes / per_step);
+  if (tb < 1) tb = 1;
+  if (tb > n_steps) tb = n_steps;
+  const size_t need = (size_t)tb * M * n;
+  if (d->runoff_cap < need) {
+    MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d->runoff_hist);
+    d->runoff_hist = nullptr;
+    d->runoff_cap = 0;
+    MHM_CUDA_OK(cudaMalloc(&d->runoff_hist, need * sizeof(double)));
+    d->runoff_cap = need;
+  }
+  for (int32_t t0 = 0; t0 < n_steps; t0 += tb) {
+    const int32_t nb = (n_steps - t0 < tb) ? n_steps - t0 : tb;
+    CellArgs a;
+    fill_args(ctx, d, a);
+    a.nSteps = nb;
+    a.tt_first = tt_first + t0;
+    a.idx = d->d_idx + (tt_first + t0 - 1);
+    a.write_fluxes = 1;
+    a.runoff_hist = d->runoff_hist;
+    if (int rc = launch_cells(ctx, d, a)) return rc;
+    d->hist_steps = nb;
+    d->hist_tt_first = tt_first + t0;
+    d->last_yId = d->h_idx[(size_t)(tt_first + t0 + nb - 2)].yId;
+    if (d->rt)
+      if (int rc = routing_run_block(ctx, d, tt_first + t0, nb)) return rc;
+  }
+  return 0;
+}
+
+int mhm_cuda_get_runoff_history(mhm_cuda_context* ctx, int32_t iDomain, int32_t member,
+                                double* out, int64_t ld) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(member >= 0 && member < d->cfg.nMembers, "get_runoff_history: bad member");
+  MHM_REQUIRE(d->hist_steps > 0 && d->runoff_hist, "get_runoff_history: no block has been run");
+  MHM_REQUIRE(out && ld >= d->cfg.nCells, "get_runoff_history: bad out/ld");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->cfg.nCells, M = (size_t)d->cfg.nMembers;
+  MHM_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)ld * sizeof(double), d->runoff_hist + (size_t)member * n,
+                                M * n * sizeof(double), n * sizeof(double), (size_t)d->hist_steps,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// --------------------------------------------------------------------------- host coherence
+int mhm_cuda_bind_host_state(mhm_cuda_context* ctx, int32_t iDomain, int32_t id, double* base,
+                             int64_t ld, int64_t offset) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(id >= 0 && id < MHM_S_COUNT && ld >= d->cfg.nCells && offset >= 0,
+              "bind_host_state: bad arguments");
+  d->sbind[id] = HostBind{base, ld, offset};
+  return 0;
+}
+int mhm_cuda_bind_host_flux(mhm_cuda_context* ctx, int32_t iDomain, int32_t id, double* base,
+                            int64_t ld, int64_t offset) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(id >= 0 && id < MHM_F_COUNT && ld >= d->cfg.nCells && offset >= 0,
+              "bind_host_flux: bad arguments");
+  d->fbind[id] = HostBind{base, ld, offset};
+  return 0;
+}
+int mhm_cuda_sync_to_host(mhm_cuda_context* ctx, int32_t iDomain) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->cfg.nCells;
+  for (int s = 0; s < MHM_S_COUNT; ++s) {
+    const HostBind& b = d->sbind[s];
+    if (!b.base) continue;
+    MHM_CUDA_OK(cudaMemcpy2DAsync(b.base + b.offset, (size_t)b.ld * sizeof(double), d->S[s],
+                                  n * sizeof(double), n * sizeof(double), state_rows(d, s),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  for (int f = 0; f < MHM_F_COUNT; ++f) {
+    const HostBind& b = d->fbind[f];
+    if (!b.base) continue;
+    MHM_CUDA_OK(cudaMemcpy2DAsync(b.base + b.offset, (size_t)b.ld * sizeof(double), d->F[f],
+                                  n * sizeof(double), n * sizeof(double), flux_rows(d, f),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ measurement
+int mhm_cuda_event_record(mhm_cuda_context* ctx, int32_t slot) {
+  MHM_REQUIRE(ctx && slot >= 0 && slot < 16, "event_record: bad slot");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaEventRecord(ctx->ev[slot], ctx->stream));
+  return 0;
+}
+int mhm_cuda_event_elapsed_ms(mhm_cuda_context* ctx, int32_t a, int32_t b, double* ms) {
+  MHM_REQUIRE(ctx && ms && a >= 0 && a < 16 && b >= 0 && b < 16, "event_elapsed_ms: bad arguments");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaEventSynchronize(ctx->ev[b]));
+  float f = 0.f;
+  MHM_CUDA_OK(cudaEventElapsedTime(&f, ctx->ev[a], ctx->ev[b]));
+  *ms = f;
+  return 0;
+}
+int mhm_cuda_synchronize(mhm_cuda_context* ctx) {
+  MHM_REQUIRE(ctx, "synchronize: null context");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  MHM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int mhm_cuda_kernel_stats(mhm_cuda_context* ctx, int32_t which, double* ms, int64_t* launches) {
+  MHM_REQUIRE(ctx && which >= 0 && which < kStatCount, "kernel_stats: bad class");
+  if (int rc = ctx->stat_flush()) return rc;
+  if (ms) *ms = ctx->stat_ms[which];
+  if (launches) *launches = ctx->stat_launches[which];
+  return 0;
+}
+int mhm_cuda_kernel_stats_reset(mhm_cuda_context* ctx, int32_t enable_timing) {
+  MHM_REQUIRE(ctx, "kernel_stats_reset: null context");
+  if (int rc = ctx->stat_flush()) return rc;
+  for (int i = 0; i < kStatCount; ++i) {
+    ctx->stat_ms[i] = 0.0;
+    ctx->stat_launches[i] = 0;
+  }
+  ctx->timing = enable_timing != 0;
+  return 0;
+}
+
+// dependent-chain-free DFMA loop: 8 independent accumulators per thread
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int mhm_cuda_measure_dfma_peak(mhm_cuda_context* ctx, double* dfma_per_s) {
+  MHM_REQUIRE(ctx && dfma_per_s, "measure_dfma_peak: bad arguments");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  MHM_CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double* buf = nullptr;
+  MHM_CUDA_OK(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, ctx->stream);
+    MHM_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = (double)blocks * threads * iters * 8.0 / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *dfma_per_s = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,575 @@
+// cell_kernel.cuh -- fused fp64 meteo prologue + L1 cell cascade for sm_100a.
+//
+// One thread owns one (cell, member) pair for a whole block of model steps and keeps
+// its 5 + nH states and its effective parameters in registers; forcing is streamed
+// [meteo step][cell] (cell-contiguous, the reference's own L1_pre(nCells, nSteps)
+// layout) with the next step's loads issued before the current step's arithmetic.
+// Members of one cell tile are adjacent in blockIdx, so a forcing row is fetched from
+// HBM once and served to the other members from L2.
+//
+// Restates (never copies) the arithmetic of
+//   meteo/mo_meteo_handler.f90:1053-1119,1166-1201,1247-1281 (PET select, disaggregation)
+//   meteo/mo_meteo_temporal_tools.f90:57,90-99,142-159
+//   mHM/mo_pet.f90:109-114,170-172,267-270,338-353,397,439
+//   mHM/mo_mhm.f90:448-499, mo_canopy_interc.f90:105-131, mo_snow_accum_melt.f90:117-156,
+//   mo_soil_moisture.f90:179-286,353-361,431-444, mo_runoff.f90:120-152,204-210,271-272
+// in the same operation order.  This file is compiled twice (csrc/Makefile):
+//   MHM_FAST=0  -fmad=false : no FMA contraction, IEEE division, literal formulas
+//   MHM_FAST=1  FMA allowed + algebraically equivalent shortcuts (<= 1e-9 relative)
+#pragma once
+#include <cfloat>
+#include <cstdint>
+
+#include "device_types.h"
+
+namespace mhm {
+
+#ifndef MHM_FAST
+#define MHM_FAST 0
+#endif
+
+constexpr double kEps = 2.220446049250313e-16;  // epsilon(1.0_dp), mo_common_constants.f90:25
+constexpr double kTwoThird = 0.6666666666666666666666666666666666667;  // FORCES twothird_dp
+constexpr double kPi = 3.141592653589793238462643383279502884197;
+constexpr double kTwoPi = 6.283185307179586476925286766559005768394;
+constexpr double kDeg2Rad = kPi / 180.0;
+constexpr double kT0 = 273.15;
+constexpr double kDaySecs = 86400.0;
+constexpr double kYearDays = 365.0;
+constexpr double kSolarConst = 1367.0;
+constexpr double kSpecHeatET = 2.45e06;
+constexpr double kPsychro = 0.0646;
+constexpr double kCp0 = 1005.0;
+constexpr double kRho0 = 1.225;
+constexpr double kHarSamConst = 17.800;  // mo_mhm_constants.f90:36
+constexpr double kDuffieDr = 0.0330, kDuffieDelta1 = 0.4090, kDuffieDelta2 = 1.3900;
+constexpr double kTetensC1 = 0.6108, kTetensC2 = 17.270, kTetensC3 = 237.30;
+constexpr double kSatPressureSlope1 = 4098.0;
+
+// ---- PET, mHM/mo_pet.f90 ---------------------------------------------------------
+__device__ __forceinline__ bool le_eps(double a, double b) {  // FORCES mo_utils::le
+  if ((kEps * fabs(b) - fabs(a - b)) < 0.0) return a < b;
+  return true;
+}
+__device__ __forceinline__ double sat_vap_pressure(double tavg) {  // :439
+  return kTetensC1 * exp(kTetensC2 * tavg / (tavg + kTetensC3));
+}
+__device__ __forceinline__ double slope_satpressure(double tavg) {  // :397
+  return kSatPressureSlope1 * sat_vap_pressure(tavg) / exp(2.0 * log(tavg + kTetensC3));
+}
+__device__ __forceinline__ double extraterr_rad_approx(int doy, double latitude) {  // :338-353
+  double dr = 1.0 + kDuffieDr * cos(kTwoPi * doy / kYearDays);
+  double delta = kDuffieDelta1 * sin(kTwoPi * doy / kYearDays - kDuffieDelta2);
+  double arg = -tan(latitude) * tan(delta);
+  if (arg < -1.0) arg = -1.0;
+  if (arg > 1.0) arg = 1.0;
+  double omega = acos(arg);
+  return kDaySecs / kPi / kSpecHeatET * kSolarConst * dr *
+         (omega * sin(latitude) * sin(delta) + cos(latitude) * cos(delta) * sin(omega));
+}
+__device__ __forceinline__ double pet_hargreaves(double coeff, double tavg, double tmax,
+                                                 double tmin, double latitude, int doy) {  // :109-114
+  double delta_temp = tmax - tmin;
+  if (le_eps(delta_temp, 0.0) || le_eps(tavg, -kHarSamConst)) return 0.0;
+  return coeff * extraterr_rad_approx(doy, kDeg2Rad * latitude) * (tavg + kHarSamConst) *
+         sqrt(delta_temp);
+}
+__device__ __forceinline__ double pet_priestly(double alpha, double Rn, double tavg) {  // :170-172
+  double delta = slope_satpressure(tavg);
+  return alpha * delta / (kPsychro + delta) * (Rn * kDaySecs / kSpecHeatET);
+}
+__device__ __forceinline__ double pet_penman(double net_rad, double tavg, double avp,
+                                             double ra, double rs) {  // :267-270, a_s = a_sh = 1
+  const double a_s = 1.0, a_sh = 1.0;
+  return kDaySecs / kSpecHeatET *
+         (slope_satpressure(tavg) * net_rad +
+          kRho0 * kCp0 * (sat_vap_pressure(tavg) - avp) * a_sh / ra) /
+         (slope_satpressure(tavg) + kPsychro * a_sh / a_s * (1.0 + rs / ra));
+}
+
+// ---- per-thread parameter set ------------------------------------------------------
+template <int NH>
+struct CellParams {
+  // land-cover-scene (yId) indexed
+  double fSealed, alpha, ddinc, ddmax_c, ddnop_c, ddthr;  // ddthr = (ddmax_c-ddnop_c)/ddinc
+  double k0r, k1r, k2r, kpr;                              // c2TSTu / k
+  double tthr;
+  double fRoots[NH], FC[NH], SAT[NH], EXPN[NH], WP[NH];
+  // constant
+  double karst, jarvis_c1, unsatThr, sealedThr;
+  // LAI-step (iLAI) indexed
+  double maxInter;
+  double petFac;  // petLAIcorFactor (case -1) or fAsp (case 0, 1)
+#if MHM_FAST
+  double inv_maxInter, inv_sealedThr, inv_SAT[NH], inv_FCWP[NH], inv_jc1;
+#endif
+};
+
+// ---- one model step for one cell ---------------------------------------------------
+// fluxes of the step, kept in registers and stored only when requested
+template <int NH>
+struct CellFluxes {
+  double pet_calc, temp_calc, prec_calc, aet_canopy, aet_sealed, baseflow, fast_interflow,
+      melt, perc, prec_effect, rain, runoff_sealed, slow_interflow, snow, throughfall,
+      total_runoff, deg_day;
+  double aet_soil[NH], infiltration[NH];
+};
+
+template <int NH>
+struct CellStates {
+  double inter, snowpack, sealed, unsat, sat;
+  double sm[NH];
+};
+
+template <int NH>
+__device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates<NH>& s,
+                                             CellFluxes<NH>& f, const int soil_case,
+                                             const double evap_coeff
+#if MHM_FAST
+                                             , const double inv_evap_coeff
+#endif
+) {
+  const double pet = f.pet_calc, temperature = f.temp_calc, prec = f.prec_calc;
+
+  // ---- canopy_interc, mo_canopy_interc.f90:105-131 ----
+  {
+    double aux = s.inter + prec;
+    double thr, ic;
+    if (aux >= p.maxInter) {
+      thr = aux - p.maxInter;
+      ic = p.maxInter;
+    } else {
+      thr = 0.0;
+      ic = aux;
+    }
+    double ev;
+    if (p.maxInter > kEps) {
+#if MHM_FAST
+      // x**(2/3) = cbrt(x*x); x = 0 is the common dry-canopy case
+      const double x = ic * p.inv_maxInter;
+      ev = (x == 0.0) ? 0.0 : pet * cbrt(x * x);
+#else
+      ev = pet * pow(ic / p.maxInter, kTwoThird);
+#endif
+    } else {
+      ev = 0.0;
+    }
+    if (ev < 0.0) ev = 0.0;
+    if (ic > ev) {
+      ic = ic - ev;
+    } else {
+      ev = ic;
+      ic = 0.0;
+    }
+    s.inter = ic;
+    f.throughfall = thr;
+    f.aet_canopy = ev;
+  }
+
+  // ---- snow_accum_melt, mo_snow_accum_melt.f90:117-156 ----
+  {
+    const bool warm = temperature > p.tthr;
+    double snow, rain, melt, dd;
+    if (warm) {
+      snow = 0.0;
+      rain = f.throughfall;
+    } else {
+      snow = f.throughfall;
+      rain = 0.0;
+    }
+    if (prec <= p.ddthr) {
+      dd = p.ddnop_c + p.ddinc * prec;
+    } else {
+      dd = p.ddmax_c;
+    }
+    if (warm) {
+      if (s.snowpack > 0.0) {
+        double aux = dd * (temperature - p.tthr);
+        if (aux > s.snowpack) {
+          melt = s.snowpack;
+          s.snowpack = 0.0;
+        } else {
+          melt = aux;
+          s.snowpack = s.snowpack - aux;
+        }
+      } else {
+        melt = 0.0;
+        s.snowpack = 0.0;
+      }
+    } else {
+      melt = 0.0;
+      s.snowpack = s.snowpack + snow;
+    }
+    f.snow = snow;
+    f.rain = rain;
+    f.melt = melt;
+    f.deg_day = dd;
+    f.prec_effect = melt + rain;
+  }
+
+  // ---- soil_moisture, mo_soil_moisture.f90:179-286 ----
+  {
+    double runoff_sealed = 0.0, aet_sealed = 0.0;
+    if (p.fSealed > 0.0) {
+      double tmp = s.sealed + f.prec_effect;
+      double st;
+      if (tmp > p.sealedThr) {
+        runoff_sealed = tmp - p.sealedThr;
+        st = p.sealedThr;
+      } else {
+        runoff_sealed = 0.0;
+        st = tmp;
+      }
+      if (p.sealedThr > kEps) {
+#if MHM_FAST
+        aet_sealed = (pet * inv_evap_coeff - f.aet_canopy) * (st * p.inv_sealedThr);
+#else
+        aet_sealed = (pet / evap_coeff - f.aet_canopy) * (st / p.sealedThr);
+#endif
+        if (aet_sealed < 0.0) aet_sealed = 0.0;
+      } else {
+        aet_sealed = DBL_MAX;  // huge(1.0_dp)
+      }
+      if (st > aet_sealed) {
+        st = st - aet_sealed;
+      } else {
+        aet_sealed = st;
+        st = 0.0;
+      }
+      s.sealed = st;
+    }
+    f.runoff_sealed = runoff_sealed;
+    f.aet_sealed = aet_sealed;
+
+    double prec_effec_soil = f.prec_effect;
+    double aet_pos_sum = 0.0;  // sum(aet(1:hh-1), mask = aet > 0), accumulated in index order
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      double sm = s.sm[hh];
+      const double sat = p.SAT[hh];
+      double inf;
+      if (hh != 0) prec_effec_soil = f.infiltration[hh - 1];
+      if (sm > sat) {
+        inf = prec_effec_soil;
+      } else {
+#if MHM_FAST
+        // prec_effec_soil == 0 (the common dry step) gives tmp = 0, inf = 0, sm unchanged
+        // exactly, whatever frac_runoff is: skip the exp/log pair.
+        if (prec_effec_soil == 0.0) {
+          inf = 0.0;
+        } else {
+          double frac_runoff = 0.0;
+          if (sm > kEps) frac_runoff = exp(p.EXPN[hh] * log(sm * p.inv_SAT[hh]));
+          double tmp = prec_effec_soil * (1.0 - frac_runoff);
+          if ((sm + tmp) > sat) {
+            inf = prec_effec_soil + (sm - sat);
+            sm = sat;
+          } else {
+            inf = prec_effec_soil - tmp;
+            sm = sm + tmp;
+          }
+        }
+#else
+        double frac_runoff;
+        if (sm > kEps) {
+          frac_runoff = exp(p.EXPN[hh] * log(sm / sat));
+        } else {
+          frac_runoff = 0.0;
+        }
+        double tmp = prec_effec_soil * (1.0 - frac_runoff);
+        if ((sm + tmp) > sat) {
+          inf = prec_effec_soil + (sm - sat);
+          sm = sat;
+        } else {
+          inf = prec_effec_soil - tmp;
+          sm = sm + tmp;
+        }
+#endif
+      }
+      f.infiltration[hh] = inf;
+
+      double a = pet - f.aet_canopy;
+      if (hh != 0) a = a - aet_pos_sum;
+      double stress;
+      if (soil_case == 1 || soil_case == 4) {  // feddes_et_reduction :353-361
+        if (sm >= p.FC[hh]) {
+          stress = p.fRoots[hh];
+        } else if (sm > p.WP[hh]) {
+#if MHM_FAST
+          stress = p.fRoots[hh] * (sm - p.WP[hh]) * p.inv_FCWP[hh];
+#else
+          stress = p.fRoots[hh] * (sm - p.WP[hh]) / (p.FC[hh] - p.WP[hh]);
+#endif
+        } else {
+          stress = 0.0;
+        }
+      } else {  // jarvis_et_reduction :431-444 (cases 2, 3)
+        double th = (sm - p.WP[hh]) / (sat - p.WP[hh]);
+        if (th < 0.0) th = 0.0;
+        if (th > 1.0) th = 1.0;
+        stress = 0.0;
+        if (th >= p.jarvis_c1) {
+          stress = p.fRoots[hh];
+        } else if (th < p.jarvis_c1) {
+          stress = p.fRoots[hh] * (th / p.jarvis_c1);
+        }
+      }
+      a = a * stress;
+      if (a < 0.0) a = 0.0;
+      if (sm > a) {
+        sm = sm - a;
+      } else {
+        a = sm - kEps;
+        sm = kEps;
+      }
+      if (sm < kEps) sm = kEps;
+      f.aet_soil[hh] = a;
+      s.sm[hh] = sm;
+      // running masked sum in index order (bit-identical to Fortran's sum(..., mask))
+      if (a > 0.0) aet_pos_sum = aet_pos_sum + a;
+    }
+  }
+
+  // ---- runoff_unsat_zone, mo_runoff.f90:120-152 ----
+  {
+    double us = s.unsat + f.infiltration[NH - 1];
+    double fast = 0.0;
+    if (us > p.unsatThr) fast = fmin(p.k0r * (us - p.unsatThr), us - kEps);
+    us = us - fast;
+    double slow = 0.0;
+    if (us > kEps) {
+#if MHM_FAST
+      slow = fmin(p.k1r * exp((1.0 + p.alpha) * log(us)), us - kEps);
+#else
+      slow = fmin(p.k1r * pow(us, 1.0 + p.alpha), us - kEps);
+#endif
+    }
+    us = us - slow;
+    double perc = p.kpr * us;
+    if (us > perc) {
+      us = us - perc;
+      s.sat = s.sat + perc * p.karst;
+    } else {
+      s.sat = s.sat + us * p.karst;
+      us = 0.0;
+    }
+    s.unsat = us;
+    f.fast_interflow = fast;
+    f.slow_interflow = slow;
+    f.perc = perc;
+  }
+  // ---- runoff_sat_zone :204-210 ----
+  if (s.sat > 0.0) {
+    f.baseflow = p.k2r * s.sat;
+    s.sat = s.sat - f.baseflow;
+  } else {
+    f.baseflow = 0.0;
+    s.sat = 0.0;
+  }
+  // ---- L1_total_runoff :271-272 ----
+  f.total_runoff = ((f.baseflow + f.slow_interflow + f.fast_interflow) * (1.0 - p.fSealed)) +
+                   (f.runoff_sealed * p.fSealed);
+}
+
+__device__ __forceinline__ double ldg_stream(const double* p) { return __ldg(p); }
+
+template <int NH>
+__global__ void __launch_bounds__(kCellThreads)
+MHM_KERNEL_NAME(const CellArgs a) {
+  const int member = blockIdx.x % a.nMembers;
+  const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
+  if (cell >= a.nCells) return;
+  const size_t n = (size_t)a.nCells;
+  const size_t mc = (size_t)member * n + cell;
+
+  CellStates<NH> s;
+  s.inter = a.S[MHM_S_INTER][mc];
+  s.snowpack = a.S[MHM_S_SNOWPACK][mc];
+  s.sealed = a.S[MHM_S_SEALSTW][mc];
+  s.unsat = a.S[MHM_S_UNSATSTW][mc];
+  s.sat = a.S[MHM_S_SATSTW][mc];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) s.sm[h] = a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + cell];
+
+  CellParams<NH> p;
+  // parameters that never change during a run
+  p.karst = a.P[MHM_P_KARSTLOSS][mc];
+  p.jarvis_c1 = a.P[MHM_P_JARVIS_C1][mc];
+  p.unsatThr = a.P[MHM_P_UNSATTHRESH][mc];
+  p.sealedThr = a.P[MHM_P_SEALEDTHRESH][mc];
+#if MHM_FAST
+  p.inv_sealedThr = 1.0 / p.sealedThr;
+  p.inv_jc1 = 1.0 / p.jarvis_c1;
+#endif
+  int cur_y = -1, cur_l = -1;
+  long long cur_row = -1;
+  CellFluxes<NH> f;
+  double raw_pre = 0.0, raw_temp = 0.0, raw_pet = 0.0;
+
+  for (int t = 0; t < a.nSteps; ++t) {
+    const StepIdx si = a.idx[t];
+    const int y = si.yId - 1, il = si.iLAI - 1, month = si.month - 1;
+
+    if (y != cur_y) {  // land-cover scene changed (new year): mo_mhm_interface_run.f90:626-628
+      cur_y = y;
+      const size_t o1 = ((size_t)member * a.nLC + y) * n + cell;  // (n, 1, nLC) arrays
+      p.fSealed = a.P[MHM_P_FSEALED][o1];
+      p.alpha = a.P[MHM_P_ALPHA][o1];
+      p.ddinc = a.P[MHM_P_DEGDAYINC][o1];
+      p.ddmax_c = a.P[MHM_P_DEGDAYMAX][o1] * a.c2TSTu;    // mo_mhm.f90:463
+      p.ddnop_c = a.P[MHM_P_DEGDAYNOPRE][o1] * a.c2TSTu;  // mo_mhm.f90:464
+      p.ddthr = (p.ddmax_c - p.ddnop_c) / p.ddinc;        // mo_snow_accum_melt.f90:127
+      p.k0r = a.c2TSTu / a.P[MHM_P_KFASTFLOW][o1];        // mo_mhm.f90:484
+      p.k1r = a.c2TSTu / a.P[MHM_P_KSLOWFLOW][o1];
+      p.kpr = a.c2TSTu / a.P[MHM_P_KPERCO][o1];
+      p.k2r = a.c2TSTu / a.P[MHM_P_KBASEFLOW][o1];        // mo_mhm.f90:488
+      p.tthr = a.P[MHM_P_TEMPTHRESH][o1];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const size_t oh = (((size_t)member * a.nLC + y) * NH + h) * n + cell;  // (n, nH, nLC)
+        p.fRoots[h] = a.P[MHM_P_FROOTS][oh];
+        p.FC[h] = a.P[MHM_P_SOILMOISTFC][oh];
+        p.SAT[h] = a.P[MHM_P_SOILMOISTSAT][oh];
+        p.EXPN[h] = a.P[MHM_P_SOILMOISTEXP][oh];
+        p.WP[h] = a.P[MHM_P_WILTINGPOINT][oh];
+#if MHM_FAST
+        p.inv_SAT[h] = 1.0 / p.SAT[h];
+        p.inv_FCWP[h] = 1.0 / (p.FC[h] - p.WP[h]);
+#endif
+      }
+      cur_l = -1;  // petLAIcorFactor / aeroResist also depend on yId
+      if (t == 0 && a.tt_first == 1 && !a.read_states) {  // mo_mhm.f90:448-450
+#pragma unroll
+        for (int h = 0; h < NH; ++h) s.sm[h] = 0.5 * p.FC[h];
+      }
+    }
+    if (il != cur_l) {  // LAI step changed: mo_common_datetime_type.f90:135-155
+      cur_l = il;
+      p.maxInter = a.P[MHM_P_MAXINTER][((size_t)member * a.nLAI + il) * n + cell];
+#if MHM_FAST
+      p.inv_maxInter = 1.0 / p.maxInter;
+#endif
+      if (a.pet_case == -1) {
+        p.petFac = a.P[MHM_P_PETLAICORFACTOR][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + cell];
+      } else if (a.pet_case == 0 || a.pet_case == 1) {
+        p.petFac = a.P[MHM_P_FASP][mc];
+      } else {
+        p.petFac = 1.0;
+      }
+    }
+
+    // ---- forcing of this step: mo_meteo_handler.f90:595-618 (iMeteoTS), rows are
+    //      [meteo step][cell]; reload only when the meteo step changes ----
+    const long long row = (long long)si.iMeteoTS;
+    if (row != cur_row) {
+      cur_row = row;
+      raw_pre = ldg_stream(a.met[MHM_M_PRE] + (size_t)(row - a.met_first[MHM_M_PRE]) * n + cell);
+      raw_temp = ldg_stream(a.met[MHM_M_TEMP] + (size_t)(row - a.met_first[MHM_M_TEMP]) * n + cell);
+      if (a.pet_case <= 0)
+        raw_pet = ldg_stream(a.met[MHM_M_PET] + (size_t)(row - a.met_first[MHM_M_PET]) * n + cell);
+    }
+
+    // ---- get_corrected_pet :1053-1119 ----
+    double pet;
+    if (a.pet_case <= 0) {
+      pet = p.petFac * raw_pet;
+    } else if (a.pet_case == 1) {
+      const double tmx = a.met[MHM_M_TMAX][(size_t)(row - a.met_first[MHM_M_TMAX]) * n + cell];
+      const double tmn = a.met[MHM_M_TMIN][(size_t)(row - a.met_first[MHM_M_TMIN]) * n + cell];
+      pet = p.petFac * pet_hargreaves(a.P[MHM_P_HARSAMCOEFF][mc], raw_temp, tmx, tmn,
+                                      a.P[MHM_P_LATITUDE][mc], si.doy);
+    } else if (a.pet_case == 2) {
+      const double rn = a.met[MHM_M_NETRAD][(size_t)(row - a.met_first[MHM_M_NETRAD]) * n + cell];
+      pet = pet_priestly(a.P[MHM_P_PRIETAYALPHA][((size_t)member * a.nLAI + il) * n + cell],
+                         fmax(rn, 0.0), raw_temp);
+    } else {
+      const double rn = a.met[MHM_M_NETRAD][(size_t)(row - a.met_first[MHM_M_NETRAD]) * n + cell];
+      const double avp =
+          a.met[MHM_M_ABSVAPPRESS][(size_t)(row - a.met_first[MHM_M_ABSVAPPRESS]) * n + cell];
+      const double ws =
+          a.met[MHM_M_WINDSPEED][(size_t)(row - a.met_first[MHM_M_WINDSPEED]) * n + cell];
+      const double ar =
+          a.P[MHM_P_AERORESIST][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + cell];
+      const double sr = a.P[MHM_P_SURFRESIST][((size_t)member * a.nLAI + il) * n + cell];
+      pet = pet_penman(fmax(rn, 0.0), raw_temp, avp / 1000.0, ar / ws, sr);
+    }
+    // ---- temporal disaggregation: mo_meteo_temporal_tools.f90 ----
+    if (a.is_hourly) {
+      f.pet_calc = pet;
+      f.temp_calc = raw_temp;
+      f.prec_calc = raw_pre;
+    } else if (a.read_weights) {
+      const size_t wo = ((size_t)si.hour * 12 + month) * n + cell;
+      f.pet_calc = (pet + 0.0) * a.w_pet[wo] - 0.0;
+      f.temp_calc = (raw_temp + kT0) * a.w_temp[wo] - kT0;
+      f.prec_calc = (raw_pre + 0.0) * a.w_pre[wo] - 0.0;
+    } else if (a.nTstepDay_dp > 1.0) {
+      const double fpet = si.isday ? a.tab.fday_pet[month] : a.tab.fnight_pet[month];
+      const double fpre = si.isday ? a.tab.fday_prec[month] : a.tab.fnight_prec[month];
+      const double ftmp = si.isday ? a.tab.fday_temp[month] : a.tab.fnight_temp[month];
+      f.pet_calc = 2.0 * pet * fpet / a.nTstepDay_dp;
+      f.prec_calc = 2.0 * raw_pre * fpre / a.nTstepDay_dp;
+      f.temp_calc = raw_temp + ftmp;
+    } else {
+      f.pet_calc = pet;
+      f.temp_calc = raw_temp;
+      f.prec_calc = raw_pre;
+    }
+
+    // prefetch the next step's forcing row into L2->L1 path before the arithmetic
+    if (t + 1 < a.nSteps) {
+      const long long nrow = (long long)a.idx[t + 1].iMeteoTS;
+      if (nrow != cur_row) {
+        cur_row = nrow;
+        raw_pre = ldg_stream(a.met[MHM_M_PRE] + (size_t)(nrow - a.met_first[MHM_M_PRE]) * n + cell);
+        raw_temp = ldg_stream(a.met[MHM_M_TEMP] + (size_t)(nrow - a.met_first[MHM_M_TEMP]) * n + cell);
+        if (a.pet_case <= 0)
+          raw_pet = ldg_stream(a.met[MHM_M_PET] + (size_t)(nrow - a.met_first[MHM_M_PET]) * n + cell);
+      }
+    }
+
+#if MHM_FAST
+    cascade_step<NH>(p, s, f, a.soil_case, a.tab.evap_coeff[month], a.tab.inv_evap_coeff[month]);
+#else
+    cascade_step<NH>(p, s, f, a.soil_case, a.tab.evap_coeff[month]);
+#endif
+
+    if (a.runoff_hist)
+      __stcs(a.runoff_hist + ((size_t)t * a.nMembers + member) * n + cell, f.total_runoff);
+  }
+
+  // ---- write back states and (optionally) the fluxes of the block's last step ----
+  a.S[MHM_S_INTER][mc] = s.inter;
+  a.S[MHM_S_SNOWPACK][mc] = s.snowpack;
+  a.S[MHM_S_SEALSTW][mc] = s.sealed;
+  a.S[MHM_S_UNSATSTW][mc] = s.unsat;
+  a.S[MHM_S_SATSTW][mc] = s.sat;
+#pragma unroll
+  for (int h = 0; h < NH; ++h) a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + cell] = s.sm[h];
+  if (a.write_fluxes) {
+    a.F[MHM_F_PET_CALC][mc] = f.pet_calc;
+    a.F[MHM_F_TEMP_CALC][mc] = f.temp_calc;
+    a.F[MHM_F_PREC_CALC][mc] = f.prec_calc;
+    a.F[MHM_F_AETCANOPY][mc] = f.aet_canopy;
+    a.F[MHM_F_AETSEALED][mc] = f.aet_sealed;
+    a.F[MHM_F_BASEFLOW][mc] = f.baseflow;
+    a.F[MHM_F_FASTRUNOFF][mc] = f.fast_interflow;
+    a.F[MHM_F_MELT][mc] = f.melt;
+    a.F[MHM_F_PERCOL][mc] = f.perc;
+    a.F[MHM_F_PREEFFECT][mc] = f.prec_effect;
+    a.F[MHM_F_RAIN][mc] = f.rain;
+    a.F[MHM_F_RUNOFFSEAL][mc] = f.runoff_sealed;
+    a.F[MHM_F_SLOWRUNOFF][mc] = f.slow_interflow;
+    a.F[MHM_F_SNOW][mc] = f.snow;
+    a.F[MHM_F_THROUGHFALL][mc] = f.throughfall;
+    a.F[MHM_F_TOTAL_RUNOFF][mc] = f.total_runoff;
+    a.F[MHM_F_DEGDAY][mc] = f.deg_day;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      a.F[MHM_F_AETSOIL][((size_t)member * NH + h) * n + cell] = f.aet_soil[h];
+      a.F[MHM_F_INFILSOIL][((size_t)member * NH + h) * n + cell] = f.infiltration[h];
+    }
+  }
+}
+
+}  // namespace mhm

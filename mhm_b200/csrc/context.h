@@ -1,0 +1,117 @@
+// context.h -- host-side objects behind the opaque handles of include/mhm_cuda.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "calendar.h"
+#include "device_types.h"
+
+namespace mhm {
+
+void set_error(const char* fmt, ...);
+
+#define MHM_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      ::mhm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                       __LINE__);                                                      \
+      return 2;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+#define MHM_REQUIRE(cond, ...)     \
+  do {                             \
+    if (!(cond)) {                 \
+      ::mhm::set_error(__VA_ARGS__); \
+      return 1;                    \
+    }                              \
+  } while (0)
+
+struct HostBind {
+  double* base = nullptr;
+  int64_t ld = 0, offset = 0;
+};
+
+struct Routing;  // routing.cu
+
+// kernel classes for mhm_cuda_kernel_stats
+enum { kStatCell = 0, kStatRouting = 1, kStatUpscale = 2, kStatCount = 3 };
+
+struct Domain {
+  int32_t id = 0;
+  mhm_domain_config cfg{};
+  std::vector<int32_t> processMatrix;
+  int soil_case = 1, pet_case = 0, rout_case = 0;
+
+  // effective parameters, device [member][dim3][dim2][nCells]
+  double* P[MHM_P_COUNT] = {};
+  int P_dim2[MHM_P_COUNT] = {}, P_dim3[MHM_P_COUNT] = {};
+  // states / fluxes, device [member][(nH)][nCells]
+  double* S[MHM_S_COUNT] = {};
+  double* F[MHM_F_COUNT] = {};
+  HostBind sbind[MHM_S_COUNT], fbind[MHM_F_COUNT];
+
+  // meteo
+  bool has_meteo_cfg = false;
+  mhm_meteo_config mcfg{};
+  double* met[MHM_M_COUNT] = {};
+  bool met_owned[MHM_M_COUNT] = {};
+  size_t met_cap[MHM_M_COUNT] = {};  // owned capacity in doubles
+  int64_t met_first[MHM_M_COUNT] = {}, met_n[MHM_M_COUNT] = {};
+  double* weights[3] = {};
+
+  // time axis
+  bool has_time = false;
+  TimeAxis axis;
+  std::vector<StepIdx> h_idx;  // steps 1..nTimeSteps
+  StepIdx* d_idx = nullptr;
+  StepIdx* d_idx_one = nullptr;  // scratch for the per-step seam
+
+  // total-runoff history of the last block, device [steps][member][nCells]
+  double* runoff_hist = nullptr;
+  size_t runoff_cap = 0;
+  int32_t hist_steps = 0, hist_tt_first = 0;
+
+  Routing* rt = nullptr;
+  int32_t last_yId = 1;  // scene of the last executed step (routing parameters, per-step seam)
+};
+
+struct TimedLaunch {
+  cudaEvent_t a, b;
+  int which;
+};
+
+}  // namespace mhm
+
+struct mhm_cuda_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::map<int32_t, mhm::Domain*> domains;
+  cudaEvent_t ev[16] = {};
+  int math_mode = 0;
+  // kernel statistics
+  bool timing = false;
+  double stat_ms[mhm::kStatCount] = {};
+  int64_t stat_launches[mhm::kStatCount] = {};
+  std::vector<mhm::TimedLaunch> pending;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t block_bytes = (size_t)24 << 30;  // memory budget of per-block history buffers
+
+  // bracket a kernel launch with events when timing is enabled
+  void stat_begin(int which);
+  void stat_end(int which);
+  int stat_flush();
+};
+
+namespace mhm {
+Domain* find_domain(mhm_cuda_context* ctx, int32_t iDomain);
+// routing hooks used by api.cu
+void routing_free(Routing* rt);
+int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_t n_steps);
+}  // namespace mhm

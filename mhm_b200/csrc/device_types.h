@@ -1,0 +1,51 @@
+// device_types.h -- argument blocks shared by the host API and the kernels.
+#pragma once
+#include <cstdint>
+
+#include "../../include/mhm_cuda.h"
+
+namespace mhm {
+
+constexpr int kCellThreads = 128;
+constexpr int kMaxHorizons = 8;
+
+// per-step calendar indices, 16 bytes (one LDG.128, warp-uniform)
+struct alignas(16) StepIdx {
+  int32_t iMeteoTS;  // 1-based meteo time index (mo_meteo_handler.f90:607)
+  int16_t yId;       // 1-based land-cover scene
+  int16_t iLAI;      // 1-based LAI step
+  int16_t doy;
+  int16_t year;
+  int8_t month;      // 1..12
+  int8_t hour;       // 0..23
+  int8_t isday;      // hour > 6 .and. hour <= 18
+  int8_t pad;
+};
+static_assert(sizeof(StepIdx) == 16, "StepIdx must be 16 bytes");
+
+struct MeteoTables {
+  double fday_prec[12], fnight_prec[12], fday_pet[12], fnight_pet[12], fday_temp[12],
+      fnight_temp[12], evap_coeff[12], inv_evap_coeff[12];
+};
+
+struct CellArgs {
+  int32_t nCells, nMembers, nSteps, tt_first;
+  int32_t nLC, nLAI;
+  int32_t soil_case, pet_case, is_hourly, read_weights, read_states, write_fluxes;
+  double nTstepDay_dp, c2TSTu;
+  const StepIdx* idx;                 // device, [nSteps]
+  const double* met[MHM_M_COUNT];     // device, [rows][nCells]
+  long long met_first[MHM_M_COUNT];   // iMeteoTS of row 0
+  const double *w_pre, *w_temp, *w_pet;  // device, [24][12][nCells]
+  const double* P[MHM_P_COUNT];       // device, [member][dim3][dim2][nCells]
+  double* S[MHM_S_COUNT];             // device, [member][(nH)][nCells]
+  double* F[MHM_F_COUNT];             // device, [member][(nH)][nCells]
+  double* runoff_hist;                // device, [nSteps][member][nCells] or null
+  MeteoTables tab;
+};
+
+// kernel launchers (cell_kernel_strict.cu / cell_kernel_fast.cu)
+int launch_cell_block_strict(const CellArgs& a, int nH, void* stream);
+int launch_cell_block_fast(const CellArgs& a, int nH, void* stream);
+
+}  // namespace mhm
