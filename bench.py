@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- L1 cell-timesteps/s of the mHM hot path on N B200s (BASELINE.json metric).
+
+Workload (config.workload): the per-GPU share of BASELINE config 5 -- a synthetic ~1M-cell
+continental domain x 32 ensemble members per GPU (256 members on 8 GPUs), hourly forcing,
+PET as input, Feddes soil moisture (nH = 2), level-scheduled Muskingum routing (case 1) on a
+Scheidegger-type river network with L11 == L1.  Weak scaling: every rank owns 32 members of
+the same domain, there is no data-path collective (members are independent evaluations,
+SURVEY.md 8e); rank 0 gathers the members' gauge series in the e2e leg.
+
+One "step" = one chunk of `block_hours` model steps for all cells and members of the rank:
+fused cell kernel (meteo prologue + cascade) + routing + gauge extraction.
+  value : forcing chunk resident in HBM (bound zero-copy), CUDA events on the library's
+          stream, max over ranks.  Every step reads a different part of a forcing chunk that
+          is larger than L2 (1M cells x 24 B x hours >> 126 MB).
+  e2e   : the same steps through the C ABI with HOST buffers: H2D of the chunk's forcing from
+          pinned memory, the run, D2H of the chunk's gauge series.
+  --impl reference : the CPU restatement of the reference (oracle/, OpenMP over cells, serial
+          routing -- the reference's own loop structure; the Fortran original cannot be built
+          here) on a bounded sample of the same workload, all host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=1180)
+    ap.add_argument("--ny", type=int, default=1000)
+    ap.add_argument("--members", type=int, default=32, help="ensemble members per GPU")
+    ap.add_argument("--block-hours", type=int, default=48)
+    ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--no-routing", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-cells", type=int, default=100000)
+    ap.add_argument("--cpu-hours", type=int, default=24)
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4)
+                          if len(r) >= 7 and r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def member_params(base, rng, m):
+    """member m's parameter set: the base set scaled inside the physical ranges (joint factors
+    keep FC <= Sat, WP <= FC, k0 <= k1 <= k2 intact)"""
+    if m == 0:
+        return base
+    P = {}
+    f = lambda lo, hi: rng.uniform(lo, hi)
+    soil = f(0.85, 1.15)
+    rec = f(0.85, 1.15)
+    for k, v in base.items():
+        if k in ("L1_soilMoistFC", "L1_soilMoistSat", "L1_wiltingPoint"):
+            P[k] = v * soil
+        elif k in ("L1_kFastFlow", "L1_kSlowFlow", "L1_kBaseFlow"):
+            P[k] = v * rec
+        elif k in ("L1_fRoots", "L1_fSealed", "L1_karstLoss", "L1_jarvis_thresh_c1", "latitude"):
+            P[k] = v
+        elif k in ("L1_degDayNoPre", "L1_degDayMax"):
+            P[k] = v  # keep ddmax >= ddnoprec
+        else:
+            P[k] = v * f(0.9, 1.1)
+    return P
+
+
+def build_problem(args, n_steps_total):
+    from mhm_b200 import synth
+
+    n_days = (n_steps_total + 23) // 24 + 1
+    rng = np.random.default_rng(synth.SEED)
+    t0 = time.time()
+    from mhm_b200.interface import routing_order
+    net = None
+    if not args.no_routing:
+        net = synth.make_network(rng, args.nx, args.ny, routing_order, 0.85, 1, 1, 2, 3, None)
+        n = net["nCells1"]
+    else:
+        n = int(args.nx * args.ny * 0.85)
+    prob = {"nH": 2, "nLAI": 12, "nLC": 2, "timestep_h": 1, "hourly": True, "soil_case": 1,
+            "pet_case": -1, "rout_case": 1, "read_weights": False, "nCells": n, "net": net,
+            "nTstepForcingDay": 24}
+    prob["processMatrix"] = synth.process_matrix(1, -1, 0 if net is None else 1)
+    prob["time"] = {"jul_start": synth.JUL_1990_01_01 + 150, "nTimeSteps": n_days * 24,
+                    "warming_days": 0, "timeStep_LAI_input": 0, "lc_year_start": 1989,
+                    "LCyearId": np.array([1, 1, 2, 2, 2, 2, 2, 2], dtype=np.int32)}
+    prob["params"] = synth.make_params(rng, n, 2, 12, 2, -1)
+    prob["horizon_depth"] = np.array([200.0, 400.0])
+    prob["states0"] = synth.default_states(n, 2, prob["horizon_depth"])
+    prob["inflowQ"] = np.zeros((0, n_days))
+    prob["setup_s"] = time.time() - t0
+    return prob, rng
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from mhm_b200 import driver, interface, synth
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, K, T, M = args.warmup, args.steps, args.block_hours, args.members
+    n_total = 2 * (W + K) * T
+    prob, rng = build_problem(args, n_total)
+    n = prob["nCells"]
+    ctx = interface.Context(local)
+    ctx.set_math_mode(args.mode)
+    mrng = np.random.default_rng(1000 + rank)
+    dom = driver.setup_domain(ctx, 1, prob, nMembers=1, upload_forcing=False) if M == 1 else None
+    if dom is None:
+        # members are uploaded one at a time to bound host memory
+        dom = ctx.register_domain(1, n, 2, 12, 2, prob["processMatrix"], timestep_h=1, nMembers=M)
+        dom.set_meteo_config(-1, 24, True, False, synth.FNIGHT_PREC, synth.FNIGHT_PET,
+                             synth.FNIGHT_TEMP, synth.EVAP_COEFF)
+        dom.set_time(prob["time"])
+        if prob["net"] is not None:
+            dom.set_network(prob["net"])
+        for m in range(M):
+            P = member_params(prob["params"], mrng, m)
+            for name, arr in P.items():
+                dom.set_param(name, arr, member=m)
+            for name, arr in prob["states0"].items():
+                dom.set_state(name, arr, member=m)
+            if prob["net"] is not None:
+                net = prob["net"]
+                dom.set_reg_rout(net["rout_param"] * mrng.uniform(0.95, 1.05, 5),
+                                 net["L11_length"][: net["nNodes"] - 1],
+                                 net["L11_slope"][: net["nNodes"] - 1], net["L11_nLinkFracFPimp"],
+                                 member=m)
+    # forcing chunk of T hours, generated on the device, mirrored into pinned host memory
+    g = torch.Generator(device="cuda")
+    g.manual_seed(synth.SEED + rank)
+    hours = torch.arange(T, device="cuda", dtype=torch.float64)[:, None]
+    wet = torch.rand((T, n), generator=g, device="cuda") < 0.2
+    gam = torch.distributions.Gamma(torch.tensor(0.7, device="cuda", dtype=torch.float64),
+                                    torch.tensor(1.0 / 1.6, device="cuda", dtype=torch.float64))
+    pre = torch.where(wet, gam.sample((T, n)), torch.zeros((), device="cuda", dtype=torch.float64))
+    temp = (12.0 + 4.0 * torch.sin(2 * np.pi * (hours % 24) / 24.0)
+            + 2.0 * torch.randn((T, n), generator=g, device="cuda", dtype=torch.float64))
+    pet = (torch.clamp(0.15 * torch.sin(np.pi * ((hours % 24) - 6.0) / 12.0), min=0.0)
+           * (0.8 + 0.4 * torch.rand((T, n), generator=g, device="cuda", dtype=torch.float64)))
+    dev = {"pre": pre.contiguous(), "temp": temp.contiguous(), "pet": pet.contiguous()}
+    host = {k: torch.empty((T, n), dtype=torch.float64, pin_memory=True).copy_(v) for k, v in dev.items()}
+    torch.cuda.synchronize()
+    nG = dom.nGaugesTotal
+    q_host = np.zeros((max(nG, 1), prob["time"]["nTimeSteps"]))
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step_value(i):
+        first = i * T + 1
+        for k, v in dev.items():
+            dom.set_meteo_device(k, v.data_ptr(), first, T)
+        dom.run_steps(first, T)
+
+    def step_e2e(i):
+        first = i * T + 1
+        for k, v in host.items():
+            dom.set_meteo_host_ptr(k, v.data_ptr(), n, first, T)
+        dom.run_steps(first, T)
+        if nG:
+            for m in range(M):
+                dom.get_runoff(first, T, member=m, out=q_host)
+        else:
+            dom.get_state("L1_satSTW")
+
+    def timed(fn, i0):
+        for i in range(W):
+            fn(i0 + i)
+        barrier()
+        ctx.kernel_stats_reset(True)
+        sampler = ClockSampler(local)
+        sampler.start()
+        ctx.event_record(0)
+        wall0 = time.time()
+        for i in range(K):
+            fn(i0 + W + i)
+        ctx.event_record(1)
+        barrier()
+        wall = time.time() - wall0
+        ms = ctx.event_elapsed_ms(0, 1)
+        clocks = sampler.summary()
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall, clocks
+
+    ms_v, wall_v, clocks = timed(step_value, 0)
+    cell_ms, cell_launches = ctx.kernel_stats(0)
+    rout_ms, rout_launches = ctx.kernel_stats(1)
+    ms_e, wall_e, _ = timed(step_e2e, W + K)
+    units_per_step = float(n) * M * T
+    value = units_per_step * K * world / (ms_v * 1e-3)
+    e2e_value = units_per_step * K * world / (wall_e)
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+        # algorithmic bytes per cell-step-member: forcing 24 B shared by M members
+        # + 8 B total runoff written for the routing
+        bytes_per_unit = 24.0 / M + 8.0
+        launches_cell = max(1, cell_launches)
+        cell_avg_ms = cell_ms / launches_cell
+        units_per_launch = units_per_step * K / launches_cell
+        achieved = units_per_launch * bytes_per_unit / (cell_avg_ms * 1e-3) / 1e9
+        dfma = ctx.measure_dfma_peak()
+        out = {
+            "metric": "L1 cell-timesteps/s", "value": value, "unit": "cell-timesteps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_v / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": "BASELINE config 5 per-GPU share: synthetic %d-cell domain x %d members "
+                            "per GPU, hourly forcing, %s" % (
+                                n, M, "Muskingum routing case 1 (L11 == L1, %d nodes)" % n
+                                if prob["net"] is not None else "no routing"),
+                "cells": n, "members_per_gpu": M, "block_hours": T, "math_mode": args.mode,
+                "nH": 2, "l2_policy": "inputs larger than L2 (forcing chunk %.1f GB, states+params "
+                                      "%.1f GB per step)" % (3 * T * n * 8 / 1e9, 88 * 8 * n * M / 1e9),
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "cell_block_kernel_%s<2>" % args.mode,
+                "kernel_ms_per_launch": cell_avg_ms, "units_per_launch": units_per_launch,
+                "bytes_per_unit": bytes_per_unit,
+                "kernel_share_of_step": cell_ms / ms_v,
+            },
+            "roofline_fp64": {
+                "note": "the fused kernel is fp64-pipe bound (BASELINE.md 3); dfma_peak measured "
+                        "live by a dependent-chain-free DFMA loop",
+                "dfma_peak_per_s": dfma, "cell_kernel_units_per_s": units_per_launch / (cell_avg_ms * 1e-3),
+            },
+            "routing": {"ms": rout_ms, "kernel_launches": rout_launches, "share_of_step": rout_ms / ms_v},
+            "e2e": {"value": e2e_value, "unit": "cell-timesteps/s",
+                    "h2d_bytes_per_step": 3 * T * n * 8,
+                    "d2h_bytes_per_step": M * max(nG, 1) * T * 8, "ms_per_step": wall_e * 1e3 / K},
+            "gpu_launches": int(cell_launches + rout_launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(out), flush=True)
+    ctx.finalize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_problem(args):
+    """bounded sample of the bench workload for the CPU arm: the first ~cpu_cells cells of a
+    domain of the same kind, one member, cpu_hours model steps"""
+    from mhm_b200 import synth
+    from mhm_b200.interface import routing_order
+
+    nx = int(round((args.cpu_cells / 0.85) ** 0.5 * 1.086))
+    ny = int(round(args.cpu_cells / 0.85 / nx))
+    prob = synth.make_problem(nx=nx, ny=ny, n_days=max(1, (args.cpu_hours + 23) // 24), hourly=True,
+                              routing=not args.no_routing, start=(1990, 6, 1),
+                              routing_order=routing_order)
+    return prob
+
+
+def cpu_run(prob, hours, threads):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc_run
+
+    o = orc_run.OracleRun(prob, num_threads=threads)
+    t0 = time.time()
+    o.run(1, hours)
+    return time.time() - t0
+
+
+def cpu_baseline(args):
+    cores = os.cpu_count() or 1
+    prob = cpu_problem(args)
+    hours = min(args.cpu_hours, prob["time"]["nTimeSteps"])
+    best = min(cpu_run(prob, hours, cores) for _ in range(2))
+    return {"value": prob["nCells"] * hours / best, "unit": "cell-timesteps/s", "cores": cores,
+            "kind": "port",
+            "sample": "%d cells x 1 member x %d hourly steps, OpenMP static over cells + serial "
+                      "routing (reference loop structure), best of 2" % (prob["nCells"], hours)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    prob = cpu_problem(args)
+    hours = min(args.cpu_hours, prob["time"]["nTimeSteps"])
+    for _ in range(args.warmup):
+        cpu_run(prob, hours, cores)
+    t = [cpu_run(prob, hours, cores) for _ in range(args.steps)]
+    total = sum(t)
+    v = prob["nCells"] * hours * args.steps / total
+    sample = ("%d cells x 1 member x %d hourly steps per step; oracle/ restatement of the reference "
+              "(Fortran original not buildable here)" % (prob["nCells"], hours))
+    print(json.dumps({
+        "impl": "reference", "metric": "L1 cell-timesteps/s", "value": v, "unit": "cell-timesteps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "bounded sample of BASELINE config 5 per-GPU share", "cells": prob["nCells"],
+                   "members_per_gpu": 1, "block_hours": hours},
+        "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -87,8 +87,8 @@ void mhm_cuda_context::stat_begin(int which) {
   cudaEventRecord(t.a, stream);
   pending.push_back(t);
 }
-void mhm_cuda_context::stat_end(int which) {
-  stat_launches[which] += 1;
+void mhm_cuda_context::stat_end(int which, int64_t launches) {
+  stat_launches[which] += launches;
   if (!timing) return;
   cudaEventRecord(pending.back().b, stream);
 }

@@ -105,7 +105,7 @@ struct mhm_cuda_context {
 
   // bracket a kernel launch with events when timing is enabled
   void stat_begin(int which);
-  void stat_end(int which);
+  void stat_end(int which, int64_t launches = 1);
   int stat_flush();
 };
 

@@ -20,9 +20,29 @@
 #include <cmath>
 #include <cstring>
 
+#include <cooperative_groups.h>
+
 #include "context.h"
 
+namespace cg = cooperative_groups;
+
 namespace mhm {
+
+constexpr int kTailCluster = 8;       // CTAs per cluster in the tail kernel (portable maximum)
+constexpr int kTailThreads = 512;     // threads per CTA in the tail kernel
+constexpr int kTailMaxLevel = 2048;   // levels wider than this get their own launch
+
+// everything a routing thread needs to know about its entry, one 32-byte record
+struct alignas(16) EntMeta {
+  int32_t node;    // 0-based L11 node
+  int32_t link;    // 0-based link (C1/C2 index)
+  int32_t flags;   // kEnt* bits
+  int32_t gslot;   // gauge slot or -1
+  int32_t level;   // network level
+  int32_t nup;     // number of upstream links
+  int32_t up[2];   // entry positions of the first two upstream links (netPerm order)
+};
+static_assert(sizeof(EntMeta) == 32, "EntMeta must be 32 bytes");
 
 enum : int32_t {
   kEntLink = 1,     // entry is a link (has Muskingum state); otherwise an outlet node
@@ -52,6 +72,9 @@ struct Routing {
   // device topology (shared by members)
   int32_t *ent_node = nullptr, *ent_link = nullptr, *ent_flags = nullptr, *ent_gslot = nullptr;
   int32_t *up_ptr = nullptr, *up_pos = nullptr;
+  EntMeta* meta = nullptr;
+  int32_t* d_lvl_ptr = nullptr;
+  int32_t tail_level = 0;  // levels >= tail_level are swept by one clustered wavefront kernel
   int32_t *cell_ptr = nullptr, *cell_idx = nullptr;  // map_flag: L1 cells of each node, ascending
   int32_t* L11_L1_Id = nullptr;                      // !map_flag
   int32_t *d_inflow_node = nullptr, *d_inflow_index = nullptr, *d_inflow_head = nullptr;
@@ -87,7 +110,7 @@ struct Routing {
 void routing_free(Routing* rt) {
   if (!rt) return;
   void* ptrs[] = {rt->ent_node, rt->ent_link,  rt->ent_flags, rt->ent_gslot, rt->up_ptr,
-                  rt->up_pos,   rt->cell_ptr,  rt->cell_idx,  rt->L11_L1_Id, rt->d_inflow_node,
+                  rt->up_pos,   rt->meta, rt->d_lvl_ptr, rt->cell_ptr,  rt->cell_idx,  rt->L11_L1_Id, rt->d_inflow_node,
                   rt->d_inflow_index, rt->d_inflow_head, rt->L1_area, rt->L11_area,
                   rt->d_gauge_col, rt->d_gauge_slot, rt->C1, rt->C2, rt->qOUT, rt->qMod,
                   rt->qTIN, rt->qTR, rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry,
@@ -269,6 +292,140 @@ __global__ void route_level_kernel(const LevelArgs a) {
   }
 }
 
+// ---- fast path: every event is one routing step (rout_loop == 1, the usual case) ----------
+struct FastArgs {
+  int32_t p0, p1;  // entry range (level kernel) / first tail entry and E (tail kernel)
+  int32_t E, M, nNodes, nEvents, nGslots;
+  int32_t tail_level, nLevels;
+  const EntMeta* meta;
+  const int32_t *up_ptr, *up_pos, *lvl_ptr;
+  const DevEvent* events;
+  const double *C1, *C2;
+  const double* qout_hist;  // [nEvents][M][E]
+  double* qtr_hist;         // [nEvents][M][E]
+  double *qTIN, *qTR, *qMod, *qOUT, *qmod_g;
+};
+
+// One wide network level: a thread owns one (entry, member), keeps qTIN/qTR in registers
+// and walks through all events of the block; the loads of D events are issued together.
+template <int D>
+__global__ void __launch_bounds__(128) route_level_fast_kernel(const FastArgs a) {
+  const int p = a.p0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.p1) return;
+  const int m = blockIdx.y;
+  const EntMeta em = a.meta[p];
+  const bool is_link = em.flags & kEntLink, add_qout = em.flags & kEntAddQout;
+  const bool zero_out = em.flags & kEntZeroOut;
+  const int u0 = em.nup > 2 ? a.up_ptr[p] : 0;
+  double c1 = 0.0, c2 = 0.0;
+  if (is_link) {
+    c1 = a.C1[(size_t)m * a.nNodes + em.link];
+    c2 = a.C2[(size_t)m * a.nNodes + em.link];
+  }
+  double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
+  double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
+  double qtin1 = tin[em.node], qtr1 = tr[em.node];
+  double qout = 0.0;
+  const size_t stride = (size_t)a.M * a.E, base = (size_t)m * a.E;
+  for (int ev0 = 0; ev0 < a.nEvents; ev0 += D) {
+    double qo[D], qa[D], qb[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if (ev0 + d < a.nEvents) {
+        const size_t off = (size_t)(ev0 + d) * stride + base;
+        qo[d] = __ldcs(a.qout_hist + off + p);
+        qa[d] = em.nup > 0 ? a.qtr_hist[off + em.up[0]] : 0.0;
+        qb[d] = em.nup > 1 ? a.qtr_hist[off + em.up[1]] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if (ev0 + d < a.nEvents) {
+        const size_t off = (size_t)(ev0 + d) * stride + base;
+        double qin = 0.0;
+        if (em.nup > 0) qin = qin + qa[d];
+        if (em.nup > 1) qin = qin + qb[d];
+        for (int u = 2; u < em.nup; ++u) qin = qin + a.qtr_hist[off + a.up_pos[u0 + u]];
+        qout = qo[d];
+        if (add_qout) qin = qin + qout;
+        if (is_link) {
+          double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (qin - qtin1);
+          if (zero_out) q = 0.0;
+          a.qtr_hist[off + p] = q;
+          qtr1 = q;
+        }
+        qtin1 = qin;
+        if (em.gslot >= 0) a.qmod_g[((size_t)(ev0 + d) * a.M + m) * a.nGslots + em.gslot] = qin;
+      }
+    }
+  }
+  tin[em.node] = qtin1;
+  tin[a.nNodes + em.node] = qtin1;
+  if (is_link) {
+    tr[em.node] = qtr1;
+    tr[a.nNodes + em.node] = qtr1;
+  }
+  a.qMod[(size_t)m * a.nNodes + em.node] = qtin1;  // rout_loop == 1: qMod = qTIN(:, IT)
+  a.qOUT[(size_t)m * a.nNodes + em.node] = qout;
+}
+
+// The narrow, deep part of the network (levels >= tail_level): one thread-block cluster per
+// member sweeps a skewed wavefront.  At wavefront step s the entries of level l work on event
+// s - l, so every (entry, event) pair only needs results of earlier wavefront steps; the
+// critical path is nLevels + nEvents cluster barriers instead of nLevels x nEvents serial
+// steps.  State lives in the node arrays (L2), read and written with .cg accesses because
+// consecutive events of one entry are handled by different threads of the cluster.
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThreads)
+    route_tail_kernel(const FastArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int m = blockIdx.x / kTailCluster;
+  const int ctid = (blockIdx.x % kTailCluster) * kTailThreads + threadIdx.x;
+  const int cthreads = kTailCluster * kTailThreads;
+  const int nLv = a.nLevels - a.tail_level;
+  double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
+  double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
+  const size_t stride = (size_t)a.M * a.E, base = (size_t)m * a.E;
+  const int last = a.nEvents - 1;
+  for (int s = 0; s < nLv + a.nEvents - 1; ++s) {
+    const int l_lo = (s - last > 0 ? s - last : 0) + a.tail_level;
+    const int l_hi = (s < nLv - 1 ? s : nLv - 1) + a.tail_level;
+    const int pb = a.lvl_ptr[l_lo], pe = a.lvl_ptr[l_hi + 1];
+    for (int p = pb + ctid; p < pe; p += cthreads) {
+      const EntMeta em = a.meta[p];
+      const int ev = s - (em.level - a.tail_level);
+      const size_t off = (size_t)ev * stride + base;
+      const double qout = __ldcs(a.qout_hist + off + p);
+      double qin = 0.0;
+      if (em.nup > 0) qin = qin + __ldcg(a.qtr_hist + off + em.up[0]);
+      if (em.nup > 1) qin = qin + __ldcg(a.qtr_hist + off + em.up[1]);
+      if (em.nup > 2) {
+        const int u0 = a.up_ptr[p];
+        for (int u = 2; u < em.nup; ++u) qin = qin + __ldcg(a.qtr_hist + off + a.up_pos[u0 + u]);
+      }
+      if (em.flags & kEntAddQout) qin = qin + qout;
+      const double qtin1 = __ldcg(tin + em.node);
+      if (em.flags & kEntLink) {
+        const double qtr1 = __ldcg(tr + em.node);
+        const double c1 = a.C1[(size_t)m * a.nNodes + em.link];
+        const double c2 = a.C2[(size_t)m * a.nNodes + em.link];
+        double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (qin - qtin1);
+        if (em.flags & kEntZeroOut) q = 0.0;
+        __stcg(a.qtr_hist + off + p, q);
+        __stcg(tr + em.node, q);
+        if (ev == last) tr[a.nNodes + em.node] = q;
+      }
+      __stcg(tin + em.node, qin);
+      if (em.gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + em.gslot] = qin;
+      if (ev == last) {
+        tin[a.nNodes + em.node] = qin;
+        a.qMod[(size_t)m * a.nNodes + em.node] = qin;
+        a.qOUT[(size_t)m * a.nNodes + em.node] = qout;
+      }
+    }
+    cluster.sync();
+  }
+}
+
 // mRM_runoff(tt, gaugeIndexList(gg)) = L11_Qmod(gaugeNodeList(gg)), plus the back-fill of
 // mo_mhm_interface_run.f90:600-603
 __global__ void gauge_kernel(int nEvents, int M, int nGauges, int nGslots, int nTimeSteps,
@@ -431,7 +588,30 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     gslot[(size_t)g] = s;
     gcol[(size_t)g] = net->gaugeIndexList[g] - 1;
   }
+  std::vector<EntMeta> meta((size_t)E);
+  for (int p = 0; p < E; ++p) {
+    EntMeta& em = meta[(size_t)p];
+    em.node = ent[(size_t)p];
+    em.link = ent_link[(size_t)p];
+    em.flags = ent_flags[(size_t)p];
+    em.gslot = ent_gslot[(size_t)p];
+    em.level = level[(size_t)ent[(size_t)p]];
+    em.nup = up_ptr[(size_t)p + 1] - up_ptr[(size_t)p];
+    em.up[0] = em.nup > 0 ? up_pos[(size_t)up_ptr[(size_t)p]] : 0;
+    em.up[1] = em.nup > 1 ? up_pos[(size_t)up_ptr[(size_t)p] + 1] : 0;
+  }
+  // levels from tail_level on are all narrower than kTailMaxLevel
+  const int nLv = (int)rt->lvl_ptr.size() - 1;
+  rt->tail_level = nLv;
+  for (int l = nLv - 1; l >= 0; --l) {
+    if (rt->lvl_ptr[(size_t)l + 1] - rt->lvl_ptr[(size_t)l] > kTailMaxLevel) break;
+    rt->tail_level = l;
+  }
+  if (nLv - rt->tail_level < 4) rt->tail_level = nLv;  // not worth a wavefront
+  if (const char* e = getenv("MHM_CUDA_NO_TAIL")) if (e[0] == '1') rt->tail_level = nLv;
   cudaStream_t st = ctx->stream;
+  if (int rc = upload(&rt->meta, meta, st)) return rc;
+  if (int rc = upload(&rt->d_lvl_ptr, rt->lvl_ptr, st)) return rc;
   if (int rc = upload(&rt->ent_node, ent, st)) return rc;
   if (int rc = upload(&rt->ent_link, ent_link, st)) return rc;
   if (int rc = upload(&rt->ent_flags, ent_flags, st)) return rc;
@@ -525,6 +705,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
   MHM_CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope in the caller
 
   ctx->stat_begin(kStatRouting);
+  int64_t launched = 0;
   QoutArgs qa{};
   qa.nCells1 = rt->nCells1;
   qa.nNodes = rt->nNodes;
@@ -555,47 +736,89 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
     q2.qout_hist = rt->qout_hist + (size_t)e0 * M * E;
     const int ne = std::min(32768, nEv - e0);
     qout_kernel<<<dim3((E + 127) / 128, M, ne), 128, 0, st>>>(q2);
+    ++launched;
   }
   MHM_CUDA_OK(cudaGetLastError());
 
-  LevelArgs la{};
-  la.E = E;
-  la.M = M;
-  la.nNodes = rt->nNodes;
-  la.nEvents = nEv;
-  la.single_node = rt->nNodes <= 1;
-  la.events = rt->d_events;
-  la.ent_node = rt->ent_node;
-  la.ent_link = rt->ent_link;
-  la.ent_flags = rt->ent_flags;
-  la.ent_gslot = rt->ent_gslot;
-  la.up_ptr = rt->up_ptr;
-  la.up_pos = rt->up_pos;
-  la.C1 = rt->C1;
-  la.C2 = rt->C2;
-  la.qout_hist = rt->qout_hist;
-  la.qtr_hist = rt->qtr_hist;
-  la.qTIN = rt->qTIN;
-  la.qTR = rt->qTR;
-  la.qMod = rt->qMod;
-  la.qOUT = rt->qOUT;
-  la.qmod_g = rt->qmod_g;
-  la.nGslots = std::max(1, rt->nGslots);
-  for (size_t l = 0; l + 1 < rt->lvl_ptr.size(); ++l) {
-    la.p0 = rt->lvl_ptr[l];
-    la.p1 = rt->lvl_ptr[l + 1];
-    const int cnt = la.p1 - la.p0;
-    const int threads = cnt >= 128 ? 128 : 32;
-    route_level_kernel<<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(la);
+  bool fast = rt->nNodes > 1;
+  for (auto& e : ev) fast = fast && e.rout_loop == 1;
+  if (getenv("MHM_CUDA_GENERIC_ROUTING")) fast = false;
+  if (fast) {
+    FastArgs fa{};
+    fa.E = E;
+    fa.M = M;
+    fa.nNodes = rt->nNodes;
+    fa.nEvents = nEv;
+    fa.nGslots = std::max(1, rt->nGslots);
+    fa.tail_level = rt->tail_level;
+    fa.nLevels = (int)rt->lvl_ptr.size() - 1;
+    fa.meta = rt->meta;
+    fa.up_ptr = rt->up_ptr;
+    fa.up_pos = rt->up_pos;
+    fa.lvl_ptr = rt->d_lvl_ptr;
+    fa.events = rt->d_events;
+    fa.C1 = rt->C1;
+    fa.C2 = rt->C2;
+    fa.qout_hist = rt->qout_hist;
+    fa.qtr_hist = rt->qtr_hist;
+    fa.qTIN = rt->qTIN;
+    fa.qTR = rt->qTR;
+    fa.qMod = rt->qMod;
+    fa.qOUT = rt->qOUT;
+    fa.qmod_g = rt->qmod_g;
+    for (int l = 0; l < rt->tail_level; ++l) {
+      fa.p0 = rt->lvl_ptr[(size_t)l];
+      fa.p1 = rt->lvl_ptr[(size_t)l + 1];
+      const int cnt = fa.p1 - fa.p0;
+      route_level_fast_kernel<8><<<dim3((cnt + 127) / 128, M), 128, 0, st>>>(fa);
+      ++launched;
+    }
+    if (rt->tail_level < fa.nLevels) {
+      route_tail_kernel<<<dim3(M * kTailCluster), kTailThreads, 0, st>>>(fa);
+      ++launched;
+    }
+  } else {
+    LevelArgs la{};
+    la.E = E;
+    la.M = M;
+    la.nNodes = rt->nNodes;
+    la.nEvents = nEv;
+    la.single_node = rt->nNodes <= 1;
+    la.events = rt->d_events;
+    la.ent_node = rt->ent_node;
+    la.ent_link = rt->ent_link;
+    la.ent_flags = rt->ent_flags;
+    la.ent_gslot = rt->ent_gslot;
+    la.up_ptr = rt->up_ptr;
+    la.up_pos = rt->up_pos;
+    la.C1 = rt->C1;
+    la.C2 = rt->C2;
+    la.qout_hist = rt->qout_hist;
+    la.qtr_hist = rt->qtr_hist;
+    la.qTIN = rt->qTIN;
+    la.qTR = rt->qTR;
+    la.qMod = rt->qMod;
+    la.qOUT = rt->qOUT;
+    la.qmod_g = rt->qmod_g;
+    la.nGslots = std::max(1, rt->nGslots);
+    for (size_t l = 0; l + 1 < rt->lvl_ptr.size(); ++l) {
+      la.p0 = rt->lvl_ptr[l];
+      la.p1 = rt->lvl_ptr[l + 1];
+      const int cnt = la.p1 - la.p0;
+      const int threads = cnt >= 128 ? 128 : 32;
+      route_level_kernel<<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(la);
+      ++launched;
+    }
   }
   MHM_CUDA_OK(cudaGetLastError());
   if (rt->nGauges > 0 || rt->nGaugesTotal > 0) {
     gauge_kernel<<<dim3((nEv + 63) / 64, M), 64, 0, st>>>(
         nEv, M, rt->nGauges, std::max(1, rt->nGslots), rt->nTimeSteps, rt->nGaugesTotal,
         rt->d_events, rt->d_gauge_col, rt->d_gauge_slot, rt->qmod_g, rt->gauge_hist);
+    ++launched;
     MHM_CUDA_OK(cudaGetLastError());
   }
-  ctx->stat_end(kStatRouting);
+  ctx->stat_end(kStatRouting, launched);
   (void)d;
   return 0;
 }

@@ -3,6 +3,7 @@ C-ABI calls the reference's driver performs after mhm_initialize / mrm_init / mp
 import numpy as np
 
 from . import synth
+from .interface import PARAM_NAMES
 
 METEO_BY_CASE = {-1: ["pet"], 0: ["pet"], 1: ["tmin", "tmax"], 2: ["netrad"],
                  3: ["netrad", "absvappress", "windspeed"]}
@@ -19,7 +20,8 @@ def setup_domain(ctx, iDomain, prob, nMembers=1, member_params=None, upload_forc
     for m in range(nMembers):
         P = prob["params"] if member_params is None else member_params[m]
         for name, arr in P.items():
-            dom.set_param(name, arr, member=m)
+            if name in PARAM_NAMES:  # e.g. "rout_param" travels with the member but is not an L1 field
+                dom.set_param(name, arr, member=m)
         for name, arr in prob["states0"].items():
             dom.set_state(name, arr, member=m)
     if upload_forcing:

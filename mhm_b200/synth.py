@@ -229,7 +229,7 @@ def make_network(rng, nx, ny, routing_order, fill=0.85, rout_case=1, l1_factor=1
 
 def make_problem(nx=20, ny=12, n_days=4, nH=2, nLAI=12, nLC=2, hourly=True, soil_case=1,
                  pet_case=-1, rout_case=1, l1_factor=1, routing=True, timestep_h=1, seed=SEED,
-                 start=(1990, 12, 28), lc_switch_year=1991, read_weights=False, inflow=None,
+                 start=(1990, 12, 30), lc_switch_year=1991, read_weights=False, inflow=None,
                  celerity=1.5, fill=0.85, n_gauges=3, timeStep_LAI_input=0, routing_order=None):
     """A complete single-domain problem.  The default period straddles a year change so that
     the land-cover scene, the LAI month and evap_coeff all switch inside the run."""
