@@ -29,25 +29,37 @@ namespace cg = cooperative_groups;
 namespace mhm {
 
 constexpr int kTailCluster = 8;       // CTAs per cluster in the tail kernel (portable maximum)
-constexpr int kTailThreads = 512;     // threads per CTA in the tail kernel
+constexpr int kTailThreads = 256;     // threads per CTA in the tail kernel
 constexpr int kTailMaxLevel = 2048;   // levels wider than this get their own launch
 
 // everything a routing thread needs to know about its entry, one 32-byte record
 struct alignas(16) EntMeta {
   int32_t node;    // 0-based L11 node
   int32_t link;    // 0-based link (C1/C2 index)
-  int32_t flags;   // kEnt* bits
+  int32_t flags;   // kEnt* bits | number of upstream links << 8
   int32_t gslot;   // gauge slot or -1
-  int32_t level;   // network level
-  int32_t nup;     // number of upstream links
-  int32_t up[2];   // entry positions of the first two upstream links (netPerm order)
+  int32_t up[4];   // entry positions of the first four upstream links (netPerm order)
 };
+constexpr int kMetaUps = 4;
 static_assert(sizeof(EntMeta) == 32, "EntMeta must be 32 bytes");
+
+// History buffers (node runoff qOUT and routed outflow qTR of every routing step of a block)
+// are tiled by 8 steps: [step / 8][member][entry][step % 8].  An entry's 8 consecutive steps
+// are one 64-byte run, so a level thread streams its own and its upstream links' series with
+// 128-bit loads, and neighbouring entries of a level are neighbouring runs.
+constexpr int kHistTile = 8;
+__host__ __device__ __forceinline__ size_t hidx(int step, int M, int E, int m, int p) {
+  return ((((size_t)(step >> 3) * M + m) * E + p) << 3) + (size_t)(step & 7);
+}
+__host__ __device__ __forceinline__ size_t hist_size(int steps, int M, int E) {
+  return (size_t)((steps + kHistTile - 1) / kHistTile) * M * E * kHistTile;
+}
 
 enum : int32_t {
   kEntLink = 1,     // entry is a link (has Muskingum state); otherwise an outlet node
   kEntAddQout = 2,  // node's own runoff is added to its inflow
   kEntZeroOut = 4,  // routed outflow feeds a non-headwater inflow gauge: set to zero
+  kEntInflow = 8,   // node is an inflow gauge: add_inflow applies to its runoff
 };
 
 struct DevEvent {
@@ -75,6 +87,11 @@ struct Routing {
   EntMeta* meta = nullptr;
   int32_t* d_lvl_ptr = nullptr;
   int32_t tail_level = 0;  // levels >= tail_level are swept by one clustered wavefront kernel
+  // aligned mode: L1 cells and L11 nodes map one to one, so the cell kernel hands its runoff
+  // straight to the routing history (no L11_runoff_acc pass)
+  bool bijective = false;
+  int32_t* d_cell_entry = nullptr;  // [nCells1] routing entry of the cell's node
+  double* d_cell_area = nullptr;    // [nCells1] area factor of mo_mrm_pre_routing.f90:125/:141
   int32_t *cell_ptr = nullptr, *cell_idx = nullptr;  // map_flag: L1 cells of each node, ascending
   int32_t* L11_L1_Id = nullptr;                      // !map_flag
   int32_t *d_inflow_node = nullptr, *d_inflow_index = nullptr, *d_inflow_head = nullptr;
@@ -110,7 +127,7 @@ struct Routing {
 void routing_free(Routing* rt) {
   if (!rt) return;
   void* ptrs[] = {rt->ent_node, rt->ent_link,  rt->ent_flags, rt->ent_gslot, rt->up_ptr,
-                  rt->up_pos,   rt->meta, rt->d_lvl_ptr, rt->cell_ptr,  rt->cell_idx,  rt->L11_L1_Id, rt->d_inflow_node,
+                  rt->up_pos,   rt->meta, rt->d_lvl_ptr, rt->d_cell_entry, rt->d_cell_area, rt->cell_ptr,  rt->cell_idx,  rt->L11_L1_Id, rt->d_inflow_node,
                   rt->d_inflow_index, rt->d_inflow_head, rt->L1_area, rt->L11_area,
                   rt->d_gauge_col, rt->d_gauge_slot, rt->C1, rt->C2, rt->qOUT, rt->qMod,
                   rt->qTIN, rt->qTR, rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry,
@@ -173,42 +190,101 @@ struct QoutArgs {
   const double *L1_area, *L11_area;
   const int32_t *inflow_node, *inflow_index, *inflow_head;
   const double* inflow_val;  // [nEvents][nInflowTotal]
-  double* qout_hist;         // [nEvents][M][E]
+  double* qout_hist;         // tiled, see hidx()
 };
 
-// L11_runoff_acc + add_inflow for every (event, member, entry)
-__global__ void qout_kernel(const QoutArgs a) {
+// L11_runoff_acc + add_inflow for every (event, member, entry); a thread produces the 8
+// events of one history tile for its entry (one 64-byte run)
+__global__ void __launch_bounds__(128) qout_kernel(const QoutArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.E) return;
-  const int m = blockIdx.y, ev = blockIdx.z;
-  const DevEvent e = a.events[ev];
+  const int m = blockIdx.y, tile = blockIdx.z;
   const int node = a.ent_node[p];  // 0-based
   const size_t n1 = (size_t)a.nCells1;
-  auto run_to_rout = [&](int k) {  // RunToRout(k): accumulated in step order
-    double acc = e.use_carry ? a.carry[(size_t)m * n1 + k] : 0.0;
-    for (int j = 0; j < e.nacc; ++j)
-      acc = acc + a.runoff_hist[((size_t)(e.t0 + j) * a.M + m) * n1 + k];
-    return acc;
-  };
-  double q;
-  if (a.map_flag) {  // mo_mrm_pre_routing.f90:112-130
-    q = 0.0;
-    for (int c = a.cell_ptr[node]; c < a.cell_ptr[node + 1]; ++c) {
-      const int k = a.cell_idx[c];
-      q = q + run_to_rout(k) * a.L1_area[k];
+  double q[kHistTile];
+#pragma unroll
+  for (int d = 0; d < kHistTile; ++d) {
+    const int ev = tile * kHistTile + d;
+    q[d] = 0.0;
+    if (ev >= a.nEvents) continue;
+    const DevEvent e = a.events[ev];
+    auto run_to_rout = [&](int k) {  // RunToRout(k): accumulated in step order
+      double acc = e.use_carry ? a.carry[(size_t)m * n1 + k] : 0.0;
+      for (int j = 0; j < e.nacc; ++j)
+        acc = acc + __ldcs(a.runoff_hist + ((size_t)(e.t0 + j) * a.M + m) * n1 + k);
+      return acc;
+    };
+    double v;
+    if (a.map_flag) {  // mo_mrm_pre_routing.f90:112-130
+      v = 0.0;
+      for (int c = a.cell_ptr[node]; c < a.cell_ptr[node + 1]; ++c) {
+        const int k = a.cell_idx[c];
+        v = v + run_to_rout(k) * a.L1_area[k];
+      }
+      v = v * 1000.0 / e.tst;
+    } else {  // :132-141
+      v = run_to_rout(a.L11_L1_Id[node] - 1);
+      v = v * a.L11_area[node] * 1000.0 / e.tst;
     }
-    q = q * 1000.0 / e.tst;
-  } else {  // :132-141
-    q = run_to_rout(a.L11_L1_Id[node] - 1);
-    q = q * a.L11_area[node] * 1000.0 / e.tst;
-  }
-  for (int g = 0; g < a.nInflowGauges; ++g) {  // add_inflow :203-213
-    if (a.inflow_node[g] - 1 == node) {
-      const double qi = a.inflow_val[(size_t)ev * a.nInflowTotal + a.inflow_index[g] - 1];
-      q = a.inflow_head[g] ? q + qi : qi;
+    for (int g = 0; g < a.nInflowGauges; ++g) {  // add_inflow :203-213
+      if (a.inflow_node[g] - 1 == node) {
+        const double qi = a.inflow_val[(size_t)ev * a.nInflowTotal + a.inflow_index[g] - 1];
+        v = a.inflow_head[g] ? v + qi : qi;
+      }
     }
+    q[d] = v;
   }
-  a.qout_hist[((size_t)ev * a.M + m) * a.E + p] = q;
+  double2* dst = reinterpret_cast<double2*>(a.qout_hist + hidx(tile * kHistTile, a.M, a.E, m, p));
+#pragma unroll
+  for (int d = 0; d < kHistTile / 2; ++d) dst[d] = make_double2(q[2 * d], q[2 * d + 1]);
+}
+
+// Same for the common one-cell-per-node case: a thread takes one L1 cell, reads its runoff
+// of the 8 events of a tile (coalesced over cells) and writes the finished 64-byte run at the
+// cell's routing entry.  Only used when every event is a single model step.
+struct QoutCellArgs {
+  int32_t nCells1, E, M, nEvents, map_flag, nInflowGauges, nInflowTotal;
+  const DevEvent* events;
+  const double* runoff_hist;  // [steps][M][nCells1]
+  const int32_t* cell_entry;  // [nCells1]
+  const double* cell_area;    // [nCells1]
+  const EntMeta* meta;
+  const int32_t *inflow_node, *inflow_index, *inflow_head;
+  const double* inflow_val;
+  double* qout_hist;
+};
+__global__ void __launch_bounds__(128) qout_cell_kernel(const QoutCellArgs a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.nCells1) return;
+  const int m = blockIdx.y, tile = blockIdx.z;
+  const size_t n1 = (size_t)a.nCells1;
+  const int p = a.cell_entry[k];
+  const double area = a.cell_area[k];
+  const EntMeta em = a.meta[p];
+  double q[kHistTile];
+#pragma unroll
+  for (int d = 0; d < kHistTile; ++d) {
+    const int ev = tile * kHistTile + d;
+    q[d] = 0.0;
+    if (ev >= a.nEvents) continue;
+    const DevEvent e = a.events[ev];
+    const double r = 0.0 + __ldcs(a.runoff_hist + ((size_t)e.t0 * a.M + m) * n1 + k);
+    // map_flag: (0 + qAll*efecArea) * 1000 / TST (:125,:129); else qAll * L11_area * 1000 / TST
+    double v = a.map_flag ? (0.0 + r * area) : r * area;
+    v = v * 1000.0 / e.tst;
+    if (em.flags & kEntInflow) {
+      for (int g = 0; g < a.nInflowGauges; ++g) {
+        if (a.inflow_node[g] - 1 == em.node) {
+          const double qi = a.inflow_val[(size_t)ev * a.nInflowTotal + a.inflow_index[g] - 1];
+          v = a.inflow_head[g] ? v + qi : qi;
+        }
+      }
+    }
+    q[d] = v;
+  }
+  double2* dst = reinterpret_cast<double2*>(a.qout_hist + hidx(tile * kHistTile, a.M, a.E, m, p));
+#pragma unroll
+  for (int d = 0; d < kHistTile / 2; ++d) dst[d] = make_double2(q[2 * d], q[2 * d + 1]);
 }
 
 // carry = (carry) + sum of the block's not yet routed runoff
@@ -225,7 +301,7 @@ __global__ void carry_kernel(int nCells1, int M, int t0, int nacc, int use_carry
 
 struct LevelArgs {
   int32_t p0, p1;  // entry range of the level
-  int32_t E, M, nNodes, nEvents, single_node, last_block_event;
+  int32_t E, M, nNodes, ev0, ev1, single_node;
   const DevEvent* events;
   const int32_t *ent_node, *ent_link, *ent_flags, *ent_gslot, *up_ptr, *up_pos;
   const double *C1, *C2;      // [M][nNodes], link indexed
@@ -255,22 +331,22 @@ __global__ void route_level_kernel(const LevelArgs a) {
   double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
   double qtin1 = tin[node], qtr1 = tr[node];  // IT1 slot
   double qmod = 0.0, qout = 0.0;
-  for (int ev = 0; ev < a.nEvents; ++ev) {
+  for (int ev = a.ev0; ev < a.ev1; ++ev) {
     const DevEvent e = a.events[ev];
-    qout = a.qout_hist[((size_t)ev * a.M + m) * a.E + p];
+    qout = a.qout_hist[hidx(ev, a.M, a.E, m, p)];
     if (a.single_node) {  // nNodes == 1: L11_Qmod = L11_qOUT (mo_mrm_routing.f90:284)
       qmod = qout;
     } else {
       double acc = 0.0;
       for (int s = 0; s < e.rout_loop; ++s) {
-        const size_t ro = ((size_t)(e.rs_first + s) * a.M + m) * a.E;
+        const int rs = e.rs_first + s;
         double qin = 0.0;
-        for (int u = u0; u < u1; ++u) qin = qin + a.qtr_hist[ro + a.up_pos[u]];
+        for (int u = u0; u < u1; ++u) qin = qin + a.qtr_hist[hidx(rs, a.M, a.E, m, a.up_pos[u])];
         if (flags & kEntAddQout) qin = qin + qout;
         if (is_link) {
           double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (qin - qtin1);
           if (flags & kEntZeroOut) q = 0.0;
-          a.qtr_hist[ro + p] = q;
+          a.qtr_hist[hidx(rs, a.M, a.E, m, p)] = q;
           qtr1 = q;
         }
         qtin1 = qin;
@@ -280,7 +356,7 @@ __global__ void route_level_kernel(const LevelArgs a) {
     }
     if (gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + gslot] = qmod;
   }
-  if (a.nEvents > 0) {
+  if (a.ev1 > a.ev0) {
     tin[node] = qtin1;
     tin[a.nNodes + node] = qtin1;
     if (is_link) {
@@ -294,29 +370,111 @@ __global__ void route_level_kernel(const LevelArgs a) {
 
 // ---- fast path: every event is one routing step (rout_loop == 1, the usual case) ----------
 struct FastArgs {
-  int32_t p0, p1;  // entry range (level kernel) / first tail entry and E (tail kernel)
+  int32_t p0, p1;          // entry range of the level (level kernel)
+  int32_t ev0, ev1;        // event range [ev0, ev1) of the block handled by this launch
   int32_t E, M, nNodes, nEvents, nGslots;
   int32_t tail_level, nLevels;
   const EntMeta* meta;
   const int32_t *up_ptr, *up_pos, *lvl_ptr;
   const DevEvent* events;
   const double *C1, *C2;
-  const double* qout_hist;  // [nEvents][M][E]
-  double* qtr_hist;         // [nEvents][M][E]
+  const double* qout_hist;  // tiled, see hidx()
+  double* qtr_hist;         // tiled
   double *qTIN, *qTR, *qMod, *qOUT, *qmod_g;
 };
 
-// One wide network level: a thread owns one (entry, member), keeps qTIN/qTR in registers
-// and walks through all events of the block; the loads of D events are issued together.
-template <int D>
-__global__ void __launch_bounds__(128) route_level_fast_kernel(const FastArgs a) {
+__device__ __forceinline__ void load_tile(const double* src, double (&v)[kHistTile]) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int d = 0; d < kHistTile / 2; ++d) {
+    const double2 t = s2[d];
+    v[2 * d] = t.x;
+    v[2 * d + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void load_tile_cg(const double* src, double (&v)[kHistTile]) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int d = 0; d < kHistTile / 2; ++d) {
+    const double2 t = __ldcg(s2 + d);
+    v[2 * d] = t.x;
+    v[2 * d + 1] = t.y;
+  }
+}
+
+// sum of the upstream links' routed outflow for the 8 events of a tile, added in netPerm
+// order starting from 0 (mo_mrm_routing.f90:428,457); whole 64-byte runs per link
+template <bool CG>
+__device__ __forceinline__ void gather_upstream(const FastArgs& a, const EntMeta& em, int nup,
+                                                int m, int p, int t0, double (&qin)[kHistTile]) {
+  double t[kMetaUps][kHistTile];
+#pragma unroll
+  for (int u = 0; u < kMetaUps; ++u) {
+    if (u < nup) {
+      const double* src = a.qtr_hist + hidx(t0, a.M, a.E, m, em.up[u]);
+      if (CG) load_tile_cg(src, t[u]); else load_tile(src, t[u]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < kHistTile; ++d) qin[d] = 0.0;
+#pragma unroll
+  for (int u = 0; u < kMetaUps; ++u) {
+    if (u < nup) {
+#pragma unroll
+      for (int d = 0; d < kHistTile; ++d) qin[d] = qin[d] + t[u][d];
+    }
+  }
+  if (nup > kMetaUps) {  // rare: more than four inflowing links
+    const int u0 = a.up_ptr[p];
+    for (int u = kMetaUps; u < nup; ++u) {
+      double x[kHistTile];
+      load_tile_cg(a.qtr_hist + hidx(t0, a.M, a.E, m, a.up_pos[u0 + u]), x);
+#pragma unroll
+      for (int d = 0; d < kHistTile; ++d) qin[d] = qin[d] + x[d];
+    }
+  }
+}
+
+// the events [e_lo, e_hi) of one history tile for one entry; shared by both fast kernels
+struct TileState {
+  double qtin1, qtr1, qout;
+};
+__device__ __forceinline__ void route_tile(const FastArgs& a, const EntMeta& em, int m, int tile0,
+                                           int e_lo, int e_hi, double c1, double c2,
+                                           const double (&qo)[kHistTile],
+                                           const double (&qup)[kHistTile],
+                                           double (&qr)[kHistTile], TileState& st) {
+  const bool is_link = em.flags & kEntLink;
+#pragma unroll
+  for (int d = 0; d < kHistTile; ++d) {
+    const int ev = tile0 + d;
+    qr[d] = 0.0;
+    if (ev >= e_lo && ev < e_hi) {
+      double qin = qup[d];
+      st.qout = qo[d];
+      if (em.flags & kEntAddQout) qin = qin + st.qout;
+      if (is_link) {
+        double q = st.qtr1 + c1 * (st.qtin1 - st.qtr1) + c2 * (qin - st.qtin1);
+        if (em.flags & kEntZeroOut) q = 0.0;
+        qr[d] = q;
+        st.qtr1 = q;
+      }
+      st.qtin1 = qin;
+      if (em.gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + em.gslot] = qin;
+    }
+  }
+}
+
+// One wide network level: a thread owns one (entry, member), keeps qTIN/qTR in registers and
+// walks through the events [ev0, ev1) of the block, one 8-event history tile (64-byte runs of
+// its own runoff and of its first two upstream links, 128-bit loads) at a time.
+__global__ void __launch_bounds__(128, 4) route_level_fast_kernel(const FastArgs a) {
   const int p = a.p0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.p1) return;
   const int m = blockIdx.y;
   const EntMeta em = a.meta[p];
-  const bool is_link = em.flags & kEntLink, add_qout = em.flags & kEntAddQout;
-  const bool zero_out = em.flags & kEntZeroOut;
-  const int u0 = em.nup > 2 ? a.up_ptr[p] : 0;
+  const bool is_link = em.flags & kEntLink;
+  const int nup = em.flags >> 8;
   double c1 = 0.0, c2 = 0.0;
   if (is_link) {
     c1 = a.C1[(size_t)m * a.nNodes + em.link];
@@ -324,103 +482,102 @@ __global__ void __launch_bounds__(128) route_level_fast_kernel(const FastArgs a)
   }
   double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
   double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
-  double qtin1 = tin[em.node], qtr1 = tr[em.node];
-  double qout = 0.0;
-  const size_t stride = (size_t)a.M * a.E, base = (size_t)m * a.E;
-  for (int ev0 = 0; ev0 < a.nEvents; ev0 += D) {
-    double qo[D], qa[D], qb[D];
+  TileState st{tin[em.node], tr[em.node], 0.0};
+  for (int t0 = a.ev0 & ~(kHistTile - 1); t0 < a.ev1; t0 += kHistTile) {
+    double qo[kHistTile], qup[kHistTile], qr[kHistTile];
+    load_tile(a.qout_hist + hidx(t0, a.M, a.E, m, p), qo);
+    gather_upstream<false>(a, em, nup, m, p, t0, qup);
+    double* own = a.qtr_hist + hidx(t0, a.M, a.E, m, p);
+    // a tile shared with the previous launch (land-cover scene change inside the tile)
+    // keeps the outflows that launch wrote
+    const bool partial = t0 < a.ev0;
+    double keep[kHistTile];
+    if (partial && is_link) load_tile(own, keep);
+    route_tile(a, em, m, t0, a.ev0, a.ev1, c1, c2, qo, qup, qr, st);
+    if (is_link) {
+      if (partial) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      if (ev0 + d < a.nEvents) {
-        const size_t off = (size_t)(ev0 + d) * stride + base;
-        qo[d] = __ldcs(a.qout_hist + off + p);
-        qa[d] = em.nup > 0 ? a.qtr_hist[off + em.up[0]] : 0.0;
-        qb[d] = em.nup > 1 ? a.qtr_hist[off + em.up[1]] : 0.0;
+        for (int d = 0; d < kHistTile; ++d)
+          if (t0 + d < a.ev0) qr[d] = keep[d];
       }
-    }
+      double2* dst = reinterpret_cast<double2*>(own);
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      if (ev0 + d < a.nEvents) {
-        const size_t off = (size_t)(ev0 + d) * stride + base;
-        double qin = 0.0;
-        if (em.nup > 0) qin = qin + qa[d];
-        if (em.nup > 1) qin = qin + qb[d];
-        for (int u = 2; u < em.nup; ++u) qin = qin + a.qtr_hist[off + a.up_pos[u0 + u]];
-        qout = qo[d];
-        if (add_qout) qin = qin + qout;
-        if (is_link) {
-          double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (qin - qtin1);
-          if (zero_out) q = 0.0;
-          a.qtr_hist[off + p] = q;
-          qtr1 = q;
-        }
-        qtin1 = qin;
-        if (em.gslot >= 0) a.qmod_g[((size_t)(ev0 + d) * a.M + m) * a.nGslots + em.gslot] = qin;
-      }
+      for (int d = 0; d < kHistTile / 2; ++d) dst[d] = make_double2(qr[2 * d], qr[2 * d + 1]);
     }
   }
-  tin[em.node] = qtin1;
-  tin[a.nNodes + em.node] = qtin1;
+  tin[em.node] = st.qtin1;
+  tin[a.nNodes + em.node] = st.qtin1;
   if (is_link) {
-    tr[em.node] = qtr1;
-    tr[a.nNodes + em.node] = qtr1;
+    tr[em.node] = st.qtr1;
+    tr[a.nNodes + em.node] = st.qtr1;
   }
-  a.qMod[(size_t)m * a.nNodes + em.node] = qtin1;  // rout_loop == 1: qMod = qTIN(:, IT)
-  a.qOUT[(size_t)m * a.nNodes + em.node] = qout;
+  a.qMod[(size_t)m * a.nNodes + em.node] = st.qtin1;  // rout_loop == 1: qMod = qTIN(:, IT)
+  a.qOUT[(size_t)m * a.nNodes + em.node] = st.qout;
 }
 
-// The narrow, deep part of the network (levels >= tail_level): one thread-block cluster per
-// member sweeps a skewed wavefront.  At wavefront step s the entries of level l work on event
-// s - l, so every (entry, event) pair only needs results of earlier wavefront steps; the
-// critical path is nLevels + nEvents cluster barriers instead of nLevels x nEvents serial
-// steps.  State lives in the node arrays (L2), read and written with .cg accesses because
-// consecutive events of one entry are handled by different threads of the cluster.
-__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThreads)
+// The narrow, deep part of the network (levels >= tail_level, every level at most
+// kTailCluster * kTailThreads entries wide): instead of one launch per level, one thread-block
+// cluster per member walks down the levels with a hardware cluster barrier between them.
+// Thread i of the cluster owns entry i of the current level for all events of the range
+// (state in registers, exactly like route_level_fast_kernel); what the next level needs from
+// this one goes through L2 (.cg stores / loads) and is ordered by the barrier's
+// release/acquire.  The per-level cost drops from a kernel launch to a cluster barrier.
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThreads, 2)
     route_tail_kernel(const FastArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ int32_t s_lvl[];  // lvl_ptr of the tail levels (or empty: read from L2)
   const int m = blockIdx.x / kTailCluster;
   const int ctid = (blockIdx.x % kTailCluster) * kTailThreads + threadIdx.x;
-  const int cthreads = kTailCluster * kTailThreads;
   const int nLv = a.nLevels - a.tail_level;
+  const bool use_smem = a.p0 != 0;  // p0 doubles as "lvl_ptr fits in shared memory"
+  if (use_smem)
+    for (int i = threadIdx.x; i <= nLv; i += kTailThreads) s_lvl[i] = a.lvl_ptr[a.tail_level + i];
+  __syncthreads();
   double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
   double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
-  const size_t stride = (size_t)a.M * a.E, base = (size_t)m * a.E;
-  const int last = a.nEvents - 1;
-  for (int s = 0; s < nLv + a.nEvents - 1; ++s) {
-    const int l_lo = (s - last > 0 ? s - last : 0) + a.tail_level;
-    const int l_hi = (s < nLv - 1 ? s : nLv - 1) + a.tail_level;
-    const int pb = a.lvl_ptr[l_lo], pe = a.lvl_ptr[l_hi + 1];
-    for (int p = pb + ctid; p < pe; p += cthreads) {
+  for (int l = 0; l < nLv; ++l) {
+    const int pb = use_smem ? s_lvl[l] : a.lvl_ptr[a.tail_level + l];
+    const int pe = use_smem ? s_lvl[l + 1] : a.lvl_ptr[a.tail_level + l + 1];
+    const int p = pb + ctid;
+    if (p < pe) {
       const EntMeta em = a.meta[p];
-      const int ev = s - (em.level - a.tail_level);
-      const size_t off = (size_t)ev * stride + base;
-      const double qout = __ldcs(a.qout_hist + off + p);
-      double qin = 0.0;
-      if (em.nup > 0) qin = qin + __ldcg(a.qtr_hist + off + em.up[0]);
-      if (em.nup > 1) qin = qin + __ldcg(a.qtr_hist + off + em.up[1]);
-      if (em.nup > 2) {
-        const int u0 = a.up_ptr[p];
-        for (int u = 2; u < em.nup; ++u) qin = qin + __ldcg(a.qtr_hist + off + a.up_pos[u0 + u]);
+      const bool is_link = em.flags & kEntLink;
+      const int nup = em.flags >> 8;
+      double c1 = 0.0, c2 = 0.0;
+      if (is_link) {
+        c1 = a.C1[(size_t)m * a.nNodes + em.link];
+        c2 = a.C2[(size_t)m * a.nNodes + em.link];
       }
-      if (em.flags & kEntAddQout) qin = qin + qout;
-      const double qtin1 = __ldcg(tin + em.node);
-      if (em.flags & kEntLink) {
-        const double qtr1 = __ldcg(tr + em.node);
-        const double c1 = a.C1[(size_t)m * a.nNodes + em.link];
-        const double c2 = a.C2[(size_t)m * a.nNodes + em.link];
-        double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (qin - qtin1);
-        if (em.flags & kEntZeroOut) q = 0.0;
-        __stcg(a.qtr_hist + off + p, q);
-        __stcg(tr + em.node, q);
-        if (ev == last) tr[a.nNodes + em.node] = q;
+      TileState st{tin[em.node], tr[em.node], 0.0};
+      for (int t0 = a.ev0 & ~(kHistTile - 1); t0 < a.ev1; t0 += kHistTile) {
+        double qo[kHistTile], qup[kHistTile], qr[kHistTile];
+        load_tile(a.qout_hist + hidx(t0, a.M, a.E, m, p), qo);
+        gather_upstream<true>(a, em, nup, m, p, t0, qup);
+        double* own = a.qtr_hist + hidx(t0, a.M, a.E, m, p);
+        const bool partial = t0 < a.ev0;
+        double keep[kHistTile];
+        if (partial && is_link) load_tile_cg(own, keep);
+        route_tile(a, em, m, t0, a.ev0, a.ev1, c1, c2, qo, qup, qr, st);
+        if (is_link) {
+          if (partial) {
+#pragma unroll
+            for (int d = 0; d < kHistTile; ++d)
+              if (t0 + d < a.ev0) qr[d] = keep[d];
+          }
+          double2* dst = reinterpret_cast<double2*>(own);
+#pragma unroll
+          for (int d = 0; d < kHistTile / 2; ++d)
+            __stcg(dst + d, make_double2(qr[2 * d], qr[2 * d + 1]));
+        }
       }
-      __stcg(tin + em.node, qin);
-      if (em.gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + em.gslot] = qin;
-      if (ev == last) {
-        tin[a.nNodes + em.node] = qin;
-        a.qMod[(size_t)m * a.nNodes + em.node] = qin;
-        a.qOUT[(size_t)m * a.nNodes + em.node] = qout;
+      tin[em.node] = st.qtin1;
+      tin[a.nNodes + em.node] = st.qtin1;
+      if (is_link) {
+        tr[em.node] = st.qtr1;
+        tr[a.nNodes + em.node] = st.qtr1;
       }
+      a.qMod[(size_t)m * a.nNodes + em.node] = st.qtin1;
+      a.qOUT[(size_t)m * a.nNodes + em.node] = st.qout;
     }
     cluster.sync();
   }
@@ -570,6 +727,8 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     } else if (nd == last_sink) {
       fl |= kEntAddQout;  // :466-467: only the last link's sink adds its own runoff
     }
+    for (int g = 0; g < net->nInflowGauges; ++g)
+      if (net->InflowGaugeNodeList[g] - 1 == nd) fl |= kEntInflow;
     ent_link[(size_t)p] = l >= 0 ? l : 0;
     ent_flags[(size_t)p] = fl;
     for (int j : up[(size_t)nd]) up_pos.push_back(pos_of_node[(size_t)net->fromN[j] - 1]);
@@ -595,16 +754,19 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     em.link = ent_link[(size_t)p];
     em.flags = ent_flags[(size_t)p];
     em.gslot = ent_gslot[(size_t)p];
-    em.level = level[(size_t)ent[(size_t)p]];
-    em.nup = up_ptr[(size_t)p + 1] - up_ptr[(size_t)p];
-    em.up[0] = em.nup > 0 ? up_pos[(size_t)up_ptr[(size_t)p]] : 0;
-    em.up[1] = em.nup > 1 ? up_pos[(size_t)up_ptr[(size_t)p] + 1] : 0;
+    const int nup = up_ptr[(size_t)p + 1] - up_ptr[(size_t)p];
+    em.flags |= nup << 8;
+    for (int u = 0; u < kMetaUps; ++u)
+      em.up[u] = u < nup ? up_pos[(size_t)up_ptr[(size_t)p] + u] : 0;
   }
   // levels from tail_level on are all narrower than kTailMaxLevel
   const int nLv = (int)rt->lvl_ptr.size() - 1;
   rt->tail_level = nLv;
+  int tail_max = kTailMaxLevel;
+  if (const char* e = getenv("MHM_CUDA_TAIL_MAX")) tail_max = atoi(e);
+  tail_max = std::min(tail_max, kTailCluster * kTailThreads);
   for (int l = nLv - 1; l >= 0; --l) {
-    if (rt->lvl_ptr[(size_t)l + 1] - rt->lvl_ptr[(size_t)l] > kTailMaxLevel) break;
+    if (rt->lvl_ptr[(size_t)l + 1] - rt->lvl_ptr[(size_t)l] > tail_max) break;
     rt->tail_level = l;
   }
   if (nLv - rt->tail_level < 4) rt->tail_level = nLv;  // not worth a wavefront
@@ -640,6 +802,41 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     for (int nd = 0; nd < nNodes; ++nd)
       MHM_REQUIRE(v[(size_t)nd] >= 1 && v[(size_t)nd] <= n1, "set_network: L11_L1_Id outside 1..%d", n1);
     if (int rc = upload(&rt->L11_L1_Id, v, st)) return rc;
+  }
+  // one-to-one mapping between L1 cells and L11 nodes?
+  {
+    rt->bijective = false;
+    if (n1 == nNodes) {
+      std::vector<int32_t> node_of_cell((size_t)n1, -1);
+      std::vector<char> seen((size_t)nNodes, 0);
+      bool ok = true;
+      if (rt->map_flag) {
+        for (int k = 0; k < n1 && ok; ++k) {
+          const int nd = net->L1_L11_Id[k] - 1;
+          ok = !seen[(size_t)nd];
+          seen[(size_t)nd] = 1;
+          node_of_cell[(size_t)k] = nd;
+        }
+      } else {
+        for (int nd = 0; nd < nNodes && ok; ++nd) {
+          const int k = net->L11_L1_Id[nd] - 1;
+          ok = node_of_cell[(size_t)k] < 0;
+          node_of_cell[(size_t)k] = nd;
+        }
+      }
+      if (ok) {
+        std::vector<int32_t> ce((size_t)n1);
+        std::vector<double> ca((size_t)n1);
+        for (int k = 0; k < n1; ++k) {
+          const int nd = node_of_cell[(size_t)k];
+          ce[(size_t)k] = pos_of_node[(size_t)nd];
+          ca[(size_t)k] = rt->map_flag ? net->L1_areaCell[k] : net->L11_areaCell[nd];
+        }
+        if (int rc = upload(&rt->d_cell_entry, ce, st)) return rc;
+        if (int rc = upload(&rt->d_cell_area, ca, st)) return rc;
+        rt->bijective = true;
+      }
+    }
   }
   std::vector<double> a1(net->L1_areaCell, net->L1_areaCell + n1),
       a11(net->L11_areaCell, net->L11_areaCell + nNodes);
@@ -679,20 +876,46 @@ static int ensure_c1c2(mhm_cuda_context* ctx, Routing* rt, int yId, double times
   return 0;
 }
 
-// run the routing of a list of events whose runoff is available on the device
+static long fortran_nint(double x) { return (long)std::lround(x); }
+
+static bool routing_accumulates(const Domain* d, const Routing* rt) {
+  return rt->rout_case != 1 && rt->TSrout / (d->cfg.timestep_h * 3600.0) >= 1.0;
+}
+static int routing_rout_loop(const Domain* d, const Routing* rt) {
+  if (rt->rout_case == 1) return 1;
+  const double f = rt->TSrout / (d->cfg.timestep_h * 3600.0);
+  const long rl = fortran_nint(1.0 / f);
+  return (int)(rl < 1 ? 1 : rl);
+}
+// aligned mode: one event per model step, one routing step per event, one cell per node
+static bool routing_aligned(const Domain* d, const Routing* rt) {
+  return rt->bijective && rt->nNodes > 1 && !routing_accumulates(d, rt) &&
+         routing_rout_loop(d, rt) == 1;
+}
+
+struct Segment {
+  int32_t ev0, ev1, yId;
+};
+
+// route the events of one block.  `aligned`: one cell per node and one model step per event,
+// so the qOUT tiles are built by the coalesced per-cell kernel.
 static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector<DevEvent>& ev,
-                      const std::vector<double>& inflow_val, const double* runoff_hist) {
+                      const std::vector<Segment>& segs, const std::vector<double>& inflow_val,
+                      const double* runoff_hist, bool aligned, double timestep_rout) {
   if (ev.empty()) return 0;
   cudaStream_t st = ctx->stream;
   const int nEv = (int)ev.size(), M = rt->M, E = rt->E;
   int RS = 0;
+  bool fast = rt->nNodes > 1;
   for (auto& e : ev) {
     e.rs_first = RS;
     RS += e.rout_loop;
+    fast = fast && e.rout_loop == 1;
   }
+  if (getenv("MHM_CUDA_GENERIC_ROUTING")) fast = false;
   if (int rc = ensure(&rt->d_events, &rt->ev_cap, (size_t)nEv, st)) return rc;
-  if (int rc = ensure(&rt->qout_hist, &rt->qout_cap, (size_t)nEv * M * E, st)) return rc;
-  if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, (size_t)RS * M * E, st)) return rc;
+  if (int rc = ensure(&rt->qout_hist, &rt->qout_cap, hist_size(nEv, M, E), st)) return rc;
+  if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(RS, M, E), st)) return rc;
   if (int rc = ensure(&rt->qmod_g, &rt->qmodg_cap, (size_t)nEv * M * std::max(1, rt->nGslots), st))
     return rc;
   if (int rc = ensure(&rt->d_inflow_val, &rt->inflow_cap, std::max<size_t>(1, inflow_val.size()), st))
@@ -706,111 +929,143 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
 
   ctx->stat_begin(kStatRouting);
   int64_t launched = 0;
-  QoutArgs qa{};
-  qa.nCells1 = rt->nCells1;
-  qa.nNodes = rt->nNodes;
-  qa.E = E;
-  qa.M = M;
-  qa.nEvents = nEv;
-  qa.map_flag = rt->map_flag;
-  qa.nInflowGauges = rt->nInflowGauges;
-  qa.nInflowTotal = rt->nInflowTotal;
-  qa.events = rt->d_events;
-  qa.runoff_hist = runoff_hist;
-  qa.carry = rt->carry;
-  qa.ent_node = rt->ent_node;
-  qa.cell_ptr = rt->cell_ptr;
-  qa.cell_idx = rt->cell_idx;
-  qa.L11_L1_Id = rt->L11_L1_Id;
-  qa.L1_area = rt->L1_area;
-  qa.L11_area = rt->L11_area;
-  qa.inflow_node = rt->d_inflow_node;
-  qa.inflow_index = rt->d_inflow_index;
-  qa.inflow_head = rt->d_inflow_head;
-  qa.inflow_val = rt->d_inflow_val;
-  qa.qout_hist = rt->qout_hist;
-  for (int e0 = 0; e0 < nEv; e0 += 32768) {  // gridDim.z limit
-    QoutArgs q2 = qa;
-    q2.events = rt->d_events + e0;
-    q2.inflow_val = rt->d_inflow_val + (size_t)e0 * rt->nInflowTotal;
-    q2.qout_hist = rt->qout_hist + (size_t)e0 * M * E;
-    const int ne = std::min(32768, nEv - e0);
-    qout_kernel<<<dim3((E + 127) / 128, M, ne), 128, 0, st>>>(q2);
-    ++launched;
-  }
-  MHM_CUDA_OK(cudaGetLastError());
-
-  bool fast = rt->nNodes > 1;
-  for (auto& e : ev) fast = fast && e.rout_loop == 1;
-  if (getenv("MHM_CUDA_GENERIC_ROUTING")) fast = false;
-  if (fast) {
-    FastArgs fa{};
-    fa.E = E;
-    fa.M = M;
-    fa.nNodes = rt->nNodes;
-    fa.nEvents = nEv;
-    fa.nGslots = std::max(1, rt->nGslots);
-    fa.tail_level = rt->tail_level;
-    fa.nLevels = (int)rt->lvl_ptr.size() - 1;
-    fa.meta = rt->meta;
-    fa.up_ptr = rt->up_ptr;
-    fa.up_pos = rt->up_pos;
-    fa.lvl_ptr = rt->d_lvl_ptr;
-    fa.events = rt->d_events;
-    fa.C1 = rt->C1;
-    fa.C2 = rt->C2;
-    fa.qout_hist = rt->qout_hist;
-    fa.qtr_hist = rt->qtr_hist;
-    fa.qTIN = rt->qTIN;
-    fa.qTR = rt->qTR;
-    fa.qMod = rt->qMod;
-    fa.qOUT = rt->qOUT;
-    fa.qmod_g = rt->qmod_g;
-    for (int l = 0; l < rt->tail_level; ++l) {
-      fa.p0 = rt->lvl_ptr[(size_t)l];
-      fa.p1 = rt->lvl_ptr[(size_t)l + 1];
-      const int cnt = fa.p1 - fa.p0;
-      route_level_fast_kernel<8><<<dim3((cnt + 127) / 128, M), 128, 0, st>>>(fa);
+  const int tiles = (nEv + kHistTile - 1) / kHistTile;
+  if (aligned) {
+    QoutCellArgs qc{};
+    qc.nCells1 = rt->nCells1;
+    qc.E = E;
+    qc.M = M;
+    qc.map_flag = rt->map_flag;
+    qc.nInflowGauges = rt->nInflowGauges;
+    qc.nInflowTotal = rt->nInflowTotal;
+    qc.runoff_hist = runoff_hist;
+    qc.cell_entry = rt->d_cell_entry;
+    qc.cell_area = rt->d_cell_area;
+    qc.meta = rt->meta;
+    qc.inflow_node = rt->d_inflow_node;
+    qc.inflow_index = rt->d_inflow_index;
+    qc.inflow_head = rt->d_inflow_head;
+    for (int t0 = 0; t0 < tiles; t0 += 32768) {
+      qc.events = rt->d_events + (size_t)t0 * kHistTile;
+      qc.nEvents = nEv - t0 * kHistTile;
+      qc.inflow_val = rt->d_inflow_val + (size_t)t0 * kHistTile * rt->nInflowTotal;
+      qc.qout_hist = rt->qout_hist + hidx(t0 * kHistTile, M, E, 0, 0);
+      const int nt = std::min(32768, tiles - t0);
+      qout_cell_kernel<<<dim3((rt->nCells1 + 127) / 128, M, nt), 128, 0, st>>>(qc);
       ++launched;
     }
-    if (rt->tail_level < fa.nLevels) {
-      route_tail_kernel<<<dim3(M * kTailCluster), kTailThreads, 0, st>>>(fa);
-      ++launched;
-    }
+    MHM_CUDA_OK(cudaGetLastError());
   } else {
-    LevelArgs la{};
-    la.E = E;
-    la.M = M;
-    la.nNodes = rt->nNodes;
-    la.nEvents = nEv;
-    la.single_node = rt->nNodes <= 1;
-    la.events = rt->d_events;
-    la.ent_node = rt->ent_node;
-    la.ent_link = rt->ent_link;
-    la.ent_flags = rt->ent_flags;
-    la.ent_gslot = rt->ent_gslot;
-    la.up_ptr = rt->up_ptr;
-    la.up_pos = rt->up_pos;
-    la.C1 = rt->C1;
-    la.C2 = rt->C2;
-    la.qout_hist = rt->qout_hist;
-    la.qtr_hist = rt->qtr_hist;
-    la.qTIN = rt->qTIN;
-    la.qTR = rt->qTR;
-    la.qMod = rt->qMod;
-    la.qOUT = rt->qOUT;
-    la.qmod_g = rt->qmod_g;
-    la.nGslots = std::max(1, rt->nGslots);
-    for (size_t l = 0; l + 1 < rt->lvl_ptr.size(); ++l) {
-      la.p0 = rt->lvl_ptr[l];
-      la.p1 = rt->lvl_ptr[l + 1];
-      const int cnt = la.p1 - la.p0;
-      const int threads = cnt >= 128 ? 128 : 32;
-      route_level_kernel<<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(la);
+    QoutArgs qa{};
+    qa.nCells1 = rt->nCells1;
+    qa.nNodes = rt->nNodes;
+    qa.E = E;
+    qa.M = M;
+    qa.nEvents = nEv;
+    qa.map_flag = rt->map_flag;
+    qa.nInflowGauges = rt->nInflowGauges;
+    qa.nInflowTotal = rt->nInflowTotal;
+    qa.runoff_hist = runoff_hist;
+    qa.carry = rt->carry;
+    qa.ent_node = rt->ent_node;
+    qa.cell_ptr = rt->cell_ptr;
+    qa.cell_idx = rt->cell_idx;
+    qa.L11_L1_Id = rt->L11_L1_Id;
+    qa.L1_area = rt->L1_area;
+    qa.L11_area = rt->L11_area;
+    qa.inflow_node = rt->d_inflow_node;
+    qa.inflow_index = rt->d_inflow_index;
+    qa.inflow_head = rt->d_inflow_head;
+    for (int t0 = 0; t0 < tiles; t0 += 32768) {  // gridDim.z limit
+      // the kernel indexes events and history tiles from `tile`; shift all three views
+      qa.events = rt->d_events + (size_t)t0 * kHistTile;
+      qa.nEvents = nEv - t0 * kHistTile;
+      qa.inflow_val = rt->d_inflow_val + (size_t)t0 * kHistTile * rt->nInflowTotal;
+      qa.qout_hist = rt->qout_hist + hidx(t0 * kHistTile, M, E, 0, 0);
+      const int nt = std::min(32768, tiles - t0);
+      qout_kernel<<<dim3((E + 127) / 128, M, nt), 128, 0, st>>>(qa);
       ++launched;
     }
+    MHM_CUDA_OK(cudaGetLastError());
   }
-  MHM_CUDA_OK(cudaGetLastError());
+
+  for (const Segment& sg : segs) {
+    if (int rc = ensure_c1c2(ctx, rt, sg.yId, timestep_rout)) return rc;
+    if (fast) {
+      FastArgs fa{};
+      fa.ev0 = sg.ev0;
+      fa.ev1 = sg.ev1;
+      fa.E = E;
+      fa.M = M;
+      fa.nNodes = rt->nNodes;
+      fa.nEvents = nEv;
+      fa.nGslots = std::max(1, rt->nGslots);
+      fa.tail_level = rt->tail_level;
+      fa.nLevels = (int)rt->lvl_ptr.size() - 1;
+      fa.meta = rt->meta;
+      fa.up_ptr = rt->up_ptr;
+      fa.up_pos = rt->up_pos;
+      fa.lvl_ptr = rt->d_lvl_ptr;
+      fa.events = rt->d_events;
+      fa.C1 = rt->C1;
+      fa.C2 = rt->C2;
+      fa.qout_hist = rt->qout_hist;
+      fa.qtr_hist = rt->qtr_hist;
+      fa.qTIN = rt->qTIN;
+      fa.qTR = rt->qTR;
+      fa.qMod = rt->qMod;
+      fa.qOUT = rt->qOUT;
+      fa.qmod_g = rt->qmod_g;
+      for (int l = 0; l < rt->tail_level; ++l) {
+        fa.p0 = rt->lvl_ptr[(size_t)l];
+        fa.p1 = rt->lvl_ptr[(size_t)l + 1];
+        const int cnt = fa.p1 - fa.p0;
+        route_level_fast_kernel<<<dim3((cnt + 127) / 128, M), 128, 0, st>>>(fa);
+        ++launched;
+      }
+      if (rt->tail_level < fa.nLevels) {
+        const int nLvTail = fa.nLevels - rt->tail_level;
+        const size_t smem = (size_t)(nLvTail + 1) * sizeof(int32_t);
+        fa.p0 = smem <= 40 * 1024 ? 1 : 0;  // lvl_ptr of the tail staged in shared memory
+        route_tail_kernel<<<dim3(M * kTailCluster), kTailThreads, fa.p0 ? smem : 0, st>>>(fa);
+        ++launched;
+      }
+    } else {
+      LevelArgs la{};
+      la.E = E;
+      la.M = M;
+      la.nNodes = rt->nNodes;
+      la.ev0 = sg.ev0;
+      la.ev1 = sg.ev1;
+      la.single_node = rt->nNodes <= 1;
+      la.events = rt->d_events;
+      la.ent_node = rt->ent_node;
+      la.ent_link = rt->ent_link;
+      la.ent_flags = rt->ent_flags;
+      la.ent_gslot = rt->ent_gslot;
+      la.up_ptr = rt->up_ptr;
+      la.up_pos = rt->up_pos;
+      la.C1 = rt->C1;
+      la.C2 = rt->C2;
+      la.qout_hist = rt->qout_hist;
+      la.qtr_hist = rt->qtr_hist;
+      la.qTIN = rt->qTIN;
+      la.qTR = rt->qTR;
+      la.qMod = rt->qMod;
+      la.qOUT = rt->qOUT;
+      la.qmod_g = rt->qmod_g;
+      la.nGslots = std::max(1, rt->nGslots);
+      for (size_t l = 0; l + 1 < rt->lvl_ptr.size(); ++l) {
+        la.p0 = rt->lvl_ptr[l];
+        la.p1 = rt->lvl_ptr[l + 1];
+        const int cnt = la.p1 - la.p0;
+        const int threads = cnt >= 128 ? 128 : 32;
+        route_level_kernel<<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(la);
+        ++launched;
+      }
+    }
+    MHM_CUDA_OK(cudaGetLastError());
+  }
   if (rt->nGauges > 0 || rt->nGaugesTotal > 0) {
     gauge_kernel<<<dim3((nEv + 63) / 64, M), 64, 0, st>>>(
         nEv, M, rt->nGauges, std::max(1, rt->nGslots), rt->nTimeSteps, rt->nGaugesTotal,
@@ -823,10 +1078,9 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
   return 0;
 }
 
-static long fortran_nint(double x) { return (long)std::lround(x); }
-
 // routing of model steps tt_first .. tt_first+n_steps-1 whose total runoff is in
-// d->runoff_hist; restates the schedule of mo_mhm_interface_run.f90:460-612
+// d->runoff_hist (or, aligned mode, already in the qOUT tiles); restates the schedule of
+// mo_mhm_interface_run.f90:460-612
 int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_t n_steps) {
   Routing* rt = d->rt;
   MHM_REQUIRE(rt->nTimeSteps == d->axis.nTimeSteps && rt->gauge_hist,
@@ -838,72 +1092,66 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
     if (rt->inflowQ.empty()) return 0.0;
     return rt->inflowQ[(size_t)g * rt->nDays + (size_t)(day - 1)];
   };
-  const bool accumulates =
-      rt->rout_case != 1 && rt->TSrout / (d->cfg.timestep_h * 3600.0) >= 1.0;
-  // split the block where the land-cover scene changes (C1/C2 of case 1 depend on it)
-  int32_t seg0 = 0;
-  while (seg0 < n_steps) {
-    const int yId = d->h_idx[(size_t)(tt_first + seg0 - 1)].yId;
-    int32_t seg1 = seg0;
-    while (seg1 < n_steps && d->h_idx[(size_t)(tt_first + seg1 - 1)].yId == yId) ++seg1;
-    std::vector<DevEvent> ev;
-    std::vector<double> inflow_val;
-    int32_t acc_t0 = seg0;                   // first block step not yet routed
-    bool carry_live = rt->carry_steps > 0;  // rt->carry holds runoff of steps before acc_t0
-    for (int32_t t = seg0; t < seg1; ++t) {
-      const int tt = tt_first + t;
-      const int day = (tt + nTstepDay - 1) / nTstepDay;  // iDischargeTS, :463
-      DevEvent e{};
-      bool fire = false;
-      if (!accumulates) {  // case 1 (:465-474) and adaptive step shorter than the model step
-        double fin = 1.0;
-        if (rt->rout_case != 1) fin = rt->TSrout / (d->cfg.timestep_h * 3600.0);
+  const bool accumulates = routing_accumulates(d, rt);
+  const bool aligned = routing_aligned(d, rt) && !getenv("MHM_CUDA_NO_ALIGNED");
+  std::vector<DevEvent> ev;
+  std::vector<Segment> segs;  // runs of events of one land-cover scene (C1/C2 of case 1)
+  std::vector<double> inflow_val;
+  int32_t acc_t0 = 0;                     // first block step not yet routed
+  bool carry_live = rt->carry_steps > 0;  // rt->carry holds runoff of steps before acc_t0
+  for (int32_t t = 0; t < n_steps; ++t) {
+    const int tt = tt_first + t;
+    const int day = (tt + nTstepDay - 1) / nTstepDay;  // iDischargeTS, :463
+    DevEvent e{};
+    bool fire = false;
+    if (!accumulates) {  // case 1 (:465-474) and adaptive step shorter than the model step
+      e.rout_loop = routing_rout_loop(d, rt);
+      e.tst = 3600.0 * d->cfg.timestep_h;
+      for (int g = 0; g < rt->nInflowTotal; ++g) rt->inflow_acc[(size_t)g] = inflow_at(g, day);
+      e.t0 = t;
+      e.nacc = 1;
+      e.use_carry = 0;
+      fire = true;
+    } else {  // routing step longer than the model step: :493-512
+      double fin = rt->TSrout / (d->cfg.timestep_h * 3600.0);
+      for (int g = 0; g < rt->nInflowTotal; ++g)
+        rt->inflow_acc[(size_t)g] = rt->inflow_acc[(size_t)g] + inflow_at(g, day);
+      if (tt == nT && (tt % fortran_nint(fin)) != 0) fin = (double)(tt % fortran_nint(fin));
+      if ((tt % fortran_nint(fin)) == 0 || tt == nT) {
+        for (int g = 0; g < rt->nInflowTotal; ++g)
+          rt->inflow_acc[(size_t)g] = rt->inflow_acc[(size_t)g] / fin;
+        e.tst = 3600.0 * (double)(d->cfg.timestep_h * (int)fortran_nint(fin));
         long rl = fortran_nint(1.0 / fin);
         e.rout_loop = (int32_t)(rl < 1 ? 1 : rl);
-        e.tst = 3600.0 * d->cfg.timestep_h;
-        for (int g = 0; g < rt->nInflowTotal; ++g) rt->inflow_acc[(size_t)g] = inflow_at(g, day);
-        e.t0 = t;
-        e.nacc = 1;
-        e.use_carry = 0;
+        e.backfill = (int32_t)fortran_nint(fin);
+        e.t0 = acc_t0;
+        e.nacc = t - acc_t0 + 1;
+        e.use_carry = carry_live ? 1 : 0;
         fire = true;
-      } else {  // routing step longer than the model step: :493-512
-        double fin = rt->TSrout / (d->cfg.timestep_h * 3600.0);
-        for (int g = 0; g < rt->nInflowTotal; ++g)
-          rt->inflow_acc[(size_t)g] = rt->inflow_acc[(size_t)g] + inflow_at(g, day);
-        if (tt == nT && (tt % fortran_nint(fin)) != 0) fin = (double)(tt % fortran_nint(fin));
-        if ((tt % fortran_nint(fin)) == 0 || tt == nT) {
-          for (int g = 0; g < rt->nInflowTotal; ++g)
-            rt->inflow_acc[(size_t)g] = rt->inflow_acc[(size_t)g] / fin;
-          e.tst = 3600.0 * (double)(d->cfg.timestep_h * (int)fortran_nint(fin));
-          long rl = fortran_nint(1.0 / fin);
-          e.rout_loop = (int32_t)(rl < 1 ? 1 : rl);
-          e.backfill = (int32_t)fortran_nint(fin);
-          e.t0 = acc_t0;
-          e.nacc = t - acc_t0 + 1;
-          e.use_carry = carry_live ? 1 : 0;
-          fire = true;
-        }
       }
-      if (!fire) continue;
-      e.tt = tt;
-      ev.push_back(e);
-      inflow_val.insert(inflow_val.end(), rt->inflow_acc.begin(), rt->inflow_acc.end());
-      std::fill(rt->inflow_acc.begin(), rt->inflow_acc.end(), 0.0);  // :596, :606
-      acc_t0 = t + 1;
-      carry_live = false;
     }
-    if (int rc = ensure_c1c2(ctx, rt, yId, (double)d->cfg.timestep_h)) return rc;
-    if (int rc = run_events(ctx, d, rt, ev, inflow_val, d->runoff_hist)) return rc;
-    // steps at the end of the segment that wait for a later routing call
-    if (accumulates && acc_t0 < seg1) {
-      carry_kernel<<<dim3((rt->nCells1 + 127) / 128, rt->M), 128, 0, ctx->stream>>>(
-          rt->nCells1, rt->M, acc_t0, seg1 - acc_t0, carry_live ? 1 : 0, d->runoff_hist, rt->carry);
-      MHM_CUDA_OK(cudaGetLastError());
-      rt->carry_steps = (carry_live ? rt->carry_steps : 0) + (seg1 - acc_t0);
-    } else {
-      rt->carry_steps = 0;
-    }
-    seg0 = seg1;
+    if (!fire) continue;
+    e.tt = tt;
+    const int yId = d->h_idx[(size_t)(tt - 1)].yId;  // scene of the step that calls mRM_routing
+    if (segs.empty() || segs.back().yId != yId) segs.push_back(Segment{(int32_t)ev.size(), 0, yId});
+    ev.push_back(e);
+    segs.back().ev1 = (int32_t)ev.size();
+    inflow_val.insert(inflow_val.end(), rt->inflow_acc.begin(), rt->inflow_acc.end());
+    std::fill(rt->inflow_acc.begin(), rt->inflow_acc.end(), 0.0);  // :596, :606
+    acc_t0 = t + 1;
+    carry_live = false;
+  }
+  if (int rc = run_events(ctx, d, rt, ev, segs, inflow_val, d->runoff_hist, aligned,
+                          (double)d->cfg.timestep_h))
+    return rc;
+  // steps at the end of the block that wait for a later routing call
+  if (accumulates && acc_t0 < n_steps) {
+    carry_kernel<<<dim3((rt->nCells1 + 127) / 128, rt->M), 128, 0, ctx->stream>>>(
+        rt->nCells1, rt->M, acc_t0, n_steps - acc_t0, carry_live ? 1 : 0, d->runoff_hist, rt->carry);
+    MHM_CUDA_OK(cudaGetLastError());
+    rt->carry_steps = (carry_live ? rt->carry_steps : 0) + (n_steps - acc_t0);
+  } else {
+    rt->carry_steps = 0;
   }
   return 0;
 }
@@ -1132,8 +1380,8 @@ int mrm_cuda_route(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, int32
   std::vector<double> inflow_val((size_t)rt->nInflowTotal, 0.0);
   if (InflowDischarge)
     for (int g = 0; g < rt->nInflowTotal; ++g) inflow_val[(size_t)g] = InflowDischarge[g];
-  if (int rc = ensure_c1c2(ctx, rt, yId, (double)timestep_rout)) return rc;
-  return run_events(ctx, d, rt, ev, inflow_val, src);
+  std::vector<Segment> segs{Segment{0, 1, yId}};
+  return run_events(ctx, d, rt, ev, segs, inflow_val, src, false, (double)timestep_rout);
 }
 
 int mrm_cuda_get_runoff(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, double* out,
