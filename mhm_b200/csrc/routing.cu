@@ -1,4 +1,5 @@
-// routing.cu -- mRM Muskingum routing on the device, time-blocked and level-scheduled.
+// routing.cu -- mRM Muskingum routing on the device: time-blocked, chain-decomposed,
+// warp-pipelined.
 //
 // Reference behaviour restated here (never copied):
 //   mRM/mo_mrm_routing.f90:104-303 (mRM_routing), :380-481 (L11_routing)
@@ -7,46 +8,58 @@
 //   mRM/mo_mrm_net_startup.f90:728-859 (L11_routing_order)
 //   mHM/mo_mhm_interface_run.f90:460-612 (routing schedule, gauge back-fill)
 //
-// The reference sweeps the links serially in netPerm order once per routing step.  Its
-// data dependence is (node, step) <- (upstream nodes, same step) and (node, step-1), so a
-// whole block of routing steps can be done level by level: every link of one network
-// level advances through all steps of the block with its Muskingum state in registers,
-// reading the already finished outflow history of its upstream links.  Upstream inflows
-// are added in netPerm order and the node's own runoff last, exactly like the serial
-// sweep, so the result is bit-identical to it.
+// The reference sweeps the links serially in netPerm order once per routing step.  Its data
+// dependence is (node, step) <- (upstream nodes, same step) and (node, step - 1).  Here a
+// whole block of routing steps is routed at once:
+//   * the river network is cut into chains (every node continues the chain of its highest
+//     upstream node; the other inflowing links are tributaries) and the chains into segments
+//     of at most 32 nodes;
+//   * one warp owns one or several whole segments, lane j owning the j-th node, and runs a
+//     software pipeline skewed by one routing step per lane: while lane j works on step s,
+//     lane j+1 works on step s-1 and receives lane j's routed outflow through a register
+//     shuffle.  Muskingum state stays in registers for the whole block;
+//   * segments are level-scheduled on the (shallow) segment DAG: O(log N + longest chain/32)
+//     launches per block instead of one per network level; only segment ends and tributary
+//     mouths ever write their outflow series to memory.
+// Upstream inflows are added in netPerm order and the node's own runoff last, exactly like
+// the serial sweep, so the result is bit-identical to it.
 //
 // This file is compiled with -fmad=false: C1*(a-b) + C2*(c-d) must round as in Fortran.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 
-#include <cooperative_groups.h>
-
 #include "context.h"
-
-namespace cg = cooperative_groups;
 
 namespace mhm {
 
-constexpr int kTailCluster = 8;       // CTAs per cluster in the tail kernel (portable maximum)
-constexpr int kTailThreads = 256;     // threads per CTA in the tail kernel
-constexpr int kTailMaxLevel = 2048;   // levels wider than this get their own launch
+constexpr int kSegLen = 32;   // nodes per segment = lanes of a warp
+constexpr int kMetaUps = 4;   // upstream links described in the lane record itself
+constexpr int kUpShuffle = -1;  // LaneMeta::up value: "outflow of the previous lane"
 
-// everything a routing thread needs to know about its entry, one 32-byte record
-struct alignas(16) EntMeta {
-  int32_t node;    // 0-based L11 node
-  int32_t link;    // 0-based link (C1/C2 index)
-  int32_t flags;   // kEnt* bits | number of upstream links << 8
-  int32_t gslot;   // gauge slot or -1
-  int32_t up[4];   // entry positions of the first four upstream links (netPerm order)
+enum : int32_t {
+  kEntValid = 1,      // lane holds a node (otherwise padding)
+  kEntLink = 2,       // node has an outgoing link (Muskingum state); otherwise an outlet
+  kEntAddQout = 4,    // node's own runoff is added to its inflow
+  kEntZeroOut = 8,    // routed outflow feeds a non-headwater inflow gauge: set to zero
+  kEntInflow = 16,    // node is an inflow gauge: add_inflow applies to its runoff
+  kEntWriteHist = 32, // somebody reads this node's outflow series from memory
 };
-constexpr int kMetaUps = 4;
-static_assert(sizeof(EntMeta) == 32, "EntMeta must be 32 bytes");
 
-// History buffers (node runoff qOUT and routed outflow qTR of every routing step of a block)
-// are tiled by 8 steps: [step / 8][member][entry][step % 8].  An entry's 8 consecutive steps
-// are one 64-byte run, so a level thread streams its own and its upstream links' series with
-// 128-bit loads, and neighbouring entries of a level are neighbouring runs.
+// everything a lane needs to know about its node, one 32-byte record
+struct alignas(16) LaneMeta {
+  int32_t node;   // 0-based L11 node
+  int32_t link;   // 0-based link (C1/C2 index)
+  int32_t flags;  // kEnt* bits | number of upstream links << 8 | position in segment << 16
+  int32_t gslot;  // gauge slot or -1
+  int32_t up[kMetaUps];  // first four upstream links in netPerm order: lane position of the
+                         // link's from-node, or kUpShuffle
+};
+static_assert(sizeof(LaneMeta) == 32, "LaneMeta must be 32 bytes");
+
+// History buffers (node runoff qOUT per event, routed outflow qTR per routing step) are tiled
+// by 8 steps: [step / 8][member][lane][step % 8]; a node's 8 consecutive steps are one
+// 64-byte run and neighbouring lanes are neighbouring runs.
 constexpr int kHistTile = 8;
 __host__ __device__ __forceinline__ size_t hidx(int step, int M, int E, int m, int p) {
   return ((((size_t)(step >> 3) * M + m) * E + p) << 3) + (size_t)(step & 7);
@@ -54,13 +67,6 @@ __host__ __device__ __forceinline__ size_t hidx(int step, int M, int E, int m, i
 __host__ __device__ __forceinline__ size_t hist_size(int steps, int M, int E) {
   return (size_t)((steps + kHistTile - 1) / kHistTile) * M * E * kHistTile;
 }
-
-enum : int32_t {
-  kEntLink = 1,     // entry is a link (has Muskingum state); otherwise an outlet node
-  kEntAddQout = 2,  // node's own runoff is added to its inflow
-  kEntZeroOut = 4,  // routed outflow feeds a non-headwater inflow gauge: set to zero
-  kEntInflow = 8,   // node is an inflow gauge: add_inflow applies to its runoff
-};
 
 struct DevEvent {
   int32_t tt;         // model step at which mRM_routing is called
@@ -77,27 +83,24 @@ struct DevEvent {
 struct Routing {
   int32_t nCells1 = 0, nNodes = 0, nLinks = 0, nOutlets = 0, map_flag = 1, rout_case = 1;
   int32_t nGauges = 0, nInflowGauges = 0, nGaugesTotal = 0, nInflowTotal = 0, M = 1;
-  int32_t E = 0;                  // entries = links + outlet nodes
-  std::vector<int32_t> lvl_ptr;   // entry range per level
+  int32_t E = 0;                 // lanes = nodes + padding
+  std::vector<int32_t> lvl_ptr;  // lane range per segment level (multiples of 32)
   std::vector<int32_t> gaugeIndexList, gaugeNodeList, inflowIndexList, inflowHeadwater,
       inflowNodeList;
   // device topology (shared by members)
-  int32_t *ent_node = nullptr, *ent_link = nullptr, *ent_flags = nullptr, *ent_gslot = nullptr;
-  int32_t *up_ptr = nullptr, *up_pos = nullptr;
-  EntMeta* meta = nullptr;
-  int32_t* d_lvl_ptr = nullptr;
-  int32_t tail_level = 0;  // levels >= tail_level are swept by one clustered wavefront kernel
-  // aligned mode: L1 cells and L11 nodes map one to one, so the cell kernel hands its runoff
-  // straight to the routing history (no L11_runoff_acc pass)
-  bool bijective = false;
-  int32_t* d_cell_entry = nullptr;  // [nCells1] routing entry of the cell's node
-  double* d_cell_area = nullptr;    // [nCells1] area factor of mo_mrm_pre_routing.f90:125/:141
+  LaneMeta* meta = nullptr;
+  int32_t *up_ptr = nullptr, *up_pos = nullptr;  // all upstream lanes (nodes with > 4 links)
+  int32_t* node_lane = nullptr;                  // [nNodes] lane of a node
   int32_t *cell_ptr = nullptr, *cell_idx = nullptr;  // map_flag: L1 cells of each node, ascending
   int32_t* L11_L1_Id = nullptr;                      // !map_flag
   int32_t *d_inflow_node = nullptr, *d_inflow_index = nullptr, *d_inflow_head = nullptr;
   double *L1_area = nullptr, *L11_area = nullptr;
   int32_t nGslots = 0;
   int32_t *d_gauge_col = nullptr, *d_gauge_slot = nullptr;  // per gauge: column-1, slot
+  // one-cell-per-node mapping: coalesced per-cell qOUT kernel
+  bool bijective = false;
+  int32_t* d_cell_entry = nullptr;  // [nCells1] lane of the cell's node
+  double* d_cell_area = nullptr;    // [nCells1] area factor of mo_mrm_pre_routing.f90:125/:141
   // per member state, device [M][...]
   double *C1 = nullptr, *C2 = nullptr, *qOUT = nullptr, *qMod = nullptr;
   double *qTIN = nullptr, *qTR = nullptr;  // [M][2][nNodes]
@@ -126,13 +129,12 @@ struct Routing {
 
 void routing_free(Routing* rt) {
   if (!rt) return;
-  void* ptrs[] = {rt->ent_node, rt->ent_link,  rt->ent_flags, rt->ent_gslot, rt->up_ptr,
-                  rt->up_pos,   rt->meta, rt->d_lvl_ptr, rt->d_cell_entry, rt->d_cell_area, rt->cell_ptr,  rt->cell_idx,  rt->L11_L1_Id, rt->d_inflow_node,
-                  rt->d_inflow_index, rt->d_inflow_head, rt->L1_area, rt->L11_area,
-                  rt->d_gauge_col, rt->d_gauge_slot, rt->C1, rt->C2, rt->qOUT, rt->qMod,
-                  rt->qTIN, rt->qTR, rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry,
-                  rt->gauge_hist, rt->qout_hist, rt->qtr_hist, rt->qmod_g, rt->d_inflow_val,
-                  rt->d_events};
+  void* ptrs[] = {rt->meta, rt->up_ptr, rt->up_pos, rt->node_lane, rt->cell_ptr, rt->cell_idx,
+                  rt->L11_L1_Id, rt->d_inflow_node, rt->d_inflow_index, rt->d_inflow_head,
+                  rt->L1_area, rt->L11_area, rt->d_gauge_col, rt->d_gauge_slot, rt->d_cell_entry,
+                  rt->d_cell_area, rt->C1, rt->C2, rt->qOUT, rt->qMod, rt->qTIN, rt->qTR,
+                  rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry, rt->gauge_hist,
+                  rt->qout_hist, rt->qtr_hist, rt->qmod_g, rt->d_inflow_val, rt->d_events};
   for (void* p : ptrs) cudaFree(p);
   delete rt;
 }
@@ -186,20 +188,34 @@ struct QoutArgs {
   const DevEvent* events;
   const double* runoff_hist;  // [steps][M][nCells1]
   const double* carry;        // [M][nCells1]
-  const int32_t *ent_node, *cell_ptr, *cell_idx, *L11_L1_Id;
+  const LaneMeta* meta;
+  const int32_t *cell_ptr, *cell_idx, *L11_L1_Id;
   const double *L1_area, *L11_area;
   const int32_t *inflow_node, *inflow_index, *inflow_head;
   const double* inflow_val;  // [nEvents][nInflowTotal]
   double* qout_hist;         // tiled, see hidx()
 };
 
-// L11_runoff_acc + add_inflow for every (event, member, entry); a thread produces the 8
-// events of one history tile for its entry (one 64-byte run)
+__device__ __forceinline__ double apply_inflow(const QoutArgs& a, int node, int ev, double v) {
+  for (int g = 0; g < a.nInflowGauges; ++g) {  // add_inflow, mo_mrm_pre_routing.f90:203-213
+    if (a.inflow_node[g] - 1 == node) {
+      const double qi = a.inflow_val[(size_t)ev * a.nInflowTotal + a.inflow_index[g] - 1];
+      v = a.inflow_head[g] ? v + qi : qi;
+    }
+  }
+  return v;
+}
+
+// L11_runoff_acc + add_inflow for every (event, member, lane); a thread produces the 8 events
+// of one history tile for its node (one 64-byte run).  General mapping (L11 coarser or finer
+// than L1, accumulated runoff).
 __global__ void __launch_bounds__(128) qout_kernel(const QoutArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.E) return;
   const int m = blockIdx.y, tile = blockIdx.z;
-  const int node = a.ent_node[p];  // 0-based
+  const LaneMeta lm = a.meta[p];
+  if (!(lm.flags & kEntValid)) return;
+  const int node = lm.node;
   const size_t n1 = (size_t)a.nCells1;
   double q[kHistTile];
 #pragma unroll
@@ -226,12 +242,7 @@ __global__ void __launch_bounds__(128) qout_kernel(const QoutArgs a) {
       v = run_to_rout(a.L11_L1_Id[node] - 1);
       v = v * a.L11_area[node] * 1000.0 / e.tst;
     }
-    for (int g = 0; g < a.nInflowGauges; ++g) {  // add_inflow :203-213
-      if (a.inflow_node[g] - 1 == node) {
-        const double qi = a.inflow_val[(size_t)ev * a.nInflowTotal + a.inflow_index[g] - 1];
-        v = a.inflow_head[g] ? v + qi : qi;
-      }
-    }
+    if (lm.flags & kEntInflow) v = apply_inflow(a, node, ev, v);
     q[d] = v;
   }
   double2* dst = reinterpret_cast<double2*>(a.qout_hist + hidx(tile * kHistTile, a.M, a.E, m, p));
@@ -239,28 +250,19 @@ __global__ void __launch_bounds__(128) qout_kernel(const QoutArgs a) {
   for (int d = 0; d < kHistTile / 2; ++d) dst[d] = make_double2(q[2 * d], q[2 * d + 1]);
 }
 
-// Same for the common one-cell-per-node case: a thread takes one L1 cell, reads its runoff
-// of the 8 events of a tile (coalesced over cells) and writes the finished 64-byte run at the
-// cell's routing entry.  Only used when every event is a single model step.
-struct QoutCellArgs {
-  int32_t nCells1, E, M, nEvents, map_flag, nInflowGauges, nInflowTotal;
-  const DevEvent* events;
-  const double* runoff_hist;  // [steps][M][nCells1]
-  const int32_t* cell_entry;  // [nCells1]
-  const double* cell_area;    // [nCells1]
-  const EntMeta* meta;
-  const int32_t *inflow_node, *inflow_index, *inflow_head;
-  const double* inflow_val;
-  double* qout_hist;
-};
-__global__ void __launch_bounds__(128) qout_cell_kernel(const QoutCellArgs a) {
+// Same for the common one-cell-per-node case with one model step per event: a thread takes one
+// L1 cell, reads its runoff of the 8 events of a tile (coalesced over cells) and writes the
+// finished 64-byte run at the lane of the cell's node.
+__global__ void __launch_bounds__(128)
+qout_cell_kernel(const QoutArgs a, const int32_t* __restrict__ cell_entry,
+                 const double* __restrict__ cell_area) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.nCells1) return;
   const int m = blockIdx.y, tile = blockIdx.z;
   const size_t n1 = (size_t)a.nCells1;
-  const int p = a.cell_entry[k];
-  const double area = a.cell_area[k];
-  const EntMeta em = a.meta[p];
+  const int p = cell_entry[k];
+  const double area = cell_area[k];
+  const LaneMeta lm = a.meta[p];
   double q[kHistTile];
 #pragma unroll
   for (int d = 0; d < kHistTile; ++d) {
@@ -272,14 +274,7 @@ __global__ void __launch_bounds__(128) qout_cell_kernel(const QoutCellArgs a) {
     // map_flag: (0 + qAll*efecArea) * 1000 / TST (:125,:129); else qAll * L11_area * 1000 / TST
     double v = a.map_flag ? (0.0 + r * area) : r * area;
     v = v * 1000.0 / e.tst;
-    if (em.flags & kEntInflow) {
-      for (int g = 0; g < a.nInflowGauges; ++g) {
-        if (a.inflow_node[g] - 1 == em.node) {
-          const double qi = a.inflow_val[(size_t)ev * a.nInflowTotal + a.inflow_index[g] - 1];
-          v = a.inflow_head[g] ? v + qi : qi;
-        }
-      }
-    }
+    if (lm.flags & kEntInflow) v = apply_inflow(a, lm.node, ev, v);
     q[d] = v;
   }
   double2* dst = reinterpret_cast<double2*>(a.qout_hist + hidx(tile * kHistTile, a.M, a.E, m, p));
@@ -299,287 +294,115 @@ __global__ void carry_kernel(int nCells1, int M, int t0, int nacc, int use_carry
   carry[(size_t)m * nCells1 + k] = acc;
 }
 
-struct LevelArgs {
-  int32_t p0, p1;  // entry range of the level
-  int32_t E, M, nNodes, ev0, ev1, single_node;
-  const DevEvent* events;
-  const int32_t *ent_node, *ent_link, *ent_flags, *ent_gslot, *up_ptr, *up_pos;
-  const double *C1, *C2;      // [M][nNodes], link indexed
-  const double* qout_hist;    // [nEvents][M][E]
-  double* qtr_hist;           // [RS][M][E]
-  double *qTIN, *qTR;         // [M][2][nNodes]
-  double *qMod, *qOUT;        // [M][nNodes]
-  double* qmod_g;             // [nEvents][M][nGslots]
-  int32_t nGslots;
+struct ChainArgs {
+  int32_t lane0, lane1;  // lane range of the segment level (multiples of 32)
+  int32_t ev0, ev1;      // events of the block routed by this launch (one land-cover scene)
+  int32_t rs0;           // first routing sub-step of ev0
+  int32_t rl;            // routing sub-steps per event (mo_mrm_routing.f90:224)
+  int32_t E, M, nNodes, nGslots, single_node;
+  const LaneMeta* meta;
+  const int32_t *up_ptr, *up_pos;
+  const double *C1, *C2;     // [M][nNodes], link indexed
+  const double* qout_hist;   // tiled by event
+  double* qtr_hist;          // tiled by routing sub-step
+  double *qTIN, *qTR;        // [M][2][nNodes]
+  double *qMod, *qOUT;       // [M][nNodes]
+  double* qmod_g;            // [nEvents][M][nGslots]
 };
 
-// L11_routing (mo_mrm_routing.f90:428-478) for all links of one level over a block of events
-__global__ void route_level_kernel(const LevelArgs a) {
-  const int p = a.p0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.p1) return;
+// L11_routing (mo_mrm_routing.f90:428-478) for the segments of one level over a block of
+// routing steps.  Lane j of a segment works on routing step (8 * S + d - j) in sub-step d of
+// macro step S, so that lane j-1 finished the same routing step one sub-step earlier and its
+// outflow arrives by __shfl_up.  Every lane reads its own 8-step windows (runoff, tributary
+// outflows) with static register indexing.
+__global__ void __launch_bounds__(128) route_chain_kernel(const ChainArgs a) {
+  const int p = a.lane0 + blockIdx.x * blockDim.x + threadIdx.x;  // lane0, blockDim: multiples of 32
+  if (p >= a.lane1) return;                                        // whole warps drop out together
   const int m = blockIdx.y;
-  const int node = a.ent_node[p], flags = a.ent_flags[p], gslot = a.ent_gslot[p];
-  const int u0 = a.up_ptr[p], u1 = a.up_ptr[p + 1];
-  const bool is_link = flags & kEntLink;
+  const LaneMeta lm = a.meta[p];
+  const bool valid = lm.flags & kEntValid, is_link = lm.flags & kEntLink;
+  const bool add_qout = lm.flags & kEntAddQout, zero_out = lm.flags & kEntZeroOut;
+  const bool write_hist = lm.flags & kEntWriteHist;
+  const int nup = (lm.flags >> 8) & 0xff, skew = lm.flags >> 16;
+  const int nRS = (a.ev1 - a.ev0) * a.rl;  // routing sub-steps of this launch
+  const int lmax = __reduce_max_sync(0xffffffffu, valid ? skew + 1 : 0);
   double c1 = 0.0, c2 = 0.0;
   if (is_link) {
-    const int link = a.ent_link[p];
-    c1 = a.C1[(size_t)m * a.nNodes + link];
-    c2 = a.C2[(size_t)m * a.nNodes + link];
+    c1 = a.C1[(size_t)m * a.nNodes + lm.link];
+    c2 = a.C2[(size_t)m * a.nNodes + lm.link];
   }
   double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
   double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
-  double qtin1 = tin[node], qtr1 = tr[node];  // IT1 slot
-  double qmod = 0.0, qout = 0.0;
-  for (int ev = a.ev0; ev < a.ev1; ++ev) {
-    const DevEvent e = a.events[ev];
-    qout = a.qout_hist[hidx(ev, a.M, a.E, m, p)];
-    if (a.single_node) {  // nNodes == 1: L11_Qmod = L11_qOUT (mo_mrm_routing.f90:284)
-      qmod = qout;
-    } else {
-      double acc = 0.0;
-      for (int s = 0; s < e.rout_loop; ++s) {
-        const int rs = e.rs_first + s;
-        double qin = 0.0;
-        for (int u = u0; u < u1; ++u) qin = qin + a.qtr_hist[hidx(rs, a.M, a.E, m, a.up_pos[u])];
-        if (flags & kEntAddQout) qin = qin + qout;
-        if (is_link) {
-          double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (qin - qtin1);
-          if (flags & kEntZeroOut) q = 0.0;
-          a.qtr_hist[hidx(rs, a.M, a.E, m, p)] = q;
-          qtr1 = q;
-        }
-        qtin1 = qin;
-        acc = acc + qin;
-      }
-      qmod = acc / (double)e.rout_loop;
+  double qtin1 = 0.0, qtr1 = 0.0, qout = 0.0, acc = 0.0, last_q = 0.0, qmod = 0.0;
+  if (valid) {
+    qtin1 = tin[lm.node];
+    qtr1 = tr[lm.node];
+  }
+  const double rl_dp = (double)a.rl;
+  const int u0 = nup > kMetaUps ? a.up_ptr[p] : 0;
+  const int nMacro = (nRS + lmax - 1 + kHistTile - 1) / kHistTile;
+  for (int S = 0; S < nMacro; ++S) {
+    const int base = kHistTile * S - skew;  // routing sub-step (relative to rs0) of sub-step 0
+    // ---- this lane's windows: own runoff and the outflow series it reads from memory ----
+    double qo[kHistTile], t[kMetaUps][kHistTile];
+#pragma unroll
+    for (int d = 0; d < kHistTile; ++d) {
+      const int r = base + d;
+      const bool in = valid && r >= 0 && r < nRS;
+      qo[d] = in ? a.qout_hist[hidx(a.ev0 + r / a.rl, a.M, a.E, m, p)] : 0.0;
+#pragma unroll
+      for (int u = 0; u < kMetaUps; ++u)
+        t[u][d] = (in && u < nup && lm.up[u] != kUpShuffle)
+                      ? a.qtr_hist[hidx(a.rs0 + r, a.M, a.E, m, lm.up[u])]
+                      : 0.0;
     }
-    if (gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + gslot] = qmod;
-  }
-  if (a.ev1 > a.ev0) {
-    tin[node] = qtin1;
-    tin[a.nNodes + node] = qtin1;
-    if (is_link) {
-      tr[node] = qtr1;
-      tr[a.nNodes + node] = qtr1;
-    }
-    a.qMod[(size_t)m * a.nNodes + node] = qmod;
-    a.qOUT[(size_t)m * a.nNodes + node] = qout;
-  }
-}
-
-// ---- fast path: every event is one routing step (rout_loop == 1, the usual case) ----------
-struct FastArgs {
-  int32_t p0, p1;          // entry range of the level (level kernel)
-  int32_t ev0, ev1;        // event range [ev0, ev1) of the block handled by this launch
-  int32_t E, M, nNodes, nEvents, nGslots;
-  int32_t tail_level, nLevels;
-  const EntMeta* meta;
-  const int32_t *up_ptr, *up_pos, *lvl_ptr;
-  const DevEvent* events;
-  const double *C1, *C2;
-  const double* qout_hist;  // tiled, see hidx()
-  double* qtr_hist;         // tiled
-  double *qTIN, *qTR, *qMod, *qOUT, *qmod_g;
-};
-
-__device__ __forceinline__ void load_tile(const double* src, double (&v)[kHistTile]) {
-  const double2* s2 = reinterpret_cast<const double2*>(src);
 #pragma unroll
-  for (int d = 0; d < kHistTile / 2; ++d) {
-    const double2 t = s2[d];
-    v[2 * d] = t.x;
-    v[2 * d + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void load_tile_cg(const double* src, double (&v)[kHistTile]) {
-  const double2* s2 = reinterpret_cast<const double2*>(src);
+    for (int d = 0; d < kHistTile; ++d) {
+      const double from_prev = __shfl_up_sync(0xffffffffu, last_q, 1);
+      const int r = base + d;
+      if (valid && r >= 0 && r < nRS) {
+        const int ev = a.ev0 + r / a.rl, sub = r % a.rl;
+        qout = qo[d];
+        double q_in;
+        if (a.single_node) {  // nNodes == 1: L11_Qmod = L11_qOUT (mo_mrm_routing.f90:284)
+          q_in = qout;
+        } else {
+          q_in = 0.0;  // :428, then upstream links in netPerm order :457
 #pragma unroll
-  for (int d = 0; d < kHistTile / 2; ++d) {
-    const double2 t = __ldcg(s2 + d);
-    v[2 * d] = t.x;
-    v[2 * d + 1] = t.y;
-  }
-}
-
-// sum of the upstream links' routed outflow for the 8 events of a tile, added in netPerm
-// order starting from 0 (mo_mrm_routing.f90:428,457); whole 64-byte runs per link
-template <bool CG>
-__device__ __forceinline__ void gather_upstream(const FastArgs& a, const EntMeta& em, int nup,
-                                                int m, int p, int t0, double (&qin)[kHistTile]) {
-  double t[kMetaUps][kHistTile];
-#pragma unroll
-  for (int u = 0; u < kMetaUps; ++u) {
-    if (u < nup) {
-      const double* src = a.qtr_hist + hidx(t0, a.M, a.E, m, em.up[u]);
-      if (CG) load_tile_cg(src, t[u]); else load_tile(src, t[u]);
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < kHistTile; ++d) qin[d] = 0.0;
-#pragma unroll
-  for (int u = 0; u < kMetaUps; ++u) {
-    if (u < nup) {
-#pragma unroll
-      for (int d = 0; d < kHistTile; ++d) qin[d] = qin[d] + t[u][d];
-    }
-  }
-  if (nup > kMetaUps) {  // rare: more than four inflowing links
-    const int u0 = a.up_ptr[p];
-    for (int u = kMetaUps; u < nup; ++u) {
-      double x[kHistTile];
-      load_tile_cg(a.qtr_hist + hidx(t0, a.M, a.E, m, a.up_pos[u0 + u]), x);
-#pragma unroll
-      for (int d = 0; d < kHistTile; ++d) qin[d] = qin[d] + x[d];
-    }
-  }
-}
-
-// the events [e_lo, e_hi) of one history tile for one entry; shared by both fast kernels
-struct TileState {
-  double qtin1, qtr1, qout;
-};
-__device__ __forceinline__ void route_tile(const FastArgs& a, const EntMeta& em, int m, int tile0,
-                                           int e_lo, int e_hi, double c1, double c2,
-                                           const double (&qo)[kHistTile],
-                                           const double (&qup)[kHistTile],
-                                           double (&qr)[kHistTile], TileState& st) {
-  const bool is_link = em.flags & kEntLink;
-#pragma unroll
-  for (int d = 0; d < kHistTile; ++d) {
-    const int ev = tile0 + d;
-    qr[d] = 0.0;
-    if (ev >= e_lo && ev < e_hi) {
-      double qin = qup[d];
-      st.qout = qo[d];
-      if (em.flags & kEntAddQout) qin = qin + st.qout;
-      if (is_link) {
-        double q = st.qtr1 + c1 * (st.qtin1 - st.qtr1) + c2 * (qin - st.qtin1);
-        if (em.flags & kEntZeroOut) q = 0.0;
-        qr[d] = q;
-        st.qtr1 = q;
-      }
-      st.qtin1 = qin;
-      if (em.gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + em.gslot] = qin;
-    }
-  }
-}
-
-// One wide network level: a thread owns one (entry, member), keeps qTIN/qTR in registers and
-// walks through the events [ev0, ev1) of the block, one 8-event history tile (64-byte runs of
-// its own runoff and of its first two upstream links, 128-bit loads) at a time.
-__global__ void __launch_bounds__(128, 4) route_level_fast_kernel(const FastArgs a) {
-  const int p = a.p0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.p1) return;
-  const int m = blockIdx.y;
-  const EntMeta em = a.meta[p];
-  const bool is_link = em.flags & kEntLink;
-  const int nup = em.flags >> 8;
-  double c1 = 0.0, c2 = 0.0;
-  if (is_link) {
-    c1 = a.C1[(size_t)m * a.nNodes + em.link];
-    c2 = a.C2[(size_t)m * a.nNodes + em.link];
-  }
-  double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
-  double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
-  TileState st{tin[em.node], tr[em.node], 0.0};
-  for (int t0 = a.ev0 & ~(kHistTile - 1); t0 < a.ev1; t0 += kHistTile) {
-    double qo[kHistTile], qup[kHistTile], qr[kHistTile];
-    load_tile(a.qout_hist + hidx(t0, a.M, a.E, m, p), qo);
-    gather_upstream<false>(a, em, nup, m, p, t0, qup);
-    double* own = a.qtr_hist + hidx(t0, a.M, a.E, m, p);
-    // a tile shared with the previous launch (land-cover scene change inside the tile)
-    // keeps the outflows that launch wrote
-    const bool partial = t0 < a.ev0;
-    double keep[kHistTile];
-    if (partial && is_link) load_tile(own, keep);
-    route_tile(a, em, m, t0, a.ev0, a.ev1, c1, c2, qo, qup, qr, st);
-    if (is_link) {
-      if (partial) {
-#pragma unroll
-        for (int d = 0; d < kHistTile; ++d)
-          if (t0 + d < a.ev0) qr[d] = keep[d];
-      }
-      double2* dst = reinterpret_cast<double2*>(own);
-#pragma unroll
-      for (int d = 0; d < kHistTile / 2; ++d) dst[d] = make_double2(qr[2 * d], qr[2 * d + 1]);
-    }
-  }
-  tin[em.node] = st.qtin1;
-  tin[a.nNodes + em.node] = st.qtin1;
-  if (is_link) {
-    tr[em.node] = st.qtr1;
-    tr[a.nNodes + em.node] = st.qtr1;
-  }
-  a.qMod[(size_t)m * a.nNodes + em.node] = st.qtin1;  // rout_loop == 1: qMod = qTIN(:, IT)
-  a.qOUT[(size_t)m * a.nNodes + em.node] = st.qout;
-}
-
-// The narrow, deep part of the network (levels >= tail_level, every level at most
-// kTailCluster * kTailThreads entries wide): instead of one launch per level, one thread-block
-// cluster per member walks down the levels with a hardware cluster barrier between them.
-// Thread i of the cluster owns entry i of the current level for all events of the range
-// (state in registers, exactly like route_level_fast_kernel); what the next level needs from
-// this one goes through L2 (.cg stores / loads) and is ordered by the barrier's
-// release/acquire.  The per-level cost drops from a kernel launch to a cluster barrier.
-__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThreads, 2)
-    route_tail_kernel(const FastArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ int32_t s_lvl[];  // lvl_ptr of the tail levels (or empty: read from L2)
-  const int m = blockIdx.x / kTailCluster;
-  const int ctid = (blockIdx.x % kTailCluster) * kTailThreads + threadIdx.x;
-  const int nLv = a.nLevels - a.tail_level;
-  const bool use_smem = a.p0 != 0;  // p0 doubles as "lvl_ptr fits in shared memory"
-  if (use_smem)
-    for (int i = threadIdx.x; i <= nLv; i += kTailThreads) s_lvl[i] = a.lvl_ptr[a.tail_level + i];
-  __syncthreads();
-  double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
-  double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
-  for (int l = 0; l < nLv; ++l) {
-    const int pb = use_smem ? s_lvl[l] : a.lvl_ptr[a.tail_level + l];
-    const int pe = use_smem ? s_lvl[l + 1] : a.lvl_ptr[a.tail_level + l + 1];
-    const int p = pb + ctid;
-    if (p < pe) {
-      const EntMeta em = a.meta[p];
-      const bool is_link = em.flags & kEntLink;
-      const int nup = em.flags >> 8;
-      double c1 = 0.0, c2 = 0.0;
-      if (is_link) {
-        c1 = a.C1[(size_t)m * a.nNodes + em.link];
-        c2 = a.C2[(size_t)m * a.nNodes + em.link];
-      }
-      TileState st{tin[em.node], tr[em.node], 0.0};
-      for (int t0 = a.ev0 & ~(kHistTile - 1); t0 < a.ev1; t0 += kHistTile) {
-        double qo[kHistTile], qup[kHistTile], qr[kHistTile];
-        load_tile(a.qout_hist + hidx(t0, a.M, a.E, m, p), qo);
-        gather_upstream<true>(a, em, nup, m, p, t0, qup);
-        double* own = a.qtr_hist + hidx(t0, a.M, a.E, m, p);
-        const bool partial = t0 < a.ev0;
-        double keep[kHistTile];
-        if (partial && is_link) load_tile_cg(own, keep);
-        route_tile(a, em, m, t0, a.ev0, a.ev1, c1, c2, qo, qup, qr, st);
-        if (is_link) {
-          if (partial) {
-#pragma unroll
-            for (int d = 0; d < kHistTile; ++d)
-              if (t0 + d < a.ev0) qr[d] = keep[d];
+          for (int u = 0; u < kMetaUps; ++u)
+            if (u < nup) q_in = q_in + (lm.up[u] == kUpShuffle ? from_prev : t[u][d]);
+          for (int u = kMetaUps; u < nup; ++u)
+            q_in = q_in + a.qtr_hist[hidx(a.rs0 + r, a.M, a.E, m, a.up_pos[u0 + u])];
+          if (add_qout) q_in = q_in + qout;  // :441 / :466-467
+          if (is_link) {
+            double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
+            if (zero_out) q = 0.0;                                         // :447-452
+            qtr1 = q;
+            last_q = q;
+            if (write_hist) a.qtr_hist[hidx(a.rs0 + r, a.M, a.E, m, p)] = q;
           }
-          double2* dst = reinterpret_cast<double2*>(own);
-#pragma unroll
-          for (int d = 0; d < kHistTile / 2; ++d)
-            __stcg(dst + d, make_double2(qr[2 * d], qr[2 * d + 1]));
+          qtin1 = q_in;
+        }
+        // mean over the sub-steps of the event, :263,:281
+        acc = (sub == 0 ? 0.0 : acc) + q_in;
+        if (sub == a.rl - 1) {
+          qmod = a.single_node ? qout : acc / rl_dp;
+          if (lm.gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + lm.gslot] = qmod;
         }
       }
-      tin[em.node] = st.qtin1;
-      tin[a.nNodes + em.node] = st.qtin1;
-      if (is_link) {
-        tr[em.node] = st.qtr1;
-        tr[a.nNodes + em.node] = st.qtr1;
-      }
-      a.qMod[(size_t)m * a.nNodes + em.node] = st.qtin1;
-      a.qOUT[(size_t)m * a.nNodes + em.node] = st.qout;
     }
-    cluster.sync();
+  }
+  if (valid && nRS > 0) {
+    if (!a.single_node) {
+      tin[lm.node] = qtin1;
+      tin[a.nNodes + lm.node] = qtin1;
+      if (is_link) {
+        tr[lm.node] = qtr1;
+        tr[a.nNodes + lm.node] = qtr1;
+      }
+    }
+    a.qMod[(size_t)m * a.nNodes + lm.node] = qmod;
+    a.qOUT[(size_t)m * a.nNodes + lm.node] = qout;
   }
 }
 
@@ -663,7 +486,8 @@ static int routing_order_linear(int32_t nNodes, int32_t nLinks, const int32_t* f
 
 static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const mrm_network* net) {
   const int nNodes = rt->nNodes, nLinks = rt->nLinks;
-  std::vector<int32_t> rank((size_t)nLinks), link_of_node((size_t)nNodes, -1);
+  std::vector<int32_t> rank((size_t)nLinks), link_of_node((size_t)nNodes, -1),
+      down((size_t)nNodes, -1);
   for (int k = 0; k < nLinks; ++k) {
     const int i = net->netPerm[k] - 1;
     MHM_REQUIRE(i >= 0 && i < nLinks, "set_network: netPerm(%d) = %d outside 1..%d", k + 1, i + 1,
@@ -675,6 +499,7 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
                     net->toN[i] <= nNodes,
                 "set_network: link %d has nodes outside 1..%d", i + 1, nNodes);
     link_of_node[(size_t)net->fromN[i] - 1] = i;
+    down[(size_t)net->fromN[i] - 1] = net->toN[i] - 1;
   }
   // upstream links of every node, in netPerm order
   std::vector<std::vector<int32_t>> up((size_t)nNodes);
@@ -682,56 +507,128 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     const int i = net->netPerm[k] - 1;
     up[(size_t)net->toN[i] - 1].push_back(i);
   }
-  // level of every node = longest chain of links above it; netPerm is a topological order
-  std::vector<int32_t> level((size_t)nNodes, 0);
+  // height of every node = longest chain of links above it; netPerm is a topological order
+  std::vector<int32_t> height((size_t)nNodes, 0);
   for (int k = 0; k < nLinks; ++k) {
     const int i = net->netPerm[k] - 1;
     const int f = net->fromN[i] - 1, t = net->toN[i] - 1;
     for (int j : up[(size_t)f])
       MHM_REQUIRE(rank[(size_t)j] < k, "set_network: netPerm is not a topological order");
-    level[(size_t)t] = std::max(level[(size_t)t], level[(size_t)f] + 1);
+    height[(size_t)t] = std::max(height[(size_t)t], height[(size_t)f] + 1);
   }
-  // entries: all links (key: level, rank) then outlet nodes (key: level, nLinks + node)
-  const int E = nNodes;
-  std::vector<int32_t> ent((size_t)E);
-  for (int nd = 0; nd < nNodes; ++nd) ent[(size_t)nd] = nd;
-  auto key = [&](int nd) {
-    const int l = link_of_node[(size_t)nd];
-    return l >= 0 ? rank[(size_t)l] : nLinks + nd;
-  };
-  std::sort(ent.begin(), ent.end(), [&](int x, int y) {
-    if (level[(size_t)x] != level[(size_t)y]) return level[(size_t)x] < level[(size_t)y];
-    return key(x) < key(y);
-  });
-  std::vector<int32_t> pos_of_node((size_t)nNodes);
-  for (int p = 0; p < E; ++p) pos_of_node[(size_t)ent[(size_t)p]] = p;
+  // ---- chains: every node continues the chain of its highest upstream node ----
+  std::vector<int32_t> pred((size_t)nNodes, -1);
+  for (int nd = 0; nd < nNodes; ++nd) {
+    int best = -1, cnt = 0;
+    for (int j : up[(size_t)nd]) {
+      if (cnt++ == kMetaUps) break;  // the chain predecessor must be described in LaneMeta::up
+      const int f = net->fromN[j] - 1;
+      if (best < 0 || height[(size_t)f] > height[(size_t)best]) best = f;
+    }
+    pred[(size_t)nd] = best;
+  }
+  // segments of at most kSegLen nodes; seg_of[node], pos_in_seg[node]
+  std::vector<int32_t> seg_of((size_t)nNodes, -1), pos_in((size_t)nNodes, 0);
+  std::vector<std::vector<int32_t>> seg_nodes;
+  for (int nd = 0; nd < nNodes; ++nd) {
+    if (pred[(size_t)nd] >= 0) continue;  // not a chain head
+    int x = nd, len = 0;
+    while (true) {
+      if (len % kSegLen == 0) seg_nodes.emplace_back();
+      seg_of[(size_t)x] = (int32_t)seg_nodes.size() - 1;
+      pos_in[(size_t)x] = len % kSegLen;
+      seg_nodes.back().push_back(x);
+      ++len;
+      const int dn = down[(size_t)x];
+      if (dn < 0 || pred[(size_t)dn] != x) break;
+      x = dn;
+    }
+  }
+  const int nSeg = (int)seg_nodes.size();
+  // segment levels: a segment runs after every segment it reads from memory.  Nodes sorted by
+  // height visit all inputs of a segment before the segments that depend on it.
+  std::vector<int32_t> by_height((size_t)nNodes);
+  for (int nd = 0; nd < nNodes; ++nd) by_height[(size_t)nd] = nd;
+  std::stable_sort(by_height.begin(), by_height.end(),
+                   [&](int x, int y) { return height[(size_t)x] < height[(size_t)y]; });
+  std::vector<int32_t> seg_level((size_t)nSeg, 0);
+  for (int nd : by_height) {
+    const int s = seg_of[(size_t)nd];
+    MHM_REQUIRE(s >= 0, "set_network: node %d is on no chain (cycle?)", nd + 1);
+    for (int j : up[(size_t)nd]) {
+      const int su = seg_of[(size_t)net->fromN[j] - 1];
+      if (su != s) seg_level[(size_t)s] = std::max(seg_level[(size_t)s], seg_level[(size_t)su] + 1);
+    }
+  }
+  // lanes: per level, segments by decreasing length, packed into warps (never straddling one)
+  int nLv = 0;
+  for (int s = 0; s < nSeg; ++s) nLv = std::max(nLv, seg_level[(size_t)s] + 1);
+  std::vector<std::vector<int32_t>> lv_segs((size_t)nLv);
+  for (int s = 0; s < nSeg; ++s) lv_segs[(size_t)seg_level[(size_t)s]].push_back(s);
+  std::vector<int32_t> lane_of((size_t)nNodes, -1);
+  rt->lvl_ptr.assign(1, 0);
+  int lane = 0;
+  for (int l = 0; l < nLv; ++l) {
+    auto& v = lv_segs[(size_t)l];
+    std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
+      return seg_nodes[(size_t)x].size() > seg_nodes[(size_t)y].size();
+    });
+    for (int s : v) {
+      const int len = (int)seg_nodes[(size_t)s].size();
+      if (lane % kSegLen + len > kSegLen) lane = (lane / kSegLen + 1) * kSegLen;
+      for (int x : seg_nodes[(size_t)s]) lane_of[(size_t)x] = lane++;
+    }
+    lane = (lane + kSegLen - 1) / kSegLen * kSegLen;
+    rt->lvl_ptr.push_back(lane);
+  }
+  const int E = lane;
   rt->E = E;
-  rt->lvl_ptr.clear();
-  for (int p = 0; p < E; ++p)
-    if (p == 0 || level[(size_t)ent[(size_t)p]] != level[(size_t)ent[(size_t)p - 1]])
-      rt->lvl_ptr.push_back(p);
-  rt->lvl_ptr.push_back(E);
 
   const int last_sink = nLinks > 0 ? net->toN[net->netPerm[nLinks - 1] - 1] - 1 : -1;
-  std::vector<int32_t> ent_link((size_t)E), ent_flags((size_t)E), ent_gslot((size_t)E, -1),
-      up_ptr((size_t)E + 1, 0), up_pos;
-  up_pos.reserve((size_t)nLinks);
+  std::vector<LaneMeta> meta((size_t)E);
+  std::memset(meta.data(), 0, meta.size() * sizeof(LaneMeta));
+  std::vector<int32_t> up_ptr((size_t)E + 1, 0), up_pos;
+  std::vector<int32_t> node_at((size_t)E, -1);
+  for (int nd = 0; nd < nNodes; ++nd) node_at[(size_t)lane_of[(size_t)nd]] = nd;
   for (int p = 0; p < E; ++p) {
-    const int nd = ent[(size_t)p], l = link_of_node[(size_t)nd];
-    int fl = 0;
+    LaneMeta& lm = meta[(size_t)p];
+    lm.gslot = -1;
+    const int nd = node_at[(size_t)p];
+    if (nd < 0) {
+      up_ptr[(size_t)p + 1] = (int32_t)up_pos.size();
+      continue;
+    }
+    const int l = link_of_node[(size_t)nd];
+    int fl = kEntValid;
     if (l >= 0) {
-      fl |= kEntLink | kEntAddQout;  // mo_mrm_routing.f90:441
+      fl |= kEntLink | kEntAddQout;                 // mo_mrm_routing.f90:441
       for (int g = 0; g < net->nInflowGauges; ++g)  // :447-452
         if (net->toN[l] == net->InflowGaugeNodeList[g] && !net->InflowGaugeHeadwater[g])
           fl |= kEntZeroOut;
+      // the outflow series goes to memory unless the only reader is the next lane
+      const int dn = down[(size_t)nd];
+      const bool by_shuffle = pred[(size_t)dn] == nd && seg_of[(size_t)dn] == seg_of[(size_t)nd];
+      if (!by_shuffle) fl |= kEntWriteHist;
     } else if (nd == last_sink) {
       fl |= kEntAddQout;  // :466-467: only the last link's sink adds its own runoff
     }
     for (int g = 0; g < net->nInflowGauges; ++g)
       if (net->InflowGaugeNodeList[g] - 1 == nd) fl |= kEntInflow;
-    ent_link[(size_t)p] = l >= 0 ? l : 0;
-    ent_flags[(size_t)p] = fl;
-    for (int j : up[(size_t)nd]) up_pos.push_back(pos_of_node[(size_t)net->fromN[j] - 1]);
+    const int nup = (int)up[(size_t)nd].size();
+    MHM_REQUIRE(nup < 256, "set_network: node %d has %d inflowing links", nd + 1, nup);
+    lm.node = nd;
+    lm.link = l >= 0 ? l : 0;
+    lm.flags = fl | (nup << 8) | (pos_in[(size_t)nd] << 16);
+    for (int u = 0; u < nup; ++u) {
+      const int f = net->fromN[up[(size_t)nd][(size_t)u]] - 1;
+      const bool shuffle = f == pred[(size_t)nd] && seg_of[(size_t)f] == seg_of[(size_t)nd];
+      const int src = shuffle ? kUpShuffle : lane_of[(size_t)f];
+      if (u < kMetaUps) lm.up[u] = src;
+      MHM_REQUIRE(u < kMetaUps || !shuffle,
+                  "set_network: node %d: chain predecessor beyond the %d-th inflowing link", nd + 1,
+                  kMetaUps);
+      up_pos.push_back(src);
+    }
     up_ptr[(size_t)p + 1] = (int32_t)up_pos.size();
   }
   // gauge slots: distinct gauge nodes
@@ -742,44 +639,16 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     MHM_REQUIRE(nd >= 0 && nd < nNodes, "set_network: gauge node %d outside 1..%d", nd + 1, nNodes);
     MHM_REQUIRE(net->gaugeIndexList[g] >= 1 && net->gaugeIndexList[g] <= net->nGaugesTotal,
                 "set_network: gaugeIndexList(%d) outside 1..nGaugesTotal", g + 1);
-    int32_t& s = ent_gslot[(size_t)pos_of_node[(size_t)nd]];
+    int32_t& s = meta[(size_t)lane_of[(size_t)nd]].gslot;
     if (s < 0) s = rt->nGslots++;
     gslot[(size_t)g] = s;
     gcol[(size_t)g] = net->gaugeIndexList[g] - 1;
   }
-  std::vector<EntMeta> meta((size_t)E);
-  for (int p = 0; p < E; ++p) {
-    EntMeta& em = meta[(size_t)p];
-    em.node = ent[(size_t)p];
-    em.link = ent_link[(size_t)p];
-    em.flags = ent_flags[(size_t)p];
-    em.gslot = ent_gslot[(size_t)p];
-    const int nup = up_ptr[(size_t)p + 1] - up_ptr[(size_t)p];
-    em.flags |= nup << 8;
-    for (int u = 0; u < kMetaUps; ++u)
-      em.up[u] = u < nup ? up_pos[(size_t)up_ptr[(size_t)p] + u] : 0;
-  }
-  // levels from tail_level on are all narrower than kTailMaxLevel
-  const int nLv = (int)rt->lvl_ptr.size() - 1;
-  rt->tail_level = nLv;
-  int tail_max = kTailMaxLevel;
-  if (const char* e = getenv("MHM_CUDA_TAIL_MAX")) tail_max = atoi(e);
-  tail_max = std::min(tail_max, kTailCluster * kTailThreads);
-  for (int l = nLv - 1; l >= 0; --l) {
-    if (rt->lvl_ptr[(size_t)l + 1] - rt->lvl_ptr[(size_t)l] > tail_max) break;
-    rt->tail_level = l;
-  }
-  if (nLv - rt->tail_level < 4) rt->tail_level = nLv;  // not worth a wavefront
-  if (const char* e = getenv("MHM_CUDA_NO_TAIL")) if (e[0] == '1') rt->tail_level = nLv;
   cudaStream_t st = ctx->stream;
   if (int rc = upload(&rt->meta, meta, st)) return rc;
-  if (int rc = upload(&rt->d_lvl_ptr, rt->lvl_ptr, st)) return rc;
-  if (int rc = upload(&rt->ent_node, ent, st)) return rc;
-  if (int rc = upload(&rt->ent_link, ent_link, st)) return rc;
-  if (int rc = upload(&rt->ent_flags, ent_flags, st)) return rc;
-  if (int rc = upload(&rt->ent_gslot, ent_gslot, st)) return rc;
   if (int rc = upload(&rt->up_ptr, up_ptr, st)) return rc;
   if (int rc = upload(&rt->up_pos, up_pos, st)) return rc;
+  if (int rc = upload(&rt->node_lane, lane_of, st)) return rc;
   if (int rc = upload(&rt->d_gauge_col, gcol, st)) return rc;
   if (int rc = upload(&rt->d_gauge_slot, gslot, st)) return rc;
 
@@ -804,38 +673,36 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     if (int rc = upload(&rt->L11_L1_Id, v, st)) return rc;
   }
   // one-to-one mapping between L1 cells and L11 nodes?
-  {
-    rt->bijective = false;
-    if (n1 == nNodes) {
-      std::vector<int32_t> node_of_cell((size_t)n1, -1);
-      std::vector<char> seen((size_t)nNodes, 0);
-      bool ok = true;
-      if (rt->map_flag) {
-        for (int k = 0; k < n1 && ok; ++k) {
-          const int nd = net->L1_L11_Id[k] - 1;
-          ok = !seen[(size_t)nd];
-          seen[(size_t)nd] = 1;
-          node_of_cell[(size_t)k] = nd;
-        }
-      } else {
-        for (int nd = 0; nd < nNodes && ok; ++nd) {
-          const int k = net->L11_L1_Id[nd] - 1;
-          ok = node_of_cell[(size_t)k] < 0;
-          node_of_cell[(size_t)k] = nd;
-        }
+  rt->bijective = false;
+  if (n1 == nNodes) {
+    std::vector<int32_t> node_of_cell((size_t)n1, -1);
+    std::vector<char> seen((size_t)nNodes, 0);
+    bool ok = true;
+    if (rt->map_flag) {
+      for (int k = 0; k < n1 && ok; ++k) {
+        const int nd = net->L1_L11_Id[k] - 1;
+        ok = !seen[(size_t)nd];
+        seen[(size_t)nd] = 1;
+        node_of_cell[(size_t)k] = nd;
       }
-      if (ok) {
-        std::vector<int32_t> ce((size_t)n1);
-        std::vector<double> ca((size_t)n1);
-        for (int k = 0; k < n1; ++k) {
-          const int nd = node_of_cell[(size_t)k];
-          ce[(size_t)k] = pos_of_node[(size_t)nd];
-          ca[(size_t)k] = rt->map_flag ? net->L1_areaCell[k] : net->L11_areaCell[nd];
-        }
-        if (int rc = upload(&rt->d_cell_entry, ce, st)) return rc;
-        if (int rc = upload(&rt->d_cell_area, ca, st)) return rc;
-        rt->bijective = true;
+    } else {
+      for (int nd = 0; nd < nNodes && ok; ++nd) {
+        const int k = net->L11_L1_Id[nd] - 1;
+        ok = node_of_cell[(size_t)k] < 0;
+        node_of_cell[(size_t)k] = nd;
       }
+    }
+    if (ok) {
+      std::vector<int32_t> ce((size_t)n1);
+      std::vector<double> ca((size_t)n1);
+      for (int k = 0; k < n1; ++k) {
+        const int nd = node_of_cell[(size_t)k];
+        ce[(size_t)k] = lane_of[(size_t)nd];
+        ca[(size_t)k] = rt->map_flag ? net->L1_areaCell[k] : net->L11_areaCell[nd];
+      }
+      if (int rc = upload(&rt->d_cell_entry, ce, st)) return rc;
+      if (int rc = upload(&rt->d_cell_area, ca, st)) return rc;
+      rt->bijective = true;
     }
   }
   std::vector<double> a1(net->L1_areaCell, net->L1_areaCell + n1),
@@ -887,32 +754,27 @@ static int routing_rout_loop(const Domain* d, const Routing* rt) {
   const long rl = fortran_nint(1.0 / f);
   return (int)(rl < 1 ? 1 : rl);
 }
-// aligned mode: one event per model step, one routing step per event, one cell per node
-static bool routing_aligned(const Domain* d, const Routing* rt) {
-  return rt->bijective && rt->nNodes > 1 && !routing_accumulates(d, rt) &&
-         routing_rout_loop(d, rt) == 1;
-}
 
 struct Segment {
   int32_t ev0, ev1, yId;
 };
 
-// route the events of one block.  `aligned`: one cell per node and one model step per event,
+// route the events of one block.  `per_cell`: one cell per node and one model step per event,
 // so the qOUT tiles are built by the coalesced per-cell kernel.
 static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector<DevEvent>& ev,
                       const std::vector<Segment>& segs, const std::vector<double>& inflow_val,
-                      const double* runoff_hist, bool aligned, double timestep_rout) {
+                      const double* runoff_hist, bool per_cell, double timestep_rout) {
   if (ev.empty()) return 0;
   cudaStream_t st = ctx->stream;
   const int nEv = (int)ev.size(), M = rt->M, E = rt->E;
+  const int rl = ev[0].rout_loop;
   int RS = 0;
-  bool fast = rt->nNodes > 1;
   for (auto& e : ev) {
+    MHM_REQUIRE(e.rout_loop == rl, "routing: sub-step count changes inside a block (%d vs %d)",
+                e.rout_loop, rl);
     e.rs_first = RS;
     RS += e.rout_loop;
-    fast = fast && e.rout_loop == 1;
   }
-  if (getenv("MHM_CUDA_GENERIC_ROUTING")) fast = false;
   if (int rc = ensure(&rt->d_events, &rt->ev_cap, (size_t)nEv, st)) return rc;
   if (int rc = ensure(&rt->qout_hist, &rt->qout_cap, hist_size(nEv, M, E), st)) return rc;
   if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(RS, M, E), st)) return rc;
@@ -929,45 +791,18 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
 
   ctx->stat_begin(kStatRouting);
   int64_t launched = 0;
-  const int tiles = (nEv + kHistTile - 1) / kHistTile;
-  if (aligned) {
-    QoutCellArgs qc{};
-    qc.nCells1 = rt->nCells1;
-    qc.E = E;
-    qc.M = M;
-    qc.map_flag = rt->map_flag;
-    qc.nInflowGauges = rt->nInflowGauges;
-    qc.nInflowTotal = rt->nInflowTotal;
-    qc.runoff_hist = runoff_hist;
-    qc.cell_entry = rt->d_cell_entry;
-    qc.cell_area = rt->d_cell_area;
-    qc.meta = rt->meta;
-    qc.inflow_node = rt->d_inflow_node;
-    qc.inflow_index = rt->d_inflow_index;
-    qc.inflow_head = rt->d_inflow_head;
-    for (int t0 = 0; t0 < tiles; t0 += 32768) {
-      qc.events = rt->d_events + (size_t)t0 * kHistTile;
-      qc.nEvents = nEv - t0 * kHistTile;
-      qc.inflow_val = rt->d_inflow_val + (size_t)t0 * kHistTile * rt->nInflowTotal;
-      qc.qout_hist = rt->qout_hist + hidx(t0 * kHistTile, M, E, 0, 0);
-      const int nt = std::min(32768, tiles - t0);
-      qout_cell_kernel<<<dim3((rt->nCells1 + 127) / 128, M, nt), 128, 0, st>>>(qc);
-      ++launched;
-    }
-    MHM_CUDA_OK(cudaGetLastError());
-  } else {
+  {
     QoutArgs qa{};
     qa.nCells1 = rt->nCells1;
     qa.nNodes = rt->nNodes;
     qa.E = E;
     qa.M = M;
-    qa.nEvents = nEv;
     qa.map_flag = rt->map_flag;
     qa.nInflowGauges = rt->nInflowGauges;
     qa.nInflowTotal = rt->nInflowTotal;
     qa.runoff_hist = runoff_hist;
     qa.carry = rt->carry;
-    qa.ent_node = rt->ent_node;
+    qa.meta = rt->meta;
     qa.cell_ptr = rt->cell_ptr;
     qa.cell_idx = rt->cell_idx;
     qa.L11_L1_Id = rt->L11_L1_Id;
@@ -976,14 +811,19 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
     qa.inflow_node = rt->d_inflow_node;
     qa.inflow_index = rt->d_inflow_index;
     qa.inflow_head = rt->d_inflow_head;
+    const int tiles = (nEv + kHistTile - 1) / kHistTile;
     for (int t0 = 0; t0 < tiles; t0 += 32768) {  // gridDim.z limit
-      // the kernel indexes events and history tiles from `tile`; shift all three views
+      // the kernels index events and history tiles from `tile`; shift all three views
       qa.events = rt->d_events + (size_t)t0 * kHistTile;
       qa.nEvents = nEv - t0 * kHistTile;
       qa.inflow_val = rt->d_inflow_val + (size_t)t0 * kHistTile * rt->nInflowTotal;
       qa.qout_hist = rt->qout_hist + hidx(t0 * kHistTile, M, E, 0, 0);
       const int nt = std::min(32768, tiles - t0);
-      qout_kernel<<<dim3((E + 127) / 128, M, nt), 128, 0, st>>>(qa);
+      if (per_cell)
+        qout_cell_kernel<<<dim3((rt->nCells1 + 127) / 128, M, nt), 128, 0, st>>>(
+            qa, rt->d_cell_entry, rt->d_cell_area);
+      else
+        qout_kernel<<<dim3((E + 127) / 128, M, nt), 128, 0, st>>>(qa);
       ++launched;
     }
     MHM_CUDA_OK(cudaGetLastError());
@@ -991,78 +831,35 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
 
   for (const Segment& sg : segs) {
     if (int rc = ensure_c1c2(ctx, rt, sg.yId, timestep_rout)) return rc;
-    if (fast) {
-      FastArgs fa{};
-      fa.ev0 = sg.ev0;
-      fa.ev1 = sg.ev1;
-      fa.E = E;
-      fa.M = M;
-      fa.nNodes = rt->nNodes;
-      fa.nEvents = nEv;
-      fa.nGslots = std::max(1, rt->nGslots);
-      fa.tail_level = rt->tail_level;
-      fa.nLevels = (int)rt->lvl_ptr.size() - 1;
-      fa.meta = rt->meta;
-      fa.up_ptr = rt->up_ptr;
-      fa.up_pos = rt->up_pos;
-      fa.lvl_ptr = rt->d_lvl_ptr;
-      fa.events = rt->d_events;
-      fa.C1 = rt->C1;
-      fa.C2 = rt->C2;
-      fa.qout_hist = rt->qout_hist;
-      fa.qtr_hist = rt->qtr_hist;
-      fa.qTIN = rt->qTIN;
-      fa.qTR = rt->qTR;
-      fa.qMod = rt->qMod;
-      fa.qOUT = rt->qOUT;
-      fa.qmod_g = rt->qmod_g;
-      for (int l = 0; l < rt->tail_level; ++l) {
-        fa.p0 = rt->lvl_ptr[(size_t)l];
-        fa.p1 = rt->lvl_ptr[(size_t)l + 1];
-        const int cnt = fa.p1 - fa.p0;
-        route_level_fast_kernel<<<dim3((cnt + 127) / 128, M), 128, 0, st>>>(fa);
-        ++launched;
-      }
-      if (rt->tail_level < fa.nLevels) {
-        const int nLvTail = fa.nLevels - rt->tail_level;
-        const size_t smem = (size_t)(nLvTail + 1) * sizeof(int32_t);
-        fa.p0 = smem <= 40 * 1024 ? 1 : 0;  // lvl_ptr of the tail staged in shared memory
-        route_tail_kernel<<<dim3(M * kTailCluster), kTailThreads, fa.p0 ? smem : 0, st>>>(fa);
-        ++launched;
-      }
-    } else {
-      LevelArgs la{};
-      la.E = E;
-      la.M = M;
-      la.nNodes = rt->nNodes;
-      la.ev0 = sg.ev0;
-      la.ev1 = sg.ev1;
-      la.single_node = rt->nNodes <= 1;
-      la.events = rt->d_events;
-      la.ent_node = rt->ent_node;
-      la.ent_link = rt->ent_link;
-      la.ent_flags = rt->ent_flags;
-      la.ent_gslot = rt->ent_gslot;
-      la.up_ptr = rt->up_ptr;
-      la.up_pos = rt->up_pos;
-      la.C1 = rt->C1;
-      la.C2 = rt->C2;
-      la.qout_hist = rt->qout_hist;
-      la.qtr_hist = rt->qtr_hist;
-      la.qTIN = rt->qTIN;
-      la.qTR = rt->qTR;
-      la.qMod = rt->qMod;
-      la.qOUT = rt->qOUT;
-      la.qmod_g = rt->qmod_g;
-      la.nGslots = std::max(1, rt->nGslots);
-      for (size_t l = 0; l + 1 < rt->lvl_ptr.size(); ++l) {
-        la.p0 = rt->lvl_ptr[l];
-        la.p1 = rt->lvl_ptr[l + 1];
-        const int cnt = la.p1 - la.p0;
-        const int threads = cnt >= 128 ? 128 : 32;
-        route_level_kernel<<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(la);
-        ++launched;
-      }
+    ChainArgs ca{};
+    ca.ev0 = sg.ev0;
+    ca.ev1 = sg.ev1;
+    ca.rs0 = ev[(size_t)sg.ev0].rs_first;
+    ca.rl = rl;
+    ca.E = E;
+    ca.M = M;
+    ca.nNodes = rt->nNodes;
+    ca.nGslots = std::max(1, rt->nGslots);
+    ca.single_node = rt->nNodes <= 1;
+    ca.meta = rt->meta;
+    ca.up_ptr = rt->up_ptr;
+    ca.up_pos = rt->up_pos;
+    ca.C1 = rt->C1;
+    ca.C2 = rt->C2;
+    ca.qout_hist = rt->qout_hist;
+    ca.qtr_hist = rt->qtr_hist;
+    ca.qTIN = rt->qTIN;
+    ca.qTR = rt->qTR;
+    ca.qMod = rt->qMod;
+    ca.qOUT = rt->qOUT;
+    ca.qmod_g = rt->qmod_g;
+    for (size_t l = 0; l + 1 < rt->lvl_ptr.size(); ++l) {
+      ca.lane0 = rt->lvl_ptr[l];
+      ca.lane1 = rt->lvl_ptr[l + 1];
+      const int cnt = ca.lane1 - ca.lane0;
+      const int threads = cnt >= 128 ? 128 : cnt;  // multiples of 32
+      route_chain_kernel<<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(ca);
+      ++launched;
     }
     MHM_CUDA_OK(cudaGetLastError());
   }
@@ -1079,8 +876,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
 }
 
 // routing of model steps tt_first .. tt_first+n_steps-1 whose total runoff is in
-// d->runoff_hist (or, aligned mode, already in the qOUT tiles); restates the schedule of
-// mo_mhm_interface_run.f90:460-612
+// d->runoff_hist; restates the schedule of mo_mhm_interface_run.f90:460-612
 int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_t n_steps) {
   Routing* rt = d->rt;
   MHM_REQUIRE(rt->nTimeSteps == d->axis.nTimeSteps && rt->gauge_hist,
@@ -1093,7 +889,7 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
     return rt->inflowQ[(size_t)g * rt->nDays + (size_t)(day - 1)];
   };
   const bool accumulates = routing_accumulates(d, rt);
-  const bool aligned = routing_aligned(d, rt) && !getenv("MHM_CUDA_NO_ALIGNED");
+  const bool per_cell = rt->bijective && !accumulates && !getenv("MHM_CUDA_NO_ALIGNED");
   std::vector<DevEvent> ev;
   std::vector<Segment> segs;  // runs of events of one land-cover scene (C1/C2 of case 1)
   std::vector<double> inflow_val;
@@ -1121,8 +917,8 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
         for (int g = 0; g < rt->nInflowTotal; ++g)
           rt->inflow_acc[(size_t)g] = rt->inflow_acc[(size_t)g] / fin;
         e.tst = 3600.0 * (double)(d->cfg.timestep_h * (int)fortran_nint(fin));
-        long rl = fortran_nint(1.0 / fin);
-        e.rout_loop = (int32_t)(rl < 1 ? 1 : rl);
+        long r = fortran_nint(1.0 / fin);
+        e.rout_loop = (int32_t)(r < 1 ? 1 : r);
         e.backfill = (int32_t)fortran_nint(fin);
         e.t0 = acc_t0;
         e.nacc = t - acc_t0 + 1;
@@ -1141,7 +937,7 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
     acc_t0 = t + 1;
     carry_live = false;
   }
-  if (int rc = run_events(ctx, d, rt, ev, segs, inflow_val, d->runoff_hist, aligned,
+  if (int rc = run_events(ctx, d, rt, ev, segs, inflow_val, d->runoff_hist, per_cell,
                           (double)d->cfg.timestep_h))
     return rc;
   // steps at the end of the block that wait for a later routing call
