@@ -616,7 +616,7 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
     a.nSteps = nb;
     a.tt_first = tt_first + t0;
     a.idx = d->d_idx + (tt_first + t0 - 1);
-    a.write_fluxes = 1;
+    a.write_fluxes = (t0 + nb >= n_steps) ? 1 : 0;  // fluxes of the call's last step
     a.runoff_hist = d->runoff_hist;
     if (int rc = launch_cells(ctx, d, a)) return rc;
     d->hist_steps = nb;

@@ -314,8 +314,10 @@ struct ChainArgs {
 // routing steps.  Lane j of a segment works on routing step (8 * S + d - j) in sub-step d of
 // macro step S, so that lane j-1 finished the same routing step one sub-step earlier and its
 // outflow arrives by __shfl_up.  Every lane reads its own 8-step windows (runoff, tributary
-// outflows) with static register indexing.
-__global__ void __launch_bounds__(128) route_chain_kernel(const ChainArgs a) {
+// outflows) with static register indexing; a window covers at most two 64-byte history runs.
+// RL1: one routing step per event (the usual case) -- no index divisions in the inner loops.
+template <bool RL1>
+__global__ void __launch_bounds__(128, 3) route_chain_kernel(const ChainArgs a) {
   const int p = a.lane0 + blockIdx.x * blockDim.x + threadIdx.x;  // lane0, blockDim: multiples of 32
   if (p >= a.lane1) return;                                        // whole warps drop out together
   const int m = blockIdx.y;
@@ -324,7 +326,8 @@ __global__ void __launch_bounds__(128) route_chain_kernel(const ChainArgs a) {
   const bool add_qout = lm.flags & kEntAddQout, zero_out = lm.flags & kEntZeroOut;
   const bool write_hist = lm.flags & kEntWriteHist;
   const int nup = (lm.flags >> 8) & 0xff, skew = lm.flags >> 16;
-  const int nRS = (a.ev1 - a.ev0) * a.rl;  // routing sub-steps of this launch
+  const int rl = RL1 ? 1 : a.rl;
+  const int nRS = (a.ev1 - a.ev0) * rl;  // routing sub-steps of this launch
   const int lmax = __reduce_max_sync(0xffffffffu, valid ? skew + 1 : 0);
   double c1 = 0.0, c2 = 0.0;
   if (is_link) {
@@ -338,8 +341,14 @@ __global__ void __launch_bounds__(128) route_chain_kernel(const ChainArgs a) {
     qtin1 = tin[lm.node];
     qtr1 = tr[lm.node];
   }
-  const double rl_dp = (double)a.rl;
+  const double rl_dp = (double)rl;
   const int u0 = nup > kMetaUps ? a.up_ptr[p] : 0;
+  const size_t tile_stride = (size_t)a.M * a.E * kHistTile;  // doubles between history tiles
+  const size_t lane_off = ((size_t)m * a.E + p) * kHistTile;
+  size_t up_off[kMetaUps];
+#pragma unroll
+  for (int u = 0; u < kMetaUps; ++u)
+    up_off[u] = ((size_t)m * a.E + (lm.up[u] > 0 ? lm.up[u] : 0)) * kHistTile;
   const int nMacro = (nRS + lmax - 1 + kHistTile - 1) / kHistTile;
   for (int S = 0; S < nMacro; ++S) {
     const int base = kHistTile * S - skew;  // routing sub-step (relative to rs0) of sub-step 0
@@ -349,19 +358,23 @@ __global__ void __launch_bounds__(128) route_chain_kernel(const ChainArgs a) {
     for (int d = 0; d < kHistTile; ++d) {
       const int r = base + d;
       const bool in = valid && r >= 0 && r < nRS;
-      qo[d] = in ? a.qout_hist[hidx(a.ev0 + r / a.rl, a.M, a.E, m, p)] : 0.0;
+      const int rs = a.rs0 + r;                       // absolute sub-step within the block
+      const int ev = RL1 ? a.ev0 + r : a.ev0 + r / rl;  // its event
+      const size_t oq = (size_t)(ev >> 3) * tile_stride + (size_t)(ev & 7);
+      const size_t ot = (size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7);
+      qo[d] = in ? a.qout_hist[oq + lane_off] : 0.0;
 #pragma unroll
       for (int u = 0; u < kMetaUps; ++u)
-        t[u][d] = (in && u < nup && lm.up[u] != kUpShuffle)
-                      ? a.qtr_hist[hidx(a.rs0 + r, a.M, a.E, m, lm.up[u])]
-                      : 0.0;
+        t[u][d] = (in && u < nup && lm.up[u] != kUpShuffle) ? a.qtr_hist[ot + up_off[u]] : 0.0;
     }
 #pragma unroll
     for (int d = 0; d < kHistTile; ++d) {
       const double from_prev = __shfl_up_sync(0xffffffffu, last_q, 1);
       const int r = base + d;
       if (valid && r >= 0 && r < nRS) {
-        const int ev = a.ev0 + r / a.rl, sub = r % a.rl;
+        const int rs = a.rs0 + r;
+        const int ev = RL1 ? a.ev0 + r : a.ev0 + r / rl;
+        const int sub = RL1 ? 0 : r % rl;
         qout = qo[d];
         double q_in;
         if (a.single_node) {  // nNodes == 1: L11_Qmod = L11_qOUT (mo_mrm_routing.f90:284)
@@ -372,22 +385,28 @@ __global__ void __launch_bounds__(128) route_chain_kernel(const ChainArgs a) {
           for (int u = 0; u < kMetaUps; ++u)
             if (u < nup) q_in = q_in + (lm.up[u] == kUpShuffle ? from_prev : t[u][d]);
           for (int u = kMetaUps; u < nup; ++u)
-            q_in = q_in + a.qtr_hist[hidx(a.rs0 + r, a.M, a.E, m, a.up_pos[u0 + u])];
+            q_in = q_in + a.qtr_hist[hidx(rs, a.M, a.E, m, a.up_pos[u0 + u])];
           if (add_qout) q_in = q_in + qout;  // :441 / :466-467
           if (is_link) {
             double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
             if (zero_out) q = 0.0;                                         // :447-452
             qtr1 = q;
             last_q = q;
-            if (write_hist) a.qtr_hist[hidx(a.rs0 + r, a.M, a.E, m, p)] = q;
+            if (write_hist)
+              a.qtr_hist[(size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7) + lane_off] = q;
           }
           qtin1 = q_in;
         }
         // mean over the sub-steps of the event, :263,:281
-        acc = (sub == 0 ? 0.0 : acc) + q_in;
-        if (sub == a.rl - 1) {
-          qmod = a.single_node ? qout : acc / rl_dp;
+        if (RL1) {
+          qmod = q_in;  // (0 + q) / 1
           if (lm.gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + lm.gslot] = qmod;
+        } else {
+          acc = (sub == 0 ? 0.0 : acc) + q_in;
+          if (sub == rl - 1) {
+            qmod = a.single_node ? qout : acc / rl_dp;
+            if (lm.gslot >= 0) a.qmod_g[((size_t)ev * a.M + m) * a.nGslots + lm.gslot] = qmod;
+          }
         }
       }
     }
@@ -858,7 +877,10 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
       ca.lane1 = rt->lvl_ptr[l + 1];
       const int cnt = ca.lane1 - ca.lane0;
       const int threads = cnt >= 128 ? 128 : cnt;  // multiples of 32
-      route_chain_kernel<<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(ca);
+      if (rl == 1)
+        route_chain_kernel<true><<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(ca);
+      else
+        route_chain_kernel<false><<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(ca);
       ++launched;
     }
     MHM_CUDA_OK(cudaGetLastError());
