@@ -11,7 +11,7 @@ from . import _cstruct
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 HEADER = os.path.join(ROOT, "include", "mhm_cuda.h")
-LIBPATH = os.path.join(PKG, "libmhm_cuda.so")
+LIBPATH = os.environ.get("MHM_CUDA_LIB", os.path.join(PKG, "libmhm_cuda.so"))
 
 
 class MhmCudaError(RuntimeError):

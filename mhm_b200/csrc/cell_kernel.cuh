@@ -27,6 +27,9 @@ namespace mhm {
 #ifndef MHM_FAST
 #define MHM_FAST 0
 #endif
+#ifndef MHM_CELL_MIN_BLOCKS
+#define MHM_CELL_MIN_BLOCKS 4
+#endif
 
 constexpr double kEps = 2.220446049250313e-16;  // epsilon(1.0_dp), mo_common_constants.f90:25
 constexpr double kTwoThird = 0.6666666666666666666666666666666666667;  // FORCES twothird_dp
@@ -106,40 +109,47 @@ struct CellParams {
 };
 
 // ---- one model step for one cell ---------------------------------------------------
-// fluxes of the step, kept in registers and stored only when requested
-template <int NH>
-struct CellFluxes {
-  double pet_calc, temp_calc, prec_calc, aet_canopy, aet_sealed, baseflow, fast_interflow,
-      melt, perc, prec_effect, rain, runoff_sealed, slow_interflow, snow, throughfall,
-      total_runoff, deg_day;
-  double aet_soil[NH], infiltration[NH];
-};
-
 template <int NH>
 struct CellStates {
   double inter, snowpack, sealed, unsat, sat;
   double sm[NH];
 };
 
-template <int NH>
-__device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates<NH>& s,
-                                             CellFluxes<NH>& f, const int soil_case,
-                                             const double evap_coeff
-#if MHM_FAST
-                                             , const double inv_evap_coeff
-#endif
-) {
-  const double pet = f.pet_calc, temperature = f.temp_calc, prec = f.prec_calc;
+// Fluxes leave the step through an emitter the moment they are final, so that none of them
+// has to stay in a register until the end of the time loop (they are only stored for the
+// last step of a block).
+struct FluxEmitter {
+  double* const* F;
+  size_t mc, n, mh;  // member*n + cell; nCells; (member*NH)*n + cell
+  bool on;
+  __device__ __forceinline__ void operator()(int id, double v) const {
+    if (on) F[id][mc] = v;
+  }
+  __device__ __forceinline__ void operator()(int id, int h, double v) const {
+    if (on) F[id][mh + (size_t)h * n] = v;
+  }
+};
 
+// returns total_runoff (mo_runoff.f90:271-272)
+template <int NH>
+__device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStates<NH>& s,
+                                               const double pet, const double temperature,
+                                               const double prec, const int soil_case,
+                                               const double evap_coeff,
+#if MHM_FAST
+                                               const double inv_evap_coeff,
+#endif
+                                               const FluxEmitter& emit) {
   // ---- canopy_interc, mo_canopy_interc.f90:105-131 ----
+  double throughfall, aet_canopy;
   {
     double aux = s.inter + prec;
-    double thr, ic;
+    double ic;
     if (aux >= p.maxInter) {
-      thr = aux - p.maxInter;
+      throughfall = aux - p.maxInter;
       ic = p.maxInter;
     } else {
-      thr = 0.0;
+      throughfall = 0.0;
       ic = aux;
     }
     double ev;
@@ -162,19 +172,21 @@ __device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates
       ic = 0.0;
     }
     s.inter = ic;
-    f.throughfall = thr;
-    f.aet_canopy = ev;
+    aet_canopy = ev;
+    emit(MHM_F_THROUGHFALL, throughfall);
+    emit(MHM_F_AETCANOPY, aet_canopy);
   }
 
   // ---- snow_accum_melt, mo_snow_accum_melt.f90:117-156 ----
+  double prec_effect;
   {
     const bool warm = temperature > p.tthr;
     double snow, rain, melt, dd;
     if (warm) {
       snow = 0.0;
-      rain = f.throughfall;
+      rain = throughfall;
     } else {
-      snow = f.throughfall;
+      snow = throughfall;
       rain = 0.0;
     }
     if (prec <= p.ddthr) {
@@ -200,18 +212,20 @@ __device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates
       melt = 0.0;
       s.snowpack = s.snowpack + snow;
     }
-    f.snow = snow;
-    f.rain = rain;
-    f.melt = melt;
-    f.deg_day = dd;
-    f.prec_effect = melt + rain;
+    prec_effect = melt + rain;
+    emit(MHM_F_SNOW, snow);
+    emit(MHM_F_RAIN, rain);
+    emit(MHM_F_MELT, melt);
+    emit(MHM_F_DEGDAY, dd);
+    emit(MHM_F_PREEFFECT, prec_effect);
   }
 
   // ---- soil_moisture, mo_soil_moisture.f90:179-286 ----
+  double runoff_sealed = 0.0, infil_last = 0.0;
   {
-    double runoff_sealed = 0.0, aet_sealed = 0.0;
+    double aet_sealed = 0.0;
     if (p.fSealed > 0.0) {
-      double tmp = s.sealed + f.prec_effect;
+      double tmp = s.sealed + prec_effect;
       double st;
       if (tmp > p.sealedThr) {
         runoff_sealed = tmp - p.sealedThr;
@@ -222,9 +236,9 @@ __device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates
       }
       if (p.sealedThr > kEps) {
 #if MHM_FAST
-        aet_sealed = (pet * inv_evap_coeff - f.aet_canopy) * (st * p.inv_sealedThr);
+        aet_sealed = (pet * inv_evap_coeff - aet_canopy) * (st * p.inv_sealedThr);
 #else
-        aet_sealed = (pet / evap_coeff - f.aet_canopy) * (st / p.sealedThr);
+        aet_sealed = (pet / evap_coeff - aet_canopy) * (st / p.sealedThr);
 #endif
         if (aet_sealed < 0.0) aet_sealed = 0.0;
       } else {
@@ -238,17 +252,17 @@ __device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates
       }
       s.sealed = st;
     }
-    f.runoff_sealed = runoff_sealed;
-    f.aet_sealed = aet_sealed;
+    emit(MHM_F_RUNOFFSEAL, runoff_sealed);
+    emit(MHM_F_AETSEALED, aet_sealed);
 
-    double prec_effec_soil = f.prec_effect;
+    double prec_effec_soil = prec_effect;
     double aet_pos_sum = 0.0;  // sum(aet(1:hh-1), mask = aet > 0), accumulated in index order
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) {
       double sm = s.sm[hh];
       const double sat = p.SAT[hh];
       double inf;
-      if (hh != 0) prec_effec_soil = f.infiltration[hh - 1];
+      if (hh != 0) prec_effec_soil = infil_last;
       if (sm > sat) {
         inf = prec_effec_soil;
       } else {
@@ -286,9 +300,10 @@ __device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates
         }
 #endif
       }
-      f.infiltration[hh] = inf;
+      infil_last = inf;
+      emit(MHM_F_INFILSOIL, hh, inf);
 
-      double a = pet - f.aet_canopy;
+      double a = pet - aet_canopy;
       if (hh != 0) a = a - aet_pos_sum;
       double stress;
       if (soil_case == 1 || soil_case == 4) {  // feddes_et_reduction :353-361
@@ -323,7 +338,7 @@ __device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates
         sm = kEps;
       }
       if (sm < kEps) sm = kEps;
-      f.aet_soil[hh] = a;
+      emit(MHM_F_AETSOIL, hh, a);
       s.sm[hh] = sm;
       // running masked sum in index order (bit-identical to Fortran's sum(..., mask))
       if (a > 0.0) aet_pos_sum = aet_pos_sum + a;
@@ -331,12 +346,11 @@ __device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates
   }
 
   // ---- runoff_unsat_zone, mo_runoff.f90:120-152 ----
+  double fast = 0.0, slow = 0.0;
   {
-    double us = s.unsat + f.infiltration[NH - 1];
-    double fast = 0.0;
+    double us = s.unsat + infil_last;
     if (us > p.unsatThr) fast = fmin(p.k0r * (us - p.unsatThr), us - kEps);
     us = us - fast;
-    double slow = 0.0;
     if (us > kEps) {
 #if MHM_FAST
       slow = fmin(p.k1r * exp((1.0 + p.alpha) * log(us)), us - kEps);
@@ -354,27 +368,31 @@ __device__ __forceinline__ void cascade_step(const CellParams<NH>& p, CellStates
       us = 0.0;
     }
     s.unsat = us;
-    f.fast_interflow = fast;
-    f.slow_interflow = slow;
-    f.perc = perc;
+    emit(MHM_F_FASTRUNOFF, fast);
+    emit(MHM_F_SLOWRUNOFF, slow);
+    emit(MHM_F_PERCOL, perc);
   }
   // ---- runoff_sat_zone :204-210 ----
+  double baseflow;
   if (s.sat > 0.0) {
-    f.baseflow = p.k2r * s.sat;
-    s.sat = s.sat - f.baseflow;
+    baseflow = p.k2r * s.sat;
+    s.sat = s.sat - baseflow;
   } else {
-    f.baseflow = 0.0;
+    baseflow = 0.0;
     s.sat = 0.0;
   }
+  emit(MHM_F_BASEFLOW, baseflow);
   // ---- L1_total_runoff :271-272 ----
-  f.total_runoff = ((f.baseflow + f.slow_interflow + f.fast_interflow) * (1.0 - p.fSealed)) +
-                   (f.runoff_sealed * p.fSealed);
+  const double total_runoff =
+      ((baseflow + slow + fast) * (1.0 - p.fSealed)) + (runoff_sealed * p.fSealed);
+  emit(MHM_F_TOTAL_RUNOFF, total_runoff);
+  return total_runoff;
 }
 
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldg(p); }
 
 template <int NH>
-__global__ void __launch_bounds__(kCellThreads)
+__global__ void __launch_bounds__(kCellThreads, MHM_CELL_MIN_BLOCKS)
 MHM_KERNEL_NAME(const CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
   const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
@@ -403,7 +421,6 @@ MHM_KERNEL_NAME(const CellArgs a) {
 #endif
   int cur_y = -1, cur_l = -1;
   long long cur_row = -1;
-  CellFluxes<NH> f;
   double raw_pre = 0.0, raw_temp = 0.0, raw_pet = 0.0;
 
   for (int t = 0; t < a.nSteps; ++t) {
@@ -494,27 +511,33 @@ MHM_KERNEL_NAME(const CellArgs a) {
       pet = pet_penman(fmax(rn, 0.0), raw_temp, avp / 1000.0, ar / ws, sr);
     }
     // ---- temporal disaggregation: mo_meteo_temporal_tools.f90 ----
+    double pet_calc, temp_calc, prec_calc;
     if (a.is_hourly) {
-      f.pet_calc = pet;
-      f.temp_calc = raw_temp;
-      f.prec_calc = raw_pre;
+      pet_calc = pet;
+      temp_calc = raw_temp;
+      prec_calc = raw_pre;
     } else if (a.read_weights) {
       const size_t wo = ((size_t)si.hour * 12 + month) * n + cell;
-      f.pet_calc = (pet + 0.0) * a.w_pet[wo] - 0.0;
-      f.temp_calc = (raw_temp + kT0) * a.w_temp[wo] - kT0;
-      f.prec_calc = (raw_pre + 0.0) * a.w_pre[wo] - 0.0;
+      pet_calc = (pet + 0.0) * a.w_pet[wo] - 0.0;
+      temp_calc = (raw_temp + kT0) * a.w_temp[wo] - kT0;
+      prec_calc = (raw_pre + 0.0) * a.w_pre[wo] - 0.0;
     } else if (a.nTstepDay_dp > 1.0) {
       const double fpet = si.isday ? a.tab.fday_pet[month] : a.tab.fnight_pet[month];
       const double fpre = si.isday ? a.tab.fday_prec[month] : a.tab.fnight_prec[month];
       const double ftmp = si.isday ? a.tab.fday_temp[month] : a.tab.fnight_temp[month];
-      f.pet_calc = 2.0 * pet * fpet / a.nTstepDay_dp;
-      f.prec_calc = 2.0 * raw_pre * fpre / a.nTstepDay_dp;
-      f.temp_calc = raw_temp + ftmp;
+      pet_calc = 2.0 * pet * fpet / a.nTstepDay_dp;
+      prec_calc = 2.0 * raw_pre * fpre / a.nTstepDay_dp;
+      temp_calc = raw_temp + ftmp;
     } else {
-      f.pet_calc = pet;
-      f.temp_calc = raw_temp;
-      f.prec_calc = raw_pre;
+      pet_calc = pet;
+      temp_calc = raw_temp;
+      prec_calc = raw_pre;
     }
+    const FluxEmitter emit{a.F, mc, n, (size_t)member * NH * n + cell,
+                           a.write_fluxes && t == a.nSteps - 1};
+    emit(MHM_F_PET_CALC, pet_calc);
+    emit(MHM_F_TEMP_CALC, temp_calc);
+    emit(MHM_F_PREC_CALC, prec_calc);
 
     // prefetch the next step's forcing row into L2->L1 path before the arithmetic
     if (t + 1 < a.nSteps) {
@@ -528,14 +551,15 @@ MHM_KERNEL_NAME(const CellArgs a) {
       }
     }
 
+    const double total_runoff =
+        cascade_step<NH>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case, a.tab.evap_coeff[month],
 #if MHM_FAST
-    cascade_step<NH>(p, s, f, a.soil_case, a.tab.evap_coeff[month], a.tab.inv_evap_coeff[month]);
-#else
-    cascade_step<NH>(p, s, f, a.soil_case, a.tab.evap_coeff[month]);
+                         a.tab.inv_evap_coeff[month],
 #endif
+                         emit);
 
     if (a.runoff_hist)
-      __stcs(a.runoff_hist + ((size_t)t * a.nMembers + member) * n + cell, f.total_runoff);
+      __stcs(a.runoff_hist + ((size_t)t * a.nMembers + member) * n + cell, total_runoff);
   }
 
   // ---- write back states and (optionally) the fluxes of the block's last step ----
@@ -546,30 +570,6 @@ MHM_KERNEL_NAME(const CellArgs a) {
   a.S[MHM_S_SATSTW][mc] = s.sat;
 #pragma unroll
   for (int h = 0; h < NH; ++h) a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + cell] = s.sm[h];
-  if (a.write_fluxes) {
-    a.F[MHM_F_PET_CALC][mc] = f.pet_calc;
-    a.F[MHM_F_TEMP_CALC][mc] = f.temp_calc;
-    a.F[MHM_F_PREC_CALC][mc] = f.prec_calc;
-    a.F[MHM_F_AETCANOPY][mc] = f.aet_canopy;
-    a.F[MHM_F_AETSEALED][mc] = f.aet_sealed;
-    a.F[MHM_F_BASEFLOW][mc] = f.baseflow;
-    a.F[MHM_F_FASTRUNOFF][mc] = f.fast_interflow;
-    a.F[MHM_F_MELT][mc] = f.melt;
-    a.F[MHM_F_PERCOL][mc] = f.perc;
-    a.F[MHM_F_PREEFFECT][mc] = f.prec_effect;
-    a.F[MHM_F_RAIN][mc] = f.rain;
-    a.F[MHM_F_RUNOFFSEAL][mc] = f.runoff_sealed;
-    a.F[MHM_F_SLOWRUNOFF][mc] = f.slow_interflow;
-    a.F[MHM_F_SNOW][mc] = f.snow;
-    a.F[MHM_F_THROUGHFALL][mc] = f.throughfall;
-    a.F[MHM_F_TOTAL_RUNOFF][mc] = f.total_runoff;
-    a.F[MHM_F_DEGDAY][mc] = f.deg_day;
-#pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      a.F[MHM_F_AETSOIL][((size_t)member * NH + h) * n + cell] = f.aet_soil[h];
-      a.F[MHM_F_INFILSOIL][((size_t)member * NH + h) * n + cell] = f.infiltration[h];
-    }
-  }
 }
 
 }  // namespace mhm
