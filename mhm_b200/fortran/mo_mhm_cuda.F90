@@ -1,0 +1,290 @@
+!> \file mo_mhm_cuda.F90
+!> \brief ISO_C_BINDING interface of libmhm_cuda.so (include/mhm_cuda.h) for the mHM driver.
+!> \details This module is what the reference's Fortran driver compiles (with -DMHM_CUDA) to
+!! reach the B200 implementation of the L1 hot path.  It holds only `interface ... bind(C)`
+!! blocks and thin wrappers that turn a non-zero status into the reference's own fatal path
+!! (`error_message`, FORCES mo_message).  It cannot be compiled in the build container of this
+!! repository (no Fortran compiler); it is written against the C header symbol by symbol and
+!! the same symbols are exercised through ctypes by tests/.  INTEGRATION.md shows the four
+!! call sites of the reference that use it.
+!!
+!! Conventions (see include/mhm_cuda.h): array sections are passed as the base address of the
+!! whole module-global array (c_loc of its first element), its leading dimension
+!! ld = size(array, 1) and offset = s1 - 1; logicals cross as integer(c_int32_t) 0/1.
+module mo_mhm_cuda
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+
+  public :: mhm_cuda_ctx, mhm_cuda_check
+  public :: mhm_domain_config, mhm_meteo_config, mhm_time_config, mhm_step_index, mrm_network
+
+  !> opaque library context (one per process / GPU), set by mhm_cuda_init
+  type(c_ptr), save :: mhm_cuda_ctx = c_null_ptr
+
+  ! enum mhm_param_id
+  integer(c_int32_t), parameter, public :: MHM_P_FSEALED = 0, MHM_P_ALPHA = 1, MHM_P_DEGDAYINC = 2, &
+    MHM_P_DEGDAYMAX = 3, MHM_P_DEGDAYNOPRE = 4, MHM_P_FROOTS = 5, MHM_P_MAXINTER = 6, MHM_P_KARSTLOSS = 7, &
+    MHM_P_KFASTFLOW = 8, MHM_P_KSLOWFLOW = 9, MHM_P_KBASEFLOW = 10, MHM_P_KPERCO = 11, &
+    MHM_P_SOILMOISTFC = 12, MHM_P_SOILMOISTSAT = 13, MHM_P_SOILMOISTEXP = 14, MHM_P_JARVIS_C1 = 15, &
+    MHM_P_TEMPTHRESH = 16, MHM_P_UNSATTHRESH = 17, MHM_P_SEALEDTHRESH = 18, MHM_P_WILTINGPOINT = 19, &
+    MHM_P_PETLAICORFACTOR = 20, MHM_P_FASP = 21, MHM_P_HARSAMCOEFF = 22, MHM_P_PRIETAYALPHA = 23, &
+    MHM_P_AERORESIST = 24, MHM_P_SURFRESIST = 25, MHM_P_LATITUDE = 26
+  ! enum mhm_state_id
+  integer(c_int32_t), parameter, public :: MHM_S_INTER = 0, MHM_S_SNOWPACK = 1, MHM_S_SEALSTW = 2, &
+    MHM_S_UNSATSTW = 3, MHM_S_SATSTW = 4, MHM_S_SOILMOIST = 5
+  ! enum mhm_flux_id
+  integer(c_int32_t), parameter, public :: MHM_F_PET_CALC = 0, MHM_F_TEMP_CALC = 1, MHM_F_PREC_CALC = 2, &
+    MHM_F_AETCANOPY = 3, MHM_F_AETSEALED = 4, MHM_F_BASEFLOW = 5, MHM_F_FASTRUNOFF = 6, MHM_F_MELT = 7, &
+    MHM_F_PERCOL = 8, MHM_F_PREEFFECT = 9, MHM_F_RAIN = 10, MHM_F_RUNOFFSEAL = 11, MHM_F_SLOWRUNOFF = 12, &
+    MHM_F_SNOW = 13, MHM_F_THROUGHFALL = 14, MHM_F_TOTAL_RUNOFF = 15, MHM_F_DEGDAY = 16, &
+    MHM_F_AETSOIL = 17, MHM_F_INFILSOIL = 18
+  ! enum mhm_meteo_var
+  integer(c_int32_t), parameter, public :: MHM_M_PRE = 0, MHM_M_TEMP = 1, MHM_M_PET = 2, MHM_M_TMIN = 3, &
+    MHM_M_TMAX = 4, MHM_M_NETRAD = 5, MHM_M_ABSVAPPRESS = 6, MHM_M_WINDSPEED = 7
+  ! enum mrm_state_id
+  integer(c_int32_t), parameter, public :: MRM_S_QOUT = 0, MRM_S_QTIN = 1, MRM_S_QTR = 2, MRM_S_QMOD = 3, &
+    MRM_S_C1 = 4, MRM_S_C2 = 5
+
+  type, bind(C) :: mhm_domain_config
+    integer(c_int32_t) :: nCells, nHorizons, nLAI, nLCscenes, nMembers, nProcesses, timestep_h, read_states
+    real(c_double) :: c2TSTu
+    type(c_ptr) :: processMatrix   !< c_loc(processMatrix(1,1)), int32 (nProcesses, 3)
+  end type mhm_domain_config
+
+  type, bind(C) :: mhm_meteo_config
+    integer(c_int32_t) :: pet_case, nTstepForcingDay, is_hourly_forcing, read_meteo_weights
+    real(c_double), dimension(12) :: fday_prec, fnight_prec, fday_pet, fnight_pet, fday_temp, fnight_temp, &
+                                     evap_coeff
+  end type mhm_meteo_config
+
+  type, bind(C) :: mhm_time_config
+    integer(c_int32_t) :: jul_start, nTimeSteps, warming_days, timeStep_LAI_input, lc_year_start, lc_nyears
+    type(c_ptr) :: LCyearId        !< c_loc(LCyearId(lc_year_start, iDomain))
+  end type mhm_time_config
+
+  type, bind(C) :: mhm_step_index
+    integer(c_int32_t) :: iMeteoTS, year
+    integer(c_int16_t) :: yId, iLAI, doy
+    integer(c_int8_t) :: month, hour, isday
+    integer(c_int8_t) :: pad_(3)
+  end type mhm_step_index
+
+  type, bind(C) :: mrm_network
+    integer(c_int32_t) :: nNodes, nOutlets, map_flag, nGauges, nInflowGauges, nGaugesTotal, nInflowTotal, &
+                          processCase
+    type(c_ptr) :: L1_L11_Id, L11_L1_Id, netPerm, fromN, toN, L1_areaCell, L11_areaCell, gaugeIndexList, &
+                   gaugeNodeList, InflowGaugeIndexList, InflowGaugeHeadwater, InflowGaugeNodeList
+  end type mrm_network
+
+  interface
+    integer(c_int) function mhm_cuda_init(device, ctx) bind(C, name = 'mhm_cuda_init')
+      import
+      integer(c_int), value :: device
+      type(c_ptr), intent(out) :: ctx
+    end function
+    integer(c_int) function mhm_cuda_finalize(ctx) bind(C, name = 'mhm_cuda_finalize')
+      import
+      type(c_ptr), value :: ctx
+    end function
+    type(c_ptr) function mhm_cuda_last_error() bind(C, name = 'mhm_cuda_last_error')
+      import
+    end function
+    integer(c_int) function mhm_cuda_register_domain(ctx, iDomain, cfg) bind(C, name = 'mhm_cuda_register_domain')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      type(mhm_domain_config), intent(in) :: cfg
+    end function
+    integer(c_int) function mhm_cuda_set_param(ctx, iDomain, member, param_id, base, ld, offset, dim2, dim3) &
+        bind(C, name = 'mhm_cuda_set_param')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, member, param_id, dim2, dim3
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_set_state(ctx, iDomain, member, state_id, base, ld, offset) &
+        bind(C, name = 'mhm_cuda_set_state')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, member, state_id
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_get_state(ctx, iDomain, member, state_id, base, ld, offset) &
+        bind(C, name = 'mhm_cuda_get_state')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, member, state_id
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_get_flux(ctx, iDomain, member, flux_id, base, ld, offset) &
+        bind(C, name = 'mhm_cuda_get_flux')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, member, flux_id
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_bind_host_state(ctx, iDomain, state_id, base, ld, offset) &
+        bind(C, name = 'mhm_cuda_bind_host_state')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, state_id
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_bind_host_flux(ctx, iDomain, flux_id, base, ld, offset) &
+        bind(C, name = 'mhm_cuda_bind_host_flux')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, flux_id
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_sync_to_host(ctx, iDomain) bind(C, name = 'mhm_cuda_sync_to_host')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+    end function
+    integer(c_int) function mhm_cuda_set_meteo_config(ctx, iDomain, cfg) bind(C, name = 'mhm_cuda_set_meteo_config')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      type(mhm_meteo_config), intent(in) :: cfg
+    end function
+    integer(c_int) function mhm_cuda_set_meteo(ctx, iDomain, var, base, ld, offset, first_step, n_steps) &
+        bind(C, name = 'mhm_cuda_set_meteo')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, var
+      integer(c_int64_t), value :: ld, offset, first_step, n_steps
+    end function
+    integer(c_int) function mhm_cuda_set_meteo_weights(ctx, iDomain, var, base, ld, offset) &
+        bind(C, name = 'mhm_cuda_set_meteo_weights')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, var
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_set_time(ctx, iDomain, cfg) bind(C, name = 'mhm_cuda_set_time')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      type(mhm_time_config), intent(in) :: cfg
+    end function
+    integer(c_int) function mhm_cuda_cell_step(ctx, iDomain, tt, idx) bind(C, name = 'mhm_cuda_cell_step')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain, tt
+      type(mhm_step_index), intent(in) :: idx
+    end function
+    integer(c_int) function mhm_cuda_run_steps(ctx, iDomain, tt_first, n_steps) bind(C, name = 'mhm_cuda_run_steps')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain, tt_first, n_steps
+    end function
+    integer(c_int) function mrm_cuda_set_network(ctx, iDomain, net) bind(C, name = 'mrm_cuda_set_network')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      type(mrm_network), intent(in) :: net
+    end function
+    integer(c_int) function mrm_cuda_set_reg_rout(ctx, iDomain, member, param5, length, slope, fFPimp) &
+        bind(C, name = 'mrm_cuda_set_reg_rout')
+      import
+      type(c_ptr), value :: ctx, param5, length, slope, fFPimp
+      integer(c_int32_t), value :: iDomain, member
+    end function
+    integer(c_int) function mrm_cuda_set_c1c2(ctx, iDomain, member, C1, C2, TSrout) bind(C, name = 'mrm_cuda_set_c1c2')
+      import
+      type(c_ptr), value :: ctx, C1, C2
+      integer(c_int32_t), value :: iDomain, member
+      real(c_double), value :: TSrout
+    end function
+    integer(c_int) function mrm_cuda_set_state(ctx, iDomain, member, state_id, base, ld, offset) &
+        bind(C, name = 'mrm_cuda_set_state')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, member, state_id
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mrm_cuda_get_state(ctx, iDomain, member, state_id, base, ld, offset) &
+        bind(C, name = 'mrm_cuda_get_state')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, member, state_id
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mrm_cuda_set_inflow(ctx, iDomain, Q, nDays) bind(C, name = 'mrm_cuda_set_inflow')
+      import
+      type(c_ptr), value :: ctx, Q
+      integer(c_int32_t), value :: iDomain
+      integer(c_int64_t), value :: nDays
+    end function
+    integer(c_int) function mrm_cuda_route(ctx, iDomain, member, tt, yId, RunToRout, timestep_rout, &
+                                           tsRoutFactorIn, InflowDischarge) bind(C, name = 'mrm_cuda_route')
+      import
+      type(c_ptr), value :: ctx, RunToRout, InflowDischarge
+      integer(c_int32_t), value :: iDomain, member, tt, yId, timestep_rout
+      real(c_double), value :: tsRoutFactorIn
+    end function
+    integer(c_int) function mrm_cuda_get_runoff(ctx, iDomain, member, out, ld, tt_first, n_steps) &
+        bind(C, name = 'mrm_cuda_get_runoff')
+      import
+      type(c_ptr), value :: ctx, out
+      integer(c_int32_t), value :: iDomain, member, tt_first, n_steps
+      integer(c_int64_t), value :: ld
+    end function
+    integer(c_int) function mpr_cuda_grid_create(ctx, nrows0, ncols0, mask0, nL1, upper, lower, left, right, &
+                                                 n_subcells, grid) bind(C, name = 'mpr_cuda_grid_create')
+      import
+      type(c_ptr), value :: ctx, mask0, upper, lower, left, right, n_subcells
+      integer(c_int32_t), value :: nrows0, ncols0, nL1
+      type(c_ptr), intent(out) :: grid
+    end function
+    integer(c_int) function mpr_cuda_upscale_arithmetic_mean(ctx, grid, nodata, L0_data, L1_out) &
+        bind(C, name = 'mpr_cuda_upscale_arithmetic_mean')
+      import
+      type(c_ptr), value :: ctx, grid, L0_data, L1_out
+      real(c_double), value :: nodata
+    end function
+    integer(c_int) function mpr_cuda_upscale_harmonic_mean(ctx, grid, nodata, L0_data, L1_out) &
+        bind(C, name = 'mpr_cuda_upscale_harmonic_mean')
+      import
+      type(c_ptr), value :: ctx, grid, L0_data, L1_out
+      real(c_double), value :: nodata
+    end function
+    integer(c_int) function mpr_cuda_l0_fractional_cover(ctx, grid, dataIn0, class_id, L1_out) &
+        bind(C, name = 'mpr_cuda_l0_fractional_cover')
+      import
+      type(c_ptr), value :: ctx, grid, dataIn0, L1_out
+      integer(c_int32_t), value :: class_id
+    end function
+  end interface
+
+  public :: mhm_cuda_init, mhm_cuda_finalize, mhm_cuda_register_domain, mhm_cuda_set_param, &
+            mhm_cuda_set_state, mhm_cuda_get_state, mhm_cuda_get_flux, mhm_cuda_bind_host_state, &
+            mhm_cuda_bind_host_flux, mhm_cuda_sync_to_host, mhm_cuda_set_meteo_config, mhm_cuda_set_meteo, &
+            mhm_cuda_set_meteo_weights, mhm_cuda_set_time, mhm_cuda_cell_step, mhm_cuda_run_steps, &
+            mrm_cuda_set_network, mrm_cuda_set_reg_rout, mrm_cuda_set_c1c2, mrm_cuda_set_state, &
+            mrm_cuda_get_state, mrm_cuda_set_inflow, mrm_cuda_route, mrm_cuda_get_runoff, &
+            mpr_cuda_grid_create, mpr_cuda_upscale_arithmetic_mean, mpr_cuda_upscale_harmonic_mean, &
+            mpr_cuda_l0_fractional_cover
+
+contains
+
+  !> turn a library status into the reference's fatal path (FORCES mo_message::error_message)
+  subroutine mhm_cuda_check(ierr)
+    use mo_message, only : error_message
+    integer(c_int), intent(in) :: ierr
+    character(kind = c_char), pointer :: cmsg(:)
+    character(len = 1024) :: msg
+    integer :: i
+    if (ierr == 0) return
+    call c_f_pointer(mhm_cuda_last_error(), cmsg, [1024])
+    msg = ''
+    do i = 1, 1024
+      if (cmsg(i) == c_null_char) exit
+      msg(i : i) = cmsg(i)
+    end do
+    call error_message('mhm_cuda: ', trim(msg))
+  end subroutine mhm_cuda_check
+
+end module mo_mhm_cuda
