@@ -141,10 +141,10 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from mhm_b200 import driver, interface, synth
+    from mhm_b200 import driver, ensemble, interface, synth
 
     rank = int(os.environ.get("RANK", 0))
-    local = int(os.environ.get("LOCAL_RANK", 0))
+    local = local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
     if world > 1:
@@ -193,7 +193,8 @@ def run_ours(args):
     host = {k: torch.empty((T, n), dtype=torch.float64, pin_memory=True).copy_(v) for k, v in dev.items()}
     torch.cuda.synchronize()
     nG = dom.nGaugesTotal
-    q_host = np.zeros((max(nG, 1), prob["time"]["nTimeSteps"]))
+    q_host = np.zeros((M, max(nG, 1), prob["time"]["nTimeSteps"]))
+    gathered = {}
 
     def barrier():
         ctx.synchronize()
@@ -214,7 +215,11 @@ def run_ours(args):
         dom.run_steps(first, T)
         if nG:
             for m in range(M):
-                dom.get_runoff(first, T, member=m, out=q_host)
+                dom.get_runoff(first, T, member=m, out=q_host[m])
+            # the ensemble's only exchange: every member's gauge series of the chunk on rank 0
+            local = np.ascontiguousarray(q_host[:, :, first - 1: first - 1 + T])
+            gathered["q"] = ensemble.gather_runoff(local, M * world, dist if world > 1 else None,
+                                                   device=torch.device("cuda", local_rank))
         else:
             dom.get_state("L1_satSTW")
 
