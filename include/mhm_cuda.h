@@ -327,6 +327,70 @@ int mpr_cuda_l0_fractional_cover(mhm_cuda_context *ctx, const mpr_l0_grid *grid,
                                  const int32_t *dataIn0, int32_t class_id, double *L1_out);
 
 /* ---------------------------------------------------------------------------------
+ * B4  MPR: gamma (global parameters) -> L1 effective parameters of one member on the device.
+ * Replaces `call mpr(...)` (MPR/mo_mpr_eval.f90:133-152 -> mo_multi_param_reg.f90:67-654)
+ * for iFlag_soilDB = 0 and processCase(10) = 0 (no neutrons).  The soil-class table of
+ * mpr_sm (mo_mpr_soilmoist.f90:222-324) is evaluated on the host (a few thousand entries),
+ * everything per L0 cell and every upscaling on the device.  Results land in the domain's
+ * device parameter arrays (no host round trip); mhm_cuda_get_param copies them into the
+ * L1_* module globals for restart / pybind coherence.
+ * --------------------------------------------------------------------------------- */
+typedef struct mpr_l0_inputs {
+  int32_t nrows0;                /* level0%nrows (first index) */
+  int32_t ncols0;                /* level0%ncols */
+  const int32_t *mask0;          /* level0%mask as int32 0/1, Fortran (nrows0, ncols0) */
+  const int32_t *upper_bound;    /* l0_l1_remap%upper_bound (nCells1) */
+  const int32_t *lower_bound;
+  const int32_t *left_bound;
+  const int32_t *right_bound;
+  const int32_t *n_subcells;
+  const int32_t *geoUnit0;       /* L0_geoUnit (nL0) */
+  const int32_t *soilId0;        /* L0_soilId(:, 1) (nL0) */
+  const int32_t *LCover0;        /* L0_LCover (nL0, nLCscenes) */
+  const double *Asp0;            /* L0_asp */
+  const double *slope_emp0;      /* L0_slope_emp */
+  const double *y0;              /* level0%y packed: latitude */
+  const double *gridded_LAI0;    /* L0_gridded_LAI (nL0, nLAI) */
+} mpr_l0_inputs;
+int mpr_cuda_set_l0(mhm_cuda_context *ctx, int32_t iDomain, const mpr_l0_inputs *in);
+
+typedef struct mpr_soil_db {
+  int32_t nSoilTypes;            /* size(soilDB%is_present) */
+  int32_t maxHorizons;           /* size(soilDB%sand, 2) */
+  int32_t nGeoUnits;             /* size(GeoUnitList) */
+  const int32_t *is_present;     /* (nSoilTypes) */
+  const int32_t *nHorizons;
+  const int32_t *nTillHorizons;
+  const double *sand;            /* (nSoilTypes, maxHorizons) */
+  const double *clay;
+  const double *DbM;
+  const double *Wd;              /* (nSoilTypes, nSoilHorizons_mHM, maxHorizons) */
+  const double *RZdepth;         /* (nSoilTypes) */
+  const double *HorizonDepth_mHM; /* (nSoilHorizons_mHM) */
+  const int32_t *GeoUnitList;    /* (nGeoUnits) */
+  const int32_t *GeoUnitKar;     /* (nGeoUnits) */
+  double fracSealed_CityArea;
+} mpr_soil_db;
+int mpr_cuda_set_soildb(mhm_cuda_context *ctx, int32_t iDomain, const mpr_soil_db *db);
+
+/* param = the flat global parameter vector (global_parameters(:, 3) or the optimiser's
+ * candidate), sliced inside by processMatrix exactly like the reference */
+int mpr_cuda_eval(mhm_cuda_context *ctx, int32_t iDomain, int32_t member, const double *param,
+                  int32_t nParam);
+int mhm_cuda_get_param(mhm_cuda_context *ctx, int32_t iDomain, int32_t member, int32_t param_id,
+                       double *base, int64_t ld, int64_t offset, int32_t dim2, int32_t dim3);
+
+/* init_lowres_level (common/mo_grid.f90:58-183): host helper, integer maps bit-exact.
+ * Call once with upper_bound = NULL to get nCells1 (return value written to *nCells1), then
+ * with arrays of that size.  mask arrays are Fortran (nrows, ncols) int32 0/1. */
+int mhm_grid_init_lowres_level(int32_t nrows0, int32_t ncols0, const int32_t *mask0,
+                               const double *cellArea0, double cellsize0, double target_resolution,
+                               int32_t *nrows1, int32_t *ncols1, int32_t *nCells1, int32_t *mask1,
+                               int32_t *cellCoor, double *cellArea1, int32_t *upper_bound,
+                               int32_t *lower_bound, int32_t *left_bound, int32_t *right_bound,
+                               int32_t *n_subcells, int32_t *lowres_id_on_highres);
+
+/* ---------------------------------------------------------------------------------
  * measurement hooks (bench.py): CUDA events on the library's own stream
  * --------------------------------------------------------------------------------- */
 int mhm_cuda_event_record(mhm_cuda_context *ctx, int32_t slot);            /* slot 0..15 */

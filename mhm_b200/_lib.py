@@ -38,6 +38,14 @@ class Network(C.Structure):
     _fields_ = _cstruct.parse_struct(HEADER, "mrm_network")
 
 
+class MprL0Inputs(C.Structure):
+    _fields_ = _cstruct.parse_struct(HEADER, "mpr_l0_inputs")
+
+
+class MprSoilDb(C.Structure):
+    _fields_ = _cstruct.parse_struct(HEADER, "mpr_soil_db")
+
+
 PARAM = _cstruct.parse_enum(HEADER, "mhm_param_id")
 STATE = _cstruct.parse_enum(HEADER, "mhm_state_id")
 FLUX = _cstruct.parse_enum(HEADER, "mhm_flux_id")
@@ -98,6 +106,11 @@ def load():
         "mpr_cuda_upscale_harmonic_mean": [vp, vp, d, pd, pd],
         "mpr_cuda_upscale_geometric_mean": [vp, vp, d, pd, pd],
         "mpr_cuda_l0_fractional_cover": [vp, vp, pi, i32, pd],
+        "mpr_cuda_set_l0": [vp, i32, C.POINTER(MprL0Inputs)],
+        "mpr_cuda_set_soildb": [vp, i32, C.POINTER(MprSoilDb)],
+        "mpr_cuda_eval": [vp, i32, i32, pd, i32],
+        "mhm_cuda_get_param": [vp, i32, i32, i32, pd, i64, i64, i32, i32],
+        "mhm_grid_init_lowres_level": [i32, i32, pi, pd, d, d, pi, pi, pi, pi, pi, pd, pi, pi, pi, pi, pi, pi],
         "mhm_cuda_event_record": [vp, i32],
         "mhm_cuda_event_elapsed_ms": [vp, i32, i32, pd],
         "mhm_cuda_synchronize": [vp],

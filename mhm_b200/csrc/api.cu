@@ -65,6 +65,7 @@ static void free_domain(Domain* d) {
   cudaFree(d->d_idx_one);
   cudaFree(d->runoff_hist);
   if (d->rt) routing_free(d->rt);
+  if (d->mpr) mpr_free(d->mpr);
   delete d;
 }
 

@@ -38,7 +38,8 @@ struct HostBind {
   int64_t ld = 0, offset = 0;
 };
 
-struct Routing;  // routing.cu
+struct Routing;   // routing.cu
+struct MprState;  // mpr.cu
 
 // kernel classes for mhm_cuda_kernel_stats
 enum { kStatCell = 0, kStatRouting = 1, kStatUpscale = 2, kStatCount = 3 };
@@ -79,6 +80,7 @@ struct Domain {
   int32_t hist_steps = 0, hist_tt_first = 0;
 
   Routing* rt = nullptr;
+  MprState* mpr = nullptr;
   int32_t last_yId = 1;  // scene of the last executed step (routing parameters, per-step seam)
 };
 
@@ -113,5 +115,6 @@ namespace mhm {
 Domain* find_domain(mhm_cuda_context* ctx, int32_t iDomain);
 // routing hooks used by api.cu
 void routing_free(Routing* rt);
+void mpr_free(MprState* s);
 int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_t n_steps);
 }  // namespace mhm

@@ -18,18 +18,10 @@
 
 #include "context.h"
 
-struct mpr_l0_grid {
-  int32_t nrows0 = 0, ncols0 = 0, nL1 = 0;
-  int64_t nL0 = 0;          // number of unmasked L0 cells
-  int32_t* cell_of = nullptr;  // device [ncols0][nrows0]: packed index or -1
-  int32_t *iu = nullptr, *id = nullptr, *jl = nullptr, *jr = nullptr, *nsub = nullptr;
-  double *d_in = nullptr, *d_out = nullptr;  // staging
-  int32_t* d_in_i = nullptr;
-};
+#include "upscale.h"
 
 namespace mhm {
 
-enum { kOpArith = 0, kOpHarm = 1, kOpGeom = 2, kOpFrac = 3 };
 
 struct UpArgs {
   int32_t nrows0, nL1, op, class_id;
@@ -105,16 +97,10 @@ __global__ void upscale_warp_kernel(const UpArgs a) {
   if (lane == 0) a.out[kk] = finish(a, kk, acc, cnt);
 }
 
-static int run_upscale(mhm_cuda_context* ctx, const mpr_l0_grid* g, int op, double nodata,
-                       const double* x, const int32_t* xi, int32_t class_id, double* out) {
-  MHM_REQUIRE(ctx && g && out && (x || xi), "upscale: null argument");
-  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+// device-resident operands (used by the MPR pipeline, mpr.cu)
+int upscale_device(mhm_cuda_context* ctx, const mpr_l0_grid* g, int op, double nodata,
+                   const double* d_x, const int32_t* d_xi, int32_t class_id, double* d_out) {
   cudaStream_t st = ctx->stream;
-  auto* gm = const_cast<mpr_l0_grid*>(g);
-  if (x)
-    MHM_CUDA_OK(cudaMemcpyAsync(gm->d_in, x, (size_t)g->nL0 * sizeof(double), cudaMemcpyHostToDevice, st));
-  else
-    MHM_CUDA_OK(cudaMemcpyAsync(gm->d_in_i, xi, (size_t)g->nL0 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   UpArgs a{};
   a.nrows0 = g->nrows0;
   a.nL1 = g->nL1;
@@ -127,9 +113,9 @@ static int run_upscale(mhm_cuda_context* ctx, const mpr_l0_grid* g, int op, doub
   a.jl = g->jl;
   a.jr = g->jr;
   a.nsub = g->nsub;
-  a.x = g->d_in;
-  a.xi = g->d_in_i;
-  a.out = g->d_out;
+  a.x = d_x;
+  a.xi = d_xi;
+  a.out = d_out;
   ctx->stat_begin(kStatUpscale);
   if (ctx->math_mode == 1) {
     const int warps_per_block = 8;
@@ -139,6 +125,20 @@ static int run_upscale(mhm_cuda_context* ctx, const mpr_l0_grid* g, int op, doub
   }
   ctx->stat_end(kStatUpscale);
   MHM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int run_upscale(mhm_cuda_context* ctx, const mpr_l0_grid* g, int op, double nodata,
+                       const double* x, const int32_t* xi, int32_t class_id, double* out) {
+  MHM_REQUIRE(ctx && g && out && (x || xi), "upscale: null argument");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  auto* gm = const_cast<mpr_l0_grid*>(g);
+  if (x)
+    MHM_CUDA_OK(cudaMemcpyAsync(gm->d_in, x, (size_t)g->nL0 * sizeof(double), cudaMemcpyHostToDevice, st));
+  else
+    MHM_CUDA_OK(cudaMemcpyAsync(gm->d_in_i, xi, (size_t)g->nL0 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (int rc = upscale_device(ctx, g, op, nodata, g->d_in, g->d_in_i, class_id, g->d_out)) return rc;
   MHM_CUDA_OK(cudaMemcpyAsync(out, g->d_out, (size_t)g->nL1 * sizeof(double), cudaMemcpyDeviceToHost, st));
   MHM_CUDA_OK(cudaStreamSynchronize(st));
   return 0;

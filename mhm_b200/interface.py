@@ -228,6 +228,12 @@ class Domain:
         check(self.L.mhm_cuda_set_param(self.h, self.id, member, PARAM[PARAM_NAMES[name]], _pd(arr),
                                         n, 0, dim2, dim3))
 
+    def get_param(self, name, dim2, dim3, member=0):
+        out = np.zeros((dim3, dim2, self.nCells))
+        check(self.L.mhm_cuda_get_param(self.h, self.id, member, PARAM[PARAM_NAMES[name]], _pd(out),
+                                        self.nCells, 0, dim2, dim3))
+        return out
+
     def set_state(self, name, arr, member=0):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         check(self.L.mhm_cuda_set_state(self.h, self.id, member, STATE[STATE_NAMES[name]], _pd(arr),
