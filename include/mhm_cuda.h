@@ -167,6 +167,13 @@ enum mhm_meteo_var {
 int mhm_cuda_set_meteo(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,
                        const double *base, int64_t ld, int64_t offset, int64_t first_step,
                        int64_t n_steps);
+/* same without waiting for the copy: `base` (ideally pinned memory) must stay unchanged until
+ * the next mhm_cuda_run_steps / mhm_cuda_cell_step of the domain has been issued and
+ * mhm_cuda_synchronize returned.  Uploads are double buffered and run on their own stream, so
+ * the H2D of chunk c+1 overlaps the kernels of chunk c. */
+int mhm_cuda_set_meteo_async(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,
+                             const double *base, int64_t ld, int64_t offset, int64_t first_step,
+                             int64_t n_steps);
 /* same, but `dev` is a device pointer to a dense [n_steps][nCells] array that the
  * caller keeps alive (zero copy; used when forcing is already resident in HBM) */
 int mhm_cuda_set_meteo_device(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,

@@ -80,6 +80,7 @@ def load():
         "mhm_cuda_get_flux": [vp, i32, i32, i32, pd, i64, i64],
         "mhm_cuda_set_meteo_config": [vp, i32, C.POINTER(MeteoConfig)],
         "mhm_cuda_set_meteo": [vp, i32, i32, pd, i64, i64, i64, i64],
+        "mhm_cuda_set_meteo_async": [vp, i32, i32, pd, i64, i64, i64, i64],
         "mhm_cuda_set_meteo_device": [vp, i32, i32, vp, i64, i64],
         "mhm_cuda_set_meteo_weights": [vp, i32, i32, pd, i64, i64],
         "mhm_cuda_set_time": [vp, i32, C.POINTER(TimeConfig)],

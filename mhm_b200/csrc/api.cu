@@ -58,8 +58,13 @@ static void free_domain(Domain* d) {
   for (auto& p : d->P) cudaFree(p);
   for (auto& p : d->S) cudaFree(p);
   for (auto& p : d->F) cudaFree(p);
-  for (int v = 0; v < MHM_M_COUNT; ++v)
-    if (d->met_owned[v]) cudaFree(d->met[v]);
+  for (int v = 0; v < MHM_M_COUNT; ++v) {
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(d->met_buf[v][b]);
+      if (d->met_free[v][b]) cudaEventDestroy(d->met_free[v][b]);
+    }
+    if (d->met_ready[v]) cudaEventDestroy(d->met_ready[v]);
+  }
   for (auto& p : d->weights) cudaFree(p);
   cudaFree(d->d_idx);
   cudaFree(d->d_idx_one);
@@ -127,6 +132,7 @@ int mhm_cuda_init(int device, mhm_cuda_context** out) {
   auto* ctx = new mhm_cuda_context();
   ctx->device = device;
   MHM_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  MHM_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) MHM_CUDA_OK(cudaEventCreate(&ev));
   if (const char* s = getenv("MHM_CUDA_BLOCK_BYTES")) ctx->block_bytes = (size_t)atoll(s);
   *out = ctx;
@@ -136,6 +142,7 @@ int mhm_cuda_init(int device, mhm_cuda_context** out) {
 int mhm_cuda_finalize(mhm_cuda_context* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->domains) free_domain(kv.second);
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
@@ -145,6 +152,7 @@ int mhm_cuda_finalize(mhm_cuda_context* ctx) {
   }
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return 0;
 }
@@ -193,6 +201,7 @@ int mhm_cuda_unregister_domain(mhm_cuda_context* ctx, int32_t iDomain) {
   Domain* d = find_domain(ctx, iDomain);
   if (!d) return 1;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   free_domain(d);
   ctx->domains.erase(iDomain);
@@ -328,33 +337,53 @@ int mhm_cuda_set_meteo_config(mhm_cuda_context* ctx, int32_t iDomain, const mhm_
   return 0;
 }
 
-static int meteo_store(mhm_cuda_context* ctx, Domain* d, int var, size_t rows) {
-  const size_t need = rows * (size_t)d->cfg.nCells;
-  if (!d->met_owned[var] || d->met_cap[var] < need) {
-    if (d->met_owned[var]) cudaFree(d->met[var]);
-    d->met[var] = nullptr;
-    MHM_CUDA_OK(cudaMalloc(&d->met[var], need * sizeof(double)));
-    d->met_owned[var] = true;
-    d->met_cap[var] = need;
+// upload into the buffer the in-flight block does not read; returns without waiting for the copy
+static int meteo_upload(mhm_cuda_context* ctx, Domain* d, int var, const double* base, int64_t ld,
+                        int64_t offset, int64_t first_step, int64_t n_steps) {
+  const size_t n = (size_t)d->cfg.nCells, need = (size_t)n_steps * n;
+  const int nb = d->met_owned[var] ? 1 - d->met_active[var] : 0;
+  if (d->met_bufcap[var][nb] < need) {
+    // (re)allocation: make sure nobody still reads the old allocation
+    MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    MHM_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));
+    cudaFree(d->met_buf[var][nb]);
+    d->met_buf[var][nb] = nullptr;
+    d->met_bufcap[var][nb] = 0;
+    MHM_CUDA_OK(cudaMalloc(&d->met_buf[var][nb], need * sizeof(double)));
+    d->met_bufcap[var][nb] = need;
   }
-  (void)ctx;
+  if (!d->met_ready[var]) MHM_CUDA_OK(cudaEventCreateWithFlags(&d->met_ready[var], cudaEventDisableTiming));
+  if (d->met_free_set[var][nb])  // the last run that read this buffer must be done
+    MHM_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, d->met_free[var][nb], 0));
+  MHM_CUDA_OK(cudaMemcpy2DAsync(d->met_buf[var][nb], n * sizeof(double), base + offset,
+                                (size_t)ld * sizeof(double), n * sizeof(double), (size_t)n_steps,
+                                cudaMemcpyHostToDevice, ctx->copy_stream));
+  MHM_CUDA_OK(cudaEventRecord(d->met_ready[var], ctx->copy_stream));
+  d->met_ready_set[var] = true;
+  d->met_active[var] = nb;
+  d->met_owned[var] = true;
+  d->met[var] = d->met_buf[var][nb];
+  d->met_first[var] = first_step;
+  d->met_n[var] = n_steps;
   return 0;
 }
 
-int mhm_cuda_set_meteo(mhm_cuda_context* ctx, int32_t iDomain, int32_t var, const double* base,
-                       int64_t ld, int64_t offset, int64_t first_step, int64_t n_steps) {
+int mhm_cuda_set_meteo_async(mhm_cuda_context* ctx, int32_t iDomain, int32_t var, const double* base,
+                             int64_t ld, int64_t offset, int64_t first_step, int64_t n_steps) {
   Domain* d = find_domain(ctx, iDomain);
   if (!d) return 1;
   MHM_REQUIRE(var >= 0 && var < MHM_M_COUNT, "set_meteo: bad variable %d", var);
   MHM_REQUIRE(base && ld >= d->cfg.nCells && offset >= 0 && first_step >= 1 && n_steps >= 1,
               "set_meteo: bad base/ld/offset/steps");
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
-  // the running block may still read the old chunk
-  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  if (int rc = meteo_store(ctx, d, var, (size_t)n_steps)) return rc;
-  d->met_first[var] = first_step;
-  d->met_n[var] = n_steps;
-  return h2d_rows(ctx, d->met[var], base, ld, offset, (size_t)d->cfg.nCells, (size_t)n_steps);
+  return meteo_upload(ctx, d, var, base, ld, offset, first_step, n_steps);
+}
+
+int mhm_cuda_set_meteo(mhm_cuda_context* ctx, int32_t iDomain, int32_t var, const double* base,
+                       int64_t ld, int64_t offset, int64_t first_step, int64_t n_steps) {
+  if (int rc = mhm_cuda_set_meteo_async(ctx, iDomain, var, base, ld, offset, first_step, n_steps)) return rc;
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse `base` at once
+  return 0;
 }
 
 int mhm_cuda_set_meteo_device(mhm_cuda_context* ctx, int32_t iDomain, int32_t var,
@@ -363,11 +392,8 @@ int mhm_cuda_set_meteo_device(mhm_cuda_context* ctx, int32_t iDomain, int32_t va
   if (!d) return 1;
   MHM_REQUIRE(var >= 0 && var < MHM_M_COUNT, "set_meteo_device: bad variable %d", var);
   MHM_REQUIRE(dev && first_step >= 1 && n_steps >= 1, "set_meteo_device: bad arguments");
-  MHM_CUDA_OK(cudaSetDevice(ctx->device));
-  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  if (d->met_owned[var]) cudaFree(d->met[var]);
   d->met_owned[var] = false;
-  d->met_cap[var] = 0;
+  d->met_ready_set[var] = false;
   d->met[var] = const_cast<double*>(dev);
   d->met_first[var] = first_step;
   d->met_n[var] = n_steps;
@@ -541,6 +567,25 @@ static void fill_args(mhm_cuda_context* ctx, Domain* d, CellArgs& a) {
   }
 }
 
+// the main stream must see the uploads of the forcing it is about to read
+static int meteo_acquire(mhm_cuda_context* ctx, Domain* d) {
+  for (int v = 0; v < MHM_M_COUNT; ++v)
+    if (d->met_owned[v] && d->met_ready_set[v])
+      MHM_CUDA_OK(cudaStreamWaitEvent(ctx->stream, d->met_ready[v], 0));
+  return 0;
+}
+// ... and later uploads must not overwrite a buffer a queued kernel still reads
+static int meteo_release(mhm_cuda_context* ctx, Domain* d) {
+  for (int v = 0; v < MHM_M_COUNT; ++v) {
+    if (!d->met_owned[v]) continue;
+    const int b = d->met_active[v];
+    if (!d->met_free[v][b]) MHM_CUDA_OK(cudaEventCreateWithFlags(&d->met_free[v][b], cudaEventDisableTiming));
+    MHM_CUDA_OK(cudaEventRecord(d->met_free[v][b], ctx->stream));
+    d->met_free_set[v][b] = true;
+  }
+  return 0;
+}
+
 static int launch_cells(mhm_cuda_context* ctx, Domain* d, const CellArgs& a) {
   ctx->stat_begin(kStatCell);
   int rc = ctx->math_mode == 1 ? launch_cell_block_fast(a, d->cfg.nHorizons, ctx->stream)
@@ -583,7 +628,9 @@ int mhm_cuda_cell_step(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt,
   a.runoff_hist = nullptr;
   d->last_yId = s.yId;
   d->hist_steps = 0;
-  return launch_cells(ctx, d, a);
+  if (int rc = meteo_acquire(ctx, d)) return rc;
+  if (int rc = launch_cells(ctx, d, a)) return rc;
+  return meteo_release(ctx, d);
 }
 
 int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first, int32_t n_steps) {
@@ -610,6 +657,7 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
     MHM_CUDA_OK(cudaMalloc(&d->runoff_hist, need * sizeof(double)));
     d->runoff_cap = need;
   }
+  if (int rc = meteo_acquire(ctx, d)) return rc;
   for (int32_t t0 = 0; t0 < n_steps; t0 += tb) {
     const int32_t nb = (n_steps - t0 < tb) ? n_steps - t0 : tb;
     CellArgs a;
@@ -626,7 +674,7 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
     if (d->rt)
       if (int rc = routing_run_block(ctx, d, tt_first + t0, nb)) return rc;
   }
-  return 0;
+  return meteo_release(ctx, d);
 }
 
 int mhm_cuda_get_runoff_history(mhm_cuda_context* ctx, int32_t iDomain, int32_t member,
@@ -706,6 +754,7 @@ int mhm_cuda_event_elapsed_ms(mhm_cuda_context* ctx, int32_t a, int32_t b, doubl
 int mhm_cuda_synchronize(mhm_cuda_context* ctx) {
   MHM_REQUIRE(ctx, "synchronize: null context");
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));
   MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   MHM_CUDA_OK(cudaGetLastError());
   return 0;

@@ -61,10 +61,17 @@ struct Domain {
   // meteo
   bool has_meteo_cfg = false;
   mhm_meteo_config mcfg{};
-  double* met[MHM_M_COUNT] = {};
+  double* met[MHM_M_COUNT] = {};      // buffer the next run reads (owned or bound zero-copy)
   bool met_owned[MHM_M_COUNT] = {};
-  size_t met_cap[MHM_M_COUNT] = {};  // owned capacity in doubles
   int64_t met_first[MHM_M_COUNT] = {}, met_n[MHM_M_COUNT] = {};
+  // owned forcing is double buffered: an upload goes (on the copy stream) into the buffer the
+  // running block does not read, so H2D of chunk c+1 overlaps the kernels of chunk c
+  double* met_buf[MHM_M_COUNT][2] = {};
+  size_t met_bufcap[MHM_M_COUNT][2] = {};   // capacity in doubles
+  int met_active[MHM_M_COUNT] = {};
+  cudaEvent_t met_ready[MHM_M_COUNT] = {};  // upload finished (copy stream)
+  cudaEvent_t met_free[MHM_M_COUNT][2] = {};  // last run reading the buffer finished (main stream)
+  bool met_ready_set[MHM_M_COUNT] = {}, met_free_set[MHM_M_COUNT][2] = {};
   double* weights[3] = {};
 
   // time axis
@@ -94,6 +101,7 @@ struct TimedLaunch {
 struct mhm_cuda_context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // forcing uploads
   std::map<int32_t, mhm::Domain*> domains;
   cudaEvent_t ev[16] = {};
   int math_mode = 0;

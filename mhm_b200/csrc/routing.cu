@@ -125,6 +125,14 @@ struct Routing {
   double *qout_hist = nullptr, *qtr_hist = nullptr, *qmod_g = nullptr, *d_inflow_val = nullptr;
   DevEvent* d_events = nullptr;
   size_t qout_cap = 0, qtr_cap = 0, qmodg_cap = 0, inflow_cap = 0, ev_cap = 0;
+  // pinned staging ring for the per-block event list / inflow values, so that run_steps never
+  // has to wait for the device (an upload slot is reused only after its copy has executed)
+  DevEvent* h_events[2] = {nullptr, nullptr};
+  double* h_inflow[2] = {nullptr, nullptr};
+  size_t h_ev_cap[2] = {0, 0}, h_inflow_cap[2] = {0, 0};
+  cudaEvent_t stage_done[2] = {nullptr, nullptr};
+  bool stage_set[2] = {false, false};
+  int stage_slot = 0;
 };
 
 void routing_free(Routing* rt) {
@@ -136,6 +144,11 @@ void routing_free(Routing* rt) {
                   rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry, rt->gauge_hist,
                   rt->qout_hist, rt->qtr_hist, rt->qmod_g, rt->d_inflow_val, rt->d_events};
   for (void* p : ptrs) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    cudaFreeHost(rt->h_events[i]);
+    cudaFreeHost(rt->h_inflow[i]);
+    if (rt->stage_done[i]) cudaEventDestroy(rt->stage_done[i]);
+  }
   delete rt;
 }
 
@@ -801,12 +814,34 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
     return rc;
   if (int rc = ensure(&rt->d_inflow_val, &rt->inflow_cap, std::max<size_t>(1, inflow_val.size()), st))
     return rc;
-  MHM_CUDA_OK(cudaMemcpyAsync(rt->d_events, ev.data(), (size_t)nEv * sizeof(DevEvent),
-                              cudaMemcpyHostToDevice, st));
-  if (!inflow_val.empty())
-    MHM_CUDA_OK(cudaMemcpyAsync(rt->d_inflow_val, inflow_val.data(),
-                                inflow_val.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-  MHM_CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope in the caller
+  {  // stage through pinned memory; no host-device synchronisation on the hot path
+    const int sl = rt->stage_slot;
+    rt->stage_slot ^= 1;
+    if (rt->stage_set[sl]) MHM_CUDA_OK(cudaEventSynchronize(rt->stage_done[sl]));
+    if (rt->h_ev_cap[sl] < (size_t)nEv) {
+      cudaFreeHost(rt->h_events[sl]);
+      rt->h_events[sl] = nullptr;
+      MHM_CUDA_OK(cudaHostAlloc(&rt->h_events[sl], (size_t)nEv * sizeof(DevEvent), cudaHostAllocDefault));
+      rt->h_ev_cap[sl] = (size_t)nEv;
+    }
+    if (rt->h_inflow_cap[sl] < inflow_val.size()) {
+      cudaFreeHost(rt->h_inflow[sl]);
+      rt->h_inflow[sl] = nullptr;
+      MHM_CUDA_OK(cudaHostAlloc(&rt->h_inflow[sl], inflow_val.size() * sizeof(double), cudaHostAllocDefault));
+      rt->h_inflow_cap[sl] = inflow_val.size();
+    }
+    std::memcpy(rt->h_events[sl], ev.data(), (size_t)nEv * sizeof(DevEvent));
+    MHM_CUDA_OK(cudaMemcpyAsync(rt->d_events, rt->h_events[sl], (size_t)nEv * sizeof(DevEvent),
+                                cudaMemcpyHostToDevice, st));
+    if (!inflow_val.empty()) {
+      std::memcpy(rt->h_inflow[sl], inflow_val.data(), inflow_val.size() * sizeof(double));
+      MHM_CUDA_OK(cudaMemcpyAsync(rt->d_inflow_val, rt->h_inflow[sl], inflow_val.size() * sizeof(double),
+                                  cudaMemcpyHostToDevice, st));
+    }
+    if (!rt->stage_done[sl]) MHM_CUDA_OK(cudaEventCreateWithFlags(&rt->stage_done[sl], cudaEventDisableTiming));
+    MHM_CUDA_OK(cudaEventRecord(rt->stage_done[sl], st));
+    rt->stage_set[sl] = true;
+  }
 
   ctx->stat_begin(kStatRouting);
   int64_t launched = 0;

@@ -156,6 +156,13 @@ module mo_mhm_cuda
       integer(c_int32_t), value :: iDomain, var
       integer(c_int64_t), value :: ld, offset, first_step, n_steps
     end function
+    integer(c_int) function mhm_cuda_set_meteo_async(ctx, iDomain, var, base, ld, offset, first_step, n_steps) &
+        bind(C, name = 'mhm_cuda_set_meteo_async')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, var
+      integer(c_int64_t), value :: ld, offset, first_step, n_steps
+    end function
     integer(c_int) function mhm_cuda_set_meteo_weights(ctx, iDomain, var, base, ld, offset) &
         bind(C, name = 'mhm_cuda_set_meteo_weights')
       import
@@ -262,7 +269,7 @@ module mo_mhm_cuda
   public :: mhm_cuda_init, mhm_cuda_finalize, mhm_cuda_register_domain, mhm_cuda_set_param, &
             mhm_cuda_set_state, mhm_cuda_get_state, mhm_cuda_get_flux, mhm_cuda_bind_host_state, &
             mhm_cuda_bind_host_flux, mhm_cuda_sync_to_host, mhm_cuda_set_meteo_config, mhm_cuda_set_meteo, &
-            mhm_cuda_set_meteo_weights, mhm_cuda_set_time, mhm_cuda_cell_step, mhm_cuda_run_steps, &
+            mhm_cuda_set_meteo_async, mhm_cuda_set_meteo_weights, mhm_cuda_set_time, mhm_cuda_cell_step, mhm_cuda_run_steps, &
             mrm_cuda_set_network, mrm_cuda_set_reg_rout, mrm_cuda_set_c1c2, mrm_cuda_set_state, &
             mrm_cuda_get_state, mrm_cuda_set_inflow, mrm_cuda_route, mrm_cuda_get_runoff, &
             mpr_cuda_grid_create, mpr_cuda_upscale_arithmetic_mean, mpr_cuda_upscale_harmonic_mean, &

@@ -288,10 +288,12 @@ class Domain:
         check(self.L.mhm_cuda_set_meteo(self.h, self.id, METEO[METEO_NAMES[var]], _pd(arr),
                                         self.nCells, 0, first_step, arr.shape[0]))
 
-    def set_meteo_host_ptr(self, var, ptr, ld, first_step, n_steps):
-        """upload from a raw host pointer (e.g. pinned torch tensor .data_ptr())"""
-        check(self.L.mhm_cuda_set_meteo(self.h, self.id, METEO[METEO_NAMES[var]],
-                                        C.cast(ptr, C.POINTER(C.c_double)), ld, 0, first_step, n_steps))
+    def set_meteo_host_ptr(self, var, ptr, ld, first_step, n_steps, async_copy=False):
+        """upload from a raw host pointer (e.g. pinned torch tensor .data_ptr()); async_copy:
+        return before the copy has finished (double buffered, own stream)"""
+        fn = self.L.mhm_cuda_set_meteo_async if async_copy else self.L.mhm_cuda_set_meteo
+        check(fn(self.h, self.id, METEO[METEO_NAMES[var]], C.cast(ptr, C.POINTER(C.c_double)), ld, 0,
+                 first_step, n_steps))
 
     def set_meteo_device(self, var, dev_ptr, first_step, n_steps):
         check(self.L.mhm_cuda_set_meteo_device(self.h, self.id, METEO[METEO_NAMES[var]],
