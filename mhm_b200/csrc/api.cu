@@ -4,6 +4,7 @@
 #include <mutex>
 
 #include "context.h"
+#include "fastmath.cuh"
 
 namespace mhm {
 
@@ -115,6 +116,11 @@ int mhm_cuda_context::stat_flush() {
 extern "C" {
 
 const char* mhm_cuda_last_error(void) { return g_err.c_str(); }
+
+// host instantiations of the fast kernel's math (tests/test_fastmath.py measures their error)
+double mhm_host_fast_log(double x) { return mhm::fm::log_pos(x); }
+double mhm_host_fast_exp(double x) { return mhm::fm::exp_bounded(x); }
+double mhm_host_fast_pow(double x, double y) { return mhm::fm::pow_pos(x, y); }
 const char* mhm_cuda_version(void) { return "mhm_cuda 0.1 (sm_100a)"; }
 
 int mhm_cuda_init(int device, mhm_cuda_context** out) {

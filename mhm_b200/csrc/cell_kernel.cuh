@@ -21,6 +21,7 @@
 #include <cstdint>
 
 #include "device_types.h"
+#include "fastmath.cuh"
 
 namespace mhm {
 
@@ -273,7 +274,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
           inf = 0.0;
         } else {
           double frac_runoff = 0.0;
-          if (sm > kEps) frac_runoff = exp(p.EXPN[hh] * log(sm * p.inv_SAT[hh]));
+          if (sm > kEps) frac_runoff = fm::pow_pos(sm * p.inv_SAT[hh], p.EXPN[hh]);
           double tmp = prec_effec_soil * (1.0 - frac_runoff);
           if ((sm + tmp) > sat) {
             inf = prec_effec_soil + (sm - sat);
@@ -353,7 +354,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
     us = us - fast;
     if (us > kEps) {
 #if MHM_FAST
-      slow = fmin(p.k1r * exp((1.0 + p.alpha) * log(us)), us - kEps);
+      slow = fmin(p.k1r * fm::pow_pos(us, 1.0 + p.alpha), us - kEps);
 #else
       slow = fmin(p.k1r * pow(us, 1.0 + p.alpha), us - kEps);
 #endif

@@ -1,0 +1,157 @@
+// fastmath.cuh -- fp64 log / exp / pow for the fast cell kernel.
+//
+// The cascade spends half of its instructions in exp(b * log(x)) (infiltration shape factor,
+// mo_soil_moisture.f90:233; slow interflow S**(1+alpha), mo_runoff.f90:134).  libdevice's
+// general-purpose exp/log carry special-case handling (negative, zero, infinite, subnormal
+// arguments) and materialise every polynomial coefficient with two 32-bit moves.  The
+// arguments here are known to be positive, finite and normal, and the exponents bounded, so the
+// textbook algorithms are enough:
+//   log : x = 2^e * m, m in [sqrt(1/2), sqrt(2)); s = f / (2 + f), f = m - 1;
+//         log(m) = 2s + s*R(s^2) with the degree-7 even polynomial of fdlibm's e_log.c
+//         (error < 1 ulp), assembled with the hi/lo split of ln 2;
+//   exp : k = rint(x / ln 2), r = x - k ln2 (two-constant Cody-Waite, |r| <= 0.3466),
+//         degree-13 Taylor polynomial (truncation error 4e-18), scaled by 2^k through the
+//         exponent field.
+// Coefficients live in __constant__ memory so that they enter DFMA as constant-bank operands.
+// Accuracy (tests/test_fastmath.py, 2e6 samples against glibc): log <= 1 ulp, exp <= 1 ulp,
+// pow_pos relative error <= 2.3e-16 * (1 + |y log x|).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define MHM_HD __host__ __device__ __forceinline__
+#else
+#define MHM_HD inline
+#endif
+
+namespace mhm {
+namespace fm {
+
+struct Coef {
+  double lg[7];       // Lg1..Lg7 of fdlibm e_log.c
+  double ln2_hi, ln2_lo, inv_ln2;
+  double ex[12];      // 1/2! .. 1/13!
+};
+
+#if defined(__CUDA_ARCH__)
+#define MHM_FM_COEF c_coef
+#else
+#define MHM_FM_COEF h_coef
+#endif
+
+static const Coef h_coef = {
+    {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+     2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+     1.479819860511658591e-01},
+    6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00,
+    {1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}};
+
+#if defined(__CUDACC__)
+__constant__ Coef c_coef = {
+    {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+     2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+     1.479819860511658591e-01},
+    6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00,
+    {1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}};
+#endif
+
+MHM_HD int hi_word(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  int64_t b;
+  std::memcpy(&b, &x, 8);
+  return (int)(b >> 32);
+#endif
+}
+MHM_HD int lo_word(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(x);
+#else
+  int64_t b;
+  std::memcpy(&b, &x, 8);
+  return (int)(b & 0xffffffff);
+#endif
+}
+MHM_HD double make_double(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, lo);
+#else
+  int64_t b = ((int64_t)hi << 32) | (uint32_t)lo;
+  double x;
+  std::memcpy(&x, &b, 8);
+  return x;
+#endif
+}
+MHM_HD double fma_(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
+// reciprocal to full precision for y in [1.7, 2.5): hardware seed + two Newton steps
+MHM_HD double recip(double y) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+#else
+  double r = (double)(1.0f / (float)y);
+#endif
+  r = fma_(fma_(-y, r, 1.0), r, r);
+  r = fma_(fma_(-y, r, 1.0), r, r);
+  return r;
+}
+
+// natural logarithm of a positive, finite, normal double
+MHM_HD double log_pos(double x) {
+  int hi = hi_word(x);
+  const int lo = lo_word(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;  // m in [1, 2)
+  if (hi >= 0x3ff6a09f) {               // m >= sqrt(2): halve it
+    hi -= 0x00100000;
+    e += 1;
+  }
+  const double f = make_double(hi, lo) - 1.0;
+  const double s = f * recip(2.0 + f);
+  const double z = s * s, w = z * z;
+  const Coef& c = MHM_FM_COEF;
+  const double t1 = w * fma_(w, fma_(w, c.lg[5], c.lg[3]), c.lg[1]);
+  const double t2 = z * fma_(w, fma_(w, fma_(w, c.lg[6], c.lg[4]), c.lg[2]), c.lg[0]);
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  const double dk = (double)e;
+  // e*ln2_hi - ((hfsq - (s*(hfsq + R) + e*ln2_lo)) - f)
+  return fma_(dk, c.ln2_hi, -((hfsq - fma_(s, hfsq + R, dk * c.ln2_lo)) - f));
+}
+
+// exp(x) for |x| < 700
+MHM_HD double exp_bounded(double x) {
+  const Coef& c = MHM_FM_COEF;
+#if defined(__CUDA_ARCH__)
+  const double kd = rint(x * c.inv_ln2);
+#else
+  const double kd = __builtin_rint(x * c.inv_ln2);
+#endif
+  double r = fma_(-kd, c.ln2_hi, x);
+  r = fma_(-kd, c.ln2_lo, r);
+  double p = c.ex[11];
+#pragma unroll
+  for (int i = 10; i >= 0; --i) p = fma_(p, r, c.ex[i]);
+  p = fma_(p * r, r, r);  // r + r^2 * P(r)
+  const int k = (int)kd;
+  // 2^k through the exponent field; split in two factors so that k down to -1070 stays exact
+  const int k1 = k / 2, k2 = k - k1;
+  const double s1 = make_double((k1 + 1023) << 20, 0), s2 = make_double((k2 + 1023) << 20, 0);
+  return fma_(p, s1, s1) * s2;  // (1 + p) * 2^k1 * 2^k2
+}
+
+// x ** y for x > 0 (finite, normal), |y log x| < 700
+MHM_HD double pow_pos(double x, double y) { return exp_bounded(y * log_pos(x)); }
+
+}  // namespace fm
+}  // namespace mhm

@@ -1,0 +1,41 @@
+"""Accuracy of the fast cell kernel's log / exp / pow (mhm_b200/csrc/fastmath.cuh) -- their host
+instantiations, exported by the library for this test -- against glibc on ~1e6 samples."""
+import ctypes as C
+
+import numpy as np
+
+from mhm_b200 import _lib
+
+
+def ulp_err(got, ref):
+    return np.abs(got - ref) / np.spacing(np.abs(ref))
+
+
+def test_fast_log_exp_pow_accuracy():
+    L = _lib.load()
+    for f, n in (("mhm_host_fast_log", 1), ("mhm_host_fast_exp", 1), ("mhm_host_fast_pow", 2)):
+        getattr(L, f).restype = C.c_double
+        getattr(L, f).argtypes = [C.c_double] * n
+    rng = np.random.default_rng(0)
+    N = 200000
+    # log over the kernel's argument range: ratios sm/sat in (1e-18, 1], storages up to 1e5
+    x = np.concatenate([10.0 ** rng.uniform(-18, 5, N), rng.uniform(0.5, 2.0, N), 1.0 + rng.normal(0, 1e-6, 1000)])
+    got = np.array([L.mhm_host_fast_log(v) for v in x])
+    ref = np.log(x)
+    e = ulp_err(got[ref != 0], ref[ref != 0])
+    assert e.max() <= 1.0, e.max()
+    # exp over the exponent range of b*log(ratio) and (1+alpha)*log(S)
+    t = np.concatenate([rng.uniform(-300, 30, N), rng.uniform(-1, 1, N)])
+    got = np.array([L.mhm_host_fast_exp(v) for v in t])
+    e = ulp_err(got, np.exp(t))
+    assert e.max() <= 1.0, e.max()
+    # pow: exp(y*log x) as the reference writes it; the rounding of log and of the product are
+    # amplified by |y log x|: relative error <= 2.3e-16 * (1 + |y log x|)
+    xs = np.concatenate([rng.uniform(1e-6, 1.0, N), rng.uniform(1e-12, 5e3, N)])
+    ys = np.concatenate([rng.uniform(1.5, 6.0, N), rng.uniform(1.05, 1.6, N)])
+    got = np.array([L.mhm_host_fast_pow(a, b) for a, b in zip(xs, ys)])
+    ref = np.power(xs, ys)
+    rel = np.abs(got - ref) / ref
+    bound = 2.3e-16 * (1.0 + np.abs(ys * np.log(xs)))
+    assert (rel <= bound).all(), (rel / bound).max()
+    assert L.mhm_host_fast_pow(1.0, 3.7) == 1.0 and L.mhm_host_fast_exp(0.0) == 1.0
