@@ -1,0 +1,74 @@
+"""Load a golden fixture (tests/golden/case_*.npz, made by tests/golden/make_golden.py from the
+reference's own saved outputs) as a problem dict in the mhm_b200.synth layout, plus the
+reference's results to compare against."""
+import datetime
+import os
+
+import numpy as np
+
+from mhm_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(case):
+    z = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    soil_case, pet_case, rout_case = [int(x) for x in z["cases"]]
+    P = {k[6:]: z[k] for k in z.files if k.startswith("param/")}
+    n = P["L1_fSealed"].shape[-1]
+    nH = P["L1_soilMoistSat"].shape[1]
+    nLC = P["L1_fSealed"].shape[0]
+    nLAI = P["L1_maxInter"].shape[1]
+    ordinal0, n_days, warming = [int(x) for x in z["time"]]
+    d0 = datetime.date.fromordinal(ordinal0)
+    prob = {"nH": nH, "nLAI": nLAI, "nLC": nLC, "timestep_h": 1, "hourly": False,
+            "soil_case": soil_case, "pet_case": pet_case, "rout_case": rout_case,
+            "read_weights": False, "nCells": n, "nTstepForcingDay": 1}
+    prob["processMatrix"] = synth.process_matrix(soil_case, pet_case, rout_case)
+    lc = z["lc_years"]
+    prob["time"] = {"jul_start": synth.JUL_1990_01_01 + (d0 - datetime.date(1990, 1, 1)).days,
+                    "nTimeSteps": n_days * 24, "warming_days": warming, "timeStep_LAI_input": 0,
+                    "lc_year_start": int(lc[0]), "LCyearId": np.asarray(lc[1:], dtype=np.int32)}
+    # parameters the cascade does not use in this process selection still need storage
+    full = synth.make_params(np.random.default_rng(0), n, nH, nLAI, nLC, pet_case)
+    P["latitude"] = z["L1_lat"][None, None, :]
+    for k, v in full.items():
+        if k not in P:
+            P[k] = v
+        assert P[k].shape == v.shape, (k, P[k].shape, v.shape)
+    prob["params"] = {k: np.ascontiguousarray(v) for k, v in P.items()}
+    prob["forcing"] = {k[8:]: np.ascontiguousarray(z[k]) for k in z.files if k.startswith("forcing/")}
+    prob["horizon_depth"] = np.ascontiguousarray(z["horizon_bnds"][:, 1])
+    prob["states0"] = synth.default_states(n, nH, prob["horizon_depth"])
+    if rout_case == 0:
+        prob["net"] = None
+        ref = {"final": {k[6:]: z[k] for k in z.files if k.startswith("final/")},
+               "warming_days": warming, "n_days": n_days}
+        return prob, ref
+    nn = int(z["net/mask11"].sum())
+    nLinks = int((z["net/L11_fromN"] > 0).sum())
+    net = {"nNodes": nn, "nOutlets": nn - nLinks, "nCells1": n, "map_flag": 1,
+           "fromN": z["net/L11_fromN"], "toN": z["net/L11_toN"], "netPerm": z["net/L11_netPerm"],
+           "rOrder": z["net/L11_rOrder"], "L1_L11_Id": z["net/L1_L11_Id"],
+           "L11_L1_Id": np.where(z["net/L11_L1_Id"] > 0, z["net/L11_L1_Id"], 1), "L1_areaCell": z["L1_areaCell_km2"],
+           "L11_areaCell": z["net/L11_areaCell_km2"], "gaugeNodeList": z["net/gaugeNodeList"],
+           "gaugeIndexList": np.arange(1, len(z["net/gaugeNodeList"]) + 1, dtype=np.int32),
+           "nGaugesTotal": len(z["net/gaugeNodeList"]),
+           "InflowGaugeNodeList": np.zeros(0, np.int32), "InflowGaugeIndexList": np.zeros(0, np.int32),
+           "InflowGaugeHeadwater": np.zeros(0, np.int32), "nInflowTotal": 0, "processCase": rout_case,
+           "L11_length": z["net/L11_length"], "L11_slope": z["net/L11_slope"],
+           "L11_nLinkFracFPimp": z["net/L11_nLinkFracFPimp"], "rout_param": z["rout_param"],
+           "TSrout": int(z["net/L11_TSrout"][0]), "celerity": float(z["celerity"][0])}
+    net = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in net.items()}
+    prob["net"] = net
+    prob["inflowQ"] = np.zeros((0, n_days))
+    ref = {"final": {k[6:]: z[k] for k in z.files if k.startswith("final/")},
+           "Qsim": np.stack([z[k] for k in z.files if k.startswith("Qsim/")]),
+           "Qsim_text": z["Qsim_text"].T, "warming_days": warming, "n_days": n_days}
+    return prob, ref
+
+
+def daily_mean(mRM_runoff, warming_days, nTstepDay=24):
+    """mRM/mo_mrm_write.f90:142-150: mean of the model steps of each day after the warming"""
+    q = np.asarray(mRM_runoff)[:, warming_days * nTstepDay:]
+    return q.reshape(q.shape[0], -1, nTstepDay).sum(axis=2) / float(nTstepDay)
