@@ -65,6 +65,26 @@ def gamma_group(par_nml, group):
     return np.array(vals)
 
 
+def gamma_vector(par_nml, cases):
+    """the flat global parameter vector and processMatrix (numpy (3, 11)) for a process selection,
+    assembled in process order like MPR/mo_mpr_read_config.f90:390-988"""
+    soil, pet, rout = cases
+    groups = ["interception1", "snow1", "soilmoisture%d" % soil, "directRunoff1",
+              {-1: "PETminus1", 0: "PET0", 1: "PET1", 2: "PET2", 3: "PET3"}[pet], "interflow1",
+              "percolation1", {0: None, 1: "routing1", 2: "routing2", 3: "routing3"}[rout], "geoparameter"]
+    case_of = [1, 1, soil, 1, pet, 1, 1, rout, 1]
+    pm = np.zeros((3, 11), dtype=np.int32)
+    vals, end = [], 0
+    for p, (g, c) in enumerate(zip(groups, case_of)):
+        v = [] if g is None else list(gamma_group(par_nml, g))
+        vals += v
+        end += len(v)
+        pm[:, p] = [c, len(v), end]
+    pm[:, 9] = [0, 0, end]
+    pm[:, 10] = [0, 0, end]
+    return np.array(vals), pm
+
+
 def make_case(case, sim_start, n_days, warming_days, lc_years, cases=(1, 0, 1), out_prefix="b1",
               restart_id="001", name=None):
     """cases = processCase(3) soil moisture, (5) PET, (8) routing of the check case's mhm.nml"""
@@ -110,6 +130,7 @@ def make_case(case, sim_start, n_days, warming_days, lc_years, cases=(1, 0, 1), 
                 out["Qsim/" + k[5:]] = q[k].read()
         txt = np.loadtxt(os.path.join(sav, "%s_daily_discharge.out" % out_prefix), skiprows=1)
         out["Qsim_text"] = txt[:, 5::2]
+    out["gamma"], out["processMatrix"] = gamma_vector(os.path.join(cdir, "mhm_parameter.nml"), cases)
     out["time"] = np.array([sim_start.toordinal(), n_days, warming_days])
     out["lc_years"] = np.array(lc_years, dtype=np.int32)   # (first year, LCyearId...)
     name = name or case

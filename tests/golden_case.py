@@ -72,3 +72,37 @@ def daily_mean(mRM_runoff, warming_days, nTstepDay=24):
     """mRM/mo_mrm_write.f90:142-150: mean of the model steps of each day after the warming"""
     q = np.asarray(mRM_runoff)[:, warming_days * nTstepDay:]
     return q.reshape(q.shape[0], -1, nTstepDay).sum(axis=2) / float(nTstepDay)
+
+
+def load_mpr(case, init_lowres_level):
+    """MPR problem (mhm_b200.synth_mpr layout) for the test basin with the gamma vector of a
+    check case, and the L1 effective parameters the reference's MPR produced for it.
+    init_lowres_level(mask0, cellsize0, target_resolution, cell_area0) -> grid dict: the
+    oracle's or the library's restatement of common/mo_grid.f90:58-183."""
+    z0 = np.load(os.path.join(HERE, "golden", "test_domain_l0.npz"))
+    zc = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    soil_case, pet_case, _ = [int(x) for x in zc["cases"]]
+    mask0 = z0["mask0"]
+    n0 = int(mask0.sum())
+    cs0 = float(z0["cellsize0"])
+    mask1 = zc["mask1"]
+    target = cs0 * mask0.shape[0] / mask1.shape[0]
+    grid = init_lowres_level(mask0, cs0, target, np.full(n0, cs0 * cs0))
+    db = {k[5:]: z0[k] for k in z0.files if k.startswith("soil/")}
+    db["nSoil"], db["maxHor"] = int(db["nSoil"]), int(db["maxHor"])
+    db["is_present"] = z0["is_present"]
+    nH = zc["param/L1_soilMoistSat"].shape[1]
+    hd = np.array(zc["horizon_bnds"][:, 1], dtype=np.float64)
+    hd[nH - 1] = float(db.pop("HorizonDepth_last"))
+    prob = {"nrows0": mask0.shape[1], "ncols0": mask0.shape[0], "nL0": n0,
+            "mask0": np.ascontiguousarray(mask0, dtype=np.int32), "grid": grid, "nL1": grid["nCells1"],
+            "nLC": z0["LCover0"].shape[0], "nLAI": 12, "nH": nH, "geoUnit0": z0["geoUnit0"],
+            "soilId0": z0["soilId0"], "LCover0": z0["LCover0"], "Asp0": z0["Asp0"],
+            "slope_emp0": z0["slope_emp0"], "y0": z0["y0"], "LAI0": z0["LAI0"], "soil_db": db,
+            "HorizonDepth": hd, "GeoUnitList": z0["GeoUnitList"], "GeoUnitKar": z0["GeoUnitKar"],
+            "fracSealed_CityArea": float(z0["fracSealed_CityArea"]), "param": zc["gamma"],
+            "processMatrix": zc["processMatrix"], "soil_case": soil_case, "pet_case": pet_case}
+    ref = {k[6:]: zc[k] for k in zc.files if k.startswith("param/")}
+    ref["mask1"] = mask1
+    ref["L1_areaCell_km2"] = zc["L1_areaCell_km2"]
+    return prob, ref

@@ -131,3 +131,30 @@ def run_mpr(prob, param=None):
     rc = L.orc_mpr(C.byref(m), C.byref(o))
     assert rc == 0
     return out
+
+
+def init_lowres_level(mask0, cellsize0, target_resolution, cell_area0=None):
+    """the oracle's init_lowres_level with the same result dict as synth_mpr.init_lowres_level"""
+    L = _lib()
+    m0 = np.ascontiguousarray(mask0, dtype=np.int32)
+    ncols0, nrows0 = m0.shape
+    nr, nc = C.c_int32(), C.c_int32()
+    xll, yll, cs = C.c_double(), C.c_double(), C.c_double()
+    L.orc_calculate_grid_properties(nrows0, ncols0, 0.0, 0.0, cellsize0, target_resolution, C.byref(nr),
+                                    C.byref(nc), C.byref(xll), C.byref(yll), C.byref(cs))
+    n0 = int(m0.sum())
+    area = np.full(n0, cellsize0 * cellsize0) if cell_area0 is None else np.ascontiguousarray(cell_area0, dtype=np.float64)
+    nmax = nr.value * nc.value
+    mask1 = np.zeros(nmax, dtype=np.int32)
+    coor = np.zeros(2 * nmax, dtype=np.int32)
+    a1 = np.zeros(nmax)
+    up, lo, le, ri, ns = (np.zeros(nmax, dtype=np.int32) for _ in range(5))
+    ids = np.zeros(nrows0 * ncols0, dtype=np.int32)
+    n1 = L.orc_init_lowres_level(nrows0, ncols0, orc.iptr(m0), orc.dptr(area), cellsize0, target_resolution,
+                                 nr.value, nc.value, orc.iptr(mask1), orc.iptr(coor), orc.dptr(a1), orc.iptr(up),
+                                 orc.iptr(lo), orc.iptr(le), orc.iptr(ri), orc.iptr(ns), orc.iptr(ids))
+    return {"nrows1": nr.value, "ncols1": nc.value, "nCells1": n1,
+            "mask1": mask1.reshape(nc.value, nr.value), "cellArea1": a1[:n1].copy(),
+            "upper_bound": up[:n1].copy(), "lower_bound": lo[:n1].copy(), "left_bound": le[:n1].copy(),
+            "right_bound": ri[:n1].copy(), "n_subcells": ns[:n1].copy(),
+            "lowres_id_on_highres": ids.reshape(ncols0, nrows0)}

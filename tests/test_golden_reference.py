@@ -85,3 +85,60 @@ def test_cuda_path_reproduces_reference_run(case, mode):
             wq = parity.assert_close(q, ref["Qsim"], case + " daily discharge", rtol=parity.RTOL_Q)
             msg += ", daily discharge %.2e" % wq
         print(msg)
+
+
+# ---- MPR: gamma -> L1 effective parameters on the real test basin ------------------------------
+MPR_CASES = ["case_00", "case_02", "case_09", "case_10", "case_12", "case_04_b2"]
+
+
+@pytest.mark.parametrize("case", MPR_CASES)
+def test_oracle_mpr_reproduces_reference_parameters(case):
+    """L0 fields of the bundled test basin (tests/golden/test_domain_l0.npz, 46 545 L0 cells,
+    1 475 soil types) + the case's gamma -> every L1 effective parameter the reference's MPR wrote
+    to its restart file, bit for bit; also pins init_lowres_level (L1 mask and cell areas at
+    24 km and 12 km) for the oracle and for the library's host helper."""
+    import orc_mpr
+    from mhm_b200 import synth_mpr
+
+    prob, ref = golden_case.load_mpr(case, orc_mpr.init_lowres_level)
+    g = prob["grid"]
+    assert np.array_equal(g["mask1"] != 0, ref["mask1"])
+    parity.assert_bit_exact(g["cellArea1"] * 1e-6, ref["L1_areaCell_km2"], "L1 cell area")
+    lib = synth_mpr.init_lowres_level(prob["mask0"], 500.0, 500.0 * 432 // ref["mask1"].shape[0],
+                                      np.full(prob["nL0"], 250000.0))
+    for k in ("mask1", "cellArea1", "upper_bound", "lower_bound", "left_bound", "right_bound",
+              "n_subcells", "lowres_id_on_highres"):
+        assert np.array_equal(lib[k], g[k]), k
+    out = orc_mpr.run_mpr(prob)
+    checked = 0
+    for name, want in ref.items():
+        if name in out:
+            parity.assert_bit_exact(out[name], want, "%s %s" % (case, name))
+            checked += 1
+    assert checked >= 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", MPR_CASES)
+def test_cuda_mpr_reproduces_reference_parameters(case):
+    """mpr_cuda_eval on the device against the reference's restart parameters: strict mode is
+    bit-identical except where device pow/exp/log enter (<= 1e-12); fast mode <= 1e-11."""
+    import orc_mpr
+    from mhm_b200 import interface, synth_mpr
+
+    prob, ref = golden_case.load_mpr(case, synth_mpr.init_lowres_level)
+    loose = {"L1_petLAIcorFactor", "L1_aeroResist"} | ({"L1_fRoots"} if prob["soil_case"] in (3, 4) else set())
+    with interface.Context() as ctx:
+        dom = ctx.register_domain(1, prob["nL1"], prob["nH"], prob["nLAI"], prob["nLC"], prob["processMatrix"])
+        synth_mpr.set_mpr_inputs(dom, prob)
+        for mode in ("strict", "fast"):
+            ctx.set_math_mode(mode)
+            synth_mpr.mpr_eval(dom, prob["param"])
+            for name in synth_mpr.outputs_for(prob["soil_case"], prob["pet_case"]):
+                d2, d3 = synth_mpr.MPR_OUTPUTS[name](prob["nH"], prob["nLAI"], prob["nLC"])
+                got = dom.get_param(name, d2, d3)
+                if mode == "strict" and name not in loose:
+                    parity.assert_bit_exact(got, ref[name], "%s %s" % (case, name))
+                else:
+                    parity.assert_close(got, ref[name], "%s %s (%s)" % (case, name, mode),
+                                        rtol=1e-12 if mode == "strict" else 1e-11, atol=0)
