@@ -37,13 +37,13 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=1180)
     ap.add_argument("--ny", type=int, default=1000)
     ap.add_argument("--members", type=int, default=32, help="ensemble members per GPU")
-    ap.add_argument("--block-hours", type=int, default=48)
+    ap.add_argument("--block-hours", type=int, default=96)
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-routing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

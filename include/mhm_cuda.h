@@ -240,7 +240,11 @@ int mhm_cuda_bind_host_flux(mhm_cuda_context *ctx, int32_t iDomain, int32_t flux
 int mhm_cuda_sync_to_host(mhm_cuda_context *ctx, int32_t iDomain);
 
 /* total runoff history of the last run_steps block, Fortran (nCells, n_steps) per member
- * (what `RunToRout = L1_total_runoff(s1:e1)` saw at each step) */
+ * (what `RunToRout = L1_total_runoff(s1:e1)` saw at each step).  When the routing grid equals
+ * the L1 grid the cell kernel writes the routing's node runoff directly (L11_runoff_acc,
+ * mRM/mo_mrm_pre_routing.f90:110-141, fused) and no history is kept unless
+ * mhm_cuda_keep_runoff_history(ctx, iDomain, 1) was called before run_steps. */
+int mhm_cuda_keep_runoff_history(mhm_cuda_context *ctx, int32_t iDomain, int32_t keep);
 int mhm_cuda_get_runoff_history(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
                                 double *out, int64_t ld);
 

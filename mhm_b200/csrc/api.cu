@@ -121,6 +121,7 @@ const char* mhm_cuda_last_error(void) { return g_err.c_str(); }
 double mhm_host_fast_log(double x) { return mhm::fm::log_pos(x); }
 double mhm_host_fast_exp(double x) { return mhm::fm::exp_bounded(x); }
 double mhm_host_fast_pow(double x, double y) { return mhm::fm::pow_pos(x, y); }
+double mhm_host_fast_pow23(double x) { return mhm::fm::pow23_pos(x); }
 const char* mhm_cuda_version(void) { return "mhm_cuda 0.1 (sm_100a)"; }
 
 int mhm_cuda_init(int device, mhm_cuda_context** out) {
@@ -140,6 +141,11 @@ int mhm_cuda_init(int device, mhm_cuda_context** out) {
   MHM_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   MHM_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) MHM_CUDA_OK(cudaEventCreate(&ev));
+  // history buffers of a time block may take 45 % of the device's memory (long blocks amortise
+  // the routing pipeline's fill/drain and the cell kernel's state/parameter loads)
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0)
+    ctx->block_bytes = (size_t)((double)total_b * 0.45);
   if (const char* s = getenv("MHM_CUDA_BLOCK_BYTES")) ctx->block_bytes = (size_t)atoll(s);
   *out = ctx;
   return 0;
@@ -592,10 +598,25 @@ static int meteo_release(mhm_cuda_context* ctx, Domain* d) {
   return 0;
 }
 
-static int launch_cells(mhm_cuda_context* ctx, Domain* d, const CellArgs& a) {
+// One block of model steps = ceil(nSteps / kIdxInline) launches: the calendar of a launch
+// travels inside the kernel arguments (constant bank), states are re-read at each launch.
+static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const StepIdx* idx) {
+  const int32_t total = a.nSteps, tt0 = a.tt_first, wf = a.write_fluxes;
+  double* const hist0 = a.runoff_hist;
+  const size_t hist_stride = (size_t)d->cfg.nMembers * (size_t)d->cfg.nCells;
   ctx->stat_begin(kStatCell);
-  int rc = ctx->math_mode == 1 ? launch_cell_block_fast(a, d->cfg.nHorizons, ctx->stream)
-                               : launch_cell_block_strict(a, d->cfg.nHorizons, ctx->stream);
+  int rc = 0;
+  for (int32_t t0 = 0; t0 < total && rc == 0; t0 += kIdxInline) {
+    const int32_t nb = total - t0 < kIdxInline ? total - t0 : kIdxInline;
+    a.nSteps = nb;
+    a.tt_first = tt0 + t0;
+    a.write_fluxes = (wf && t0 + nb >= total) ? 1 : 0;
+    a.runoff_hist = hist0 ? hist0 + (size_t)t0 * hist_stride : nullptr;
+    a.qout_step0 = t0;
+    memcpy(a.idx_in, idx + t0, (size_t)nb * sizeof(StepIdx));
+    rc = ctx->math_mode == 1 ? launch_cell_block_fast(a, d->cfg.nHorizons, ctx->stream)
+                             : launch_cell_block_strict(a, d->cfg.nHorizons, ctx->stream);
+  }
   ctx->stat_end(kStatCell);
   MHM_REQUIRE(rc == 0, "cell kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   return 0;
@@ -623,19 +644,16 @@ int mhm_cuda_cell_step(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt,
   s.hour = idx->hour;
   s.isday = idx->isday;
   if (int rc = check_inputs(d, &s, 1)) return rc;
-  MHM_CUDA_OK(cudaMemcpyAsync(d->d_idx_one, &s, sizeof(s), cudaMemcpyHostToDevice, ctx->stream));
-  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // &s is a stack object
   CellArgs a;
   fill_args(ctx, d, a);
   a.nSteps = 1;
   a.tt_first = tt;
-  a.idx = d->d_idx_one;
   a.write_fluxes = 1;
   a.runoff_hist = nullptr;
   d->last_yId = s.yId;
   d->hist_steps = 0;
   if (int rc = meteo_acquire(ctx, d)) return rc;
-  if (int rc = launch_cells(ctx, d, a)) return rc;
+  if (int rc = launch_cells(ctx, d, a, &s)) return rc;
   return meteo_release(ctx, d);
 }
 
@@ -650,12 +668,15 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
   if (int rc = check_inputs(d, d->h_idx.data() + (tt_first - 1), n_steps)) return rc;
   const size_t n = (size_t)d->cfg.nCells, M = (size_t)d->cfg.nMembers;
   // time blocks sized by the history-buffer budget (runoff + routing histories)
-  size_t per_step = 3 * M * n * sizeof(double);
+  CellArgs probe;
+  fill_args(ctx, d, probe);
+  const bool fused = routing_fuse_qout(ctx, d, 1, &probe);  // routing input written by the cells
+  size_t per_step = (fused ? 2 : 3) * M * n * sizeof(double);
   int32_t tb = (int32_t)(ctx->block_bytes / per_step);
   if (tb < 1) tb = 1;
   if (tb > n_steps) tb = n_steps;
   const size_t need = (size_t)tb * M * n;
-  if (d->runoff_cap < need) {
+  if (!fused && d->runoff_cap < need) {
     MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d->runoff_hist);
     d->runoff_hist = nullptr;
@@ -670,17 +691,24 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
     fill_args(ctx, d, a);
     a.nSteps = nb;
     a.tt_first = tt_first + t0;
-    a.idx = d->d_idx + (tt_first + t0 - 1);
     a.write_fluxes = (t0 + nb >= n_steps) ? 1 : 0;  // fluxes of the call's last step
-    a.runoff_hist = d->runoff_hist;
-    if (int rc = launch_cells(ctx, d, a)) return rc;
-    d->hist_steps = nb;
+    a.runoff_hist = fused ? nullptr : d->runoff_hist;
+    if (fused) routing_fuse_qout(ctx, d, nb, &a);
+    if (int rc = launch_cells(ctx, d, a, d->h_idx.data() + (tt_first + t0 - 1))) return rc;
+    d->hist_steps = fused ? 0 : nb;
     d->hist_tt_first = tt_first + t0;
     d->last_yId = d->h_idx[(size_t)(tt_first + t0 + nb - 2)].yId;
     if (d->rt)
-      if (int rc = routing_run_block(ctx, d, tt_first + t0, nb)) return rc;
+      if (int rc = routing_run_block(ctx, d, tt_first + t0, nb, fused)) return rc;
   }
   return meteo_release(ctx, d);
+}
+
+int mhm_cuda_keep_runoff_history(mhm_cuda_context* ctx, int32_t iDomain, int32_t keep) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  d->keep_runoff_hist = keep != 0;
+  return 0;
 }
 
 int mhm_cuda_get_runoff_history(mhm_cuda_context* ctx, int32_t iDomain, int32_t member,
@@ -688,7 +716,9 @@ int mhm_cuda_get_runoff_history(mhm_cuda_context* ctx, int32_t iDomain, int32_t 
   Domain* d = find_domain(ctx, iDomain);
   if (!d) return 1;
   MHM_REQUIRE(member >= 0 && member < d->cfg.nMembers, "get_runoff_history: bad member");
-  MHM_REQUIRE(d->hist_steps > 0 && d->runoff_hist, "get_runoff_history: no block has been run");
+  MHM_REQUIRE(d->hist_steps > 0 && d->runoff_hist,
+              "get_runoff_history: no block has been run, or the history was fused into the routing "
+              "input (call mhm_cuda_keep_runoff_history first)");
   MHM_REQUIRE(out && ld >= d->cfg.nCells, "get_runoff_history: bad out/ld");
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)d->cfg.nCells, M = (size_t)d->cfg.nMembers;

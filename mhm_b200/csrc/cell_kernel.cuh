@@ -19,6 +19,7 @@
 #pragma once
 #include <cfloat>
 #include <cstdint>
+#include <type_traits>
 
 #include "device_types.h"
 #include "fastmath.cuh"
@@ -117,30 +118,41 @@ struct CellStates {
 };
 
 // Fluxes leave the step through an emitter the moment they are final, so that none of them
-// has to stay in a register until the end of the time loop (they are only stored for the
-// last step of a block).
+// has to stay in a register until the end of the time loop.  They are only stored for the
+// last step of a block: the time loop is compiled twice, with EMIT = false for steps
+// 1..n-1 (the emitter vanishes) and EMIT = true for the last one.
+template <bool EMIT>
 struct FluxEmitter {
   double* const* F;
   size_t mc, n, mh;  // member*n + cell; nCells; (member*NH)*n + cell
   bool on;
   __device__ __forceinline__ void operator()(int id, double v) const {
-    if (on) F[id][mc] = v;
+    if (EMIT) {
+      if (on) F[id][mc] = v;
+    }
   }
   __device__ __forceinline__ void operator()(int id, int h, double v) const {
-    if (on) F[id][mh + (size_t)h * n] = v;
+    if (EMIT) {
+      if (on) F[id][mh + (size_t)h * n] = v;
+    }
   }
 };
 
+// kernel variants: the generic one takes every process selection at run time; the two
+// specialised ones cover the configurations every large run uses (hourly forcing with PET as
+// input, i.e. processCase(5) <= 0) with the soil-moisture scheme fixed at compile time.
+enum CellVariant { kGeneric = 0, kHourlyFeddes = 1, kHourlyJarvis = 2 };
+
 // returns total_runoff (mo_runoff.f90:271-272)
-template <int NH>
+template <int NH, int VARIANT, bool EMIT>
 __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStates<NH>& s,
                                                const double pet, const double temperature,
                                                const double prec, const int soil_case,
                                                const double evap_coeff,
 #if MHM_FAST
-                                               const double inv_evap_coeff,
+                                               const double inv_evap_coeff, double2* warp_tasks,
 #endif
-                                               const FluxEmitter& emit) {
+                                               const FluxEmitter<EMIT>& emit) {
   // ---- canopy_interc, mo_canopy_interc.f90:105-131 ----
   double throughfall, aet_canopy;
   {
@@ -156,9 +168,9 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
     double ev;
     if (p.maxInter > kEps) {
 #if MHM_FAST
-      // x**(2/3) = cbrt(x*x); x = 0 is the common dry-canopy case
+      // x**(2/3) = x * x**(-1/3); x = 0 is the common dry-canopy case
       const double x = ic * p.inv_maxInter;
-      ev = (x == 0.0) ? 0.0 : pet * cbrt(x * x);
+      ev = (x == 0.0) ? 0.0 : pet * fm::pow23_pos(x);
 #else
       ev = pet * pow(ic / p.maxInter, kTwoThird);
 #endif
@@ -258,6 +270,46 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
 
     double prec_effec_soil = prec_effect;
     double aet_pos_sum = 0.0;  // sum(aet(1:hh-1), mask = aet > 0), accumulated in index order
+#if MHM_FAST
+    // frac_runoff_h = (sm_h / sat_h) ** exp_h depends only on the states the step starts from,
+    // so all horizons' powers are known up front.  Only cells that receive water need them
+    // (a dry step leaves inf = 0 and sm unchanged whatever frac is): the (cell, horizon)
+    // pairs of the warp that need one are compacted through shared memory and evaluated by
+    // as few warp-wide pow_pos rounds as possible, instead of NH rounds at a fraction of
+    // the lanes each.  Same function, same arguments -> same values as the direct evaluation.
+    double frac_pre[NH];
+    {
+      const unsigned lane = threadIdx.x & 31u;
+      const unsigned lt = (1u << lane) - 1u;
+      const bool wet = prec_effect != 0.0;
+      unsigned base = 0;
+      unsigned slot[NH];
+      bool need[NH];
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) {
+        need[hh] = wet && s.sm[hh] > kEps && !(s.sm[hh] > p.SAT[hh]);
+        const unsigned m = __ballot_sync(0xffffffffu, need[hh]);
+        slot[hh] = base + __popc(m & lt);
+        base += __popc(m);
+        frac_pre[hh] = 0.0;
+      }
+      if (base != 0) {  // warp-uniform
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh)
+          if (need[hh]) warp_tasks[slot[hh]] = make_double2(s.sm[hh] * p.inv_SAT[hh], p.EXPN[hh]);
+        __syncwarp();
+        for (unsigned k = lane; k < base; k += 32u) {
+          const double2 tk = warp_tasks[k];
+          warp_tasks[k].x = fm::pow_pos(tk.x, tk.y);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh)
+          if (need[hh]) frac_pre[hh] = warp_tasks[slot[hh]].x;
+        __syncwarp();
+      }
+    }
+#endif
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) {
       double sm = s.sm[hh];
@@ -273,8 +325,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
         if (prec_effec_soil == 0.0) {
           inf = 0.0;
         } else {
-          double frac_runoff = 0.0;
-          if (sm > kEps) frac_runoff = fm::pow_pos(sm * p.inv_SAT[hh], p.EXPN[hh]);
+          const double frac_runoff = frac_pre[hh];
           double tmp = prec_effec_soil * (1.0 - frac_runoff);
           if ((sm + tmp) > sat) {
             inf = prec_effec_soil + (sm - sat);
@@ -307,7 +358,10 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
       double a = pet - aet_canopy;
       if (hh != 0) a = a - aet_pos_sum;
       double stress;
-      if (soil_case == 1 || soil_case == 4) {  // feddes_et_reduction :353-361
+      const bool feddes = VARIANT == kHourlyFeddes ? true
+                          : VARIANT == kHourlyJarvis ? false
+                                                     : (soil_case == 1 || soil_case == 4);
+      if (feddes) {  // feddes_et_reduction :353-361
         if (sm >= p.FC[hh]) {
           stress = p.fRoots[hh];
         } else if (sm > p.WP[hh]) {
@@ -392,14 +446,34 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
 
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldg(p); }
 
-template <int NH>
+// everything of the time loop that lives across steps besides states and parameters
+struct CellCursor {
+  int cur_y, cur_l;
+  long long cur_row;
+  double raw_pre, raw_temp, raw_pet;
+  const double *ppre, *ptemp, *ppet;  // this cell in forcing row cur_row
+  double* hist;                       // this cell/member in the total-runoff row of step t
+};
+
+template <int NH, int VARIANT>
 __global__ void __launch_bounds__(kCellThreads, MHM_CELL_MIN_BLOCKS)
-MHM_KERNEL_NAME(const CellArgs a) {
+MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
   const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
+#if MHM_FAST
+  __shared__ double2 sh_tasks[kCellThreads * NH];
+  double2* const warp_tasks = sh_tasks + (threadIdx.x >> 5) * (32 * NH);
+  // out-of-range lanes of the last tile stay alive (warp collectives) on a valid cell
+  const bool live = cell < a.nCells;
+  const int c = live ? cell : a.nCells - 1;
+#else
   if (cell >= a.nCells) return;
+  const bool live = true;
+  const int c = cell;
+#endif
   const size_t n = (size_t)a.nCells;
-  const size_t mc = (size_t)member * n + cell;
+  const size_t mc = (size_t)member * n + c;
+  constexpr bool kHourlyPetIn = VARIANT != kGeneric;
 
   CellStates<NH> s;
   s.inter = a.S[MHM_S_INTER][mc];
@@ -408,7 +482,7 @@ MHM_KERNEL_NAME(const CellArgs a) {
   s.unsat = a.S[MHM_S_UNSATSTW][mc];
   s.sat = a.S[MHM_S_SATSTW][mc];
 #pragma unroll
-  for (int h = 0; h < NH; ++h) s.sm[h] = a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + cell];
+  for (int h = 0; h < NH; ++h) s.sm[h] = a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + c];
 
   CellParams<NH> p;
   // parameters that never change during a run
@@ -420,17 +494,37 @@ MHM_KERNEL_NAME(const CellArgs a) {
   p.inv_sealedThr = 1.0 / p.sealedThr;
   p.inv_jc1 = 1.0 / p.jarvis_c1;
 #endif
-  int cur_y = -1, cur_l = -1;
-  long long cur_row = -1;
-  double raw_pre = 0.0, raw_temp = 0.0, raw_pet = 0.0;
+  CellCursor cu;
+  cu.cur_y = -1;
+  cu.cur_l = -1;
+  cu.cur_row = a.idx_in[0].iMeteoTS;
+  cu.ppre = a.met[MHM_M_PRE] + (size_t)(cu.cur_row - a.met_first[MHM_M_PRE]) * n + c;
+  cu.ptemp = a.met[MHM_M_TEMP] + (size_t)(cu.cur_row - a.met_first[MHM_M_TEMP]) * n + c;
+  cu.ppet = a.pet_case <= 0 ? a.met[MHM_M_PET] + (size_t)(cu.cur_row - a.met_first[MHM_M_PET]) * n + c
+                            : nullptr;
+  cu.raw_pre = ldg_stream(cu.ppre);
+  cu.raw_temp = ldg_stream(cu.ptemp);
+  cu.raw_pet = cu.ppet ? ldg_stream(cu.ppet) : 0.0;
+  cu.hist = a.runoff_hist ? a.runoff_hist + (size_t)member * n + c : nullptr;
+  const size_t hist_stride = (size_t)a.nMembers * n;
+  // fused L11_runoff_acc (mo_mrm_pre_routing.f90:110-141): this cell is the only one of its node
+  double* qout = nullptr;
+  double qarea = 0.0;
+  if (a.qout_hist) {
+    qout = a.qout_hist + (((size_t)member * a.qout_E + a.cell_lane[c]) << 3);
+    qarea = a.cell_area[c];
+  }
+  const size_t qtile_stride = ((size_t)a.nMembers * a.qout_E) << 3;
 
-  for (int t = 0; t < a.nSteps; ++t) {
-    const StepIdx si = a.idx[t];
+  // one model step; EMIT is a compile-time tag so that steps 1..n-1 carry no flux stores
+  auto step = [&](auto emit_tag, const int t) {
+    constexpr bool EMIT = decltype(emit_tag)::value;
+    const StepIdx si = a.idx_in[t];  // kernel-parameter space: uniform constant loads
     const int y = si.yId - 1, il = si.iLAI - 1, month = si.month - 1;
 
-    if (y != cur_y) {  // land-cover scene changed (new year): mo_mhm_interface_run.f90:626-628
-      cur_y = y;
-      const size_t o1 = ((size_t)member * a.nLC + y) * n + cell;  // (n, 1, nLC) arrays
+    if (y != cu.cur_y) {  // land-cover scene changed (new year): mo_mhm_interface_run.f90:626-628
+      cu.cur_y = y;
+      const size_t o1 = ((size_t)member * a.nLC + y) * n + c;  // (n, 1, nLC) arrays
       p.fSealed = a.P[MHM_P_FSEALED][o1];
       p.alpha = a.P[MHM_P_ALPHA][o1];
       p.ddinc = a.P[MHM_P_DEGDAYINC][o1];
@@ -444,7 +538,7 @@ MHM_KERNEL_NAME(const CellArgs a) {
       p.tthr = a.P[MHM_P_TEMPTHRESH][o1];
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
-        const size_t oh = (((size_t)member * a.nLC + y) * NH + h) * n + cell;  // (n, nH, nLC)
+        const size_t oh = (((size_t)member * a.nLC + y) * NH + h) * n + c;  // (n, nH, nLC)
         p.fRoots[h] = a.P[MHM_P_FROOTS][oh];
         p.FC[h] = a.P[MHM_P_SOILMOISTFC][oh];
         p.SAT[h] = a.P[MHM_P_SOILMOISTSAT][oh];
@@ -455,20 +549,20 @@ MHM_KERNEL_NAME(const CellArgs a) {
         p.inv_FCWP[h] = 1.0 / (p.FC[h] - p.WP[h]);
 #endif
       }
-      cur_l = -1;  // petLAIcorFactor / aeroResist also depend on yId
+      cu.cur_l = -1;  // petLAIcorFactor / aeroResist also depend on yId
       if (t == 0 && a.tt_first == 1 && !a.read_states) {  // mo_mhm.f90:448-450
 #pragma unroll
         for (int h = 0; h < NH; ++h) s.sm[h] = 0.5 * p.FC[h];
       }
     }
-    if (il != cur_l) {  // LAI step changed: mo_common_datetime_type.f90:135-155
-      cur_l = il;
-      p.maxInter = a.P[MHM_P_MAXINTER][((size_t)member * a.nLAI + il) * n + cell];
+    if (il != cu.cur_l) {  // LAI step changed: mo_common_datetime_type.f90:135-155
+      cu.cur_l = il;
+      p.maxInter = a.P[MHM_P_MAXINTER][((size_t)member * a.nLAI + il) * n + c];
 #if MHM_FAST
       p.inv_maxInter = 1.0 / p.maxInter;
 #endif
       if (a.pet_case == -1) {
-        p.petFac = a.P[MHM_P_PETLAICORFACTOR][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + cell];
+        p.petFac = a.P[MHM_P_PETLAICORFACTOR][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + c];
       } else if (a.pet_case == 0 || a.pet_case == 1) {
         p.petFac = a.P[MHM_P_FASP][mc];
       } else {
@@ -476,49 +570,43 @@ MHM_KERNEL_NAME(const CellArgs a) {
       }
     }
 
-    // ---- forcing of this step: mo_meteo_handler.f90:595-618 (iMeteoTS), rows are
-    //      [meteo step][cell]; reload only when the meteo step changes ----
-    const long long row = (long long)si.iMeteoTS;
-    if (row != cur_row) {
-      cur_row = row;
-      raw_pre = ldg_stream(a.met[MHM_M_PRE] + (size_t)(row - a.met_first[MHM_M_PRE]) * n + cell);
-      raw_temp = ldg_stream(a.met[MHM_M_TEMP] + (size_t)(row - a.met_first[MHM_M_TEMP]) * n + cell);
-      if (a.pet_case <= 0)
-        raw_pet = ldg_stream(a.met[MHM_M_PET] + (size_t)(row - a.met_first[MHM_M_PET]) * n + cell);
-    }
+    // ---- forcing of this step: mo_meteo_handler.f90:595-618 (iMeteoTS); rows are
+    //      [meteo step][cell]; the row of step t was loaded during step t-1 ----
+    const long long row = cu.cur_row;
+    const double raw_pre = cu.raw_pre, raw_temp = cu.raw_temp, raw_pet = cu.raw_pet;
 
     // ---- get_corrected_pet :1053-1119 ----
     double pet;
-    if (a.pet_case <= 0) {
+    if (kHourlyPetIn || a.pet_case <= 0) {
       pet = p.petFac * raw_pet;
     } else if (a.pet_case == 1) {
-      const double tmx = a.met[MHM_M_TMAX][(size_t)(row - a.met_first[MHM_M_TMAX]) * n + cell];
-      const double tmn = a.met[MHM_M_TMIN][(size_t)(row - a.met_first[MHM_M_TMIN]) * n + cell];
+      const double tmx = a.met[MHM_M_TMAX][(size_t)(row - a.met_first[MHM_M_TMAX]) * n + c];
+      const double tmn = a.met[MHM_M_TMIN][(size_t)(row - a.met_first[MHM_M_TMIN]) * n + c];
       pet = p.petFac * pet_hargreaves(a.P[MHM_P_HARSAMCOEFF][mc], raw_temp, tmx, tmn,
                                       a.P[MHM_P_LATITUDE][mc], si.doy);
     } else if (a.pet_case == 2) {
-      const double rn = a.met[MHM_M_NETRAD][(size_t)(row - a.met_first[MHM_M_NETRAD]) * n + cell];
-      pet = pet_priestly(a.P[MHM_P_PRIETAYALPHA][((size_t)member * a.nLAI + il) * n + cell],
+      const double rn = a.met[MHM_M_NETRAD][(size_t)(row - a.met_first[MHM_M_NETRAD]) * n + c];
+      pet = pet_priestly(a.P[MHM_P_PRIETAYALPHA][((size_t)member * a.nLAI + il) * n + c],
                          fmax(rn, 0.0), raw_temp);
     } else {
-      const double rn = a.met[MHM_M_NETRAD][(size_t)(row - a.met_first[MHM_M_NETRAD]) * n + cell];
+      const double rn = a.met[MHM_M_NETRAD][(size_t)(row - a.met_first[MHM_M_NETRAD]) * n + c];
       const double avp =
-          a.met[MHM_M_ABSVAPPRESS][(size_t)(row - a.met_first[MHM_M_ABSVAPPRESS]) * n + cell];
+          a.met[MHM_M_ABSVAPPRESS][(size_t)(row - a.met_first[MHM_M_ABSVAPPRESS]) * n + c];
       const double ws =
-          a.met[MHM_M_WINDSPEED][(size_t)(row - a.met_first[MHM_M_WINDSPEED]) * n + cell];
+          a.met[MHM_M_WINDSPEED][(size_t)(row - a.met_first[MHM_M_WINDSPEED]) * n + c];
       const double ar =
-          a.P[MHM_P_AERORESIST][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + cell];
-      const double sr = a.P[MHM_P_SURFRESIST][((size_t)member * a.nLAI + il) * n + cell];
+          a.P[MHM_P_AERORESIST][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + c];
+      const double sr = a.P[MHM_P_SURFRESIST][((size_t)member * a.nLAI + il) * n + c];
       pet = pet_penman(fmax(rn, 0.0), raw_temp, avp / 1000.0, ar / ws, sr);
     }
     // ---- temporal disaggregation: mo_meteo_temporal_tools.f90 ----
     double pet_calc, temp_calc, prec_calc;
-    if (a.is_hourly) {
+    if (kHourlyPetIn || a.is_hourly) {
       pet_calc = pet;
       temp_calc = raw_temp;
       prec_calc = raw_pre;
     } else if (a.read_weights) {
-      const size_t wo = ((size_t)si.hour * 12 + month) * n + cell;
+      const size_t wo = ((size_t)si.hour * 12 + month) * n + c;
       pet_calc = (pet + 0.0) * a.w_pet[wo] - 0.0;
       temp_calc = (raw_temp + kT0) * a.w_temp[wo] - kT0;
       prec_calc = (raw_pre + 0.0) * a.w_pre[wo] - 0.0;
@@ -534,43 +622,65 @@ MHM_KERNEL_NAME(const CellArgs a) {
       temp_calc = raw_temp;
       prec_calc = raw_pre;
     }
-    const FluxEmitter emit{a.F, mc, n, (size_t)member * NH * n + cell,
-                           a.write_fluxes && t == a.nSteps - 1};
+    const FluxEmitter<EMIT> emit{a.F, mc, n, (size_t)member * NH * n + c, a.write_fluxes && live};
     emit(MHM_F_PET_CALC, pet_calc);
     emit(MHM_F_TEMP_CALC, temp_calc);
     emit(MHM_F_PREC_CALC, prec_calc);
 
-    // prefetch the next step's forcing row into L2->L1 path before the arithmetic
+    // the next step's forcing row is requested before this step's arithmetic
     if (t + 1 < a.nSteps) {
-      const long long nrow = (long long)a.idx[t + 1].iMeteoTS;
-      if (nrow != cur_row) {
-        cur_row = nrow;
-        raw_pre = ldg_stream(a.met[MHM_M_PRE] + (size_t)(nrow - a.met_first[MHM_M_PRE]) * n + cell);
-        raw_temp = ldg_stream(a.met[MHM_M_TEMP] + (size_t)(nrow - a.met_first[MHM_M_TEMP]) * n + cell);
-        if (a.pet_case <= 0)
-          raw_pet = ldg_stream(a.met[MHM_M_PET] + (size_t)(nrow - a.met_first[MHM_M_PET]) * n + cell);
+      const long long nrow = (long long)a.idx_in[t + 1].iMeteoTS;
+      if (nrow != row) {
+        const size_t adv = (size_t)(nrow - row) * n;
+        cu.cur_row = nrow;
+        cu.ppre += adv;
+        cu.ptemp += adv;
+        cu.raw_pre = ldg_stream(cu.ppre);
+        cu.raw_temp = ldg_stream(cu.ptemp);
+        if (kHourlyPetIn || a.pet_case <= 0) {
+          cu.ppet += adv;
+          cu.raw_pet = ldg_stream(cu.ppet);
+        }
       }
     }
 
-    const double total_runoff =
-        cascade_step<NH>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case, a.tab.evap_coeff[month],
+    const double total_runoff = cascade_step<NH, VARIANT, EMIT>(
+        p, s, pet_calc, temp_calc, prec_calc, a.soil_case, a.tab.evap_coeff[month],
 #if MHM_FAST
-                         a.tab.inv_evap_coeff[month],
+        a.tab.inv_evap_coeff[month], warp_tasks,
 #endif
-                         emit);
+        emit);
 
-    if (a.runoff_hist)
-      __stcs(a.runoff_hist + ((size_t)t * a.nMembers + member) * n + cell, total_runoff);
-  }
+    if (cu.hist) {
+      if (live) __stcs(cu.hist, total_runoff);
+      cu.hist += hist_stride;
+    }
+    if (qout) {
+      const int st = a.qout_step0 + t;
+      const double r = 0.0 + total_runoff;
+      double v = a.qout_map_flag ? (0.0 + r * qarea) : r * qarea;
+#if MHM_FAST
+      v = v * a.qout_scale;
+#else
+      v = v * 1000.0 / a.qout_tst;
+#endif
+      if (live) qout[(size_t)(st >> 3) * qtile_stride + (size_t)(st & 7)] = v;
+    }
+  };
 
-  // ---- write back states and (optionally) the fluxes of the block's last step ----
-  a.S[MHM_S_INTER][mc] = s.inter;
-  a.S[MHM_S_SNOWPACK][mc] = s.snowpack;
-  a.S[MHM_S_SEALSTW][mc] = s.sealed;
-  a.S[MHM_S_UNSATSTW][mc] = s.unsat;
-  a.S[MHM_S_SATSTW][mc] = s.sat;
+  for (int t = 0; t < a.nSteps - 1; ++t) step(std::false_type{}, t);
+  step(std::true_type{}, a.nSteps - 1);
+
+  // ---- write back states ----
+  if (live) {
+    a.S[MHM_S_INTER][mc] = s.inter;
+    a.S[MHM_S_SNOWPACK][mc] = s.snowpack;
+    a.S[MHM_S_SEALSTW][mc] = s.sealed;
+    a.S[MHM_S_UNSATSTW][mc] = s.unsat;
+    a.S[MHM_S_SATSTW][mc] = s.sat;
 #pragma unroll
-  for (int h = 0; h < NH; ++h) a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + cell] = s.sm[h];
+    for (int h = 0; h < NH; ++h) a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + c] = s.sm[h];
+  }
 }
 
 }  // namespace mhm

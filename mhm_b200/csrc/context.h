@@ -85,6 +85,7 @@ struct Domain {
   double* runoff_hist = nullptr;
   size_t runoff_cap = 0;
   int32_t hist_steps = 0, hist_tt_first = 0;
+  bool keep_runoff_hist = false;  // mhm_cuda_keep_runoff_history: never fuse the history away
 
   Routing* rt = nullptr;
   MprState* mpr = nullptr;
@@ -124,5 +125,9 @@ Domain* find_domain(mhm_cuda_context* ctx, int32_t iDomain);
 // routing hooks used by api.cu
 void routing_free(Routing* rt);
 void mpr_free(MprState* s);
-int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_t n_steps);
+int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_t n_steps,
+                      bool qout_ready);
+// can the cell kernel write the routing's node runoff itself for a block of n_steps?  (one cell
+// per node, one model step per routing event, no inflow gauges); fills the CellArgs fields
+bool routing_fuse_qout(mhm_cuda_context* ctx, Domain* d, int32_t n_steps, CellArgs* a);
 }  // namespace mhm

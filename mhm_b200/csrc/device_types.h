@@ -8,6 +8,7 @@ namespace mhm {
 
 constexpr int kCellThreads = 128;
 constexpr int kMaxHorizons = 8;
+constexpr int kIdxInline = 64;  // model steps per cell-kernel launch (calendar rides in the arguments)
 
 // per-step calendar indices, 16 bytes (one LDG.128, warp-uniform)
 struct alignas(16) StepIdx {
@@ -33,7 +34,7 @@ struct CellArgs {
   int32_t nLC, nLAI;
   int32_t soil_case, pet_case, is_hourly, read_weights, read_states, write_fluxes;
   double nTstepDay_dp, c2TSTu;
-  const StepIdx* idx;                 // device, [nSteps]
+  StepIdx idx_in[kIdxInline];         // calendar of the launch's steps: constant-bank loads
   const double* met[MHM_M_COUNT];     // device, [rows][nCells]
   long long met_first[MHM_M_COUNT];   // iMeteoTS of row 0
   const double *w_pre, *w_temp, *w_pet;  // device, [24][12][nCells]
@@ -41,6 +42,13 @@ struct CellArgs {
   double* S[MHM_S_COUNT];             // device, [member][(nH)][nCells]
   double* F[MHM_F_COUNT];             // device, [member][(nH)][nCells]
   double* runoff_hist;                // device, [nSteps][member][nCells] or null
+  // routing input produced in place (one cell per node, one model step per routing event):
+  // node runoff qOUT of L11_runoff_acc in the tiled layout [step/8][member][lane][step%8]
+  double* qout_hist;                  // null: not fused
+  const int32_t* cell_lane;           // [nCells] routing lane of the cell's node
+  const double* cell_area;            // [nCells] area factor (mo_mrm_pre_routing.f90:125/:141)
+  int32_t qout_step0, qout_E, qout_map_flag;
+  double qout_tst, qout_scale;        // seconds per model step; 1000 / tst
   MeteoTables tab;
 };
 

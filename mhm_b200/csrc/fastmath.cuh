@@ -25,6 +25,10 @@
 #define MHM_HD inline
 #endif
 
+#ifndef MHM_FM_ESTRIN
+#define MHM_FM_ESTRIN 1
+#endif
+
 namespace mhm {
 namespace fm {
 
@@ -139,10 +143,21 @@ MHM_HD double exp_bounded(double x) {
 #endif
   double r = fma_(-kd, c.ln2_hi, x);
   r = fma_(-kd, c.ln2_lo, r);
+#if MHM_FM_ESTRIN
+  // Estrin's scheme: 14 operations in a dependency chain of depth 5 instead of 11 of depth 11
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double a0 = fma_(c.ex[1], r, c.ex[0]), a1 = fma_(c.ex[3], r, c.ex[2]);
+  const double a2 = fma_(c.ex[5], r, c.ex[4]), a3 = fma_(c.ex[7], r, c.ex[6]);
+  const double a4 = fma_(c.ex[9], r, c.ex[8]), a5 = fma_(c.ex[11], r, c.ex[10]);
+  const double b0 = fma_(a1, r2, a0), b1 = fma_(a3, r2, a2), b2 = fma_(a5, r2, a4);
+  double p = fma_(b2, r8, fma_(b1, r4, b0));
+  p = fma_(p, r2, r);  // r + r^2 * P(r)
+#else
   double p = c.ex[11];
 #pragma unroll
   for (int i = 10; i >= 0; --i) p = fma_(p, r, c.ex[i]);
   p = fma_(p * r, r, r);  // r + r^2 * P(r)
+#endif
   const int k = (int)kd;
   // 2^k through the exponent field; split in two factors so that k down to -1070 stays exact
   const int k1 = k / 2, k2 = k - k1;
@@ -152,6 +167,38 @@ MHM_HD double exp_bounded(double x) {
 
 // x ** y for x > 0 (finite, normal), |y log x| < 700
 MHM_HD double pow_pos(double x, double y) { return exp_bounded(y * log_pos(x)); }
+
+// x ** (2/3) for x > 0 (canopy evaporation, mo_canopy_interc.f90:117): r = x ** (-1/3) from a
+// single-precision seed (relative error < 2^-20) refined by two Newton steps of
+// f(r) = r^-3 - x -- division-free, r <- r + r (1 - x r^3) / 3, error -> 2 e^2 -- then x * r.
+MHM_HD double pow23_core(double x);
+MHM_HD double pow23_pos(double x) {
+  if (x > 1.0e30) return pow_pos(x, 0.6666666666666666666666666666666666667);
+  if (x < 1.0e-30) {  // outside the single-precision seed's range: x = m 2^(3k), result m^(2/3) 2^(2k)
+    const int k = ((hi_word(x) >> 20) - 1023) / 3;  // k < 0
+    const double m = x * make_double((1023 - 3 * k) << 20, 0);
+    return pow23_core(m) * make_double((1023 + 2 * k) << 20, 0);
+  }
+  return pow23_core(x);
+}
+MHM_HD double pow23_core(double x) {
+#if defined(__CUDA_ARCH__)
+  float l, r0;
+  const float xf = (float)x;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(xf));
+  l *= -0.333333333f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(l));
+#else
+  const float r0 = __builtin_exp2f(-0.333333333f * __builtin_log2f((float)x));
+#endif
+  double r = (double)r0;
+  const double third = 0.33333333333333333333;
+  double e = fma_(-x * (r * r), r, 1.0);
+  r = fma_(r * e, third, r);
+  e = fma_(-x * (r * r), r, 1.0);
+  r = fma_(r * e, third, r);
+  return x * r;
+}
 
 }  // namespace fm
 }  // namespace mhm

@@ -795,7 +795,8 @@ struct Segment {
 // so the qOUT tiles are built by the coalesced per-cell kernel.
 static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector<DevEvent>& ev,
                       const std::vector<Segment>& segs, const std::vector<double>& inflow_val,
-                      const double* runoff_hist, bool per_cell, double timestep_rout) {
+                      const double* runoff_hist, bool per_cell, bool qout_ready,
+                      double timestep_rout) {
   if (ev.empty()) return 0;
   cudaStream_t st = ctx->stream;
   const int nEv = (int)ev.size(), M = rt->M, E = rt->E;
@@ -845,7 +846,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
 
   ctx->stat_begin(kStatRouting);
   int64_t launched = 0;
-  {
+  if (!qout_ready) {
     QoutArgs qa{};
     qa.nCells1 = rt->nCells1;
     qa.nNodes = rt->nNodes;
@@ -934,7 +935,25 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
 
 // routing of model steps tt_first .. tt_first+n_steps-1 whose total runoff is in
 // d->runoff_hist; restates the schedule of mo_mhm_interface_run.f90:460-612
-int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_t n_steps) {
+bool routing_fuse_qout(mhm_cuda_context* ctx, Domain* d, int32_t n_steps, CellArgs* a) {
+  Routing* rt = d->rt;
+  if (!rt || !rt->bijective || rt->nInflowGauges > 0 || rt->nInflowTotal > 0 || d->keep_runoff_hist ||
+      routing_accumulates(d, rt) || getenv("MHM_CUDA_NO_ALIGNED") || getenv("MHM_CUDA_NO_FUSED_QOUT"))
+    return false;
+  if (ensure(&rt->qout_hist, &rt->qout_cap, hist_size(n_steps, rt->M, rt->E), ctx->stream)) return false;
+  a->qout_hist = rt->qout_hist;
+  a->cell_lane = rt->d_cell_entry;
+  a->cell_area = rt->d_cell_area;
+  a->qout_step0 = 0;
+  a->qout_E = rt->E;
+  a->qout_map_flag = rt->map_flag;
+  a->qout_tst = 3600.0 * d->cfg.timestep_h;
+  a->qout_scale = 1000.0 / a->qout_tst;
+  return true;
+}
+
+int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_t n_steps,
+                      bool qout_ready) {
   Routing* rt = d->rt;
   MHM_REQUIRE(rt->nTimeSteps == d->axis.nTimeSteps && rt->gauge_hist,
               "routing: time axis changed after mrm_cuda_set_network");
@@ -994,7 +1013,9 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
     acc_t0 = t + 1;
     carry_live = false;
   }
-  if (int rc = run_events(ctx, d, rt, ev, segs, inflow_val, d->runoff_hist, per_cell,
+  MHM_REQUIRE(!qout_ready || (per_cell && (int32_t)ev.size() == n_steps),
+              "routing: fused node runoff does not match the block's routing schedule");
+  if (int rc = run_events(ctx, d, rt, ev, segs, inflow_val, d->runoff_hist, per_cell, qout_ready,
                           (double)d->cfg.timestep_h))
     return rc;
   // steps at the end of the block that wait for a later routing call
@@ -1234,7 +1255,7 @@ int mrm_cuda_route(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, int32
   if (InflowDischarge)
     for (int g = 0; g < rt->nInflowTotal; ++g) inflow_val[(size_t)g] = InflowDischarge[g];
   std::vector<Segment> segs{Segment{0, 1, yId}};
-  return run_events(ctx, d, rt, ev, segs, inflow_val, src, false, (double)timestep_rout);
+  return run_events(ctx, d, rt, ev, segs, inflow_val, src, false, false, (double)timestep_rout);
 }
 
 int mrm_cuda_get_runoff(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, double* out,

@@ -319,6 +319,9 @@ class Domain:
     def run_steps(self, tt_first, n_steps):
         check(self.L.mhm_cuda_run_steps(self.h, self.id, tt_first, n_steps))
 
+    def keep_runoff_history(self, keep=True):
+        check(self.L.mhm_cuda_keep_runoff_history(self.h, self.id, int(keep)))
+
     def get_runoff_history(self, n_steps, member=0):
         out = np.zeros((n_steps, self.nCells))
         check(self.L.mhm_cuda_get_runoff_history(self.h, self.id, member, _pd(out), self.nCells))

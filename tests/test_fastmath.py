@@ -39,3 +39,18 @@ def test_fast_log_exp_pow_accuracy():
     bound = 2.3e-16 * (1.0 + np.abs(ys * np.log(xs)))
     assert (rel <= bound).all(), (rel / bound).max()
     assert L.mhm_host_fast_pow(1.0, 3.7) == 1.0 and L.mhm_host_fast_exp(0.0) == 1.0
+
+
+def test_fast_pow23_accuracy():
+    """canopy evaporation's x**(2/3) via the Newton-refined inverse cube root: <= 2 ulp"""
+    L = _lib.load()
+    L.mhm_host_fast_pow23.restype = C.c_double
+    L.mhm_host_fast_pow23.argtypes = [C.c_double]
+    rng = np.random.default_rng(1)
+    x = np.concatenate([10.0 ** rng.uniform(-29, 0, 200000), rng.uniform(0.0, 1.0, 100000) + 1e-300,
+                        10.0 ** rng.uniform(-300, -30, 1000)])
+    got = np.array([L.mhm_host_fast_pow23(v) for v in x])
+    ref = np.array([float(np.longdouble(v) ** (np.longdouble(2) / 3)) for v in x])
+    e = ulp_err(got, ref)
+    assert e.max() <= 2.0, e.max()
+    assert L.mhm_host_fast_pow23(1.0) == 1.0

@@ -236,3 +236,30 @@ def test_default_state_init_and_errors(ctx):
     with pytest.raises(interface._lib.MhmCudaError, match="holds steps"):
         dom.set_meteo("pre", prob["forcing"]["pre"][:10])
         dom.run_steps(1, 24)
+
+
+def test_fused_node_runoff_equals_separate_runoff_accumulation(ctx):
+    """L11 == L1: the cell kernel writes the routing's node runoff itself (fused L11_runoff_acc).
+    Strict mode: bit-identical to the unfused path (runoff history + qout kernel); asking for the
+    runoff history switches the fusion off and returns the same series."""
+    prob = synth.make_problem(nx=40, ny=30, n_days=6, hourly=True)
+    nT = prob["time"]["nTimeSteps"]
+    ctx.set_math_mode("strict")
+    dom = fresh(ctx, prob)
+    dom.run_steps(1, nT)
+    q_fused = dom.get_runoff()
+    with pytest.raises(RuntimeError):
+        dom.get_runoff_history(nT)
+    dom = fresh(ctx, prob)
+    dom.keep_runoff_history(True)
+    dom.run_steps(1, nT)
+    parity.assert_bit_exact(dom.get_runoff(), q_fused, "gauge series fused vs unfused")
+    assert dom.get_runoff_history(nT).shape == (nT, prob["nCells"])
+    o = orc_run.OracleRun(prob)
+    o.run(1, nT)
+    parity.assert_close(q_fused, o.mRM_runoff, "gauge discharge", rtol=parity.RTOL_Q)
+    ctx.set_math_mode("fast")
+    dom = fresh(ctx, prob)
+    dom.run_steps(1, nT)
+    parity.assert_close(dom.get_runoff(), o.mRM_runoff, "gauge discharge (fast, fused)", rtol=parity.RTOL_Q)
+    ctx.set_math_mode("strict")
