@@ -122,6 +122,9 @@ double mhm_host_fast_log(double x) { return mhm::fm::log_pos(x); }
 double mhm_host_fast_exp(double x) { return mhm::fm::exp_bounded(x); }
 double mhm_host_fast_pow(double x, double y) { return mhm::fm::pow_pos(x, y); }
 double mhm_host_fast_pow23(double x) { return mhm::fm::pow23_pos(x); }
+double mhm_host_tab_log(double x) { return mhm::fm::log_tab(mhm::fm::h_tables, x); }
+double mhm_host_tab_exp(double x) { return mhm::fm::exp_tab(mhm::fm::h_tables, x); }
+double mhm_host_tab_pow(double x, double y) { return mhm::fm::pow_tab(mhm::fm::h_tables, x, y); }
 const char* mhm_cuda_version(void) { return "mhm_cuda 0.1 (sm_100a)"; }
 
 int mhm_cuda_init(int device, mhm_cuda_context** out) {

@@ -33,7 +33,11 @@ namespace mhm {
 #define MHM_CELL_MIN_BLOCKS 4
 #endif
 
+#if MHM_FAST && defined(__CUDA_ARCH__)
+#define kEps (fm::c_coef.eps)  // constant bank: one uniform load instead of two 32-bit moves
+#else
 constexpr double kEps = 2.220446049250313e-16;  // epsilon(1.0_dp), mo_common_constants.f90:25
+#endif
 constexpr double kTwoThird = 0.6666666666666666666666666666666666667;  // FORCES twothird_dp
 constexpr double kPi = 3.141592653589793238462643383279502884197;
 constexpr double kTwoPi = 6.283185307179586476925286766559005768394;
@@ -151,6 +155,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
                                                const double evap_coeff,
 #if MHM_FAST
                                                const double inv_evap_coeff, double2* warp_tasks,
+                                               const fm::Tables& tab,
 #endif
                                                const FluxEmitter<EMIT>& emit) {
   // ---- canopy_interc, mo_canopy_interc.f90:105-131 ----
@@ -300,7 +305,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
         __syncwarp();
         for (unsigned k = lane; k < base; k += 32u) {
           const double2 tk = warp_tasks[k];
-          warp_tasks[k].x = fm::pow_pos(tk.x, tk.y);
+          warp_tasks[k].x = fm::pow_tab(tab, tk.x, tk.y);
         }
         __syncwarp();
 #pragma unroll
@@ -408,7 +413,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
     us = us - fast;
     if (us > kEps) {
 #if MHM_FAST
-      slow = fmin(p.k1r * fm::pow_pos(us, 1.0 + p.alpha), us - kEps);
+      slow = fmin(p.k1r * fm::pow_tab(tab, us, 1.0 + p.alpha), us - kEps);
 #else
       slow = fmin(p.k1r * pow(us, 1.0 + p.alpha), us - kEps);
 #endif
@@ -462,6 +467,14 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
 #if MHM_FAST
   __shared__ double2 sh_tasks[kCellThreads * NH];
+  __shared__ fm::Tables sh_tab;  // log / exp tables of fastmath.cuh, 4 KB
+  {
+    static_assert(sizeof(fm::Tables) == 256 * sizeof(double2), "table layout");
+    const double2* src = reinterpret_cast<const double2*>(&fm::d_tables);
+    double2* dst = reinterpret_cast<double2*>(&sh_tab);
+    for (int i = threadIdx.x; i < 256; i += kCellThreads) dst[i] = src[i];
+    __syncthreads();
+  }
   double2* const warp_tasks = sh_tasks + (threadIdx.x >> 5) * (32 * NH);
   // out-of-range lanes of the last tile stay alive (warp collectives) on a valid cell
   const bool live = cell < a.nCells;
@@ -647,7 +660,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     const double total_runoff = cascade_step<NH, VARIANT, EMIT>(
         p, s, pet_calc, temp_calc, prec_calc, a.soil_case, a.tab.evap_coeff[month],
 #if MHM_FAST
-        a.tab.inv_evap_coeff[month], warp_tasks,
+        a.tab.inv_evap_coeff[month], warp_tasks, sh_tab,
 #endif
         emit);
 

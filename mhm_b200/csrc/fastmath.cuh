@@ -25,6 +25,8 @@
 #define MHM_HD inline
 #endif
 
+#include "fastmath_tables.h"
+
 #ifndef MHM_FM_ESTRIN
 #define MHM_FM_ESTRIN 1
 #endif
@@ -36,6 +38,12 @@ struct Coef {
   double lg[7];       // Lg1..Lg7 of fdlibm e_log.c
   double ln2_hi, ln2_lo, inv_ln2;
   double ex[12];      // 1/2! .. 1/13!
+  // table-driven versions: Taylor coefficients that are not exact in the high word, range
+  // reduction constants, and epsilon(1.0_dp).  Kept in the constant bank because a 64-bit
+  // literal costs two moves into a uniform register at every use.
+  double third, fifth, msixth, c3, c4, c5;
+  double ln2hi42, ln2lo42, invln2n, mln2hin, mln2lon;
+  double eps;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -50,7 +58,10 @@ static const Coef h_coef = {
      1.479819860511658591e-01},
     6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00,
     {1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
-     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}};
+     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0},
+    0.33333333333333333, 0.2, -0.16666666666666666, 0.16666666666666666, 0.041666666666666664,
+    0.0083333333333333332, kLn2Hi42, kLn2Lo42, kInvLn2N, -kLn2HiN, -kLn2LoN,
+    2.220446049250313e-16};
 
 #if defined(__CUDACC__)
 __constant__ Coef c_coef = {
@@ -59,7 +70,10 @@ __constant__ Coef c_coef = {
      1.479819860511658591e-01},
     6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00,
     {1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
-     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}};
+     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0},
+    0.33333333333333333, 0.2, -0.16666666666666666, 0.16666666666666666, 0.041666666666666664,
+    0.0083333333333333332, kLn2Hi42, kLn2Lo42, kInvLn2N, -kLn2HiN, -kLn2LoN,
+    2.220446049250313e-16};
 #endif
 
 MHM_HD int hi_word(double x) {
@@ -199,6 +213,69 @@ MHM_HD double pow23_core(double x) {
   r = fma_(r * e, third, r);
   return x * r;
 }
+
+// ---- table-driven log / exp (128 entries each, 4 KB; the cell kernel stages them in shared
+// memory).  Half the operations and less than half the dependency depth of the polynomial-only
+// versions above: no division in log, degree-5 polynomials.  Absolute error of log_tab
+// <= 0.6 ulp(|log x|) + 6e-17, relative error of exp_tab <= 0.6 ulp; see tests/test_fastmath.py.
+struct LogEntry {
+  double invc, logc;
+};
+struct ExpEntry {
+  double tail;
+  unsigned long long sbits;
+};
+struct Tables {
+  LogEntry lg[128];
+  ExpEntry ex[128];
+};
+static const Tables h_tables = {{MHM_FM_LOG_TABLE}, {MHM_FM_EXP_TABLE}};
+#if defined(__CUDACC__)
+__device__ const Tables d_tables = {{MHM_FM_LOG_TABLE}, {MHM_FM_EXP_TABLE}};
+#endif
+
+// natural logarithm of a positive, finite, normal double
+MHM_HD double log_tab(const Tables& T, double x) {
+  const int hi = hi_word(x), lo = lo_word(x);
+  const int tmp = hi - 0x3fe60000;         // high word of bits(x) - OFF (the low word of OFF is 0)
+  const int i = (tmp >> 13) & 127;         // bits 45..51 of the offset
+  const int k = tmp >> 20;                 // arithmetic shift: exponent relative to [0.6875, 1.375)
+  const double z = make_double(hi - (tmp & (int)0xfff00000), lo);
+  const LogEntry e = T.lg[i];
+  const double r = fma_(z, e.invc, -1.0);  // exact argument of log1p, |r| < 2^-7.9
+  const double kd = (double)k;
+  const Coef& c = MHM_FM_COEF;
+  const double h = fma_(kd, c.ln2hi42, e.logc);
+  const double r2 = r * r;
+  // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6), truncation < 2e-18
+  const double q = fma_(r2, fma_(r2, c.msixth, fma_(c.fifth, r, -0.25)), fma_(c.third, r, -0.5));
+  const double l = fma_(kd, c.ln2lo42, r2 * q);
+  return h + (r + l);
+}
+
+// exp(x) for |x| < 700
+MHM_HD double exp_tab(const Tables& T, double x) {
+  const Coef& c = MHM_FM_COEF;
+#if defined(__CUDA_ARCH__)
+  const double kd = rint(x * c.invln2n);
+#else
+  const double kd = __builtin_rint(x * c.invln2n);
+#endif
+  const int ki = (int)kd;
+  double r = fma_(kd, c.mln2hin, x);
+  r = fma_(kd, c.mln2lon, r);              // |r| <= ln2 / 256
+  const ExpEntry e = T.ex[ki & 127];
+  // 2^(ki / 128): the table's bit pattern plus ki << 45 (exponent and index in one addition)
+  const double scale = make_double((int)(e.sbits >> 32) + (ki << 13), (int)(e.sbits & 0xffffffffu));
+  const double r2 = r * r;
+  // e^r - 1 = r + r^2/2 + r^3/6 + r^4/24 + r^5/120, truncation < 1e-18
+  double t = fma_(r2, fma_(c.c3, r, 0.5), e.tail + r);
+  t = fma_(r2 * r2, fma_(c.c5, r, c.c4), t);
+  return fma_(scale, t, scale);
+}
+
+// x ** y for x > 0 (finite, normal), |y log x| < 700
+MHM_HD double pow_tab(const Tables& T, double x, double y) { return exp_tab(T, y * log_tab(T, x)); }
 
 }  // namespace fm
 }  // namespace mhm

@@ -751,6 +751,107 @@ static void orc_step_cells(orc_domain *d, int32_t tt, const orc_dt *s, int32_t i
 }
 
 /* mo_mhm_eval.f90:136-150 + mo_mhm_interface_run.f90:341-638 */
+/* ---- gridded outputs ------------------------------------------------------------------ */
+int32_t orc_output_slots(const int32_t *f, int32_t nH, int32_t *var, int32_t *hor, int32_t *avg) {
+  /* order of the `ii = ii + 1` blocks of mHM_updateDataset (mo_write_fluxes_states.f90:326-436);
+   * averaged = created with avg=.true. in mHM_OutputDataset (:98-160): variables 1-8 and 18 */
+  static const int32_t order[21] = {1, 2, 3, 4, 5, 6, 7, 8, 18, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 20, 21};
+  int32_t n = 0, i, h;
+  for (i = 0; i < 21; i++) {
+    const int32_t v = order[i];
+    const int32_t per_h = (v == 3 || v == 4 || v == 17 || v == 19);
+    if (!f[v - 1]) continue;
+    for (h = 0; h < (per_h ? nH : 1); h++) {
+      if (var) var[n] = v;
+      if (hor) hor[n] = per_h ? h : -1;
+      if (avg) avg[n] = (v <= 8 || v == 18);
+      n++;
+    }
+  }
+  return n;
+}
+
+/* mHM_updateDataset for cell k with the land-cover scene yId the driver holds when it calls
+ * write_output, i.e. AFTER the date increment of the step (mo_mhm_interface_run.f90:623-628,690) */
+static double out_value(const orc_domain *d, int32_t v, int32_t hor, int32_t k, int32_t yId) {
+  const size_t n = (size_t)d->nCells;
+  const int32_t nH = d->nH;
+  const double fS = d->fSealed[(size_t)(yId - 1) * n + k];
+  const double fNS = 1.0 - fS; /* L1_fNotSealed, mo_mhm_interface_run.f90:238-239 */
+  int32_t h;
+  double a, b;
+  switch (v) {
+    case 1: return d->inter[k];
+    case 2: return d->snowPack[k];
+    case 3: return d->soilMoist[(size_t)hor * n + k];
+    case 4: return d->soilMoist[(size_t)hor * n + k] / d->soilMoistSat[((size_t)(yId - 1) * nH + hor) * n + k];
+    case 5:
+      a = 0.0;
+      b = 0.0;
+      for (h = 0; h < nH; h++) a = a + d->soilMoist[(size_t)h * n + k];
+      for (h = 0; h < nH; h++) b = b + d->soilMoistSat[((size_t)(yId - 1) * nH + h) * n + k];
+      return a / b;
+    case 6: return d->sealSTW[k];
+    case 7: return d->unsatSTW[k];
+    case 8: return d->satSTW[k];
+    case 9: return d->pet_calc[k];
+    case 10:
+      a = 0.0;
+      for (h = 0; h < nH; h++) a = a + d->aETSoil[(size_t)h * n + k];
+      return a * fNS + d->aETCanopy[k] + d->aETSealed[k] * fS;
+    case 11: return d->total_runoff[k];
+    case 12: return d->runoffSeal[k] * fS;
+    case 13: return d->fastRunoff[k] * fNS;
+    case 14: return d->slowRunoff[k] * fNS;
+    case 15: return d->baseflow[k] * fNS;
+    case 16: return d->percol[k] * fNS;
+    case 17: return d->infilSoil[(size_t)hor * n + k] * fNS;
+    case 19: return d->aETSoil[(size_t)hor * n + k] * fNS;
+    case 20: return d->preEffect[k];
+    case 21: return d->melt[k];
+    default: return 0.0; /* 18: neutrons, out of scope */
+  }
+}
+
+/* mhm_interface_run_write_output (:641-742) for the gridded mHM outputs; s is the date AFTER
+ * the increment of step tt */
+static void write_output(orc_domain *d, int32_t tt, const orc_dt *s) {
+  int32_t var[64], hor[64], avg[64], ns, sl, k, wr = 0;
+  const int32_t tIndex_out = tt - d->warming_days * d->nTstepDay; /* :621 */
+  const int32_t ts = d->timeStep_model_outputs;
+  const size_t n = (size_t)d->nCells;
+  if (!d->out_acc || tIndex_out <= 0) return;
+  ns = orc_output_slots(d->out_flags, d->nH, var, hor, avg);
+  if (ns == 0) return;
+  for (sl = 0; sl < ns; sl++) /* updateVariable, mo_nc_output.f90:140-149 */
+    for (k = 0; k < d->nCells; k++)
+      d->out_acc[(size_t)sl * n + k] = d->out_acc[(size_t)sl * n + k] + out_value(d, var[sl], hor[sl], k, s->yId);
+  d->out_counter += 1;
+  /* datetimeinfo_writeout, mo_common_datetime_type.f90:157-184 */
+  if (ts > 0) {
+    wr = (tIndex_out % ts == 0) || tt == d->nTimeSteps;
+  } else if (ts == 0) {
+    wr = tt == d->nTimeSteps;
+  } else if (ts == -1) {
+    wr = s->is_new_day || tt == d->nTimeSteps;
+  } else if (ts == -2) {
+    wr = s->is_new_month || tt == d->nTimeSteps;
+  } else if (ts == -3) {
+    wr = s->is_new_year || tt == d->nTimeSteps;
+  }
+  if (!wr || d->out_nwin >= d->out_max_windows) return;
+  for (sl = 0; sl < ns; sl++) /* writeVariableTimestep, mo_nc_output.f90:158-175 */
+    for (k = 0; k < d->nCells; k++) {
+      double v = d->out_acc[(size_t)sl * n + k];
+      if (avg[sl]) v = v / (double)d->out_counter;
+      d->out_win[((size_t)d->out_nwin * ns + sl) * n + k] = v;
+      d->out_acc[(size_t)sl * n + k] = 0.0;
+    }
+  d->out_win_tt[d->out_nwin] = tt;
+  d->out_nwin += 1;
+  d->out_counter = 0;
+}
+
 int32_t orc_run(orc_domain *d, int32_t tt_first, int32_t tt_last) {
   orc_dt s;
   int32_t tt, k, g, jj;
@@ -825,6 +926,7 @@ int32_t orc_run(orc_domain *d, int32_t tt_first, int32_t tt_last) {
     }
     dt_increment(d, &s); /* :623 */
     if (s.is_new_year && tt < d->nTimeSteps) s.yId = lc_yid(d, s.year); /* :626-628 */
+    if (tt >= tt_first) write_output(d, tt, &s);                        /* mo_mhm_eval.f90:141 */
   }
   free(qAcc);
   return 0;

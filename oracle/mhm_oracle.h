@@ -274,6 +274,18 @@ typedef struct orc_domain {
   double *flux_history;
   int32_t flux_history_stride;
   int32_t num_threads;
+  /* gridded outputs: mHM_updateDataset + OutputVariable (mo_write_fluxes_states.f90:283-438,
+   * mo_nc_output.f90:140-175).  out_flags[v-1] = outputFlxState(v), v = 1..21; slots follow the
+   * order of mHM_updateDataset (orc_output_slots).  out_acc [nSlots][nCells] holds the open
+   * window, out_win [out_max_windows][nSlots][nCells] the written ones, out_win_tt their step. */
+  int32_t out_flags[21];
+  int32_t timeStep_model_outputs;
+  int32_t out_counter;
+  int32_t out_nwin;
+  int32_t out_max_windows;
+  double *out_acc;
+  double *out_win;
+  int32_t *out_win_tt;
 } orc_domain;
 
 /* number of per-cell records written per step into flux_history (see .c) */
@@ -284,6 +296,10 @@ int32_t orc_flux_record_size(int32_t nH);
  * tt_first must be 1 on the first call (state of the date stepping is recomputed
  * from tt, so any split of the time axis gives identical results). */
 int32_t orc_run(orc_domain *d, int32_t tt_first, int32_t tt_last);
+/* slots of the enabled output variables in mHM_updateDataset order: var[s] in 1..21, hor[s] the
+ * 0-based horizon of per-horizon variables (else -1), avg[s] = averaged over the window */
+int32_t orc_output_slots(const int32_t *out_flags, int32_t nH, int32_t *var, int32_t *hor,
+                         int32_t *avg);
 
 /* per-step index vectors (month 1-12, hour, yId 1-based, iLAI 1-based, iMeteoTS 1-based,
  * isday, doy) for tt = 1..n; arrays of length n */

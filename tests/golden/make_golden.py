@@ -130,6 +130,20 @@ def make_case(case, sim_start, n_days, warming_days, lc_years, cases=(1, 0, 1), 
                 out["Qsim/" + k[5:]] = q[k].read()
         txt = np.loadtxt(os.path.join(sav, "%s_daily_discharge.out" % out_prefix), skiprows=1)
         out["Qsim_text"] = txt[:, 5::2]
+    # gridded outputs of the run (mhm_outputs.nml: outputFlxState, timeStep_model_outputs)
+    fs = os.path.join(sav, "%s_mHM_Fluxes_States.nc" % out_prefix)
+    if os.path.exists(fs):
+        txt = re.sub(r"!.*", "", open(os.path.join(cdir, "mhm_outputs.nml")).read())
+        flags = np.zeros(21, dtype=np.int32)
+        for m in re.finditer(r"outputFlxState\((\d+)\)\s*=\s*\.(TRUE|FALSE)\.", txt, re.I):
+            flags[int(m.group(1)) - 1] = m.group(2).upper() == "TRUE"
+        out["out_flags"] = flags
+        out["out_timestep"] = np.array(int(re.search(r"timeStep_model_outputs\s*=\s*(-?\d+)", txt, re.I).group(1)))
+        f = h5lite.H5File(fs)
+        for k in f.keys():
+            if len(f[k].shape) == 3:
+                out["out/" + k] = pick(f[k].read())       # (windows, nCells)
+        out["out_time_bnds"] = f["time_bnds"].read()
     out["gamma"], out["processMatrix"] = gamma_vector(os.path.join(cdir, "mhm_parameter.nml"), cases)
     out["time"] = np.array([sim_start.toordinal(), n_days, warming_days])
     out["lc_years"] = np.array(lc_years, dtype=np.int32)   # (first year, LCyearId...)

@@ -40,10 +40,25 @@ def load(case):
     prob["forcing"] = {k[8:]: np.ascontiguousarray(z[k]) for k in z.files if k.startswith("forcing/")}
     prob["horizon_depth"] = np.ascontiguousarray(z["horizon_bnds"][:, 1])
     prob["states0"] = synth.default_states(n, nH, prob["horizon_depth"])
+    outs = None
+    if "out_flags" in z.files:
+        # NetCDF name -> (outputFlxState index, 0-based horizon or -1)
+        names = {"interception": (1, -1), "snowpack": (2, -1), "SM_Lall": (5, -1), "sealedSTW": (6, -1),
+                 "unsatSTW": (7, -1), "satSTW": (8, -1), "PET": (9, -1), "aET": (10, -1), "Q": (11, -1),
+                 "QD": (12, -1), "QIf": (13, -1), "QIs": (14, -1), "QB": (15, -1), "recharge": (16, -1),
+                 "preEffect": (20, -1), "Qsm": (21, -1)}
+        for h in range(nH):
+            names["SWC_L%02d" % (h + 1)] = (3, h)
+            names["SM_L%02d" % (h + 1)] = (4, h)
+            names["soil_infil_L%02d" % (h + 1)] = (17, h)
+            names["aET_L%02d" % (h + 1)] = (19, h)
+        outs = {"flags": z["out_flags"], "timestep": int(z["out_timestep"]),
+                "fields": {names[k[4:]]: z[k] for k in z.files if k.startswith("out/")},
+                "time_bnds": z["out_time_bnds"]}
     if rout_case == 0:
         prob["net"] = None
         ref = {"final": {k[6:]: z[k] for k in z.files if k.startswith("final/")},
-               "warming_days": warming, "n_days": n_days}
+               "warming_days": warming, "n_days": n_days, "outputs": outs}
         return prob, ref
     nn = int(z["net/mask11"].sum())
     nLinks = int((z["net/L11_fromN"] > 0).sum())
@@ -64,7 +79,7 @@ def load(case):
     prob["inflowQ"] = np.zeros((0, n_days))
     ref = {"final": {k[6:]: z[k] for k in z.files if k.startswith("final/")},
            "Qsim": np.stack([z[k] for k in z.files if k.startswith("Qsim/")]),
-           "Qsim_text": z["Qsim_text"].T, "warming_days": warming, "n_days": n_days}
+           "Qsim_text": z["Qsim_text"].T, "warming_days": warming, "n_days": n_days, "outputs": outs}
     return prob, ref
 
 

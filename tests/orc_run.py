@@ -40,7 +40,9 @@ S2FIELD = {"L1_inter": "inter", "L1_snowPack": "snowPack", "L1_sealSTW": "sealST
 class OracleRun:
     """Owns the numpy buffers behind an orc_domain and exposes results by reference name."""
 
-    def __init__(self, prob, params=None, history=False, num_threads=1):
+    def __init__(self, prob, params=None, history=False, num_threads=1, outputs=None, max_windows=64):
+        """outputs = (outputFlxState[21], timeStep_model_outputs) switches the gridded output
+        accumulation on; results in self.out_windows() after run()"""
         self.prob = prob
         self.keep = []
         d = self.d = orc.OrcDomain()
@@ -132,6 +134,29 @@ class OracleRun:
             self.history = np.zeros((nT, self.rs, n))
             d.flux_history = self._d(self.history)
         d.num_threads = num_threads
+        self.n_slots = 0
+        if outputs is not None:
+            flags, ts = outputs
+            for i in range(21):
+                d.out_flags[i] = int(flags[i])
+            d.timeStep_model_outputs = int(ts)
+            self.slot_var = np.zeros(64, dtype=np.int32)
+            self.slot_hor = np.zeros(64, dtype=np.int32)
+            self.slot_avg = np.zeros(64, dtype=np.int32)
+            L = orc.lib()
+            L.orc_output_slots.restype = C.c_int32
+            L.orc_output_slots.argtypes = [C.POINTER(C.c_int32)] * 1 + [C.c_int32] + [C.POINTER(C.c_int32)] * 3
+            fl = np.ascontiguousarray(flags, dtype=np.int32)
+            self.n_slots = L.orc_output_slots(orc.iptr(fl), nH, orc.iptr(self.slot_var), orc.iptr(self.slot_hor),
+                                              orc.iptr(self.slot_avg))
+            self.out_acc = np.zeros((max(1, self.n_slots), n))
+            self.out_win = np.zeros((max_windows, max(1, self.n_slots), n))
+            self.out_win_tt = np.zeros(max_windows, dtype=np.int32)
+            d.out_acc, d.out_win = self._d(self.out_acc), self._d(self.out_win)
+            self.out_acc, self.out_win = self.keep[-2], self.keep[-1]
+            d.out_win_tt = self._i(self.out_win_tt)
+            self.out_win_tt = self.keep[-1]
+            d.out_max_windows = max_windows
 
     def _d(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
@@ -146,6 +171,15 @@ class OracleRun:
     def run(self, tt_first, tt_last):
         rc = orc.lib().orc_run(C.byref(self.d), tt_first, tt_last)
         assert rc == 0
+
+    def out_windows(self):
+        """list of (tt_end, {(var, horizon): values}) of the written output windows"""
+        res = []
+        for w in range(self.d.out_nwin):
+            fields = {(int(self.slot_var[sl]), int(self.slot_hor[sl])): self.out_win[w, sl]
+                      for sl in range(self.n_slots)}
+            res.append((int(self.out_win_tt[w]), fields))
+        return res
 
     def hist(self, name, tt):
         """value of a flux/state after step tt (1-based) from the history"""

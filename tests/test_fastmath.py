@@ -54,3 +54,29 @@ def test_fast_pow23_accuracy():
     e = ulp_err(got, ref)
     assert e.max() <= 2.0, e.max()
     assert L.mhm_host_fast_pow23(1.0) == 1.0
+
+
+def test_table_driven_log_exp_pow_accuracy():
+    """the 128-entry table versions the fast kernel uses for x**y: log absolute error within
+    1 ulp(|log x|) + 6e-17, exp <= 1 ulp, pow relative error <= 3e-16 * (1 + |y log x|)"""
+    L = _lib.load()
+    for f, n in (("mhm_host_tab_log", 1), ("mhm_host_tab_exp", 1), ("mhm_host_tab_pow", 2)):
+        getattr(L, f).restype = C.c_double
+        getattr(L, f).argtypes = [C.c_double] * n
+    rng = np.random.default_rng(2)
+    N = 200000
+    x = np.concatenate([10.0 ** rng.uniform(-18, 5, N), rng.uniform(0.5, 2.0, N), 1.0 + rng.normal(0, 1e-6, 1000),
+                        10.0 ** rng.uniform(-300, 300, 20000)])
+    got = np.array([L.mhm_host_tab_log(v) for v in x])
+    ref = np.log(x)
+    assert (np.abs(got - ref) <= np.spacing(np.abs(ref)) + 6e-17).all()
+    t = np.concatenate([rng.uniform(-690, 690, N), rng.uniform(-1, 1, N)])
+    got = np.array([L.mhm_host_tab_exp(v) for v in t])
+    assert ulp_err(got, np.exp(t)).max() <= 1.0
+    xs = np.concatenate([rng.uniform(1e-6, 1.0, N), rng.uniform(1e-12, 5e3, N), 1.0 - 10.0 ** rng.uniform(-16, -1, 20000)])
+    ys = np.concatenate([rng.uniform(1.5, 6.0, N), rng.uniform(1.05, 1.6, N), rng.uniform(1.0, 6.0, 20000)])
+    got = np.array([L.mhm_host_tab_pow(a, b) for a, b in zip(xs, ys)])
+    ref = np.power(xs, ys)
+    rel = np.abs(got - ref) / ref
+    assert (rel <= 3.0e-16 * (1.0 + np.abs(ys * np.log(xs)))).all()
+    assert L.mhm_host_tab_pow(1.0, 3.7) == 1.0 and L.mhm_host_tab_exp(0.0) == 1.0
