@@ -231,6 +231,30 @@ int mhm_cuda_run_steps(mhm_cuda_context *ctx, int32_t iDomain, int32_t tt_first,
  * default), 1 = fast (same algorithm, FMA + hoisted reciprocals; <= 1e-9 relative) */
 int mhm_cuda_set_math_mode(mhm_cuda_context *ctx, int32_t mode);
 
+/* ---------------------------------------------------------------------------------
+ * A10 / N1  gridded outputs accumulated on the device while blocks of steps run.
+ * Replaces, for run_steps, the per-step `call mHM_updateDataset(...)`
+ * (mHM/mo_write_fluxes_states.f90:283-438, called from mo_mhm_interface_run.f90:690-717)
+ * and OutputVariable%updateVariable / writeVariableTimestep (common/mo_nc_output.f90:140-175):
+ * every step with tIndex_out > 0 adds the enabled variables (same derived expressions, same
+ * land-cover scene -- the one AFTER the date increment -- and the same sequential summation
+ * in time) to the open window; a window closes where datetimeinfo%writeout
+ * (common/mo_common_datetime_type.f90:157-184) fires, averaged for the state variables
+ * 1-8, summed for the fluxes.  outputFlxState is mhm_outputs.nml's array (1..21; 18 =
+ * neutrons is not supported), timeStep_model_outputs its window selector (-3 yearly,
+ * -2 monthly, -1 daily, 0 end of run, > 0 every n steps).  After a run_steps call the
+ * windows it closed can be fetched; the Fortran writer then calls nc%setData for each.
+ * --------------------------------------------------------------------------------- */
+int mhm_cuda_set_outputs(mhm_cuda_context *ctx, int32_t iDomain, const int32_t *outputFlxState,
+                         int32_t timeStep_model_outputs);
+/* number of windows closed by the last run_steps call; tt_end[w] = model step that closed it */
+int mhm_cuda_get_output_windows(mhm_cuda_context *ctx, int32_t iDomain, int32_t *n_windows,
+                                int32_t *tt_end, int32_t capacity);
+/* one variable (1..21; horizon 1..nH for variables 3, 4, 17, 19, else 0) of one closed
+ * window of one member, out[nCells] */
+int mhm_cuda_get_output(mhm_cuda_context *ctx, int32_t iDomain, int32_t member, int32_t window,
+                        int32_t variable, int32_t horizon, double *out);
+
 /* keep host module globals coherent (pybind get%L1_variable, restart writing): bind once,
  * then mhm_cuda_sync_to_host copies every bound state/flux of every member 0 array back */
 int mhm_cuda_bind_host_state(mhm_cuda_context *ctx, int32_t iDomain, int32_t state_id,

@@ -93,6 +93,9 @@ def load():
         "mhm_cuda_sync_to_host": [vp, i32],
         "mhm_cuda_get_runoff_history": [vp, i32, i32, pd, i64],
         "mhm_cuda_keep_runoff_history": [vp, i32, i32],
+        "mhm_cuda_set_outputs": [vp, i32, pi, i32],
+        "mhm_cuda_get_output_windows": [vp, i32, pi, pi, i32],
+        "mhm_cuda_get_output": [vp, i32, i32, i32, i32, i32, pd],
         "mrm_cuda_set_network": [vp, i32, C.POINTER(Network)],
         "mrm_routing_order": [i32, i32, pi, pi, pi, pi],
         "mrm_cuda_set_reg_rout": [vp, i32, i32, pd, pd, pd, pd],

@@ -70,6 +70,8 @@ static void free_domain(Domain* d) {
   cudaFree(d->d_idx);
   cudaFree(d->d_idx_one);
   cudaFree(d->runoff_hist);
+  cudaFree(d->out_acc);
+  cudaFree(d->out_win);
   if (d->rt) routing_free(d->rt);
   if (d->mpr) mpr_free(d->mpr);
   delete d;
@@ -601,27 +603,167 @@ static int meteo_release(mhm_cuda_context* ctx, Domain* d) {
   return 0;
 }
 
-// One block of model steps = ceil(nSteps / kIdxInline) launches: the calendar of a launch
-// travels inside the kernel arguments (constant bank), states are re-read at each launch.
-static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const StepIdx* idx) {
+// ---- gridded outputs: window logic of mo_common_datetime_type.f90:157-184 ------------------
+static inline bool out_active(const Domain* d, int32_t tt) {  // tIndex_out > 0, :621
+  return tt - d->axis.warming_days * (24 / d->cfg.timestep_h) > 0;
+}
+static inline bool out_writes(const Domain* d, int32_t tt) {
+  if (!out_active(d, tt)) return false;
+  const int32_t nT = d->axis.nTimeSteps, ts = d->out_ts;
+  const int32_t tIndex_out = tt - d->axis.warming_days * (24 / d->cfg.timestep_h);
+  const int8_t fl = d->h_idx[(size_t)tt - 1].flags;
+  if (tt == nT) return ts >= -3;
+  if (ts > 0) return tIndex_out % ts == 0;
+  if (ts == -1) return (fl & 1) != 0;
+  if (ts == -2) return (fl & 2) != 0;
+  if (ts == -3) return (fl & 4) != 0;
+  return false;
+}
+
+__global__ void out_finalize_kernel(double* __restrict__ acc, double* __restrict__ win, size_t per_slot,
+                                    int nslots, uint64_t avg_mask, double counter) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_slot) return;
+  for (int s = 0; s < nslots; ++s) {  // writeVariableTimestep, mo_nc_output.f90:158-175
+    double v = acc[(size_t)s * per_slot + i];
+    if ((avg_mask >> s) & 1) v = v / counter;
+    win[(size_t)s * per_slot + i] = v;
+    acc[(size_t)s * per_slot + i] = 0.0;
+  }
+}
+
+// One block of model steps = a sequence of launches of at most kIdxInline steps: the calendar
+// of a launch travels inside the kernel arguments (constant bank), states are re-read at each
+// launch.  With gridded outputs on, a launch also ends where an output window closes.
+static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const StepIdx* idx,
+                        bool block_mode) {
   const int32_t total = a.nSteps, tt0 = a.tt_first, wf = a.write_fluxes;
   double* const hist0 = a.runoff_hist;
-  const size_t hist_stride = (size_t)d->cfg.nMembers * (size_t)d->cfg.nCells;
+  const size_t per_slot = (size_t)d->cfg.nMembers * (size_t)d->cfg.nCells;
+  const bool outputs = block_mode && d->out_mask != 0;  // the per-step seam leaves outputs to the host
   ctx->stat_begin(kStatCell);
   int rc = 0;
-  for (int32_t t0 = 0; t0 < total && rc == 0; t0 += kIdxInline) {
-    const int32_t nb = total - t0 < kIdxInline ? total - t0 : kIdxInline;
+  for (int32_t t0 = 0; t0 < total && rc == 0;) {
+    int32_t nb = total - t0 < kIdxInline ? total - t0 : kIdxInline;
+    bool closes = false;
+    a.out_mask = 0;
+    if (outputs) {
+      int32_t first = nb;
+      for (int32_t t = 0; t < nb; ++t) {
+        const int32_t tt = tt0 + t0 + t;
+        if (out_active(d, tt) && first == nb) first = t;
+        a.out_yid[t] = (int8_t)(tt < d->axis.nTimeSteps ? d->h_idx[(size_t)tt].yId
+                                                        : d->h_idx[(size_t)tt - 1].yId);
+        if (out_writes(d, tt)) {
+          nb = t + 1;
+          closes = true;
+          break;
+        }
+      }
+      if (first < nb) {
+        a.out_mask = d->out_mask;
+        a.out_first = first;
+        a.out_acc = d->out_acc;
+        d->out_counter += nb - first;
+      }
+    }
     a.nSteps = nb;
     a.tt_first = tt0 + t0;
     a.write_fluxes = (wf && t0 + nb >= total) ? 1 : 0;
-    a.runoff_hist = hist0 ? hist0 + (size_t)t0 * hist_stride : nullptr;
+    a.runoff_hist = hist0 ? hist0 + (size_t)t0 * per_slot : nullptr;
     a.qout_step0 = t0;
     memcpy(a.idx_in, idx + t0, (size_t)nb * sizeof(StepIdx));
     rc = ctx->math_mode == 1 ? launch_cell_block_fast(a, d->cfg.nHorizons, ctx->stream)
                              : launch_cell_block_strict(a, d->cfg.nHorizons, ctx->stream);
+    if (rc == 0 && closes) {
+      const size_t w = d->out_win_tt.size();
+      const size_t need = (w + 1) * (size_t)d->out_nslots * per_slot;
+      if (need > d->out_win_cap) {
+        rc = 2;  // sized by run_steps for every window of the call
+      } else {
+        out_finalize_kernel<<<(unsigned)((per_slot + 255) / 256), 256, 0, ctx->stream>>>(
+            d->out_acc, d->out_win + w * (size_t)d->out_nslots * per_slot, per_slot, d->out_nslots,
+            d->out_avg_mask, (double)d->out_counter);
+        rc = (int)cudaGetLastError();
+        d->out_win_tt.push_back(tt0 + t0 + nb - 1);
+        d->out_counter = 0;
+      }
+    }
+    t0 += nb;
   }
   ctx->stat_end(kStatCell);
   MHM_REQUIRE(rc == 0, "cell kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}
+
+int mhm_cuda_set_outputs(mhm_cuda_context* ctx, int32_t iDomain, const int32_t* outputFlxState,
+                         int32_t timeStep_model_outputs) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(outputFlxState, "set_outputs: null outputFlxState");
+  MHM_REQUIRE(!outputFlxState[17], "set_outputs: variable 18 (neutrons) is not supported");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  // order of the `ii = ii + 1` blocks of mHM_updateDataset, mo_write_fluxes_states.f90:326-436
+  static const int order[20] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 20, 21};
+  d->out_mask = 0;
+  d->out_avg_mask = 0;
+  d->out_slot_var.clear();
+  d->out_slot_hor.clear();
+  for (int v : order) {
+    if (!outputFlxState[v - 1]) continue;
+    d->out_mask |= 1u << v;
+    const bool per_h = v == 3 || v == 4 || v == 17 || v == 19;
+    for (int h = 0; h < (per_h ? d->cfg.nHorizons : 1); ++h) {
+      if (v <= 8) d->out_avg_mask |= (uint64_t)1 << d->out_slot_var.size();
+      d->out_slot_var.push_back((int8_t)v);
+      d->out_slot_hor.push_back((int8_t)(per_h ? h : -1));
+    }
+  }
+  d->out_nslots = (int32_t)d->out_slot_var.size();
+  MHM_REQUIRE(d->out_nslots <= 64, "set_outputs: too many output slots (%d)", d->out_nslots);
+  d->out_ts = timeStep_model_outputs;
+  d->out_counter = 0;
+  d->out_win_tt.clear();
+  cudaFree(d->out_acc);
+  d->out_acc = nullptr;
+  if (d->out_nslots > 0) {
+    const size_t bytes = (size_t)d->out_nslots * d->cfg.nMembers * d->cfg.nCells * sizeof(double);
+    MHM_CUDA_OK(cudaMalloc(&d->out_acc, bytes));
+    MHM_CUDA_OK(cudaMemsetAsync(d->out_acc, 0, bytes, ctx->stream));
+  }
+  return 0;
+}
+
+int mhm_cuda_get_output_windows(mhm_cuda_context* ctx, int32_t iDomain, int32_t* n_windows,
+                                int32_t* tt_end, int32_t capacity) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(n_windows, "get_output_windows: null n_windows");
+  *n_windows = (int32_t)d->out_win_tt.size();
+  for (int32_t w = 0; tt_end && w < *n_windows && w < capacity; ++w) tt_end[w] = d->out_win_tt[(size_t)w];
+  return 0;
+}
+
+int mhm_cuda_get_output(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, int32_t window,
+                        int32_t variable, int32_t horizon, double* out) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(out && member >= 0 && member < d->cfg.nMembers && window >= 0 &&
+                  window < (int32_t)d->out_win_tt.size(),
+              "get_output: bad member/window (%d windows closed by the last run_steps)",
+              (int)d->out_win_tt.size());
+  int slot = -1;
+  for (int s = 0; s < d->out_nslots; ++s)
+    if (d->out_slot_var[(size_t)s] == variable &&
+        (d->out_slot_hor[(size_t)s] < 0 || d->out_slot_hor[(size_t)s] == horizon - 1))
+      slot = s;
+  MHM_REQUIRE(slot >= 0, "get_output: variable %d (horizon %d) is not enabled", variable, horizon);
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d->cfg.nCells, per_slot = n * (size_t)d->cfg.nMembers;
+  MHM_CUDA_OK(cudaMemcpyAsync(out, d->out_win + ((size_t)window * d->out_nslots + slot) * per_slot + (size_t)member * n,
+                              n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
@@ -656,7 +798,7 @@ int mhm_cuda_cell_step(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt,
   d->last_yId = s.yId;
   d->hist_steps = 0;
   if (int rc = meteo_acquire(ctx, d)) return rc;
-  if (int rc = launch_cells(ctx, d, a, &s)) return rc;
+  if (int rc = launch_cells(ctx, d, a, &s, false)) return rc;
   return meteo_release(ctx, d);
 }
 
@@ -687,6 +829,20 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
     MHM_CUDA_OK(cudaMalloc(&d->runoff_hist, need * sizeof(double)));
     d->runoff_cap = need;
   }
+  d->out_win_tt.clear();
+  if (d->out_mask) {  // every window this call closes gets a slot
+    size_t nwin = 0;
+    for (int32_t tt = tt_first; tt < tt_first + n_steps; ++tt) nwin += out_writes(d, tt) ? 1 : 0;
+    const size_t need_w = nwin * (size_t)d->out_nslots * M * n;
+    if (need_w > d->out_win_cap) {
+      MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(d->out_win);
+      d->out_win = nullptr;
+      d->out_win_cap = 0;
+      MHM_CUDA_OK(cudaMalloc(&d->out_win, need_w * sizeof(double)));
+      d->out_win_cap = need_w;
+    }
+  }
   if (int rc = meteo_acquire(ctx, d)) return rc;
   for (int32_t t0 = 0; t0 < n_steps; t0 += tb) {
     const int32_t nb = (n_steps - t0 < tb) ? n_steps - t0 : tb;
@@ -697,7 +853,7 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
     a.write_fluxes = (t0 + nb >= n_steps) ? 1 : 0;  // fluxes of the call's last step
     a.runoff_hist = fused ? nullptr : d->runoff_hist;
     if (fused) routing_fuse_qout(ctx, d, nb, &a);
-    if (int rc = launch_cells(ctx, d, a, d->h_idx.data() + (tt_first + t0 - 1))) return rc;
+    if (int rc = launch_cells(ctx, d, a, d->h_idx.data() + (tt_first + t0 - 1), true)) return rc;
     d->hist_steps = fused ? 0 : nb;
     d->hist_tt_first = tt_first + t0;
     d->last_yId = d->h_idx[(size_t)(tt_first + t0 + nb - 2)].yId;

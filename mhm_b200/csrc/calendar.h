@@ -77,7 +77,7 @@ inline void fill_step_indices(const TimeAxis& ax, int timestep_h, int nTstepForc
     s.month = (int8_t)m;
     s.hour = (int8_t)hour;
     s.isday = (int8_t)((hour > 6) && (hour <= 18));
-    s.pad = 0;
+    s.flags = 0;
     // increment
     const int pd = d, pm = m, py = y;
     hour += timestep_h;
@@ -87,6 +87,7 @@ inline void fill_step_indices(const TimeAxis& ax, int timestep_h, int nTstepForc
     new_day = pd != d;
     new_month = pm != m;
     new_year = py != y;
+    s.flags = (int8_t)((new_day ? 1 : 0) | (new_month ? 2 : 0) | (new_year ? 4 : 0));
     if (new_year && tt < ax.nTimeSteps) yId = ax.scene_of_year(y);
   }
 }

@@ -125,22 +125,92 @@ struct CellStates {
 // has to stay in a register until the end of the time loop.  They are only stored for the
 // last step of a block: the time loop is compiled twice, with EMIT = false for steps
 // 1..n-1 (the emitter vanishes) and EMIT = true for the last one.
-template <bool EMIT>
+// fluxes of the step the gridded outputs are built from (kept only by the OUT kernels)
+struct FluxCapture {
+  double v[MHM_F_COUNT];
+  double aet_soil[kMaxHorizons], infil[kMaxHorizons];
+};
+
+template <bool EMIT, bool OUT = false>
 struct FluxEmitter {
   double* const* F;
   size_t mc, n, mh;  // member*n + cell; nCells; (member*NH)*n + cell
   bool on;
+  FluxCapture* cap;
   __device__ __forceinline__ void operator()(int id, double v) const {
     if (EMIT) {
       if (on) F[id][mc] = v;
     }
+    if (OUT) cap->v[id] = v;
   }
   __device__ __forceinline__ void operator()(int id, int h, double v) const {
     if (EMIT) {
       if (on) F[id][mh + (size_t)h * n] = v;
     }
+    if (OUT) (id == MHM_F_AETSOIL ? cap->aet_soil : cap->infil)[h] = v;
   }
 };
+
+// mHM_updateDataset (mo_write_fluxes_states.f90:326-436): add the step's value of every enabled
+// output variable to the open window, slots in the order of the reference's `ii = ii + 1`
+// blocks.  fS / fNS / sat_o belong to the land-cover scene the driver holds after the step's
+// date increment (mo_mhm_interface_run.f90:623-628, 690-696).
+template <int NH>
+__device__ __forceinline__ void accumulate_outputs(const uint32_t mask, double* ap, const size_t stride,
+                                                   const FluxCapture& f, const CellStates<NH>& s,
+                                                   const double fS, const double* sat_o) {
+  const double fNS = 1.0 - fS;  // L1_fNotSealed, mo_mhm_interface_run.f90:238-239
+  auto add = [&](double v) {
+    *ap = *ap + v;  // OutputVariable%updateVariable, mo_nc_output.f90:140-149
+    ap += stride;
+  };
+  auto on = [&](int v) { return (mask >> v) & 1u; };
+  if (on(1)) add(s.inter);
+  if (on(2)) add(s.snowpack);
+  if (on(3)) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h) add(s.sm[h]);
+  }
+  if (on(4)) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h) add(s.sm[h] / sat_o[h]);
+  }
+  if (on(5)) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) a = a + s.sm[h];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) b = b + sat_o[h];
+    add(a / b);
+  }
+  if (on(6)) add(s.sealed);
+  if (on(7)) add(s.unsat);
+  if (on(8)) add(s.sat);
+  if (on(9)) add(f.v[MHM_F_PET_CALC]);
+  if (on(10)) {
+    double a = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) a = a + f.aet_soil[h];
+    const double t1 = a * fNS, t2 = f.v[MHM_F_AETSEALED] * fS;
+    add((t1 + f.v[MHM_F_AETCANOPY]) + t2);
+  }
+  if (on(11)) add(f.v[MHM_F_TOTAL_RUNOFF]);
+  if (on(12)) add(f.v[MHM_F_RUNOFFSEAL] * fS);
+  if (on(13)) add(f.v[MHM_F_FASTRUNOFF] * fNS);
+  if (on(14)) add(f.v[MHM_F_SLOWRUNOFF] * fNS);
+  if (on(15)) add(f.v[MHM_F_BASEFLOW] * fNS);
+  if (on(16)) add(f.v[MHM_F_PERCOL] * fNS);
+  if (on(17)) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h) add(f.infil[h] * fNS);
+  }
+  if (on(19)) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h) add(f.aet_soil[h] * fNS);
+  }
+  if (on(20)) add(f.v[MHM_F_PREEFFECT]);
+  if (on(21)) add(f.v[MHM_F_MELT]);
+}
 
 // kernel variants: the generic one takes every process selection at run time; the two
 // specialised ones cover the configurations every large run uses (hourly forcing with PET as
@@ -148,7 +218,7 @@ struct FluxEmitter {
 enum CellVariant { kGeneric = 0, kHourlyFeddes = 1, kHourlyJarvis = 2 };
 
 // returns total_runoff (mo_runoff.f90:271-272)
-template <int NH, int VARIANT, bool EMIT>
+template <int NH, int VARIANT, bool EMIT, bool OUT>
 __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStates<NH>& s,
                                                const double pet, const double temperature,
                                                const double prec, const int soil_case,
@@ -157,7 +227,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
                                                const double inv_evap_coeff, double2* warp_tasks,
                                                const fm::Tables& tab,
 #endif
-                                               const FluxEmitter<EMIT>& emit) {
+                                               const FluxEmitter<EMIT, OUT>& emit) {
   // ---- canopy_interc, mo_canopy_interc.f90:105-131 ----
   double throughfall, aet_canopy;
   {
@@ -460,7 +530,7 @@ struct CellCursor {
   double* hist;                       // this cell/member in the total-runoff row of step t
 };
 
-template <int NH, int VARIANT>
+template <int NH, int VARIANT, bool OUT>
 __global__ void __launch_bounds__(kCellThreads, MHM_CELL_MIN_BLOCKS)
 MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
@@ -635,7 +705,9 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       temp_calc = raw_temp;
       prec_calc = raw_pre;
     }
-    const FluxEmitter<EMIT> emit{a.F, mc, n, (size_t)member * NH * n + c, a.write_fluxes && live};
+    FluxCapture cap;
+    const FluxEmitter<EMIT, OUT> emit{a.F, mc, n, (size_t)member * NH * n + c, a.write_fluxes && live,
+                                      &cap};
     emit(MHM_F_PET_CALC, pet_calc);
     emit(MHM_F_TEMP_CALC, temp_calc);
     emit(MHM_F_PREC_CALC, prec_calc);
@@ -657,13 +729,24 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       }
     }
 
-    const double total_runoff = cascade_step<NH, VARIANT, EMIT>(
+    const double total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(
         p, s, pet_calc, temp_calc, prec_calc, a.soil_case, a.tab.evap_coeff[month],
 #if MHM_FAST
         a.tab.inv_evap_coeff[month], warp_tasks, sh_tab,
 #endif
         emit);
 
+    if (OUT) {
+      if (live && t >= a.out_first) {
+        const int yo = a.out_yid[t] - 1;
+        const double fS = a.P[MHM_P_FSEALED][((size_t)member * a.nLC + yo) * n + c];
+        double sat_o[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+          sat_o[h] = a.P[MHM_P_SOILMOISTSAT][(((size_t)member * a.nLC + yo) * NH + h) * n + c];
+        accumulate_outputs<NH>(a.out_mask, a.out_acc + mc, hist_stride, cap, s, fS, sat_o);
+      }
+    }
     if (cu.hist) {
       if (live) __stcs(cu.hist, total_runoff);
       cu.hist += hist_stride;

@@ -87,6 +87,16 @@ struct Domain {
   int32_t hist_steps = 0, hist_tt_first = 0;
   bool keep_runoff_hist = false;  // mhm_cuda_keep_runoff_history: never fuse the history away
 
+  // gridded outputs (mhm_cuda_set_outputs): slots in mHM_updateDataset order
+  uint32_t out_mask = 0;
+  int32_t out_ts = 0, out_nslots = 0, out_counter = 0;
+  uint64_t out_avg_mask = 0;            // bit s: slot s is averaged over its window
+  std::vector<int8_t> out_slot_var, out_slot_hor;
+  double* out_acc = nullptr;            // [slot][member][nCells], the open window
+  double* out_win = nullptr;            // [window of the last run_steps][slot][member][nCells]
+  size_t out_win_cap = 0;
+  std::vector<int32_t> out_win_tt;      // model step that closed each window
+
   Routing* rt = nullptr;
   MprState* mpr = nullptr;
   int32_t last_yId = 1;  // scene of the last executed step (routing parameters, per-step seam)

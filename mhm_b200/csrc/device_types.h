@@ -20,7 +20,7 @@ struct alignas(16) StepIdx {
   int8_t month;      // 1..12
   int8_t hour;       // 0..23
   int8_t isday;      // hour > 6 .and. hour <= 18
-  int8_t pad;
+  int8_t flags;      // after the step's date increment: 1 new day, 2 new month, 4 new year
 };
 static_assert(sizeof(StepIdx) == 16, "StepIdx must be 16 bytes");
 
@@ -49,6 +49,12 @@ struct CellArgs {
   const double* cell_area;            // [nCells] area factor (mo_mrm_pre_routing.f90:125/:141)
   int32_t qout_step0, qout_E, qout_map_flag;
   double qout_tst, qout_scale;        // seconds per model step; 1000 / tst
+  // gridded outputs (mo_write_fluxes_states.f90:283-438): bit v = outputFlxState(v), slots in
+  // the order of mHM_updateDataset; out_acc [slot][member][nCells] is the open window
+  uint32_t out_mask;
+  int32_t out_first;                  // first step of the launch with tIndex_out > 0
+  double* out_acc;
+  int8_t out_yid[kIdxInline];         // land-cover scene the driver holds after each step
   MeteoTables tab;
 };
 

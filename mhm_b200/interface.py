@@ -319,6 +319,25 @@ class Domain:
     def run_steps(self, tt_first, n_steps):
         check(self.L.mhm_cuda_run_steps(self.h, self.id, tt_first, n_steps))
 
+    def set_outputs(self, outputFlxState, timeStep_model_outputs):
+        """mhm_outputs.nml: outputFlxState(1:21), timeStep_model_outputs"""
+        f = np.ascontiguousarray(outputFlxState, dtype=np.int32)
+        assert f.shape == (21,)
+        check(self.L.mhm_cuda_set_outputs(self.h, self.id, _pi(f), int(timeStep_model_outputs)))
+
+    def output_windows(self):
+        """model steps that closed the output windows of the last run_steps call"""
+        n = C.c_int32()
+        check(self.L.mhm_cuda_get_output_windows(self.h, self.id, C.byref(n), C.POINTER(C.c_int32)(), 0))
+        tt = np.zeros(max(1, n.value), dtype=np.int32)
+        check(self.L.mhm_cuda_get_output_windows(self.h, self.id, C.byref(n), _pi(tt), n.value))
+        return tt[: n.value].tolist()
+
+    def get_output(self, window, variable, horizon=0, member=0):
+        out = np.zeros(self.nCells)
+        check(self.L.mhm_cuda_get_output(self.h, self.id, member, window, variable, horizon, _pd(out)))
+        return out
+
     def keep_runoff_history(self, keep=True):
         check(self.L.mhm_cuda_keep_runoff_history(self.h, self.id, int(keep)))
 

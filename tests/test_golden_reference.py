@@ -142,3 +142,19 @@ def test_cuda_mpr_reproduces_reference_parameters(case):
                 else:
                     parity.assert_close(got, ref[name], "%s %s (%s)" % (case, name, mode),
                                         rtol=1e-12 if mode == "strict" else 1e-11, atol=0)
+
+
+@pytest.mark.parametrize("case", ["case_00", "case_02", "case_09", "case_04_b2", "case_04_b5"])
+def test_oracle_reproduces_reference_gridded_outputs(case):
+    """mHM_updateDataset + writeVariableTimestep restated in the oracle against the reference's
+    *_mHM_Fluxes_States.nc: soil water content per horizon (window mean), PET, aET (derived with
+    the scene of the NEXT step), total runoff, recharge (window sums) -- bit-identical."""
+    prob, ref = _load(case)
+    outs = ref["outputs"]
+    o = orc_run.OracleRun(prob, outputs=(outs["flags"], outs["timestep"]))
+    o.run(1, prob["time"]["nTimeSteps"])
+    W = o.out_windows()
+    assert [tt for tt, _ in W] == [prob["time"]["nTimeSteps"]]
+    assert set(W[0][1]) == set(outs["fields"])
+    for key, want in outs["fields"].items():
+        parity.assert_bit_exact(W[0][1][key], want[0], "%s output %s" % (case, key))
