@@ -297,8 +297,45 @@ typedef struct mrm_network {
   const int32_t *InflowGaugeIndexList;  /* (nInflowGauges) */
   const int32_t *InflowGaugeHeadwater;  /* (nInflowGauges) 0/1 */
   const int32_t *InflowGaugeNodeList;   /* (nInflowGauges) */
+  /* sub-catchment sharding of one domain over several GPUs, zero / null for an
+   * unsharded domain.  Ghost sources are local nodes that stand for the from-node of a cut
+   * link owned by another shard: their link is in the local link list (so that the inflows of
+   * its to-node are summed in the reference's netPerm order) but its routed outflow series is
+   * received (mrm_cuda_import_outflow) instead of computed.  Exports are owned from-nodes of
+   * cut links: their outflow series is kept for mrm_cuda_export_outflow.  ssMax > 0 replaces
+   * the local maxval(L11_slope) of reg_rout (mRM/mo_mrm_mpr.f90:97) by the whole domain's. */
+  int32_t nGhostSources;
+  int32_t nExports;
+  const int32_t *ghostSourceNodeList;   /* (nGhostSources) local node ids, 1-based */
+  const int32_t *exportNodeList;        /* (nExports) local node ids, 1-based */
+  double ssMax;
+  /* the reference adds the own runoff of ONE sink only, the to-node of the last link in netPerm
+   * (mo_mrm_routing.f90:466-467): 0 = derive it from the local netPerm (unsharded), > 0 = local
+   * id of the whole domain's last sink if this shard owns it, < 0 = another shard owns it */
+  int32_t lastSinkNode;
 } mrm_network;
 int mrm_cuda_set_network(mhm_cuda_context *ctx, int32_t iDomain, const mrm_network *net);
+
+/* ---- sub-catchment sharding -------------------------------------------------------------
+ * Host helper: cut the river forest into sub-catchments (whole subtrees hanging off one link)
+ * of at least total/(8 nParts) nodes, pack them onto nParts shards by weight, and give the
+ * remaining trunk (every node with a cut link above it, all outlets) to shard 0.  A cut link's
+ * from-node is owned by an upstream shard, its to-node by shard 0, so the exchange has one
+ * level: shards 1..nParts-1 route, send the outflow series of their cut links for the whole
+ * time block, shard 0 routes.  part_of_node[nNodes] receives 0-based shard ids. */
+int mrm_partition_subcatchments(int32_t nNodes, int32_t nLinks, const int32_t *fromN,
+                                const int32_t *toN, const int32_t *netPerm, int32_t nParts,
+                                int32_t *part_of_node);
+/* With deferred routing mhm_cuda_run_steps only runs the cells of one time block (n_steps must
+ * fit one block) and mrm_cuda_route_pending routes it later -- after the ghost outflows of the
+ * block have arrived. */
+int mrm_cuda_set_deferred(mhm_cuda_context *ctx, int32_t iDomain, int32_t deferred);
+int mrm_cuda_route_pending(mhm_cuda_context *ctx, int32_t iDomain);
+/* routed outflow of the export nodes over the last routed block / of the ghost sources over the
+ * pending block, DEVICE buffers laid out [member][node in list order][n_steps]; both are
+ * enqueued on the library's stream (mhm_cuda_synchronize before handing the buffer to NCCL) */
+int mrm_cuda_export_outflow(mhm_cuda_context *ctx, int32_t iDomain, double *dev_out, int32_t n_steps);
+int mrm_cuda_import_outflow(mhm_cuda_context *ctx, int32_t iDomain, const double *dev_in, int32_t n_steps);
 
 /* L11_routing_order (mRM/mo_mrm_net_startup.f90:728-859) in O(nLinks): host helper that
  * yields the identical rOrder/netPerm as the reference's O(nLinks^2) sweeps */

@@ -94,6 +94,11 @@ def load():
         "mhm_cuda_get_runoff_history": [vp, i32, i32, pd, i64],
         "mhm_cuda_keep_runoff_history": [vp, i32, i32],
         "mhm_cuda_set_outputs": [vp, i32, pi, i32],
+        "mrm_partition_subcatchments": [i32, i32, pi, pi, pi, i32, pi],
+        "mrm_cuda_set_deferred": [vp, i32, i32],
+        "mrm_cuda_route_pending": [vp, i32],
+        "mrm_cuda_export_outflow": [vp, i32, vp, i32],
+        "mrm_cuda_import_outflow": [vp, i32, vp, i32],
         "mhm_cuda_get_output_windows": [vp, i32, pi, pi, i32],
         "mhm_cuda_get_output": [vp, i32, i32, i32, i32, i32, pd],
         "mrm_cuda_set_network": [vp, i32, C.POINTER(Network)],

@@ -820,6 +820,8 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
   int32_t tb = (int32_t)(ctx->block_bytes / per_step);
   if (tb < 1) tb = 1;
   if (tb > n_steps) tb = n_steps;
+  MHM_REQUIRE(!(d->rt && routing_is_deferred(d)) || n_steps <= tb,
+              "run_steps: with deferred routing a call must fit one time block (%d steps)", tb);
   const size_t need = (size_t)tb * M * n;
   if (!fused && d->runoff_cap < need) {
     MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -857,7 +859,7 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
     d->hist_steps = fused ? 0 : nb;
     d->hist_tt_first = tt_first + t0;
     d->last_yId = d->h_idx[(size_t)(tt_first + t0 + nb - 2)].yId;
-    if (d->rt)
+    if (d->rt && !routing_defer_block(d, tt_first + t0, nb, fused))
       if (int rc = routing_run_block(ctx, d, tt_first + t0, nb, fused)) return rc;
   }
   return meteo_release(ctx, d);

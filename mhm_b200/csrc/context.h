@@ -139,5 +139,8 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
                       bool qout_ready);
 // can the cell kernel write the routing's node runoff itself for a block of n_steps?  (one cell
 // per node, one model step per routing event, no inflow gauges); fills the CellArgs fields
+// deferred routing (sub-catchment sharding): remember the block instead of routing it
+bool routing_is_deferred(const Domain* d);
+bool routing_defer_block(Domain* d, int32_t tt_first, int32_t n_steps, bool fused);
 bool routing_fuse_qout(mhm_cuda_context* ctx, Domain* d, int32_t n_steps, CellArgs* a);
 }  // namespace mhm

@@ -44,6 +44,7 @@ enum : int32_t {
   kEntZeroOut = 8,    // routed outflow feeds a non-headwater inflow gauge: set to zero
   kEntInflow = 16,    // node is an inflow gauge: add_inflow applies to its runoff
   kEntWriteHist = 32, // somebody reads this node's outflow series from memory
+  kEntGhost = 64,     // from-node of a cut link owned by another shard: outflow is prescribed
 };
 
 // everything a lane needs to know about its node, one 32-byte record
@@ -99,6 +100,13 @@ struct Routing {
   int32_t *d_gauge_col = nullptr, *d_gauge_slot = nullptr;  // per gauge: column-1, slot
   // one-cell-per-node mapping: coalesced per-cell qOUT kernel
   bool bijective = false;
+  // sub-catchment sharding
+  int32_t nGhost = 0, nExport = 0;
+  int32_t *d_ghost_lane = nullptr, *d_export_lane = nullptr;
+  bool deferred = false;
+  int32_t pend_tt = 0, pend_n = 0;  // block whose cells ran but whose routing is pending
+  bool pend_fused = false;
+  int32_t last_n = 0;               // steps of the last routed block (export)
   int32_t* d_cell_entry = nullptr;  // [nCells1] lane of the cell's node
   double* d_cell_area = nullptr;    // [nCells1] area factor of mo_mrm_pre_routing.f90:125/:141
   // per member state, device [M][...]
@@ -108,7 +116,7 @@ struct Routing {
   std::vector<std::vector<double>> param5;  // per member, empty = C1/C2 given
   std::vector<int32_t> c1c2_yId;            // scene the member's C1/C2 were computed for
   double *d_length = nullptr, *d_slope = nullptr, *d_fFPimp = nullptr;  // fFPimp [M][nLC][nNodes]
-  double ssMax = 0.0;
+  double ssMax = 0.0, ssMax_global = 0.0;  // ssMax_global: maxval(slope) of the unsharded domain
   int32_t nLC = 1;
   double TSrout = 0.0;  // case 2/3 [s]
   // inflow series, host (nDays, nInflowTotal) Fortran layout
@@ -139,7 +147,7 @@ void routing_free(Routing* rt) {
   if (!rt) return;
   void* ptrs[] = {rt->meta, rt->up_ptr, rt->up_pos, rt->node_lane, rt->cell_ptr, rt->cell_idx,
                   rt->L11_L1_Id, rt->d_inflow_node, rt->d_inflow_index, rt->d_inflow_head,
-                  rt->L1_area, rt->L11_area, rt->d_gauge_col, rt->d_gauge_slot, rt->d_cell_entry,
+                  rt->L1_area, rt->L11_area, rt->d_gauge_col, rt->d_gauge_slot, rt->d_cell_entry, rt->d_ghost_lane, rt->d_export_lane,
                   rt->d_cell_area, rt->C1, rt->C2, rt->qOUT, rt->qMod, rt->qTIN, rt->qTR,
                   rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry, rt->gauge_hist,
                   rt->qout_hist, rt->qtr_hist, rt->qmod_g, rt->d_inflow_val, rt->d_events};
@@ -172,6 +180,7 @@ static int ensure(T** p, size_t* cap, size_t need, cudaStream_t st) {
   *p = nullptr;
   *cap = 0;
   MHM_CUDA_OK(cudaMalloc(p, (need ? need : 1) * sizeof(T)));
+  MHM_CUDA_OK(cudaMemsetAsync(*p, 0, (need ? need : 1) * sizeof(T), st));  // lanes nobody writes read as 0
   *cap = need;
   return 0;
 }
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(128, 3) route_chain_kernel(const ChainArgs a) 
   const LaneMeta lm = a.meta[p];
   const bool valid = lm.flags & kEntValid, is_link = lm.flags & kEntLink;
   const bool add_qout = lm.flags & kEntAddQout, zero_out = lm.flags & kEntZeroOut;
-  const bool write_hist = lm.flags & kEntWriteHist;
+  const bool write_hist = lm.flags & kEntWriteHist, ghost = lm.flags & kEntGhost;
   const int nup = (lm.flags >> 8) & 0xff, skew = lm.flags >> 16;
   const int rl = RL1 ? 1 : a.rl;
   const int nRS = (a.ev1 - a.ev0) * rl;  // routing sub-steps of this launch
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(128, 3) route_chain_kernel(const ChainArgs a) 
       const int ev = RL1 ? a.ev0 + r : a.ev0 + r / rl;  // its event
       const size_t oq = (size_t)(ev >> 3) * tile_stride + (size_t)(ev & 7);
       const size_t ot = (size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7);
-      qo[d] = in ? a.qout_hist[oq + lane_off] : 0.0;
+      qo[d] = (in && !ghost) ? a.qout_hist[oq + lane_off] : 0.0;
 #pragma unroll
       for (int u = 0; u < kMetaUps; ++u)
         t[u][d] = (in && u < nup && lm.up[u] != kUpShuffle) ? a.qtr_hist[ot + up_off[u]] : 0.0;
@@ -401,12 +410,17 @@ __global__ void __launch_bounds__(128, 3) route_chain_kernel(const ChainArgs a) 
             q_in = q_in + a.qtr_hist[hidx(rs, a.M, a.E, m, a.up_pos[u0 + u])];
           if (add_qout) q_in = q_in + qout;  // :441 / :466-467
           if (is_link) {
-            double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
-            if (zero_out) q = 0.0;                                         // :447-452
+            double q;
+            if (ghost) {  // routed by the shard that owns the node, received for the whole block
+              q = a.qtr_hist[(size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7) + lane_off];
+            } else {
+              q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
+              if (zero_out) q = 0.0;                                  // :447-452
+              if (write_hist)
+                a.qtr_hist[(size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7) + lane_off] = q;
+            }
             qtr1 = q;
             last_q = q;
-            if (write_hist)
-              a.qtr_hist[(size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7) + lane_off] = q;
           }
           qtin1 = q_in;
         }
@@ -616,7 +630,19 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
   const int E = lane;
   rt->E = E;
 
-  const int last_sink = nLinks > 0 ? net->toN[net->netPerm[nLinks - 1] - 1] - 1 : -1;
+  std::vector<char> is_ghost((size_t)nNodes, 0), is_export((size_t)nNodes, 0);
+  for (int g = 0; g < net->nGhostSources; ++g) {
+    MHM_REQUIRE(net->ghostSourceNodeList && net->ghostSourceNodeList[g] >= 1 && net->ghostSourceNodeList[g] <= nNodes,
+                "set_network: ghostSourceNodeList(%d) outside 1..%d", g + 1, nNodes);
+    is_ghost[(size_t)net->ghostSourceNodeList[g] - 1] = 1;
+  }
+  for (int g = 0; g < net->nExports; ++g) {
+    MHM_REQUIRE(net->exportNodeList && net->exportNodeList[g] >= 1 && net->exportNodeList[g] <= nNodes,
+                "set_network: exportNodeList(%d) outside 1..%d", g + 1, nNodes);
+    is_export[(size_t)net->exportNodeList[g] - 1] = 1;
+  }
+  int last_sink = nLinks > 0 ? net->toN[net->netPerm[nLinks - 1] - 1] - 1 : -1;
+  if (net->lastSinkNode != 0) last_sink = net->lastSinkNode > 0 ? net->lastSinkNode - 1 : -1;
   std::vector<LaneMeta> meta((size_t)E);
   std::memset(meta.data(), 0, meta.size() * sizeof(LaneMeta));
   std::vector<int32_t> up_ptr((size_t)E + 1, 0), up_pos;
@@ -646,6 +672,14 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     }
     for (int g = 0; g < net->nInflowGauges; ++g)
       if (net->InflowGaugeNodeList[g] - 1 == nd) fl |= kEntInflow;
+    if (is_ghost[(size_t)nd]) {
+      MHM_REQUIRE(l >= 0 && up[(size_t)nd].empty(), "set_network: ghost source %d must be a headwater with a link", nd + 1);
+      fl = (fl | kEntGhost) & ~(kEntAddQout | kEntZeroOut | kEntWriteHist);
+    }
+    if (is_export[(size_t)nd]) {
+      MHM_REQUIRE(l >= 0, "set_network: export node %d has no link", nd + 1);
+      fl |= kEntWriteHist;
+    }
     const int nup = (int)up[(size_t)nd].size();
     MHM_REQUIRE(nup < 256, "set_network: node %d has %d inflowing links", nd + 1, nup);
     lm.node = nd;
@@ -683,6 +717,15 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
   if (int rc = upload(&rt->node_lane, lane_of, st)) return rc;
   if (int rc = upload(&rt->d_gauge_col, gcol, st)) return rc;
   if (int rc = upload(&rt->d_gauge_slot, gslot, st)) return rc;
+  {
+    std::vector<int32_t> gl((size_t)net->nGhostSources), el((size_t)net->nExports);
+    for (int g = 0; g < net->nGhostSources; ++g) gl[(size_t)g] = lane_of[(size_t)net->ghostSourceNodeList[g] - 1];
+    for (int g = 0; g < net->nExports; ++g) el[(size_t)g] = lane_of[(size_t)net->exportNodeList[g] - 1];
+    rt->nGhost = net->nGhostSources;
+    rt->nExport = net->nExports;
+    if (int rc = upload(&rt->d_ghost_lane, gl, st)) return rc;
+    if (int rc = upload(&rt->d_export_lane, el, st)) return rc;
+  }
 
   // L1 <-> L11 mapping
   const int n1 = d->cfg.nCells;
@@ -706,7 +749,9 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
   }
   // one-to-one mapping between L1 cells and L11 nodes?
   rt->bijective = false;
-  if (n1 == nNodes) {
+  const bool sharded = net->nGhostSources > 0 || net->nExports > 0;
+  MHM_REQUIRE(!sharded || rt->map_flag, "set_network: sharded domains need map_flag (L11 >= L1)");
+  if (n1 == nNodes || (sharded && n1 < nNodes)) {
     std::vector<int32_t> node_of_cell((size_t)n1, -1);
     std::vector<char> seen((size_t)nNodes, 0);
     bool ok = true;
@@ -729,6 +774,7 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
       std::vector<double> ca((size_t)n1);
       for (int k = 0; k < n1; ++k) {
         const int nd = node_of_cell[(size_t)k];
+        MHM_REQUIRE(!is_ghost[(size_t)nd], "set_network: L1 cell %d maps to a ghost node", k + 1);
         ce[(size_t)k] = lane_of[(size_t)nd];
         ca[(size_t)k] = rt->map_flag ? net->L1_areaCell[k] : net->L11_areaCell[nd];
       }
@@ -935,6 +981,16 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
 
 // routing of model steps tt_first .. tt_first+n_steps-1 whose total runoff is in
 // d->runoff_hist; restates the schedule of mo_mhm_interface_run.f90:460-612
+bool routing_is_deferred(const Domain* d) { return d->rt && d->rt->deferred; }
+bool routing_defer_block(Domain* d, int32_t tt_first, int32_t n_steps, bool fused) {
+  Routing* rt = d->rt;
+  if (!rt || !rt->deferred) return false;
+  rt->pend_tt = tt_first;
+  rt->pend_n = n_steps;
+  rt->pend_fused = fused;
+  return true;
+}
+
 bool routing_fuse_qout(mhm_cuda_context* ctx, Domain* d, int32_t n_steps, CellArgs* a) {
   Routing* rt = d->rt;
   if (!rt || !rt->bijective || rt->nInflowGauges > 0 || rt->nInflowTotal > 0 || d->keep_runoff_hist ||
@@ -1013,6 +1069,9 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
     acc_t0 = t + 1;
     carry_live = false;
   }
+  rt->last_n = n_steps;
+  MHM_REQUIRE((rt->nGhost == 0 && rt->nExport == 0) || (!accumulates && routing_rout_loop(d, rt) == 1),
+              "routing: sharded domains need one routing step per model step");
   MHM_REQUIRE(!qout_ready || (per_cell && (int32_t)ev.size() == n_steps),
               "routing: fused node runoff does not match the block's routing schedule");
   if (int rc = run_events(ctx, d, rt, ev, segs, inflow_val, d->runoff_hist, per_cell, qout_ready,
@@ -1035,6 +1094,133 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
 using namespace mhm;
 
 extern "C" {
+
+
+// ---- sub-catchment sharding ---------------------------------------------------------------
+__global__ void export_outflow_kernel(int nList, int M, int E, int T, const int32_t* __restrict__ lanes,
+                                      const double* __restrict__ qtr_hist, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y, m = blockIdx.z;
+  if (t >= T) return;
+  out[((size_t)m * nList + e) * T + t] = qtr_hist[hidx(t, M, E, m, lanes[e])];
+}
+__global__ void import_outflow_kernel(int nList, int M, int E, int T, const int32_t* __restrict__ lanes,
+                                      const double* __restrict__ in, double* __restrict__ qtr_hist) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y, m = blockIdx.z;
+  if (t >= T) return;
+  qtr_hist[hidx(t, M, E, m, lanes[e])] = in[((size_t)m * nList + e) * T + t];
+}
+
+int mrm_partition_subcatchments(int32_t nNodes, int32_t nLinks, const int32_t* fromN,
+                                const int32_t* toN, const int32_t* netPerm, int32_t nParts,
+                                int32_t* part_of_node) {
+  MHM_REQUIRE(nNodes >= 1 && nLinks >= 0 && nLinks <= nNodes && nParts >= 1 && part_of_node &&
+                  (nLinks == 0 || (fromN && toN && netPerm)),
+              "partition_subcatchments: bad arguments");
+  // subtree weights; netPerm is a topological order (upstream links first)
+  std::vector<int64_t> w((size_t)nNodes, 1);
+  std::vector<int32_t> down((size_t)nNodes, -1);
+  for (int k = 0; k < nLinks; ++k) {
+    const int i = netPerm[k] - 1;
+    MHM_REQUIRE(i >= 0 && i < nLinks, "partition_subcatchments: netPerm(%d) outside 1..%d", k + 1, nLinks);
+    const int f = fromN[i] - 1, t = toN[i] - 1;
+    MHM_REQUIRE(f >= 0 && f < nNodes && t >= 0 && t < nNodes, "partition_subcatchments: link %d", i + 1);
+    w[(size_t)t] += w[(size_t)f];
+    down[(size_t)f] = t;
+  }
+  // skeleton = nodes whose subtree holds at least total / (8 nParts) nodes: the trunk, shard 0's.
+  // Every maximal subtree beside the skeleton is a sub-catchment: it hangs off the skeleton by
+  // one link (the cut) or is a whole small basin with its own outlet (no cut at all).
+  // Sub-catchments smaller than 1/64 of the threshold stay with the trunk (too many cuts else).
+  const int64_t thr = std::max<int64_t>(1, (int64_t)nNodes / ((int64_t)nParts * 8));
+  const int64_t minw = std::max<int64_t>(1, thr / 64);
+  std::vector<char> skel((size_t)nNodes, 0);
+  for (int nd = 0; nd < nNodes; ++nd) skel[(size_t)nd] = nParts > 1 && w[(size_t)nd] >= thr;
+  std::vector<int32_t> roots;
+  int64_t trunk = 0;
+  for (int nd = 0; nd < nNodes; ++nd) {
+    if (skel[(size_t)nd]) {
+      ++trunk;
+      continue;
+    }
+    const int dn = down[(size_t)nd];
+    if (dn >= 0 && !skel[(size_t)dn]) continue;  // inside a sub-catchment
+    if (nParts > 1 && (dn < 0 || w[(size_t)nd] >= minw)) roots.push_back(nd);
+    else trunk += w[(size_t)nd];
+  }
+  std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) { return w[(size_t)a] > w[(size_t)b]; });
+  std::vector<int64_t> load((size_t)nParts, 0);
+  load[0] = trunk;
+  std::vector<int32_t> owner((size_t)nNodes, -2);  // -2 unknown
+  for (int rnode : roots) {  // heaviest first onto the least loaded shard
+    int best = 0;
+    for (int p = 1; p < nParts; ++p)
+      if (load[(size_t)p] < load[(size_t)best]) best = p;
+    owner[(size_t)rnode] = best;
+    load[(size_t)best] += w[(size_t)rnode];
+  }
+  for (int nd = 0; nd < nNodes; ++nd)
+    if (owner[(size_t)nd] == -2 && (skel[(size_t)nd] || down[(size_t)nd] < 0 || skel[(size_t)down[(size_t)nd]]))
+      owner[(size_t)nd] = 0;  // skeleton, and small sub-catchments kept with the trunk
+  // everything else takes the shard of the node below it (reverse topological order)
+  for (int k = nLinks - 1; k >= 0; --k) {
+    const int i = netPerm[k] - 1;
+    const int f = fromN[i] - 1, t = toN[i] - 1;
+    if (owner[(size_t)f] == -2) owner[(size_t)f] = owner[(size_t)t];
+  }
+  for (int nd = 0; nd < nNodes; ++nd) part_of_node[nd] = owner[(size_t)nd] < 0 ? 0 : owner[(size_t)nd];
+  return 0;
+}
+
+int mrm_cuda_set_deferred(mhm_cuda_context* ctx, int32_t iDomain, int32_t deferred) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(d->rt, "set_deferred: no network set");
+  d->rt->deferred = deferred != 0;
+  d->rt->pend_n = 0;
+  return 0;
+}
+
+int mrm_cuda_route_pending(mhm_cuda_context* ctx, int32_t iDomain) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  Routing* rt = d->rt;
+  MHM_REQUIRE(rt && rt->deferred && rt->pend_n > 0, "route_pending: no block is waiting for its routing");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  const int32_t tt = rt->pend_tt, n = rt->pend_n;
+  rt->pend_n = 0;
+  return routing_run_block(ctx, d, tt, n, rt->pend_fused);
+}
+
+int mrm_cuda_export_outflow(mhm_cuda_context* ctx, int32_t iDomain, double* dev_out, int32_t n_steps) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  Routing* rt = d->rt;
+  MHM_REQUIRE(rt && dev_out && n_steps >= 1 && n_steps == rt->last_n && rt->qtr_hist,
+              "export_outflow: the last routed block has %d steps", rt ? rt->last_n : 0);
+  if (rt->nExport == 0) return 0;
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  export_outflow_kernel<<<dim3((n_steps + 63) / 64, rt->nExport, rt->M), 64, 0, ctx->stream>>>(
+      rt->nExport, rt->M, rt->E, n_steps, rt->d_export_lane, rt->qtr_hist, dev_out);
+  MHM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int mrm_cuda_import_outflow(mhm_cuda_context* ctx, int32_t iDomain, const double* dev_in, int32_t n_steps) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  Routing* rt = d->rt;
+  MHM_REQUIRE(rt && dev_in && rt->deferred && n_steps == rt->pend_n,
+              "import_outflow: the pending block has %d steps", rt ? rt->pend_n : 0);
+  if (rt->nGhost == 0) return 0;
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(n_steps, rt->M, rt->E), ctx->stream)) return rc;
+  import_outflow_kernel<<<dim3((n_steps + 63) / 64, rt->nGhost, rt->M), 64, 0, ctx->stream>>>(
+      rt->nGhost, rt->M, rt->E, n_steps, rt->d_ghost_lane, dev_in, rt->qtr_hist);
+  MHM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int mrm_routing_order(int32_t nNodes, int32_t nLinks, const int32_t* fromN, const int32_t* toN,
                       int32_t* rOrder, int32_t* netPerm) {
@@ -1074,6 +1260,7 @@ int mrm_cuda_set_network(mhm_cuda_context* ctx, int32_t iDomain, const mrm_netwo
   rt->M = d->cfg.nMembers;
   rt->nLC = d->cfg.nLCscenes;
   rt->nTimeSteps = d->axis.nTimeSteps;
+  rt->ssMax_global = net->ssMax;
   rt->gaugeIndexList.assign(net->gaugeIndexList, net->gaugeIndexList + net->nGauges);
   rt->gaugeNodeList.assign(net->gaugeNodeList, net->gaugeNodeList + net->nGauges);
   if (int rc = build_topology(ctx, d, rt, net)) {
@@ -1126,7 +1313,7 @@ int mrm_cuda_set_reg_rout(mhm_cuda_context* ctx, int32_t iDomain, int32_t member
     MHM_CUDA_OK(cudaMemcpyAsync(rt->d_slope, slope, ns * sizeof(double), cudaMemcpyHostToDevice, st));
     double mx = slope[0];
     for (size_t i = 1; i < ns; ++i) mx = slope[i] > mx ? slope[i] : mx;  // maxval(slope(:))
-    rt->ssMax = mx;
+    rt->ssMax = rt->ssMax_global > 0.0 ? rt->ssMax_global : mx;
   }
   MHM_CUDA_OK(cudaMemcpyAsync(rt->d_fFPimp + (size_t)member * rt->nLC * nn, fFPimp,
                               (size_t)rt->nLC * nn * sizeof(double), cudaMemcpyHostToDevice, st));

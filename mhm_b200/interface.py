@@ -376,6 +376,13 @@ class Domain:
             setattr(nw, k, ip(k))
         nw.L1_areaCell = dp("L1_areaCell")
         nw.L11_areaCell = dp("L11_areaCell")
+        # sub-catchment sharding (mhm_b200.shard.extract)
+        nw.nGhostSources = len(net.get("ghostSourceNodeList", []))
+        nw.nExports = len(net.get("exportNodeList", []))
+        nw.ghostSourceNodeList = ip("ghostSourceNodeList")
+        nw.exportNodeList = ip("exportNodeList")
+        nw.lastSinkNode = int(net.get("lastSinkNode", 0))
+        nw.ssMax = float(net.get("ssMax", 0.0)) if (nw.nGhostSources or nw.nExports or "ghostSourceNodeList" in net) else 0.0
         check(self.L.mrm_cuda_set_network(self.h, self.id, C.byref(nw)))
         self.nNodes, self.nGaugesTotal = nw.nNodes, nw.nGaugesTotal
         del keep
