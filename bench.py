@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=100000)
     ap.add_argument("--cpu-hours", type=int, default=24)
+    ap.add_argument("--shard", action="store_true",
+                    help="strong scaling of ONE domain cut into sub-catchments (SURVEY 8e-3, BASELINE "
+                         "config 4 shape): cut-link outflow series exchanged over NCCL once per time block")
     return ap.parse_args()
 
 
@@ -352,6 +355,76 @@ def run_ours(args):
     return out
 
 
+def run_shard(args):
+    """one ~500k-cell domain x `members` parameter sets, sub-catchment sharded over the ranks"""
+    import torch
+    import torch.distributed as dist
+
+    from mhm_b200 import interface, shard, synth
+    from mhm_b200.interface import routing_order
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, K, T, M = args.warmup, args.steps, min(args.block_hours, 48), args.members
+    if (args.nx, args.ny) == (1180, 1000):
+        args.nx, args.ny = 1000, 590  # ~500k cells at 85 % fill
+    n_days = ((W + K) * T + 23) // 24
+    prob = synth.make_problem(nx=args.nx, ny=args.ny, n_days=n_days, hourly=True, start=(1990, 6, 1),
+                              routing_order=routing_order)
+    part = shard.partition(prob["net"], world)
+    ctx = interface.Context(local)
+    ctx.set_math_mode(args.mode)
+    run = shard.ShardedRun(ctx, prob, part, rank, world, dist if world > 1 else None, nMembers=M)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for i in range(W):
+        run.run_block(i * T + 1, T)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.kernel_stats_reset(True)
+    t0 = time.time()
+    for i in range(W, W + K):
+        run.run_block(i * T + 1, T)
+    barrier()
+    wall = time.time() - t0
+    clocks = sampler.summary()
+    if world > 1:
+        t = torch.tensor([wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t[0])
+    cell_ms, cell_l = ctx.kernel_stats(0)
+    rout_ms, rout_l = ctx.kernel_stats(1)
+    if rank == 0:
+        n = prob["nCells"]
+        sh = run.sub["shard"]
+        print(json.dumps({
+            "metric": "L1 cell-timesteps/s", "value": float(n) * M * T * K / wall, "unit": "cell-timesteps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": wall * 1e3 / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4 shape: ONE synthetic %d-cell domain x %d members, "
+                                   "sub-catchment sharded over %d GPUs, %d cut links, routing case 1" % (
+                                       n, M, world, sh["n_ghost"]),
+                       "cells": n, "members": M, "block_hours": T, "math_mode": args.mode,
+                       "cells_per_shard": np.bincount(part, minlength=world).tolist(),
+                       "exchange_bytes_per_block": int(sh["n_ghost"]) * M * T * 8},
+            "rank0": {"cell_ms": cell_ms, "routing_ms": rout_ms, "launches": int(cell_l + rout_l)},
+            "gpu_launches": int(cell_l + rout_l), "clocks": clocks}), flush=True)
+    ctx.finalize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def cpu_problem(args):
     """bounded sample of the bench workload for the CPU arm: the first ~cpu_cells cells of a
     domain of the same kind, one member, cpu_hours model steps"""
@@ -418,5 +491,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.shard:
+        run_shard(a)
     else:
         run_ours(a)

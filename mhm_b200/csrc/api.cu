@@ -643,6 +643,7 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
   const bool outputs = block_mode && d->out_mask != 0;  // the per-step seam leaves outputs to the host
   ctx->stat_begin(kStatCell);
   int rc = 0;
+  int64_t launches = 0;
   for (int32_t t0 = 0; t0 < total && rc == 0;) {
     int32_t nb = total - t0 < kIdxInline ? total - t0 : kIdxInline;
     bool closes = false;
@@ -675,6 +676,7 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
     memcpy(a.idx_in, idx + t0, (size_t)nb * sizeof(StepIdx));
     rc = ctx->math_mode == 1 ? launch_cell_block_fast(a, d->cfg.nHorizons, ctx->stream)
                              : launch_cell_block_strict(a, d->cfg.nHorizons, ctx->stream);
+    ++launches;
     if (rc == 0 && closes) {
       const size_t w = d->out_win_tt.size();
       const size_t need = (w + 1) * (size_t)d->out_nslots * per_slot;
@@ -691,7 +693,7 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
     }
     t0 += nb;
   }
-  ctx->stat_end(kStatCell);
+  ctx->stat_end(kStatCell, launches);
   MHM_REQUIRE(rc == 0, "cell kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   return 0;
 }

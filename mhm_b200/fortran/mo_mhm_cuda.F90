@@ -75,7 +75,27 @@ module mo_mhm_cuda
                           processCase
     type(c_ptr) :: L1_L11_Id, L11_L1_Id, netPerm, fromN, toN, L1_areaCell, L11_areaCell, gaugeIndexList, &
                    gaugeNodeList, InflowGaugeIndexList, InflowGaugeHeadwater, InflowGaugeNodeList
+    ! sub-catchment sharding (zero / c_null_ptr for an unsharded domain)
+    integer(c_int32_t) :: nGhostSources = 0, nExports = 0
+    type(c_ptr) :: ghostSourceNodeList = c_null_ptr, exportNodeList = c_null_ptr
+    real(c_double) :: ssMax = 0.0_c_double
+    integer(c_int32_t) :: lastSinkNode = 0
   end type mrm_network
+
+  !> L0 inputs of mpr (MPR/mo_multi_param_reg.f90:67-75), see include/mhm_cuda.h
+  type, bind(C) :: mpr_l0_inputs
+    integer(c_int32_t) :: nrows0, ncols0
+    type(c_ptr) :: mask0, upper_bound, lower_bound, left_bound, right_bound, n_subcells, geoUnit0, soilId0, &
+                   LCover0, Asp0, slope_emp0, y0, gridded_LAI0
+  end type mpr_l0_inputs
+
+  !> soilDB + geological units (MPR/mo_mpr_global_variables.f90)
+  type, bind(C) :: mpr_soil_db
+    integer(c_int32_t) :: nSoilTypes, maxHorizons, nGeoUnits
+    type(c_ptr) :: is_present, nHorizons, nTillHorizons, sand, clay, DbM, Wd, RZdepth, HorizonDepth_mHM, &
+                   GeoUnitList, GeoUnitKar
+    real(c_double) :: fracSealed_CityArea
+  end type mpr_soil_db
 
   interface
     integer(c_int) function mhm_cuda_init(device, ctx) bind(C, name = 'mhm_cuda_init')
@@ -264,6 +284,92 @@ module mo_mhm_cuda
       type(c_ptr), value :: ctx, grid, dataIn0, L1_out
       integer(c_int32_t), value :: class_id
     end function
+    ! ---- B4: the whole of mpr_eval on the device -------------------------------------------
+    integer(c_int) function mpr_cuda_set_l0(ctx, iDomain, l0) bind(C, name = 'mpr_cuda_set_l0')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      type(mpr_l0_inputs), intent(in) :: l0
+    end function
+    integer(c_int) function mpr_cuda_set_soildb(ctx, iDomain, db) bind(C, name = 'mpr_cuda_set_soildb')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      type(mpr_soil_db), intent(in) :: db
+    end function
+    integer(c_int) function mpr_cuda_eval(ctx, iDomain, member, param, nParam) bind(C, name = 'mpr_cuda_eval')
+      import
+      type(c_ptr), value :: ctx, param
+      integer(c_int32_t), value :: iDomain, member, nParam
+    end function
+    integer(c_int) function mhm_cuda_get_param(ctx, iDomain, member, param_id, base, ld, offset, dim2, dim3) &
+        bind(C, name = 'mhm_cuda_get_param')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, member, param_id, dim2, dim3
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_states_default_init(ctx, iDomain, HorizonDepth_mHM) &
+        bind(C, name = 'mhm_cuda_states_default_init')
+      import
+      type(c_ptr), value :: ctx, HorizonDepth_mHM
+      integer(c_int32_t), value :: iDomain
+    end function
+    ! ---- A10: gridded outputs accumulated on the device ------------------------------------
+    integer(c_int) function mhm_cuda_set_outputs(ctx, iDomain, outputFlxState, timeStep_model_outputs) &
+        bind(C, name = 'mhm_cuda_set_outputs')
+      import
+      type(c_ptr), value :: ctx, outputFlxState        !< int32 (21), 0/1
+      integer(c_int32_t), value :: iDomain, timeStep_model_outputs
+    end function
+    integer(c_int) function mhm_cuda_get_output_windows(ctx, iDomain, n_windows, tt_end, capacity) &
+        bind(C, name = 'mhm_cuda_get_output_windows')
+      import
+      type(c_ptr), value :: ctx, tt_end
+      integer(c_int32_t), value :: iDomain, capacity
+      integer(c_int32_t), intent(out) :: n_windows
+    end function
+    integer(c_int) function mhm_cuda_get_output(ctx, iDomain, member, window, variable, horizon, out) &
+        bind(C, name = 'mhm_cuda_get_output')
+      import
+      type(c_ptr), value :: ctx, out
+      integer(c_int32_t), value :: iDomain, member, window, variable, horizon
+    end function
+    ! ---- sub-catchment sharding (one domain over several GPUs / MPI ranks) -----------------
+    integer(c_int) function mrm_partition_subcatchments(nNodes, nLinks, fromN, toN, netPerm, nParts, part_of_node) &
+        bind(C, name = 'mrm_partition_subcatchments')
+      import
+      integer(c_int32_t), value :: nNodes, nLinks, nParts
+      type(c_ptr), value :: fromN, toN, netPerm, part_of_node
+    end function
+    integer(c_int) function mrm_cuda_set_deferred(ctx, iDomain, deferred) bind(C, name = 'mrm_cuda_set_deferred')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain, deferred
+    end function
+    integer(c_int) function mrm_cuda_route_pending(ctx, iDomain) bind(C, name = 'mrm_cuda_route_pending')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+    end function
+    integer(c_int) function mrm_cuda_export_outflow(ctx, iDomain, dev_out, n_steps) &
+        bind(C, name = 'mrm_cuda_export_outflow')
+      import
+      type(c_ptr), value :: ctx, dev_out               !< DEVICE buffer (member, export, step)
+      integer(c_int32_t), value :: iDomain, n_steps
+    end function
+    integer(c_int) function mrm_cuda_import_outflow(ctx, iDomain, dev_in, n_steps) &
+        bind(C, name = 'mrm_cuda_import_outflow')
+      import
+      type(c_ptr), value :: ctx, dev_in
+      integer(c_int32_t), value :: iDomain, n_steps
+    end function
+    integer(c_int) function mrm_routing_order(nNodes, nLinks, fromN, toN, rOrder, netPerm) &
+        bind(C, name = 'mrm_routing_order')
+      import
+      integer(c_int32_t), value :: nNodes, nLinks
+      type(c_ptr), value :: fromN, toN, rOrder, netPerm
+    end function
   end interface
 
   public :: mhm_cuda_init, mhm_cuda_finalize, mhm_cuda_register_domain, mhm_cuda_set_param, &
@@ -273,7 +379,12 @@ module mo_mhm_cuda
             mrm_cuda_set_network, mrm_cuda_set_reg_rout, mrm_cuda_set_c1c2, mrm_cuda_set_state, &
             mrm_cuda_get_state, mrm_cuda_set_inflow, mrm_cuda_route, mrm_cuda_get_runoff, &
             mpr_cuda_grid_create, mpr_cuda_upscale_arithmetic_mean, mpr_cuda_upscale_harmonic_mean, &
-            mpr_cuda_l0_fractional_cover
+            mpr_cuda_l0_fractional_cover, mpr_cuda_set_l0, mpr_cuda_set_soildb, mpr_cuda_eval, &
+            mhm_cuda_get_param, mhm_cuda_states_default_init, mhm_cuda_set_outputs, &
+            mhm_cuda_get_output_windows, mhm_cuda_get_output, mrm_partition_subcatchments, &
+            mrm_cuda_set_deferred, mrm_cuda_route_pending, mrm_cuda_export_outflow, mrm_cuda_import_outflow, &
+            mrm_routing_order
+  public :: mpr_l0_inputs, mpr_soil_db
 
 contains
 
