@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=100000)
     ap.add_argument("--cpu-hours", type=int, default=24)
+    ap.add_argument("--mpr", action="store_true",
+                    help="time mpr_eval (gamma -> all L1 effective parameters) on the per-GPU share of "
+                         "BASELINE config 4: ~1.45e7 L0 cells (500 m) under a 1/16 deg L1 grid, factor 14")
     ap.add_argument("--shard", action="store_true",
                     help="strong scaling of ONE domain cut into sub-catchments (SURVEY 8e-3, BASELINE "
                          "config 4 shape): cut-link outflow series exchanged over NCCL once per time block")
@@ -355,6 +358,54 @@ def run_ours(args):
     return out
 
 
+def run_mpr(args):
+    """MPR on the device: every transfer function and all (13 + 8 nH) nLC + 12 upscalings"""
+    from mhm_b200 import interface, synth_mpr
+
+    nx0, ny0, f = (3500, 4130, 14) if (args.nx, args.ny) == (1180, 1000) else (args.nx, args.ny, 14)
+    prob = synth_mpr.make_mpr_problem(nx0=nx0, ny0=ny0, factor=f, nLC=2, nLAI=12, nH=2, soil_case=1,
+                                      pet_case=-1, n_soil=1475, n_geo=10, fill=0.85)
+    ctx = interface.Context(0)
+    out = {}
+    for mode in ("strict", "fast"):
+        ctx.set_math_mode(mode)
+        dom = ctx.register_domain(1 if mode == "strict" else 2, prob["nL1"], prob["nH"], prob["nLAI"], prob["nLC"],
+                                  prob["processMatrix"])
+        synth_mpr.set_mpr_inputs(dom, prob)
+        for _ in range(args.warmup):
+            synth_mpr.mpr_eval(dom, prob["param"])
+        ctx.synchronize()
+        ctx.event_record(0)
+        for _ in range(args.steps):
+            synth_mpr.mpr_eval(dom, prob["param"])
+        ctx.event_record(1)
+        ctx.synchronize()
+        out[mode] = ctx.event_elapsed_ms(0, 1) / args.steps
+    nH, nLC = prob["nH"], prob["nLC"]
+    fields = (13 + 8 * nH) * nLC + 12          # L0 fields upscaled per evaluation (SURVEY 8d)
+    algo_bytes = fields * prob["nL0"] * 12.0   # 8 B value + 4 B cell index per L0 cell and field
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    ms = out["fast"]
+    print(json.dumps({
+        "metric": "MPR L0 cells/s (gamma -> all L1 effective parameters)", "value": prob["nL0"] / (ms * 1e-3),
+        "unit": "L0 cells/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "per-GPU share of BASELINE config 4: %d L0 cells (%d x %d, 85 %% fill) -> %d L1 "
+                               "cells, 1475 soil types, nH = 2, 2 land-cover scenes, 12 LAI steps" % (
+                                   prob["nL0"], nx0, ny0, prob["nL1"]),
+                   "fields_upscaled": fields},
+        "ms_strict": out["strict"], "ms_fast": out["fast"],
+        "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "bytes_per_unit": fields * 12.0}}), flush=True)
+    ctx.finalize()
+
+
 def run_shard(args):
     """one ~500k-cell domain x `members` parameter sets, sub-catchment sharded over the ranks"""
     import torch
@@ -491,6 +542,8 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mpr:
+        run_mpr(a)
     elif a.shard:
         run_shard(a)
     else:

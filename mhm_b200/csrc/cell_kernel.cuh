@@ -29,6 +29,9 @@ namespace mhm {
 #ifndef MHM_FAST
 #define MHM_FAST 0
 #endif
+#ifndef MHM_SELECT_FORM
+#define MHM_SELECT_FORM 1
+#endif
 #ifndef MHM_CELL_MIN_BLOCKS
 #define MHM_CELL_MIN_BLOCKS 4
 #endif
@@ -519,6 +522,165 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
   return total_runoff;
 }
 
+#if MHM_FAST
+// Select form of cascade_step for the specialised fast variants: the same arithmetic written as
+// straight-line code with selects instead of branches (both sides of every small `if` are a
+// couple of operations and free of side effects), so that the independent parts of the water
+// balance (canopy / snow / sealed store / soil horizons / reservoirs) overlap in the pipeline
+// instead of being serialised by branch reconvergence.  Every value equals the branch form's
+// (a discarded side may be inf/NaN, never the selected one); the powers keep warp-uniform skips.
+template <int NH, int VARIANT, bool EMIT>
+__device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, CellStates<NH>& s,
+                                                   const double pet, const double temperature,
+                                                   const double prec, const double inv_evap_coeff,
+                                                   double2* warp_tasks, const fm::Tables& tab,
+                                                   const FluxEmitter<EMIT, false>& emit) {
+  constexpr bool kFeddes = VARIANT == kHourlyFeddes;
+  // ---- canopy_interc ----
+  const double aux = s.inter + prec;
+  const bool over = aux >= p.maxInter;
+  const double throughfall = over ? aux - p.maxInter : 0.0;
+  const double ic0 = over ? p.maxInter : aux;
+  const double x = ic0 * p.inv_maxInter;
+  const bool has = (p.maxInter > kEps) && (x != 0.0);
+  double ev = 0.0;
+  if (__any_sync(0xffffffffu, has)) ev = has ? pet * fm::pow23_pos(has ? x : 1.0) : 0.0;
+  ev = ev < 0.0 ? 0.0 : ev;
+  const bool more_c = ic0 > ev;
+  const double aet_canopy = more_c ? ev : ic0;
+  s.inter = more_c ? ic0 - ev : 0.0;
+  emit(MHM_F_THROUGHFALL, throughfall);
+  emit(MHM_F_AETCANOPY, aet_canopy);
+
+  // ---- snow_accum_melt ----
+  const bool warm = temperature > p.tthr;
+  const double snow = warm ? 0.0 : throughfall, rain = warm ? throughfall : 0.0;
+  const double dd = (prec <= p.ddthr) ? p.ddnop_c + p.ddinc * prec : p.ddmax_c;
+  const double pot = dd * (temperature - p.tthr);
+  const bool pack = s.snowpack > 0.0, all = pot > s.snowpack;
+  const double melt_w = pack ? (all ? s.snowpack : pot) : 0.0;
+  const double pack_w = pack ? (all ? 0.0 : s.snowpack - pot) : 0.0;
+  const double melt = warm ? melt_w : 0.0;
+  s.snowpack = warm ? pack_w : s.snowpack + snow;
+  const double prec_effect = melt + rain;
+  emit(MHM_F_SNOW, snow);
+  emit(MHM_F_RAIN, rain);
+  emit(MHM_F_MELT, melt);
+  emit(MHM_F_DEGDAY, dd);
+  emit(MHM_F_PREEFFECT, prec_effect);
+
+  // ---- sealed store ----
+  const bool sealed_on = p.fSealed > 0.0;
+  const double tmp_s = s.sealed + prec_effect;
+  const bool spill = tmp_s > p.sealedThr;
+  const double rs_on = spill ? tmp_s - p.sealedThr : 0.0;
+  const double st0 = spill ? p.sealedThr : tmp_s;
+  double ae = (pet * inv_evap_coeff - aet_canopy) * (st0 * p.inv_sealedThr);
+  ae = ae < 0.0 ? 0.0 : ae;
+  ae = (p.sealedThr > kEps) ? ae : DBL_MAX;
+  const bool more_s = st0 > ae;
+  const double aet_sealed = sealed_on ? (more_s ? ae : st0) : 0.0;
+  const double runoff_sealed = sealed_on ? rs_on : 0.0;
+  s.sealed = sealed_on ? (more_s ? st0 - ae : 0.0) : s.sealed;
+  emit(MHM_F_RUNOFFSEAL, runoff_sealed);
+  emit(MHM_F_AETSEALED, aet_sealed);
+
+  // ---- infiltration powers of the warp, compacted (see cascade_step) ----
+  double frac_pre[NH];
+  {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    const bool wet = prec_effect != 0.0;
+    unsigned base = 0;
+    unsigned slot[NH];
+    bool need[NH];
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      need[hh] = wet && s.sm[hh] > kEps && !(s.sm[hh] > p.SAT[hh]);
+      const unsigned m = __ballot_sync(0xffffffffu, need[hh]);
+      slot[hh] = base + __popc(m & lt);
+      base += __popc(m);
+      frac_pre[hh] = 0.0;
+    }
+    if (base != 0) {  // warp-uniform
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh)
+        if (need[hh]) warp_tasks[slot[hh]] = make_double2(s.sm[hh] * p.inv_SAT[hh], p.EXPN[hh]);
+      __syncwarp();
+      for (unsigned k = lane; k < base; k += 32u) {
+        const double2 tk = warp_tasks[k];
+        warp_tasks[k].x = fm::pow_tab(tab, tk.x, tk.y);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh)
+        if (need[hh]) frac_pre[hh] = warp_tasks[slot[hh]].x;
+      __syncwarp();
+    }
+  }
+
+  // ---- soil horizons ----
+  double infil_last = 0.0, aet_pos_sum = 0.0;
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    const double sm0 = s.sm[hh], sat = p.SAT[hh];
+    const double pe = hh == 0 ? prec_effect : infil_last;
+    const bool oversat = sm0 > sat;
+    const double tmp = pe * (1.0 - frac_pre[hh]);
+    const bool fill = (sm0 + tmp) > sat;
+    const double inf = oversat ? pe : (fill ? pe + (sm0 - sat) : pe - tmp);
+    const double sm1 = oversat ? sm0 : (fill ? sat : sm0 + tmp);
+    infil_last = inf;
+    emit(MHM_F_INFILSOIL, hh, inf);
+    double a = pet - aet_canopy;
+    if (hh != 0) a = a - aet_pos_sum;
+    double stress;
+    if (kFeddes) {
+      const double part = p.fRoots[hh] * (sm1 - p.WP[hh]) * p.inv_FCWP[hh];
+      stress = sm1 >= p.FC[hh] ? p.fRoots[hh] : (sm1 > p.WP[hh] ? part : 0.0);
+    } else {
+      double th = (sm1 - p.WP[hh]) / (sat - p.WP[hh]);
+      th = th < 0.0 ? 0.0 : th;
+      th = th > 1.0 ? 1.0 : th;
+      stress = th >= p.jarvis_c1 ? p.fRoots[hh] : (th < p.jarvis_c1 ? p.fRoots[hh] * (th / p.jarvis_c1) : 0.0);
+    }
+    a = a * stress;
+    a = a < 0.0 ? 0.0 : a;
+    const bool more = sm1 > a;
+    const double a2 = more ? a : sm1 - kEps;
+    double sm2 = more ? sm1 - a : kEps;
+    sm2 = sm2 < kEps ? kEps : sm2;
+    emit(MHM_F_AETSOIL, hh, a2);
+    s.sm[hh] = sm2;
+    aet_pos_sum = a2 > 0.0 ? aet_pos_sum + a2 : aet_pos_sum;
+  }
+
+  // ---- runoff_unsat_zone ----
+  double us = s.unsat + infil_last;
+  const double fast = us > p.unsatThr ? fmin(p.k0r * (us - p.unsatThr), us - kEps) : 0.0;
+  us = us - fast;
+  const bool wetu = us > kEps;
+  const double pw = fm::pow_tab(tab, wetu ? us : 1.0, 1.0 + p.alpha);
+  const double slow = wetu ? fmin(p.k1r * pw, us - kEps) : 0.0;
+  us = us - slow;
+  const double perc = p.kpr * us;
+  const bool gt = us > perc;
+  s.sat = s.sat + (gt ? perc : us) * p.karst;
+  s.unsat = gt ? us - perc : 0.0;
+  emit(MHM_F_FASTRUNOFF, fast);
+  emit(MHM_F_SLOWRUNOFF, slow);
+  emit(MHM_F_PERCOL, perc);
+  // ---- runoff_sat_zone ----
+  const bool pos = s.sat > 0.0;
+  const double baseflow = pos ? p.k2r * s.sat : 0.0;
+  s.sat = pos ? s.sat - baseflow : 0.0;
+  emit(MHM_F_BASEFLOW, baseflow);
+  const double total_runoff = ((baseflow + slow + fast) * (1.0 - p.fSealed)) + (runoff_sealed * p.fSealed);
+  emit(MHM_F_TOTAL_RUNOFF, total_runoff);
+  return total_runoff;
+}
+#endif
+
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldg(p); }
 
 // everything of the time loop that lives across steps besides states and parameters
@@ -729,12 +891,24 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       }
     }
 
+#if MHM_FAST && MHM_SELECT_FORM
+    double total_runoff;
+    if constexpr (VARIANT != kGeneric && !OUT) {
+      total_runoff = cascade_step_sel<NH, VARIANT, EMIT>(p, s, pet_calc, temp_calc, prec_calc,
+                                                         a.tab.inv_evap_coeff[month], warp_tasks, sh_tab, emit);
+    } else {
+      total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case,
+                                                          a.tab.evap_coeff[month], a.tab.inv_evap_coeff[month],
+                                                          warp_tasks, sh_tab, emit);
+    }
+#else
     const double total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(
         p, s, pet_calc, temp_calc, prec_calc, a.soil_case, a.tab.evap_coeff[month],
 #if MHM_FAST
         a.tab.inv_evap_coeff[month], warp_tasks, sh_tab,
 #endif
         emit);
+#endif
 
     if (OUT) {
       if (live && t >= a.out_first) {
