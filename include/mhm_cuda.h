@@ -337,6 +337,66 @@ int mrm_cuda_route_pending(mhm_cuda_context *ctx, int32_t iDomain);
 int mrm_cuda_export_outflow(mhm_cuda_context *ctx, int32_t iDomain, double *dev_out, int32_t n_steps);
 int mrm_cuda_import_outflow(mhm_cuda_context *ctx, int32_t iDomain, const double *dev_in, int32_t n_steps);
 
+/* ---------------------------------------------------------------------------------
+ * N2  river-network initialisation in linear time (host helper, no device needed).
+ * Replaces, for the arrays the routing consumes, L11_flow_direction, L11_set_network_topology,
+ * L11_routing_order, L11_link_location, L11_set_drain_outlet_gauges and the length / slope part
+ * of L11_stream_features (mRM/mo_mrm_net_startup.f90:227-1477), called from mrm_init
+ * (mRM/mo_mrm_init.f90:221-231).  2-D arrays are Fortran (nrows, ncols) (first index west ->
+ * east), flow directions the rotated in-memory codes (mo_mrm_read_data.f90:527-600), ids and
+ * coordinates 1-based; outputs sized nNodes are valid 1..nLinks like the reference's.
+ * --------------------------------------------------------------------------------- */
+typedef struct mrm_net_inputs {
+  int32_t nrows0;                /* level0%nrows */
+  int32_t ncols0;                /* level0%ncols */
+  int32_t nrows11;               /* level11%nrows */
+  int32_t ncols11;               /* level11%ncols */
+  int32_t nNodes;                /* level11%nCells */
+  int32_t nGauges;               /* domain_mrm%nGauges */
+  int32_t coord_sys;             /* iFlag_cordinate_sys */
+  int32_t outlet_capacity;       /* size of L0_rowOutlet / L0_colOutlet */
+  double cellsize0;              /* level0%cellsize */
+  double xllcorner0;
+  double yllcorner0;
+  const int32_t *mask0;          /* level0%mask 0/1 (nrows0, ncols0) */
+  const int32_t *mask11;         /* level11%mask 0/1 (nrows11, ncols11) */
+  const int32_t *fDir0;          /* L0_fDir packed (nCells0) */
+  const int32_t *fAcc0;          /* L0_fAcc packed */
+  const double *elev0;           /* L0_elev packed (null: no length / slope) */
+  const int32_t *gaugeLoc0;      /* L0_gaugeLoc packed (null: no gauges) */
+  const int32_t *gaugeIdList;    /* domain_mrm%gaugeIdList (nGauges) */
+  const int32_t *upper_bound;    /* l0_l11_remap%upper_bound (nNodes) ... */
+  const int32_t *lower_bound;
+  const int32_t *left_bound;
+  const int32_t *right_bound;
+  const int32_t *lowres_id_on_highres; /* l0_l11_remap%lowres_id_on_highres (nrows0, ncols0) */
+} mrm_net_inputs;
+typedef struct mrm_net_outputs {
+  int32_t nCells0;
+  int32_t nLinks;
+  int32_t nOutlets11;            /* L11_nOutlets */
+  int32_t L0_nOutlets;           /* domain_mrm%L0_Noutlet */
+  int32_t *fDir11;               /* L11_fDir (nNodes) */
+  int32_t *rowOut;               /* L11_rowOut (nNodes) */
+  int32_t *colOut;               /* L11_colOut */
+  int32_t *fromN;                /* L11_fromN (nNodes) */
+  int32_t *toN;
+  int32_t *rOrder;
+  int32_t *netPerm;
+  int32_t *fRow;                 /* L11_fRow (nNodes) */
+  int32_t *fCol;
+  int32_t *tRow;
+  int32_t *tCol;
+  int32_t *gaugeNodeList;        /* (nGauges) */
+  int32_t *draSC0;               /* L0_draSC packed (nCells0) or null */
+  int32_t *draCell0;             /* L0_draCell packed (nCells0) or null */
+  int32_t *L0_rowOutlet;         /* (outlet_capacity) or null */
+  int32_t *L0_colOutlet;
+  double *length;                /* L11_length (nNodes) */
+  double *slope;                 /* L11_slope */
+} mrm_net_outputs;
+int mrm_net_init(const mrm_net_inputs *in, mrm_net_outputs *out);
+
 /* L11_routing_order (mRM/mo_mrm_net_startup.f90:728-859) in O(nLinks): host helper that
  * yields the identical rOrder/netPerm as the reference's O(nLinks^2) sweeps */
 int mrm_routing_order(int32_t nNodes, int32_t nLinks, const int32_t *fromN,

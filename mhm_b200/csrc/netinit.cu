@@ -1,0 +1,353 @@
+// netinit.cu -- river-network initialisation on the host in linear time.
+//
+// Restates the integer / index work of mRM/mo_mrm_net_startup.f90 that produces the arrays the
+// routing kernel consumes -- never copies it:
+//   L11_flow_direction        :227-599   fDir11, rowOut/colOut (draining L0 cell), draSC0, L0 outlets
+//   L11_set_network_topology  :630-698   fromN / toN
+//   L11_routing_order         :728-859   rOrder / netPerm   (routing.cu, O(nLinks))
+//   L11_link_location         :887-1055  fRow/fCol/tRow/tCol of every link on the L0 grid
+//   L11_set_drain_outlet_gauges :1088-1200  draCell0, gauge nodes
+//   L11_stream_features       :1233-1477 link length and slope (flood plains: not yet)
+// The reference's loops over all outlets per link (:997-1000) and its repeated downstream walks
+// (:1147-1150) are replaced by an outlet mask and memoised walks; results are identical
+// (tests/test_netinit.py: bit-exact against the reference's own restart files).
+//
+// Index conventions of the reference: 2-D arrays are (nrows, ncols) with the FIRST index running
+// west -> east (it is the file's column) and the second north -> south; flow directions are the
+// rotated in-memory codes of mo_mrm_read_data.f90:527-600 (4 = first index + 1, ...); all ids and
+// coordinates are 1-based in the interface.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "context.h"
+
+namespace mhm {
+namespace {
+
+constexpr int32_t kNoData = -9999;
+constexpr double kSqrt2 = 1.41421356237309504880168872420969807856967;
+constexpr double kRadiusEarth = 6371228.0;
+constexpr double kTwoPi = 6.283185307179586476925286766559005768394;
+
+inline void move_down(int32_t fdir, int& i, int& j) {  // moveDownOneCell :1768-1801
+  switch (fdir) {
+    case 1: j += 1; break;
+    case 2: i += 1; j += 1; break;
+    case 4: i += 1; break;
+    case 8: i += 1; j -= 1; break;
+    case 16: j -= 1; break;
+    case 32: i -= 1; j -= 1; break;
+    case 64: i -= 1; break;
+    case 128: i -= 1; j += 1; break;
+    default: break;
+  }
+}
+
+struct Grid2 {
+  int nr, nc;
+  inline size_t at(int i, int j) const { return (size_t)(j - 1) * nr + (size_t)(i - 1); }  // Fortran (i, j), 1-based
+  inline bool inside(int i, int j) const { return i >= 1 && i <= nr && j >= 1 && j <= nc; }
+};
+
+double cell_length(int32_t fdir, int i, int j, int coord_sys, double cellsize, double xll, double yll,
+                   int ncols0, double prev) {  // cellLength :1831-1894
+  if (coord_sys == 0) {
+    double len = prev;  // no matching case leaves the reference's variable untouched
+    if (fdir == 1 || fdir == 4 || fdir == 16 || fdir == 64) len = 1.0;
+    else if (fdir == 2 || fdir == 8 || fdir == 32 || fdir == 128) len = kSqrt2;
+    else return prev;
+    return len * cellsize;
+  }
+  int it = i, jt = j;
+  move_down(fdir, it, jt);
+  const double lat1 = yll + (double)(ncols0 - j) * cellsize + 0.5 * cellsize;
+  const double lon1 = xll + (double)(i - 1) * cellsize + 0.5 * cellsize;
+  const double lat2 = yll + (double)(ncols0 - jt) * cellsize + 0.5 * cellsize;
+  const double lon2 = xll + (double)(it - 1) * cellsize + 0.5 * cellsize;
+  const double dtor = kTwoPi / 360.0;  // get_distance_two_lat_lon_points :1926-1970
+  const double t1 = dtor * lon1, p1 = dtor * lat1, t2 = dtor * lon2, p2 = dtor * lat2;
+  const double term1 = cos(p1) * cos(t1) * cos(p2) * cos(t2);
+  const double term2 = cos(p1) * sin(t1) * cos(p2) * sin(t2);
+  const double term3 = sin(p1) * sin(p2);
+  double temp = term1 + term2 + term3;
+  if (temp > 1.0) temp = 1.0;
+  return kRadiusEarth * acos(temp);
+}
+
+}  // namespace
+}  // namespace mhm
+
+using namespace mhm;
+
+extern "C" int mrm_net_init(const mrm_net_inputs* in, mrm_net_outputs* out) {
+  MHM_REQUIRE(in && out, "mrm_net_init: null arguments");
+  const Grid2 g0{in->nrows0, in->ncols0}, g11{in->nrows11, in->ncols11};
+  MHM_REQUIRE(g0.nr >= 1 && g0.nc >= 1 && g11.nr >= 1 && g11.nc >= 1 && in->mask0 && in->mask11 &&
+                  in->fDir0 && in->fAcc0 && in->upper_bound && in->lower_bound && in->left_bound &&
+                  in->right_bound && in->lowres_id_on_highres,
+              "mrm_net_init: missing inputs");
+  const size_t n0g = (size_t)g0.nr * g0.nc, n11g = (size_t)g11.nr * g11.nc;
+  // ---- unpack: ids, coordinates, 2-D fields (Fortran element order = memory order) ----
+  std::vector<int32_t> id0(n0g, kNoData), fdir0(n0g, kNoData), facc0(n0g, kNoData), coor0i, coor0j;
+  std::vector<double> elev0;
+  if (in->elev0) elev0.assign(n0g, -9999.0);
+  int32_t nCells0 = 0;
+  for (int j = 1; j <= g0.nc; ++j)
+    for (int i = 1; i <= g0.nr; ++i) {
+      const size_t a = g0.at(i, j);
+      if (!in->mask0[a]) continue;
+      id0[a] = nCells0 + 1;
+      fdir0[a] = in->fDir0[nCells0];
+      facc0[a] = in->fAcc0[nCells0];
+      if (in->elev0) elev0[a] = in->elev0[nCells0];
+      coor0i.push_back(i);
+      coor0j.push_back(j);
+      ++nCells0;
+    }
+  std::vector<int32_t> id11(n11g, kNoData), coor11i, coor11j;
+  int32_t nNodes = 0;
+  for (int j = 1; j <= g11.nc; ++j)
+    for (int i = 1; i <= g11.nr; ++i) {
+      const size_t a = g11.at(i, j);
+      if (!in->mask11[a]) continue;
+      id11[a] = ++nNodes;
+      coor11i.push_back(i);
+      coor11j.push_back(j);
+    }
+  MHM_REQUIRE(nNodes == in->nNodes, "mrm_net_init: mask11 holds %d nodes, nNodes = %d", nNodes, in->nNodes);
+  out->nCells0 = nCells0;
+
+  // ---- L11_flow_direction :227-599 -----------------------------------------------------
+  std::vector<int32_t> fdir11(n11g, kNoData), rowOut((size_t)nNodes, kNoData), colOut((size_t)nNodes, kNoData);
+  std::vector<int32_t> draSC0(n0g, kNoData);
+  std::vector<char> outlet0(n0g, 0);
+  int32_t nOut0 = 0;
+  if (nCells0 == nNodes) {  // routing on the L0 grid :304-327
+    int bi = 1, bj = 1, best = INT32_MIN;
+    for (int j = 1; j <= g0.nc; ++j)  // maxloc: first maximum in element order
+      for (int i = 1; i <= g0.nr; ++i)
+        if (in->mask0[g0.at(i, j)] && facc0[g0.at(i, j)] > best) {
+          best = facc0[g0.at(i, j)];
+          bi = i;
+          bj = j;
+        }
+    const int kk = in->lowres_id_on_highres[g0.at(bi, bj)];
+    if (nCells0 == 1) fdir11[0] = fdir0[g0.at(bi, bj)];
+    else
+      for (size_t a = 0; a < n0g && a < n11g; ++a) fdir11[a] = fdir0[a];
+    fdir11[g11.at(coor11i[(size_t)kk - 1], coor11j[(size_t)kk - 1])] = 0;
+    for (int k = 0; k < nNodes; ++k) {
+      rowOut[(size_t)k] = coor11i[(size_t)k];
+      colOut[(size_t)k] = coor11j[(size_t)k];
+    }
+    for (int k = 0; k < nCells0; ++k) draSC0[g0.at(coor0i[(size_t)k], coor0j[(size_t)k])] = k + 1;
+  } else {
+    for (int c = 0; c < nCells0; ++c) {  // L0 outlets :329-364
+      const int ci = coor0i[(size_t)c], cj = coor0j[(size_t)c];
+      int i = ci, j = cj;
+      move_down(fdir0[g0.at(ci, cj)], i, j);
+      bool is_outlet = !g0.inside(i, j);
+      if (!is_outlet) is_outlet = fdir0[g0.at(i, j)] <= 0;
+      if (!is_outlet) continue;
+      if (out->L0_rowOutlet && nOut0 < in->outlet_capacity) {
+        out->L0_rowOutlet[nOut0] = ci;
+        out->L0_colOutlet[nOut0] = cj;
+      }
+      ++nOut0;
+      outlet0[g0.at(ci, cj)] = 1;
+      const int kk = in->lowres_id_on_highres[g0.at(ci, cj)];
+      draSC0[g0.at(ci, cj)] = kk;
+      const int iu = in->upper_bound[kk - 1], idn = in->lower_bound[kk - 1];
+      const int jl = in->left_bound[kk - 1], jr = in->right_bound[kk - 1];
+      int32_t mx = INT32_MIN;
+      for (int j2 = jl; j2 <= jr; ++j2)
+        for (int i2 = iu; i2 <= idn; ++i2) mx = std::max(mx, facc0[g0.at(i2, j2)]);
+      if (mx == facc0[g0.at(ci, cj)]) {
+        rowOut[(size_t)kk - 1] = ci;
+        colOut[(size_t)kk - 1] = cj;
+        fdir11[g11.at(coor11i[(size_t)kk - 1], coor11j[(size_t)kk - 1])] = 0;
+      }
+    }
+    for (int k = 0; k < nNodes; ++k) {  // draining cell of every other node :420-560
+      if (rowOut[(size_t)k] > 0) continue;
+      const int ic = coor11i[(size_t)k], jc = coor11j[(size_t)k];
+      const int iu = in->upper_bound[k], idn = in->lower_bound[k], jl = in->left_bound[k], jr = in->right_bound[k];
+      int32_t fmax = -9, idmax = 0;
+      int side = -1;
+      auto f = [&](int i, int j) { return fdir0[g0.at(i, j)]; };
+      auto acc = [&](int i, int j) { return facc0[g0.at(i, j)]; };
+      for (int j = jl; j <= jr; ++j)
+        if (acc(iu, j) > fmax && (f(iu, j) == 32 || f(iu, j) == 64 || f(iu, j) == 128)) {
+          fmax = acc(iu, j);
+          idmax = id0[g0.at(iu, j)];
+          side = 4;
+        }
+      for (int i = iu; i <= idn; ++i)
+        if (acc(i, jr) > fmax && (f(i, jr) == 1 || f(i, jr) == 2 || f(i, jr) == 128)) {
+          fmax = acc(i, jr);
+          idmax = id0[g0.at(i, jr)];
+          side = 1;
+        }
+      for (int j = jl; j <= jr; ++j)
+        if (acc(idn, j) > fmax && (f(idn, j) == 2 || f(idn, j) == 4 || f(idn, j) == 8)) {
+          fmax = acc(idn, j);
+          idmax = id0[g0.at(idn, j)];
+          side = 2;
+        }
+      for (int i = iu; i <= idn; ++i)
+        if (acc(i, jl) > fmax && (f(i, jl) == 8 || f(i, jl) == 16 || f(i, jl) == 32)) {
+          fmax = acc(i, jl);
+          idmax = id0[g0.at(i, jl)];
+          side = 3;
+        }
+      MHM_REQUIRE(idmax >= 1, "mrm_net_init: L11 node %d has no cell draining out of it (side = -1)", k + 1);
+      const int ii = coor0i[(size_t)idmax - 1], jj = coor0j[(size_t)idmax - 1];
+      rowOut[(size_t)k] = ii;
+      colOut[(size_t)k] = jj;
+      draSC0[g0.at(ii, jj)] = k + 1;
+      int32_t& d11 = fdir11[g11.at(ic, jc)];
+      const int32_t fd = f(ii, jj);
+      if (ii == iu && jj == jl) {
+        if (fd == 8 || fd == 16) d11 = 16;
+        else if (fd == 32) d11 = 32;
+        else if (fd == 64 || fd == 128) d11 = 64;
+      } else if (ii == iu && jj == jr) {
+        if (fd == 32 || fd == 64) d11 = 64;
+        else if (fd == 128) d11 = 128;
+        else if (fd == 1 || fd == 2) d11 = 1;
+      } else if (ii == idn && jj == jl) {
+        if (fd == 2 || fd == 4) d11 = 4;
+        else if (fd == 8) d11 = 8;
+        else if (fd == 16 || fd == 32) d11 = 16;
+      } else if (ii == idn && jj == jr) {
+        if (fd == 128 || fd == 1) d11 = 1;
+        else if (fd == 2) d11 = 2;
+        else if (fd == 4 || fd == 8) d11 = 4;
+      } else {
+        d11 = side == 1 ? 1 : side == 2 ? 4 : side == 3 ? 16 : 64;
+      }
+    }
+  }
+  out->L0_nOutlets = nOut0;
+  int32_t nOut11 = 0;
+  for (int k = 0; k < nNodes; ++k) {
+    const int32_t d = fdir11[g11.at(coor11i[(size_t)k], coor11j[(size_t)k])];
+    out->fDir11[k] = d;
+    out->rowOut[k] = rowOut[(size_t)k];
+    out->colOut[k] = colOut[(size_t)k];
+    nOut11 += d == 0;
+  }
+  out->nOutlets11 = nOut11;
+  if (out->draSC0)
+    for (int c = 0; c < nCells0; ++c) out->draSC0[c] = draSC0[g0.at(coor0i[(size_t)c], coor0j[(size_t)c])];
+
+  // ---- L11_set_network_topology :630-698 -------------------------------------------------
+  int32_t nLinks = 0;
+  for (int k = 0; k < nNodes; ++k) {
+    out->fromN[k] = kNoData;
+    out->toN[k] = kNoData;
+  }
+  for (int k = 0; k < nNodes; ++k) {
+    int ic = coor11i[(size_t)k], jc = coor11j[(size_t)k];
+    move_down(fdir11[g11.at(ic, jc)], ic, jc);
+    MHM_REQUIRE(g11.inside(ic, jc) && id11[g11.at(ic, jc)] >= 1,
+                "mrm_net_init: L11 node %d drains out of the routing grid", k + 1);
+    const int32_t tn = id11[g11.at(ic, jc)];
+    if (tn == k + 1) continue;
+    out->fromN[nLinks] = k + 1;
+    out->toN[nLinks] = tn;
+    ++nLinks;
+  }
+  out->nLinks = nLinks;
+  MHM_REQUIRE(nLinks == nNodes - nOut11, "mrm_net_init: %d links but %d nodes and %d outlets", nLinks, nNodes, nOut11);
+
+  // ---- L11_routing_order :728-859 (O(nLinks), routing.cu) --------------------------------
+  for (int k = 0; k < nNodes; ++k) out->rOrder[k] = out->netPerm[k] = kNoData;
+  if (nLinks > 0)
+    if (int rc = mrm_routing_order(nNodes, nLinks, out->fromN, out->toN, out->rOrder, out->netPerm)) return rc;
+
+  // ---- L11_link_location :887-1055 ----------------------------------------------------------
+  for (int k = 0; k < nNodes; ++k) out->fRow[k] = out->fCol[k] = out->tRow[k] = out->tCol[k] = kNoData;
+  if (nNodes > 1) {
+    for (int rr = 0; rr < nLinks; ++rr) {
+      const int ii = out->netPerm[rr] - 1;
+      const int node = out->fromN[ii] - 1;
+      int i = rowOut[(size_t)node], j = colOut[(size_t)node];
+      move_down(fdir0[g0.at(i, j)], i, j);
+      out->fRow[ii] = i;
+      out->fCol[ii] = j;
+      MHM_REQUIRE(g0.inside(i, j), "mrm_net_init: link %d leaves the L0 grid", ii + 1);
+      if (!outlet0[g0.at(i, j)]) {
+        size_t guard = 0;
+        while (!(draSC0[g0.at(i, j)] > 0)) {
+          const int pi = i, pj = j;
+          move_down(fdir0[g0.at(i, j)], i, j);
+          MHM_REQUIRE(g0.inside(i, j) && !(pi == i && pj == j) && ++guard <= n0g,
+                      "mrm_net_init: link %d: downstream walk got stuck at (%d, %d)", ii + 1, pi, pj);
+        }
+      }
+      out->tRow[ii] = i;
+      out->tCol[ii] = j;
+    }
+  }
+
+  // ---- L11_set_drain_outlet_gauges :1088-1200: draCell0 (memoised walk), gauge nodes -----
+  if (out->draCell0) {
+    std::vector<int32_t> dra(n0g, 0);
+    std::vector<size_t> path;
+    for (int c = 0; c < nCells0; ++c) {
+      int i = coor0i[(size_t)c], j = coor0j[(size_t)c];
+      path.clear();
+      int32_t sc;
+      while (true) {
+        const size_t a = g0.at(i, j);
+        if (dra[a] > 0) { sc = dra[a]; break; }
+        if (draSC0[a] > 0) { sc = draSC0[a]; path.push_back(a); break; }
+        path.push_back(a);
+        move_down(fdir0[a], i, j);
+        MHM_REQUIRE(g0.inside(i, j) && path.size() <= n0g, "mrm_net_init: L0 cell %d never reaches a draining cell", c + 1);
+      }
+      for (size_t a : path) dra[a] = sc;
+      out->draCell0[c] = sc;
+    }
+  }
+  for (int gidx = 0; gidx < in->nGauges; ++gidx) out->gaugeNodeList[gidx] = kNoData;
+  if (in->gaugeLoc0 && in->nGauges > 0)
+    for (int c = 0; c < nCells0; ++c) {
+      const int32_t gl = in->gaugeLoc0[c];
+      if (gl == kNoData) continue;
+      for (int gidx = 0; gidx < in->nGauges; ++gidx)
+        if (in->gaugeIdList[gidx] == gl)
+          out->gaugeNodeList[gidx] = in->lowres_id_on_highres[g0.at(coor0i[(size_t)c], coor0j[(size_t)c])];
+    }
+
+  // ---- L11_stream_features :1233-1477: length and slope of every link --------------------
+  for (int k = 0; k < nNodes; ++k) out->length[k] = out->slope[k] = -9999.0;
+  if (nNodes > 1 && in->elev0) {
+    for (int rr = 0; rr < nLinks; ++rr) {
+      const int ii = out->netPerm[rr] - 1;
+      int fr = out->fRow[ii], fc = out->fCol[ii];
+      double len = cell_length(fdir0[g0.at(fr, fc)], fr, fc, in->coord_sys, in->cellsize0, in->xllcorner0,
+                               in->yllcorner0, g0.nc, 0.0);
+      double total = len;
+      const double e_from = elev0[g0.at(fr, fc)];
+      int32_t fId = id0[g0.at(fr, fc)];
+      const int32_t tId = id0[g0.at(out->tRow[ii], out->tCol[ii])];
+      size_t guard = 0;
+      while (fId != tId) {
+        move_down(fdir0[g0.at(fr, fc)], fr, fc);
+        MHM_REQUIRE(g0.inside(fr, fc) && ++guard <= n0g, "mrm_net_init: link %d never reaches its end", ii + 1);
+        fId = id0[g0.at(fr, fc)];
+        len = cell_length(fdir0[g0.at(fr, fc)], fr, fc, in->coord_sys, in->cellsize0, in->xllcorner0,
+                          in->yllcorner0, g0.nc, len);
+        total = total + len;
+      }
+      double s = (e_from - elev0[g0.at(fr, fc)]) / total;
+      if (s < 0.0001) s = 0.0001;
+      out->length[ii] = total;
+      out->slope[ii] = s;
+    }
+  }
+  return 0;
+}

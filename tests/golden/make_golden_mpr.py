@@ -163,7 +163,16 @@ def main():
     db = soil_database(os.path.join(M, "soil_classdefinition.txt"), [200.0, 0.0], 200.0)
     present = np.zeros(db["nSoil"], dtype=np.int32)
     present[np.unique(soil) - 1] = 1
-    out = {"mask0": mask0, "cellsize0": hdr["cellsize"], "geoUnit0": geo, "soilId0": soil, "LCover0": lc,
+    # river-network inputs (mRM/mo_mrm_read_data.f90:139-203): flow accumulation, flow direction
+    # in the reference's rotated in-memory convention (:527-600), gauge locations, elevation
+    rot = {1: 4, 2: 2, 4: 1, 8: 128, 16: 64, 32: 32, 64: 16, 128: 8}
+    fdir_file = pick(asc(os.path.join(M, "fdir.asc"), np.int64)[0])
+    fdir = np.array([rot.get(int(v), int(v)) for v in fdir_file], dtype=np.int32)
+    facc = pick(asc(os.path.join(M, "facc.asc"), np.int64)[0]).astype(np.int32)
+    gauges = pick(asc(os.path.join(M, "idgauges.asc"), np.int64)[0]).astype(np.int32)
+    out = {"fDir0": fdir, "fAcc0": facc, "gaugeLoc0": gauges, "elev0": pick(dem),
+           "xllcorner0": hdr["xllcorner"], "yllcorner0": hdr["yllcorner"],
+           "mask0": mask0, "cellsize0": hdr["cellsize"], "geoUnit0": geo, "soilId0": soil, "LCover0": lc,
            "Asp0": aspect, "slope_emp0": emp, "y0": pick(rst["L0_domain_lat"].read()), "LAI0": LAI0,
            "GeoUnitList": np.array(gl, dtype=np.int32), "GeoUnitKar": np.array(gk, dtype=np.int32),
            "is_present": present, "fracSealed_CityArea": 0.6, "tillageDepth": 200.0}

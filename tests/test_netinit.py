@@ -1,0 +1,73 @@
+"""River-network initialisation (mhm_b200/csrc/netinit.cu, host only) against the
+reference's own mRM restart files: flow direction at L11, draining cells, link topology, routing
+order, link locations on the L0 grid, gauge nodes, link length and slope -- all bit-identical,
+for the bundled test basin at 24 km and 12 km routing resolution."""
+import numpy as np
+import pytest
+
+import golden_case
+from mhm_b200 import netinit, synth_mpr
+
+PAIRS = [("fDir11", "L11_fDir"), ("rowOut", "L11_rowOut"), ("colOut", "L11_colOut"), ("fromN", "L11_fromN"),
+         ("toN", "L11_toN"), ("rOrder", "L11_rOrder"), ("netPerm", "L11_netPerm"), ("fRow", "L11_fRow"),
+         ("fCol", "L11_fCol"), ("tRow", "L11_tRow"), ("tCol", "L11_tCol")]
+
+
+@pytest.mark.parametrize("case,res11", [("case_00", 24000.0), ("case_10", 24000.0), ("case_04_b1", 24000.0),
+                                        ("case_04_b2", 24000.0), ("case_04_b4", 24000.0), ("case_04_b5", 12000.0)])
+def test_network_equals_reference_restart(case, res11):
+    z0 = np.load(golden_case.HERE + "/golden/test_domain_l0.npz")
+    zc = np.load(golden_case.HERE + "/golden/%s.npz" % case)
+    n0 = int(z0["mask0"].sum())
+    g = synth_mpr.init_lowres_level(z0["mask0"], float(z0["cellsize0"]), res11, np.full(n0, float(z0["cellsize0"]) ** 2))
+    assert np.array_equal(g["mask1"] != 0, zc["net/mask11"])
+    r = netinit.net_init(z0["mask0"], z0["fDir0"], z0["fAcc0"], z0["elev0"], float(z0["cellsize0"]), g,
+                         z0["gaugeLoc0"], [398], xll=float(z0["xllcorner0"]), yll=float(z0["yllcorner0"]))
+    nl = r["nLinks"]
+    assert nl == int((zc["net/L11_fromN"] > 0).sum()) and r["nOutlets11"] == g["nCells1"] - nl
+    for ours, theirs in PAIRS:
+        n = g["nCells1"] if ours in ("fDir11", "rowOut", "colOut") else nl
+        assert np.array_equal(r[ours][:n], zc["net/" + theirs][:n]), ours
+    assert np.array_equal(r["gaugeNodeList"], zc["net/gaugeNodeList"])
+    # link length [m] and slope: same operations in the same order -> identical doubles
+    assert np.array_equal(r["length"][:nl], zc["net/L11_length"][:nl])
+    assert np.array_equal(r["slope"][:nl], zc["net/L11_slope"][:nl])
+    # every L0 cell drains to the node whose draining cell it reaches first
+    assert (r["draCell0"] >= 1).all() and (r["draCell0"] <= g["nCells1"]).all()
+    assert r["L0_nOutlets"] == 1 and (r["draSC0"] > 0).sum() == g["nCells1"]
+
+
+def test_network_init_scales_linearly_and_feeds_the_routing():
+    """a 400 x 300 synthetic D8 grid (tilted plane + noise, pits filled by construction): the
+    network comes out as a forest whose netPerm is a valid topological order"""
+    rng = np.random.default_rng(11)
+    ny, nx, f = 300, 400, 4   # numpy (ncols0, nrows0): x is the fast index
+    mask0 = np.ones((ny, nx), dtype=bool)
+    # every cell drains east / south-east / north-east: in-memory codes 4 (i+1), 2 (i+1, j+1), 128 (i-1, j+1)?
+    # use codes that move the FIRST index up: 4 = (i+1, j), 2 = (i+1, j+1), 8 = (i+1, j-1)
+    codes = rng.choice(np.array([4, 2, 8], dtype=np.int32), size=(ny, nx))
+    codes[0, codes[0] == 8] = 4      # stay inside at j = 1
+    codes[-1, codes[-1] == 2] = 4    # ... and at j = ncols0
+    # flow accumulation by a sweep in x
+    acc = np.ones((ny, nx), dtype=np.int64)
+    for i in range(nx - 1):
+        for dj, c in ((0, 4), (1, 2), (-1, 8)):
+            src = np.nonzero(codes[:, i] == c)[0]
+            np.add.at(acc[:, i + 1], src + dj, acc[src, i])
+    elev = (nx - np.arange(nx))[None, :] * 1.0 + rng.random((ny, nx)) * 0.1
+    n0 = ny * nx
+    g = synth_mpr.init_lowres_level(mask0, 100.0, 100.0 * f, np.full(n0, 1.0e4))
+    r = netinit.net_init(mask0, codes.ravel(), acc.ravel().astype(np.int32), elev.ravel(), 100.0, g)
+    nn, nl = g["nCells1"], r["nLinks"]
+    assert r["L0_nOutlets"] == ny and r["nOutlets11"] >= 1 and nl == nn - r["nOutlets11"]
+    seen = np.zeros(nn + 1, dtype=bool)
+    has_up = np.zeros(nn + 1, dtype=bool)
+    has_up[r["toN"][:nl]] = True
+    pos = np.zeros(nl, dtype=np.int64)
+    pos[r["netPerm"][:nl] - 1] = np.arange(nl)
+    link_of = np.full(nn + 1, -1)
+    link_of[r["fromN"][:nl]] = np.arange(nl)
+    down = link_of[r["toN"][:nl]]
+    ok = down < 0
+    assert (pos[np.where(ok, 0, down)][~ok] > pos[~ok]).all()   # a link is routed before the link below it
+    assert (r["length"][:nl] > 0).all() and (r["slope"][:nl] >= 0.0001).all()
