@@ -370,6 +370,11 @@ typedef struct mrm_net_inputs {
   const int32_t *left_bound;
   const int32_t *right_bound;
   const int32_t *lowres_id_on_highres; /* l0_l11_remap%lowres_id_on_highres (nrows0, ncols0) */
+  /* flood plains (L11_stream_features, L11_fraction_sealed_floodplain); all optional */
+  const double *cellArea0;       /* level0%CellArea packed (null: cellsize0^2) */
+  const int32_t *LCover0;        /* L0_LCover (nCells0, nLCoverScene) */
+  int32_t nLCoverScene;
+  int32_t LCClassImp;            /* 2 in mrm_init (mo_mrm_init.f90:258) */
 } mrm_net_inputs;
 typedef struct mrm_net_outputs {
   int32_t nCells0;
@@ -394,6 +399,9 @@ typedef struct mrm_net_outputs {
   int32_t *L0_colOutlet;
   double *length;                /* L11_length (nNodes) */
   double *slope;                 /* L11_slope */
+  double *aFloodPlain;           /* L11_aFloodPlain (nNodes) or null: no flood plains */
+  double *nLinkFracFPimp;        /* L11_nLinkFracFPimp (nNodes, nLCoverScene) or null */
+  int32_t *floodPlain0;          /* L0_floodPlain packed (nCells0) or null */
 } mrm_net_outputs;
 int mrm_net_init(const mrm_net_inputs *in, mrm_net_outputs *out);
 

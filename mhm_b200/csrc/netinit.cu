@@ -7,7 +7,8 @@
 //   L11_routing_order         :728-859   rOrder / netPerm   (routing.cu, O(nLinks))
 //   L11_link_location         :887-1055  fRow/fCol/tRow/tCol of every link on the L0 grid
 //   L11_set_drain_outlet_gauges :1088-1200  draCell0, gauge nodes
-//   L11_stream_features       :1233-1477 link length and slope (flood plains: not yet)
+//   L11_stream_features       :1233-1477 link length, slope, flood plain (moveUp :1595-1741)
+//   L11_fraction_sealed_floodplain :1510-1564  impervious share of every link's flood plain
 // The reference's loops over all outlets per link (:997-1000) and its repeated downstream walks
 // (:1147-1150) are replaced by an outlet mask and memoised walks; results are identical
 // (tests/test_netinit.py: bit-exact against the reference's own restart files).
@@ -16,8 +17,10 @@
 // west -> east (it is the file's column) and the second north -> south; flow directions are the
 // rotated in-memory codes of mo_mrm_read_data.f90:527-600 (4 = first index + 1, ...); all ids and
 // coordinates are 1-based in the interface.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "context.h"
@@ -73,6 +76,16 @@ double cell_length(int32_t fdir, int i, int j, int coord_sys, double cellsize, d
   double temp = term1 + term2 + term3;
   if (temp > 1.0) temp = 1.0;
   return kRadiusEarth * acos(temp);
+}
+
+// FORCES mo_utils le / ge: equal within epsilon counts as equal
+inline bool le_eps(double a, double b) {
+  if ((2.220446049250313e-16 * fabs(b) - fabs(a - b)) < 0.0) return a < b;
+  return true;
+}
+inline bool ge_eps(double a, double b) {
+  if ((2.220446049250313e-16 * fabs(b) - fabs(a - b)) < 0.0) return a > b;
+  return true;
 }
 
 }  // namespace
@@ -322,12 +335,38 @@ extern "C" int mrm_net_init(const mrm_net_inputs* in, mrm_net_outputs* out) {
           out->gaugeNodeList[gidx] = in->lowres_id_on_highres[g0.at(coor0i[(size_t)c], coor0j[(size_t)c])];
     }
 
-  // ---- L11_stream_features :1233-1477: length and slope of every link --------------------
+  // ---- L11_stream_features :1233-1477: length, slope and flood plain of every link ---------
+  // Flood plain of a link: from every stream cell of the link (except its last one) the
+  // cells draining into it whose elevation lies within deltaH above the stream cell are
+  // collected breadth first (moveUp :1595-1741, with its index quirks: seven of the eight
+  // "not lower than the stream" tests read the elevation of the cell (ii, jp)).  A cell
+  // belongs to the LAST link that reached it; the area of a link is summed when the link is
+  // done (before later links take cells away), in array element order.
   for (int k = 0; k < nNodes; ++k) out->length[k] = out->slope[k] = -9999.0;
+  if (out->aFloodPlain)
+    for (int k = 0; k < nNodes; ++k) out->aFloodPlain[k] = -9999.0;
+  std::vector<int32_t> flood0, stream0;
+  const bool do_fp = out->aFloodPlain != nullptr && in->elev0 != nullptr;
+  if (do_fp) {
+    flood0.assign(n0g, kNoData);
+    stream0.assign(n0g, kNoData);
+  }
+  const double deltaH = 5.0;  // mo_mrm_constants.F90:38
   if (nNodes > 1 && in->elev0) {
+    std::vector<std::pair<int, int>> queue;
+    std::vector<size_t> marked;
     for (int rr = 0; rr < nLinks; ++rr) {
       const int ii = out->netPerm[rr] - 1;
       int fr = out->fRow[ii], fc = out->fCol[ii];
+      marked.clear();
+      auto mark = [&](int i, int j) {
+        flood0[g0.at(i, j)] = ii + 1;
+        marked.push_back(g0.at(i, j));
+      };
+      if (do_fp) {
+        stream0[g0.at(fr, fc)] = ii + 1;
+        mark(fr, fc);
+      }
       double len = cell_length(fdir0[g0.at(fr, fc)], fr, fc, in->coord_sys, in->cellsize0, in->xllcorner0,
                                in->yllcorner0, g0.nc, 0.0);
       double total = len;
@@ -336,17 +375,71 @@ extern "C" int mrm_net_init(const mrm_net_inputs* in, mrm_net_outputs* out) {
       const int32_t tId = id0[g0.at(out->tRow[ii], out->tCol[ii])];
       size_t guard = 0;
       while (fId != tId) {
+        if (do_fp) {  // breadth-first climb from the stream cell (fr, fc)
+          const double ef = elev0[g0.at(fr, fc)];
+          queue.clear();
+          queue.emplace_back(fr, fc);
+          for (size_t head = 0; head < queue.size(); ++head) {
+            const int qi = queue[head].first, qj = queue[head].second;
+            const int ip = qi + 1, im = qi - 1, jp = qj + 1, jm = qj - 1;
+            auto fd = [&](int i, int j) { return fdir0[g0.at(i, j)]; };
+            auto el = [&](int i, int j) { return elev0[g0.at(i, j)]; };
+            auto take = [&](int i, int j, int code, bool strict_own) {
+              const double ref = strict_own ? el(i, j) : el(qi, jp);
+              if (fd(i, j) == code && le_eps(el(i, j) - ef, deltaH) && ge_eps(ref - ef, 0.0)) queue.emplace_back(i, j);
+            };
+            if (jp <= g0.nc) take(qi, jp, 16, true);
+            if (ip <= g0.nr && jp <= g0.nc) take(ip, jp, 32, false);
+            if (ip <= g0.nr && jp <= g0.nc) take(ip, qj, 64, false);
+            if (ip <= g0.nr && jp <= g0.nc && jm >= 1) take(ip, jm, 128, false);
+            if (jm >= 1 && jp <= g0.nc) take(qi, jm, 1, false);
+            if (im >= 1 && jp <= g0.nc && jm >= 1) take(im, jm, 2, false);
+            if (im >= 1 && jp <= g0.nc) take(im, qj, 4, false);
+            if (im >= 1 && jp <= g0.nc) take(im, jp, 8, false);
+            if (head + 1 < queue.size()) mark(queue[head + 1].first, queue[head + 1].second);
+            MHM_REQUIRE(queue.size() <= n0g, "mrm_net_init: flood-plain search of link %d does not end", ii + 1);
+          }
+        }
         move_down(fdir0[g0.at(fr, fc)], fr, fc);
         MHM_REQUIRE(g0.inside(fr, fc) && ++guard <= n0g, "mrm_net_init: link %d never reaches its end", ii + 1);
+        if (do_fp) {
+          stream0[g0.at(fr, fc)] = ii + 1;
+          mark(fr, fc);
+        }
         fId = id0[g0.at(fr, fc)];
         len = cell_length(fdir0[g0.at(fr, fc)], fr, fc, in->coord_sys, in->cellsize0, in->xllcorner0,
                           in->yllcorner0, g0.nc, len);
         total = total + len;
       }
-      double s = (e_from - elev0[g0.at(fr, fc)]) / total;
-      if (s < 0.0001) s = 0.0001;
+      double sl = (e_from - elev0[g0.at(fr, fc)]) / total;
+      if (sl < 0.0001) sl = 0.0001;
       out->length[ii] = total;
-      out->slope[ii] = s;
+      out->slope[ii] = sl;
+      if (do_fp) {  // sum(cellarea0, mask = floodPlain0 == ii) in array element order
+        std::sort(marked.begin(), marked.end());
+        marked.erase(std::unique(marked.begin(), marked.end()), marked.end());
+        double area = 0.0;
+        for (size_t a : marked)
+          if (flood0[a] == ii + 1) area = area + (in->cellArea0 ? in->cellArea0[id0[a] - 1] : in->cellsize0 * in->cellsize0);
+        out->aFloodPlain[ii] = area;
+      }
+    }
+  }
+  if (do_fp && out->floodPlain0)
+    for (int c = 0; c < nCells0; ++c) out->floodPlain0[c] = flood0[g0.at(coor0i[(size_t)c], coor0j[(size_t)c])];
+  // ---- L11_fraction_sealed_floodplain :1510-1564 (loops to nLinks + 1 like the reference) ----
+  if (do_fp && out->nLinkFracFPimp && in->LCover0 && in->nLCoverScene > 0) {
+    std::vector<double> imp((size_t)nNodes + 1);
+    for (int lc = 0; lc < in->nLCoverScene; ++lc) {
+      std::fill(imp.begin(), imp.end(), 0.0);
+      for (int c = 0; c < nCells0; ++c) {  // packed order == the reference's masked sum order
+        const int32_t l = flood0[g0.at(coor0i[(size_t)c], coor0j[(size_t)c])];
+        if (l >= 1 && in->LCover0[(size_t)lc * nCells0 + c] == in->LCClassImp)
+          imp[(size_t)l] = imp[(size_t)l] + (in->cellArea0 ? in->cellArea0[c] : in->cellsize0 * in->cellsize0);
+      }
+      for (int k = 0; k < nNodes; ++k) out->nLinkFracFPimp[(size_t)lc * nNodes + k] = -9999.0;
+      for (int l = 1; l <= nLinks + 1 && l <= nNodes; ++l)
+        out->nLinkFracFPimp[(size_t)lc * nNodes + (l - 1)] = imp[(size_t)l] / out->aFloodPlain[l - 1];
     }
   }
   return 0;

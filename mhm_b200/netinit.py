@@ -17,7 +17,7 @@ class NetOutputs(C.Structure):
 
 
 def net_init(mask0, fDir0, fAcc0, elev0, cellsize0, grid11, gaugeLoc0=None, gaugeIdList=(), coord_sys=0,
-             xll=0.0, yll=0.0):
+             xll=0.0, yll=0.0, LCover0=None, LCClassImp=2):
     """mask0: numpy bool (ncols0, nrows0) == Fortran (nrows0, ncols0); packed L0 vectors; grid11 =
     init_lowres_level(mask0, cellsize0, resolutionRouting) (mhm_b200.synth_mpr).  Returns a dict
     of the reference's L11_* network arrays."""
@@ -67,6 +67,18 @@ def net_init(mask0, fDir0, fAcc0, elev0, cellsize0, grid11, gaugeLoc0=None, gaug
         res[k] = np.zeros(nn)
         setattr(o, k, dp(res[k]))
         res[k] = keep[-1]
+    res["aFloodPlain"] = np.zeros(nn)
+    o.aFloodPlain = dp(res["aFloodPlain"])
+    res["aFloodPlain"] = keep[-1]
+    res["floodPlain0"] = np.zeros(n0, dtype=np.int32)
+    o.floodPlain0 = ip(res["floodPlain0"])
+    res["floodPlain0"] = keep[-1]
+    if LCover0 is not None:
+        lc = np.ascontiguousarray(LCover0, dtype=np.int32)   # numpy (nLC, nCells0)
+        i.LCover0, i.nLCoverScene, i.LCClassImp = ip(lc), lc.shape[0], LCClassImp
+        res["nLinkFracFPimp"] = np.zeros((lc.shape[0], nn))
+        o.nLinkFracFPimp = dp(res["nLinkFracFPimp"])
+        res["nLinkFracFPimp"] = keep[-1]
     check(L.mrm_net_init(C.byref(i), C.byref(o)))
     res.update(nLinks=o.nLinks, nOutlets11=o.nOutlets11, L0_nOutlets=o.L0_nOutlets, nCells0=o.nCells0)
     res["gaugeNodeList"] = res["gaugeNodeList"][: len(gaugeIdList)]

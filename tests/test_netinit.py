@@ -1,6 +1,7 @@
 """River-network initialisation (mhm_b200/csrc/netinit.cu, host only) against the
 reference's own mRM restart files: flow direction at L11, draining cells, link topology, routing
-order, link locations on the L0 grid, gauge nodes, link length and slope -- all bit-identical,
+order, link locations on the L0 grid, gauge nodes, link length, slope, flood-plain area and its
+impervious fraction -- all bit-identical,
 for the bundled test basin at 24 km and 12 km routing resolution."""
 import numpy as np
 import pytest
@@ -22,7 +23,8 @@ def test_network_equals_reference_restart(case, res11):
     g = synth_mpr.init_lowres_level(z0["mask0"], float(z0["cellsize0"]), res11, np.full(n0, float(z0["cellsize0"]) ** 2))
     assert np.array_equal(g["mask1"] != 0, zc["net/mask11"])
     r = netinit.net_init(z0["mask0"], z0["fDir0"], z0["fAcc0"], z0["elev0"], float(z0["cellsize0"]), g,
-                         z0["gaugeLoc0"], [398], xll=float(z0["xllcorner0"]), yll=float(z0["yllcorner0"]))
+                         z0["gaugeLoc0"], [398], xll=float(z0["xllcorner0"]), yll=float(z0["yllcorner0"]),
+                         LCover0=z0["LCover0"])
     nl = r["nLinks"]
     assert nl == int((zc["net/L11_fromN"] > 0).sum()) and r["nOutlets11"] == g["nCells1"] - nl
     for ours, theirs in PAIRS:
@@ -32,6 +34,11 @@ def test_network_equals_reference_restart(case, res11):
     # link length [m] and slope: same operations in the same order -> identical doubles
     assert np.array_equal(r["length"][:nl], zc["net/L11_length"][:nl])
     assert np.array_equal(r["slope"][:nl], zc["net/L11_slope"][:nl])
+    # flood plains: area per link and its impervious share per land-cover scene (the reference
+    # evaluates the latter for nLinks + 1 entries, the last one is -0.0 / nodata)
+    assert np.array_equal(r["aFloodPlain"][:nl], zc["net/L11_aFloodPlain"][:nl])
+    got, want = r["nLinkFracFPimp"][:, : nl + 1], zc["net/L11_nLinkFracFPimp"][:, : nl + 1]
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
     # every L0 cell drains to the node whose draining cell it reaches first
     assert (r["draCell0"] >= 1).all() and (r["draCell0"] <= g["nCells1"]).all()
     assert r["L0_nOutlets"] == 1 and (r["draSC0"] > 0).sum() == g["nCells1"]
