@@ -404,6 +404,10 @@ typedef struct mrm_net_outputs {
   int32_t *floodPlain0;          /* L0_floodPlain packed (nCells0) or null */
 } mrm_net_outputs;
 int mrm_net_init(const mrm_net_inputs *in, mrm_net_outputs *out);
+/* L11_L1_mapping (mRM/mo_mrm_net_startup.f90:61-166): masks are Fortran (nrows, ncols) 0/1 */
+int mrm_net_l1_l11_mapping(int32_t nrows1, int32_t ncols1, const int32_t *mask1, double cellsize1,
+                           int32_t nrows11, int32_t ncols11, const int32_t *mask11, double cellsize11,
+                           int32_t *L1_L11_Id, int32_t *L11_L1_Id);
 
 /* L11_routing_order (mRM/mo_mrm_net_startup.f90:728-859) in O(nLinks): host helper that
  * yields the identical rOrder/netPerm as the reference's O(nLinks^2) sweeps */

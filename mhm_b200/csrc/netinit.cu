@@ -444,3 +444,48 @@ extern "C" int mrm_net_init(const mrm_net_inputs* in, mrm_net_outputs* out) {
   }
   return 0;
 }
+
+// L11_L1_mapping :61-166: L1_L11_Id (L11 node of every L1 cell) when the routing grid is not
+// finer than the hydrology grid, else L11_L1_Id (L1 cell of every L11 node); the other vector is
+// left at nodata like the reference's never-initialised array
+extern "C" int mrm_net_l1_l11_mapping(int32_t nrows1, int32_t ncols1, const int32_t* mask1, double cellsize1,
+                                      int32_t nrows11, int32_t ncols11, const int32_t* mask11, double cellsize11,
+                                      int32_t* L1_L11_Id, int32_t* L11_L1_Id) {
+  MHM_REQUIRE(mask1 && mask11 && L1_L11_Id && L11_L1_Id && nrows1 >= 1 && ncols1 >= 1 && nrows11 >= 1 && ncols11 >= 1,
+              "mrm_net_l1_l11_mapping: bad arguments");
+  const Grid2 g1{nrows1, ncols1}, g11{nrows11, ncols11};
+  std::vector<int32_t> on1((size_t)nrows1 * ncols1, kNoData), on11((size_t)nrows11 * ncols11, kNoData);
+  const double f = cellsize11 / cellsize1;
+  if (f < 1.0) {
+    const int inv = (int)(1.0 / f);
+    int id = 0;
+    for (int j = 1; j <= ncols1; ++j)
+      for (int i = 1; i <= nrows1; ++i) {
+        if (!mask1[g1.at(i, j)]) continue;
+        ++id;
+        const int iu = (i - 1) * inv + 1, idn = std::min(i * inv, nrows11);
+        const int jl = (j - 1) * inv + 1, jr = std::min(j * inv, ncols11);
+        for (int jj = jl; jj <= jr; ++jj)
+          for (int ii = iu; ii <= idn; ++ii) on11[g11.at(ii, jj)] = mask11[g11.at(ii, jj)] ? id : kNoData;
+      }
+  } else {
+    const int k = (int)std::lround(f);
+    int id = 0;
+    for (int j = 1; j <= ncols11; ++j)
+      for (int i = 1; i <= nrows11; ++i) {
+        if (!mask11[g11.at(i, j)]) continue;
+        ++id;
+        const int iu = std::max((i - 1) * k + 1, 1), idn = std::min(i * k, nrows1);
+        const int jl = std::max((j - 1) * k + 1, 1), jr = std::min(j * k, ncols1);
+        for (int jj = jl; jj <= jr; ++jj)
+          for (int ii = iu; ii <= idn; ++ii) on1[g1.at(ii, jj)] = mask1[g1.at(ii, jj)] ? id : kNoData;
+      }
+  }
+  int n = 0;
+  for (size_t a = 0; a < on1.size(); ++a)
+    if (mask1[a]) L1_L11_Id[n++] = on1[a];
+  n = 0;
+  for (size_t a = 0; a < on11.size(); ++a)
+    if (mask11[a]) L11_L1_Id[n++] = on11[a];
+  return 0;
+}

@@ -85,3 +85,19 @@ def net_init(mask0, fDir0, fAcc0, elev0, cellsize0, grid11, gaugeLoc0=None, gaug
     res["L0_rowOutlet"] = res["L0_rowOutlet"][: o.L0_nOutlets]
     res["L0_colOutlet"] = res["L0_colOutlet"][: o.L0_nOutlets]
     return res
+
+
+def l1_l11_mapping(grid1, cellsize1, grid11, cellsize11):
+    """L11_L1_mapping: (L1_L11_Id[nCells1], L11_L1_Id[nNodes]) from two init_lowres_level grids"""
+    L = _lib.load()
+    pi = C.POINTER(C.c_int32)
+    L.mrm_net_l1_l11_mapping.argtypes = [C.c_int32, C.c_int32, pi, C.c_double, C.c_int32, C.c_int32, pi,
+                                         C.c_double, pi, pi]
+    m1 = np.ascontiguousarray(grid1["mask1"], dtype=np.int32)
+    m11 = np.ascontiguousarray(grid11["mask1"], dtype=np.int32)
+    a = np.zeros(grid1["nCells1"], dtype=np.int32)
+    b = np.zeros(grid11["nCells1"], dtype=np.int32)
+    check(L.mrm_net_l1_l11_mapping(grid1["nrows1"], grid1["ncols1"], m1.ctypes.data_as(pi), cellsize1,
+                                   grid11["nrows1"], grid11["ncols1"], m11.ctypes.data_as(pi), cellsize11,
+                                   a.ctypes.data_as(pi), b.ctypes.data_as(pi)))
+    return a, b
