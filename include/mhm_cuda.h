@@ -176,6 +176,20 @@ int mhm_cuda_set_meteo_async(mhm_cuda_context *ctx, int32_t iDomain, int32_t var
                              int64_t n_steps);
 /* same, but `dev` is a device pointer to a dense [n_steps][nCells] array that the
  * caller keeps alive (zero copy; used when forcing is already resident in HBM) */
+/* N3 forcing ingest: a chunk of the METEO grid (level 2) exactly as read from NetCDF -- Fortran
+ * (nrows2, ncols2, n_steps), float64 or float32 (is_f32) -- is remapped to the packed L1 cells on
+ * the device: spatial_aggregation (mean over the valid level-2 cells of an L1 cell, summed in the
+ * reference's element order, meteo/mo_meteo_spatial_tools.f90:94-200), spatial_disaggregation
+ * (value of the parent cell, :313-377) or plain packing for equal resolutions
+ * (meteo/mo_meteo_helper.f90:98-130).  Replaces meteo_forcings_wrapper's remap + pack and the
+ * upload of the packed L1 array; masks are int32 0/1 Fortran (nrows, ncols). */
+int mhm_cuda_set_meteo_l2(mhm_cuda_context *ctx, int32_t iDomain, int32_t var, const void *data2,
+                          int32_t is_f32, int32_t nrows2, int32_t ncols2, const int32_t *mask2,
+                          double cellsize2, int32_t nrows1, int32_t ncols1, const int32_t *mask1,
+                          double cellsize1, int64_t first_step, int64_t n_steps);
+/* the resident L1 forcing of steps [first_step, first_step + n_steps), Fortran (nCells, n_steps) */
+int mhm_cuda_get_meteo(mhm_cuda_context *ctx, int32_t iDomain, int32_t var, double *out, int64_t ld,
+                       int64_t first_step, int64_t n_steps);
 int mhm_cuda_set_meteo_device(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,
                               const double *dev, int64_t first_step, int64_t n_steps);
 /* L1_pre_weights / L1_temp_weights / L1_pet_weights (nCellsTot, 12, 24); var = PRE/TEMP/PET */

@@ -94,6 +94,8 @@ def load():
         "mhm_cuda_get_runoff_history": [vp, i32, i32, pd, i64],
         "mhm_cuda_keep_runoff_history": [vp, i32, i32],
         "mhm_cuda_set_outputs": [vp, i32, pi, i32],
+        "mhm_cuda_get_meteo": [vp, i32, i32, pd, i64, i64, i64],
+        "mhm_cuda_set_meteo_l2": [vp, i32, i32, vp, i32, i32, i32, pi, d, i32, i32, pi, d, i64, i64],
         "mrm_partition_subcatchments": [i32, i32, pi, pi, pi, i32, pi],
         "mrm_cuda_set_deferred": [vp, i32, i32],
         "mrm_cuda_route_pending": [vp, i32],

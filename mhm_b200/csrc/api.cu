@@ -1,5 +1,6 @@
 // api.cu -- C ABI (include/mhm_cuda.h): lifecycle, parameter/state/flux/meteo transfer,
 // calendar, and the drivers of the fused cell kernel (per-step seam and time blocks).
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -400,6 +401,141 @@ int mhm_cuda_set_meteo(mhm_cuda_context* ctx, int32_t iDomain, int32_t var, cons
                        int64_t ld, int64_t offset, int64_t first_step, int64_t n_steps) {
   if (int rc = mhm_cuda_set_meteo_async(ctx, iDomain, var, base, ld, offset, first_step, n_steps)) return rc;
   MHM_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse `base` at once
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- N3: level-2 chunk -> packed L1 forcing on the device ---------------------------------
+// one thread per (L1 cell, step); the valid level-2 cells of an L1 cell are summed with the
+// second index outermost, like the reference's loops (mo_meteo_spatial_tools.f90:172-196)
+template <class T>
+__global__ void meteo_l2_to_l1_kernel(const T* __restrict__ data2, int nr2, int nc2, const int32_t* __restrict__ mask2,
+                                      const int32_t* __restrict__ ci1, const int32_t* __restrict__ cj1, int nCells,
+                                      int mode, int f, double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nCells) return;
+  const size_t t = blockIdx.y;
+  const T* d2 = data2 + t * (size_t)nr2 * nc2;
+  const int i = ci1[k], j = cj1[k];  // 1-based L1 coordinates
+  double v;
+  if (mode == 0) {
+    v = (double)d2[(size_t)(j - 1) * nr2 + (i - 1)];
+  } else if (mode == 1) {  // aggregation, f = cellsize1 / cellsize2
+    double s = 0.0;
+    int cnt = 0;
+    const int i0 = (i - 1) * f + 1, i1 = min(i * f, nr2), j0 = (j - 1) * f + 1, j1 = min(j * f, nc2);
+    for (int jj = j0; jj <= j1; ++jj)
+      for (int ii = i0; ii <= i1; ++ii) {
+        if (!mask2[(size_t)(jj - 1) * nr2 + (ii - 1)]) continue;
+        s = s + (double)d2[(size_t)(jj - 1) * nr2 + (ii - 1)];
+        ++cnt;
+      }
+    v = s / (double)cnt;
+  } else {  // disaggregation, f = cellsize2 / cellsize1
+    const int ic = (i + f - 1) / f, jc = (j + f - 1) / f;
+    v = mask2[(size_t)(jc - 1) * nr2 + (ic - 1)] ? (double)d2[(size_t)(jc - 1) * nr2 + (ic - 1)] : -9999.0;
+  }
+  out[t * (size_t)nCells + k] = v;
+}
+
+extern "C" {
+
+int mhm_cuda_set_meteo_l2(mhm_cuda_context* ctx, int32_t iDomain, int32_t var, const void* data2,
+                          int32_t is_f32, int32_t nrows2, int32_t ncols2, const int32_t* mask2,
+                          double cellsize2, int32_t nrows1, int32_t ncols1, const int32_t* mask1,
+                          double cellsize1, int64_t first_step, int64_t n_steps) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(var >= 0 && var < MHM_M_COUNT && data2 && mask2 && mask1 && nrows2 >= 1 && ncols2 >= 1 &&
+                  nrows1 >= 1 && ncols1 >= 1 && cellsize1 > 0 && cellsize2 > 0 && first_step >= 1 && n_steps >= 1,
+              "set_meteo_l2: bad arguments");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  int mode = 0, f = 1;
+  const double r = cellsize1 / cellsize2;
+  if (r > 1.0) {
+    mode = 1;
+    f = (int)std::lround(r);
+    MHM_REQUIRE(fabs(r - f) < 1e-9, "set_meteo_l2: resolutions %g / %g are not multiples", cellsize1, cellsize2);
+  } else if (r < 1.0) {
+    mode = 2;
+    f = (int)std::lround(1.0 / r);
+    MHM_REQUIRE(fabs(1.0 / r - f) < 1e-9, "set_meteo_l2: resolutions %g / %g are not multiples", cellsize1, cellsize2);
+  } else {
+    MHM_REQUIRE(nrows1 == nrows2 && ncols1 == ncols2, "set_meteo_l2: equal resolutions need equal grids");
+  }
+  // coordinates of the packed L1 cells (element order of the mask)
+  std::vector<int32_t> ci, cj;
+  for (int j = 1; j <= ncols1; ++j)
+    for (int i = 1; i <= nrows1; ++i)
+      if (mask1[(size_t)(j - 1) * nrows1 + (i - 1)]) {
+        ci.push_back(i);
+        cj.push_back(j);
+      }
+  MHM_REQUIRE((int)ci.size() == d->cfg.nCells, "set_meteo_l2: mask1 holds %d cells, the domain %d", (int)ci.size(),
+              d->cfg.nCells);
+  const size_t n = (size_t)d->cfg.nCells, need = (size_t)n_steps * n;
+  const size_t n2 = (size_t)nrows2 * ncols2, raw_bytes = n2 * (size_t)n_steps * (is_f32 ? 4 : 8);
+  void* raw = nullptr;
+  int32_t *dm2 = nullptr, *dci = nullptr, *dcj = nullptr;
+  cudaStream_t cs = ctx->copy_stream;
+  const int nb = d->met_owned[var] ? 1 - d->met_active[var] : 0;
+  if (d->met_bufcap[var][nb] < need) {
+    MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    MHM_CUDA_OK(cudaStreamSynchronize(cs));
+    cudaFree(d->met_buf[var][nb]);
+    d->met_buf[var][nb] = nullptr;
+    d->met_bufcap[var][nb] = 0;
+    MHM_CUDA_OK(cudaMalloc(&d->met_buf[var][nb], need * sizeof(double)));
+    d->met_bufcap[var][nb] = need;
+  }
+  MHM_CUDA_OK(cudaMallocAsync(&raw, raw_bytes, cs));
+  MHM_CUDA_OK(cudaMallocAsync((void**)&dm2, n2 * sizeof(int32_t), cs));
+  MHM_CUDA_OK(cudaMallocAsync((void**)&dci, n * sizeof(int32_t), cs));
+  MHM_CUDA_OK(cudaMallocAsync((void**)&dcj, n * sizeof(int32_t), cs));
+  if (!d->met_ready[var]) MHM_CUDA_OK(cudaEventCreateWithFlags(&d->met_ready[var], cudaEventDisableTiming));
+  if (d->met_free_set[var][nb]) MHM_CUDA_OK(cudaStreamWaitEvent(cs, d->met_free[var][nb], 0));
+  MHM_CUDA_OK(cudaMemcpyAsync(raw, data2, raw_bytes, cudaMemcpyHostToDevice, cs));
+  MHM_CUDA_OK(cudaMemcpyAsync(dm2, mask2, n2 * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+  MHM_CUDA_OK(cudaMemcpyAsync(dci, ci.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+  MHM_CUDA_OK(cudaMemcpyAsync(dcj, cj.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+  const dim3 grid((unsigned)((n + 127) / 128), (unsigned)n_steps);
+  if (is_f32)
+    meteo_l2_to_l1_kernel<float><<<grid, 128, 0, cs>>>((const float*)raw, nrows2, ncols2, dm2, dci, dcj, (int)n, mode, f,
+                                                       d->met_buf[var][nb]);
+  else
+    meteo_l2_to_l1_kernel<double><<<grid, 128, 0, cs>>>((const double*)raw, nrows2, ncols2, dm2, dci, dcj, (int)n, mode,
+                                                        f, d->met_buf[var][nb]);
+  MHM_CUDA_OK(cudaGetLastError());
+  MHM_CUDA_OK(cudaFreeAsync(raw, cs));
+  MHM_CUDA_OK(cudaFreeAsync(dm2, cs));
+  MHM_CUDA_OK(cudaFreeAsync(dci, cs));
+  MHM_CUDA_OK(cudaFreeAsync(dcj, cs));
+  MHM_CUDA_OK(cudaEventRecord(d->met_ready[var], cs));
+  MHM_CUDA_OK(cudaStreamSynchronize(cs));  // ci / cj / the caller's buffers may go away
+  d->met_ready_set[var] = true;
+  d->met_active[var] = nb;
+  d->met_owned[var] = true;
+  d->met[var] = d->met_buf[var][nb];
+  d->met_first[var] = first_step;
+  d->met_n[var] = n_steps;
+  return 0;
+}
+
+int mhm_cuda_get_meteo(mhm_cuda_context* ctx, int32_t iDomain, int32_t var, double* out, int64_t ld,
+                       int64_t first_step, int64_t n_steps) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(var >= 0 && var < MHM_M_COUNT && out && ld >= d->cfg.nCells && d->met[var] &&
+                  first_step >= d->met_first[var] && first_step + n_steps <= d->met_first[var] + d->met_n[var],
+              "get_meteo: steps outside the resident chunk");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  if (d->met_owned[var] && d->met_ready_set[var]) MHM_CUDA_OK(cudaStreamWaitEvent(ctx->stream, d->met_ready[var], 0));
+  const size_t n = (size_t)d->cfg.nCells;
+  MHM_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)ld * sizeof(double),
+                                d->met[var] + (size_t)(first_step - d->met_first[var]) * n, n * sizeof(double),
+                                n * sizeof(double), (size_t)n_steps, cudaMemcpyDeviceToHost, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

@@ -315,6 +315,28 @@ module mo_mhm_cuda
       type(c_ptr), value :: ctx, HorizonDepth_mHM
       integer(c_int32_t), value :: iDomain
     end function
+    ! ---- N3: meteo chunk on the level-2 grid, remapped and packed on the device --------------
+    integer(c_int) function mhm_cuda_set_meteo_l2(ctx, iDomain, var, data2, is_f32, nrows2, ncols2, mask2, cellsize2, &
+        nrows1, ncols1, mask1, cellsize1, first_step, n_steps) bind(C, name = 'mhm_cuda_set_meteo_l2')
+      import
+      type(c_ptr), value :: ctx, data2, mask2, mask1
+      integer(c_int32_t), value :: iDomain, var, is_f32, nrows2, ncols2, nrows1, ncols1
+      real(c_double), value :: cellsize2, cellsize1
+      integer(c_int64_t), value :: first_step, n_steps
+    end function
+    ! ---- N2: river-network initialisation (host, linear time); mrm_net_inputs / mrm_net_outputs
+    !      are plain structs of sizes and c_ptr in the order of include/mhm_cuda.h -------------
+    integer(c_int) function mrm_net_init(net_in, net_out) bind(C, name = 'mrm_net_init')
+      import
+      type(c_ptr), value :: net_in, net_out
+    end function
+    integer(c_int) function mrm_net_l1_l11_mapping(nrows1, ncols1, mask1, cellsize1, nrows11, ncols11, mask11, &
+        cellsize11, L1_L11_Id, L11_L1_Id) bind(C, name = 'mrm_net_l1_l11_mapping')
+      import
+      integer(c_int32_t), value :: nrows1, ncols1, nrows11, ncols11
+      real(c_double), value :: cellsize1, cellsize11
+      type(c_ptr), value :: mask1, mask11, L1_L11_Id, L11_L1_Id
+    end function
     ! ---- A10: gridded outputs accumulated on the device ------------------------------------
     integer(c_int) function mhm_cuda_set_outputs(ctx, iDomain, outputFlxState, timeStep_model_outputs) &
         bind(C, name = 'mhm_cuda_set_outputs')
@@ -383,7 +405,7 @@ module mo_mhm_cuda
             mhm_cuda_get_param, mhm_cuda_states_default_init, mhm_cuda_set_outputs, &
             mhm_cuda_get_output_windows, mhm_cuda_get_output, mrm_partition_subcatchments, &
             mrm_cuda_set_deferred, mrm_cuda_route_pending, mrm_cuda_export_outflow, mrm_cuda_import_outflow, &
-            mrm_routing_order
+            mrm_routing_order, mhm_cuda_set_meteo_l2, mrm_net_init, mrm_net_l1_l11_mapping
   public :: mpr_l0_inputs, mpr_soil_db
 
 contains

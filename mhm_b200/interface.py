@@ -288,6 +288,25 @@ class Domain:
         check(self.L.mhm_cuda_set_meteo(self.h, self.id, METEO[METEO_NAMES[var]], _pd(arr),
                                         self.nCells, 0, first_step, arr.shape[0]))
 
+    def set_meteo_l2(self, var, data2, mask2, cellsize2, mask1, cellsize1, first_step=1):
+        """level-2 chunk, numpy (n_steps, ncols2, nrows2) float64 or float32 == Fortran
+        (nrows2, ncols2, n_steps); masks numpy (ncols, nrows) 0/1"""
+        a = np.ascontiguousarray(data2)
+        assert a.dtype in (np.float64, np.float32) and a.ndim == 3
+        m2 = np.ascontiguousarray(mask2, dtype=np.int32)
+        m1 = np.ascontiguousarray(mask1, dtype=np.int32)
+        assert a.shape[1:] == m2.shape
+        check(self.L.mhm_cuda_set_meteo_l2(self.h, self.id, METEO[METEO_NAMES[var]],
+                                           C.c_void_p(a.ctypes.data), int(a.dtype == np.float32), m2.shape[1],
+                                           m2.shape[0], _pi(m2), float(cellsize2), m1.shape[1], m1.shape[0], _pi(m1),
+                                           float(cellsize1), first_step, a.shape[0]))
+
+    def get_meteo(self, var, n_steps, first_step=1):
+        out = np.zeros((n_steps, self.nCells))
+        check(self.L.mhm_cuda_get_meteo(self.h, self.id, METEO[METEO_NAMES[var]], _pd(out), self.nCells,
+                                        first_step, n_steps))
+        return out
+
     def set_meteo_host_ptr(self, var, ptr, ld, first_step, n_steps, async_copy=False):
         """upload from a raw host pointer (e.g. pinned torch tensor .data_ptr()); async_copy:
         return before the copy has finished (double buffered, own stream)"""

@@ -931,3 +931,54 @@ int32_t orc_run(orc_domain *d, int32_t tt_first, int32_t tt_last) {
   free(qAcc);
   return 0;
 }
+
+/* ---- forcing ingest: L2 -> L1 ---------------------------------------------------------- */
+int32_t orc_meteo_l2_to_l1(const double *data2, int32_t nr2, int32_t nc2, int32_t nT, const int32_t *mask2,
+                           double cellsize2, int32_t nr1, int32_t nc1, const int32_t *mask1,
+                           double cellsize1, double *out_packed, double *out_grid) {
+  const double f = cellsize1 / cellsize2; /* cellFactorHbyM, mo_meteo_helper.f90:110 */
+  const size_t n2 = (size_t)nr2 * nc2, n1 = (size_t)nr1 * nc1;
+  double *g = (double *)malloc(sizeof(double) * n1);
+  int32_t *cnt = (int32_t *)calloc(n1, sizeof(int32_t));
+  int32_t t, i, j, ncell = 0;
+  for (i = 0; i < (int32_t)n1; i++) ncell += mask1[i] != 0;
+  if (f > 1.0) /* nTCells, mo_meteo_spatial_tools.f90:160-170 */
+    for (j = 1; j <= nc2; j++)
+      for (i = 1; i <= nr2; i++) {
+        const int32_t jc = (int32_t)ceil((double)j / f), ic = (int32_t)ceil((double)i / f);
+        if (mask2[(size_t)(j - 1) * nr2 + (i - 1)]) cnt[(size_t)(jc - 1) * nr1 + (ic - 1)] += 1;
+      }
+  for (t = 0; t < nT; t++) {
+    const double *d2 = data2 + (size_t)t * n2;
+    int32_t k = 0;
+    if (f > 1.0) { /* spatial_aggregation_3d :172-196 */
+      for (i = 0; i < (int32_t)n1; i++) g[i] = 0.0;
+      for (j = 1; j <= nc2; j++)
+        for (i = 1; i <= nr2; i++) {
+          const int32_t jc = (int32_t)ceil((double)j / f), ic = (int32_t)ceil((double)i / f);
+          if (!mask2[(size_t)(j - 1) * nr2 + (i - 1)]) continue;
+          g[(size_t)(jc - 1) * nr1 + (ic - 1)] = g[(size_t)(jc - 1) * nr1 + (ic - 1)] + d2[(size_t)(j - 1) * nr2 + (i - 1)];
+        }
+      for (i = 0; i < (int32_t)n1; i++) g[i] = mask1[i] ? g[i] / (double)cnt[i] : -9999.0;
+    } else if (f < 1.0) { /* spatial_disaggregation_3d :353-372, cellFactor = cellsize2 / cellsize1 */
+      const double fd = cellsize2 / cellsize1;
+      for (i = 0; i < (int32_t)n1; i++) g[i] = -9999.0;
+      for (j = 1; j <= nc1; j++)
+        for (i = 1; i <= nr1; i++) {
+          const int32_t jc = (int32_t)ceil((double)j / fd), ic = (int32_t)ceil((double)i / fd);
+          if (!mask2[(size_t)(jc - 1) * nr2 + (ic - 1)]) continue;
+          g[(size_t)(j - 1) * nr1 + (i - 1)] = d2[(size_t)(jc - 1) * nr2 + (ic - 1)];
+        }
+    } else {
+      for (i = 0; i < (int32_t)n1; i++) g[i] = d2[i];
+    }
+    if (out_grid)
+      for (i = 0; i < (int32_t)n1; i++) out_grid[(size_t)t * n1 + i] = g[i];
+    if (out_packed)
+      for (i = 0; i < (int32_t)n1; i++)
+        if (mask1[i]) out_packed[(size_t)t * ncell + k++] = g[i];
+  }
+  free(g);
+  free(cnt);
+  return ncell;
+}

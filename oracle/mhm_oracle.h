@@ -296,6 +296,12 @@ int32_t orc_flux_record_size(int32_t nH);
  * tt_first must be 1 on the first call (state of the date stepping is recomputed
  * from tt, so any split of the time axis gives identical results). */
 int32_t orc_run(orc_domain *d, int32_t tt_first, int32_t tt_last);
+/* meteo_forcings_wrapper (meteo/mo_meteo_helper.f90:98-130): L2 chunk, Fortran (nr2, nc2, nT), ->
+ * packed L1 (nCells1, nT) by spatial_aggregation / spatial_disaggregation
+ * (meteo/mo_meteo_spatial_tools.f90:94-200, 313-377) or a plain copy; masks are 0/1 */
+int32_t orc_meteo_l2_to_l1(const double *data2, int32_t nr2, int32_t nc2, int32_t nT, const int32_t *mask2,
+                           double cellsize2, int32_t nr1, int32_t nc1, const int32_t *mask1,
+                           double cellsize1, double *out_packed, double *out_grid);
 /* slots of the enabled output variables in mHM_updateDataset order: var[s] in 1..21, hor[s] the
  * 0-based horizon of per-horizon variables (else -1), avg[s] = averaged over the window */
 int32_t orc_output_slots(const int32_t *out_flags, int32_t nH, int32_t *var, int32_t *hor,
