@@ -314,6 +314,14 @@ def run_ours(args):
         units_per_launch = units_per_step * K / launches_cell
         achieved = units_per_launch * bytes_per_unit / (cell_avg_ms * 1e-3) / 1e9
         dfma = ctx.measure_dfma_peak()
+        traffic = None
+        try:  # DRAM bytes per unit of the same kernel from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_cell_traffic.json")))
+            traffic = tj["dram_bytes_per_unit"] * units_per_launch / (cell_avg_ms * 1e-3) / 1e9
+        except Exception:
+            pass
+        # useful fp64 lane operations per unit (DFMA + DADD + DMUL, predicated on), same capture
+        fp64_ops_per_unit = 94.0
         out = {
             "metric": "L1 cell-timesteps/s", "value": value, "unit": "cell-timesteps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_v / K,
@@ -330,7 +338,7 @@ def run_ours(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "cell_block_kernel_%s<2>" % args.mode,
                 "kernel_ms_per_launch": cell_avg_ms, "units_per_launch": units_per_launch,
                 "bytes_per_unit": bytes_per_unit,
@@ -340,6 +348,9 @@ def run_ours(args):
                 "note": "the fused kernel is fp64-pipe bound (BASELINE.md 3); dfma_peak measured "
                         "live by a dependent-chain-free DFMA loop",
                 "dfma_peak_per_s": dfma, "cell_kernel_units_per_s": units_per_launch / (cell_avg_ms * 1e-3),
+                "fp64_lane_ops_per_unit": fp64_ops_per_unit,
+                "achieved_lane_ops_per_s": fp64_ops_per_unit * units_per_launch / (cell_avg_ms * 1e-3),
+                "frac": fp64_ops_per_unit * units_per_launch / (cell_avg_ms * 1e-3) / dfma if dfma else None,
             },
             "routing": {"ms": rout_ms, "kernel_launches": rout_launches, "share_of_step": rout_ms / ms_v},
             "e2e": {"value": e2e_value, "unit": "cell-timesteps/s",

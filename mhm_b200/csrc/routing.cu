@@ -338,8 +338,11 @@ struct ChainArgs {
 // outflow arrives by __shfl_up.  Every lane reads its own 8-step windows (runoff, tributary
 // outflows) with static register indexing; a window covers at most two 64-byte history runs.
 // RL1: one routing step per event (the usual case) -- no index divisions in the inner loops.
+#ifndef MHM_CHAIN_MIN_BLOCKS
+#define MHM_CHAIN_MIN_BLOCKS 3
+#endif
 template <bool RL1>
-__global__ void __launch_bounds__(128, 3) route_chain_kernel(const ChainArgs a) {
+__global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(const ChainArgs a) {
   const int p = a.lane0 + blockIdx.x * blockDim.x + threadIdx.x;  // lane0, blockDim: multiples of 32
   if (p >= a.lane1) return;                                        // whole warps drop out together
   const int m = blockIdx.y;
