@@ -86,6 +86,7 @@ struct Routing {
   int32_t nGauges = 0, nInflowGauges = 0, nGaugesTotal = 0, nInflowTotal = 0, M = 1;
   int32_t E = 0;                 // lanes = nodes + padding
   std::vector<int32_t> lvl_ptr;  // lane range per segment level (multiples of 32)
+  std::vector<int32_t> lvl_ku, lvl_mem;  // per level: upstream slots in use, any memory tributary
   std::vector<int32_t> gaugeIndexList, gaugeNodeList, inflowIndexList, inflowHeadwater,
       inflowNodeList;
   // device topology (shared by members)
@@ -341,7 +342,9 @@ struct ChainArgs {
 #ifndef MHM_CHAIN_MIN_BLOCKS
 #define MHM_CHAIN_MIN_BLOCKS 3
 #endif
-template <bool RL1>
+// KU: upstream-link slots any lane of the launch uses (1..kMetaUps); MEM: some lane reads a
+// tributary's outflow series from memory (false for the headwater level: no windows at all)
+template <bool RL1, int KU, bool MEM>
 __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(const ChainArgs a) {
   const int p = a.lane0 + blockIdx.x * blockDim.x + threadIdx.x;  // lane0, blockDim: multiples of 32
   if (p >= a.lane1) return;                                        // whole warps drop out together
@@ -370,15 +373,15 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
   const int u0 = nup > kMetaUps ? a.up_ptr[p] : 0;
   const size_t tile_stride = (size_t)a.M * a.E * kHistTile;  // doubles between history tiles
   const size_t lane_off = ((size_t)m * a.E + p) * kHistTile;
-  size_t up_off[kMetaUps];
+  size_t up_off[KU];
 #pragma unroll
-  for (int u = 0; u < kMetaUps; ++u)
+  for (int u = 0; u < KU; ++u)
     up_off[u] = ((size_t)m * a.E + (lm.up[u] > 0 ? lm.up[u] : 0)) * kHistTile;
   const int nMacro = (nRS + lmax - 1 + kHistTile - 1) / kHistTile;
   for (int S = 0; S < nMacro; ++S) {
     const int base = kHistTile * S - skew;  // routing sub-step (relative to rs0) of sub-step 0
     // ---- this lane's windows: own runoff and the outflow series it reads from memory ----
-    double qo[kHistTile], t[kMetaUps][kHistTile];
+    double qo[kHistTile], t[MEM ? KU : 1][kHistTile];
 #pragma unroll
     for (int d = 0; d < kHistTile; ++d) {
       const int r = base + d;
@@ -388,9 +391,11 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
       const size_t oq = (size_t)(ev >> 3) * tile_stride + (size_t)(ev & 7);
       const size_t ot = (size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7);
       qo[d] = (in && !ghost) ? a.qout_hist[oq + lane_off] : 0.0;
+      if (MEM) {
 #pragma unroll
-      for (int u = 0; u < kMetaUps; ++u)
-        t[u][d] = (in && u < nup && lm.up[u] != kUpShuffle) ? a.qtr_hist[ot + up_off[u]] : 0.0;
+        for (int u = 0; u < KU; ++u)
+          t[u][d] = (in && u < nup && lm.up[u] != kUpShuffle) ? a.qtr_hist[ot + up_off[u]] : 0.0;
+      }
     }
 #pragma unroll
     for (int d = 0; d < kHistTile; ++d) {
@@ -407,8 +412,8 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
         } else {
           q_in = 0.0;  // :428, then upstream links in netPerm order :457
 #pragma unroll
-          for (int u = 0; u < kMetaUps; ++u)
-            if (u < nup) q_in = q_in + (lm.up[u] == kUpShuffle ? from_prev : t[u][d]);
+          for (int u = 0; u < KU; ++u)
+            if (u < nup) q_in = q_in + ((!MEM || lm.up[u] == kUpShuffle) ? from_prev : t[u][d]);
           for (int u = kMetaUps; u < nup; ++u)
             q_in = q_in + a.qtr_hist[hidx(rs, a.M, a.E, m, a.up_pos[u0 + u])];
           if (add_qout) q_in = q_in + qout;  // :441 / :466-467
@@ -700,6 +705,19 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     }
     up_ptr[(size_t)p + 1] = (int32_t)up_pos.size();
   }
+  // per level: how many of the kMetaUps slots are in use, and whether any is read from memory
+  rt->lvl_ku.assign(rt->lvl_ptr.size() - 1, 1);
+  rt->lvl_mem.assign(rt->lvl_ptr.size() - 1, 0);
+  for (size_t l = 0; l + 1 < rt->lvl_ptr.size(); ++l)
+    for (int p = rt->lvl_ptr[l]; p < rt->lvl_ptr[l + 1]; ++p) {
+      const LaneMeta& lm = meta[(size_t)p];
+      if (!(lm.flags & kEntValid)) continue;
+      const int nup = std::min((lm.flags >> 8) & 0xff, kMetaUps);
+      rt->lvl_ku[l] = std::max(rt->lvl_ku[l], nup);
+      for (int u = 0; u < nup; ++u)
+        if (lm.up[u] != kUpShuffle) rt->lvl_mem[l] = 1;
+      if (((lm.flags >> 8) & 0xff) > kMetaUps) rt->lvl_mem[l] = 1;
+    }
   // gauge slots: distinct gauge nodes
   std::vector<int32_t> gcol((size_t)net->nGauges), gslot((size_t)net->nGauges);
   rt->nGslots = 0;
@@ -962,10 +980,23 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
       ca.lane1 = rt->lvl_ptr[l + 1];
       const int cnt = ca.lane1 - ca.lane0;
       const int threads = cnt >= 128 ? 128 : cnt;  // multiples of 32
-      if (rl == 1)
-        route_chain_kernel<true><<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(ca);
-      else
-        route_chain_kernel<false><<<dim3((cnt + threads - 1) / threads, M), threads, 0, st>>>(ca);
+      const dim3 grid((cnt + threads - 1) / threads, M);
+      const int ku = rt->lvl_ku[l];
+      const bool mem = rt->lvl_mem[l] != 0;
+#define MHM_CHAIN(R, K, Mm) route_chain_kernel<R, K, Mm><<<grid, threads, 0, st>>>(ca)
+#define MHM_CHAIN_K(R)                                   \
+  if (!mem) MHM_CHAIN(R, 1, false);                      \
+  else if (ku <= 1) MHM_CHAIN(R, 1, true);               \
+  else if (ku == 2) MHM_CHAIN(R, 2, true);               \
+  else if (ku == 3) MHM_CHAIN(R, 3, true);               \
+  else MHM_CHAIN(R, 4, true)
+      if (rl == 1) {
+        MHM_CHAIN_K(true);
+      } else {
+        MHM_CHAIN_K(false);
+      }
+#undef MHM_CHAIN_K
+#undef MHM_CHAIN
       ++launched;
     }
     MHM_CUDA_OK(cudaGetLastError());
