@@ -339,8 +339,12 @@ struct ChainArgs {
 // outflow arrives by __shfl_up.  Every lane reads its own 8-step windows (runoff, tributary
 // outflows) with static register indexing; a window covers at most two 64-byte history runs.
 // RL1: one routing step per event (the usual case) -- no index divisions in the inner loops.
+#ifndef MHM_CHAIN_WIN
+#define MHM_CHAIN_WIN 4
+#endif
+constexpr int kWin = MHM_CHAIN_WIN;  // routing steps per macro step (register windows of every lane)
 #ifndef MHM_CHAIN_MIN_BLOCKS
-#define MHM_CHAIN_MIN_BLOCKS 3
+#define MHM_CHAIN_MIN_BLOCKS 4
 #endif
 // KU: upstream-link slots any lane of the launch uses (1..kMetaUps); MEM: some lane reads a
 // tributary's outflow series from memory (false for the headwater level: no windows at all)
@@ -377,13 +381,13 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
 #pragma unroll
   for (int u = 0; u < KU; ++u)
     up_off[u] = ((size_t)m * a.E + (lm.up[u] > 0 ? lm.up[u] : 0)) * kHistTile;
-  const int nMacro = (nRS + lmax - 1 + kHistTile - 1) / kHistTile;
+  const int nMacro = (nRS + lmax - 1 + kWin - 1) / kWin;
   for (int S = 0; S < nMacro; ++S) {
-    const int base = kHistTile * S - skew;  // routing sub-step (relative to rs0) of sub-step 0
+    const int base = kWin * S - skew;  // routing sub-step (relative to rs0) of sub-step 0
     // ---- this lane's windows: own runoff and the outflow series it reads from memory ----
-    double qo[kHistTile], t[MEM ? KU : 1][kHistTile];
+    double qo[kWin], t[MEM ? KU : 1][kWin];
 #pragma unroll
-    for (int d = 0; d < kHistTile; ++d) {
+    for (int d = 0; d < kWin; ++d) {
       const int r = base + d;
       const bool in = valid && r >= 0 && r < nRS;
       const int rs = a.rs0 + r;                       // absolute sub-step within the block
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
       }
     }
 #pragma unroll
-    for (int d = 0; d < kHistTile; ++d) {
+    for (int d = 0; d < kWin; ++d) {
       const double from_prev = __shfl_up_sync(0xffffffffu, last_q, 1);
       const int r = base + d;
       if (valid && r >= 0 && r < nRS) {
