@@ -541,8 +541,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "bounded sample of BASELINE config 5 per-GPU share", "cells": prob["nCells"],
-                   "members_per_gpu": 1, "block_hours": hours},
+        "config": {"workload": "BASELINE config 5 per-GPU share (synthetic ~1M-cell domain x 32 members per "
+                               "GPU, hourly forcing, Muskingum routing case 1), timed on a bounded sample: see "
+                               "cpu_baseline.sample",
+                   "cells": prob["nCells"], "members_per_gpu": 1, "block_hours": hours},
         "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
