@@ -68,8 +68,6 @@ static void free_domain(Domain* d) {
     if (d->met_ready[v]) cudaEventDestroy(d->met_ready[v]);
   }
   for (auto& p : d->weights) cudaFree(p);
-  cudaFree(d->d_idx);
-  cudaFree(d->d_idx_one);
   cudaFree(d->runoff_hist);
   cudaFree(d->out_acc);
   cudaFree(d->out_win);
@@ -209,7 +207,6 @@ int mhm_cuda_register_domain(mhm_cuda_context* ctx, int32_t iDomain, const mhm_d
     MHM_CUDA_OK(cudaMalloc(&d->F[f], sz));
     MHM_CUDA_OK(cudaMemsetAsync(d->F[f], 0, sz, ctx->stream));
   }
-  MHM_CUDA_OK(cudaMalloc(&d->d_idx_one, sizeof(StepIdx)));
   MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   ctx->domains[iDomain] = d;
   return 0;
@@ -622,12 +619,6 @@ static int ensure_calendar(mhm_cuda_context* ctx, Domain* d) {
   MHM_REQUIRE(d->has_meteo_cfg, "domain %d: mhm_cuda_set_meteo_config has not been called", d->id);
   fill_step_indices(d->axis, d->cfg.timestep_h, d->mcfg.nTstepForcingDay, d->axis.nTimeSteps,
                     d->h_idx);
-  cudaFree(d->d_idx);
-  d->d_idx = nullptr;
-  MHM_CUDA_OK(cudaMalloc(&d->d_idx, d->h_idx.size() * sizeof(StepIdx)));
-  MHM_CUDA_OK(cudaMemcpyAsync(d->d_idx, d->h_idx.data(), d->h_idx.size() * sizeof(StepIdx),
-                              cudaMemcpyHostToDevice, ctx->stream));
-  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

@@ -29,6 +29,9 @@ namespace mhm {
 #ifndef MHM_FAST
 #define MHM_FAST 0
 #endif
+#ifndef MHM_PARAMS_SMEM
+#define MHM_PARAMS_SMEM 1
+#endif
 #ifndef MHM_SELECT_FORM
 #define MHM_SELECT_FORM 1
 #endif
@@ -115,6 +118,43 @@ struct CellParams {
 #if MHM_FAST
   double inv_maxInter, inv_sealedThr, inv_SAT[NH], inv_FCWP[NH], inv_jc1;
 #endif
+};
+
+// The same parameter set as a structure of arrays in shared memory (one column per thread of
+// the CTA, conflict-free): frees ~60 registers per thread for a higher occupancy.
+template <int NH>
+struct CellParamsShared {
+  double fSealed[kCellThreads], alpha[kCellThreads], ddinc[kCellThreads], ddmax_c[kCellThreads],
+      ddnop_c[kCellThreads], ddthr[kCellThreads];
+  double k0r[kCellThreads], k1r[kCellThreads], k2r[kCellThreads], kpr[kCellThreads];
+  double tthr[kCellThreads];
+  double fRoots[NH][kCellThreads], FC[NH][kCellThreads], SAT[NH][kCellThreads], EXPN[NH][kCellThreads],
+      WP[NH][kCellThreads];
+  double karst[kCellThreads], jarvis_c1[kCellThreads], unsatThr[kCellThreads], sealedThr[kCellThreads];
+  double maxInter[kCellThreads];
+  double petFac[kCellThreads];
+  double inv_maxInter[kCellThreads], inv_sealedThr[kCellThreads], inv_SAT[NH][kCellThreads],
+      inv_FCWP[NH][kCellThreads], inv_jc1[kCellThreads];
+};
+// one access syntax for both stores: a member is a double (registers) or a column (shared)
+__device__ __forceinline__ double& pcol(double& x) { return x; }
+__device__ __forceinline__ const double& pcol(const double& x) { return x; }
+__device__ __forceinline__ double& pcol(double (&x)[kCellThreads]) { return x[threadIdx.x]; }
+__device__ __forceinline__ const double& pcol(const double (&x)[kCellThreads]) { return x[threadIdx.x]; }
+#define PX(m_) pcol(p.m_)
+#define PH(m_, h_) pcol(p.m_[h_])
+struct EmptyParams {};
+template <bool FIRST, class A, class B>
+__device__ __forceinline__ auto& pick_ref(A& a, B& b) {
+  if constexpr (FIRST) return a;
+  else return b;
+}
+// fast build, up to 2 soil horizons (43 KB of shared memory per CTA): parameters in shared
+// memory, 84 registers, 5 CTAs/SM; otherwise in registers, 128 registers, 4 CTAs/SM
+template <int NH>
+struct ParamPlace {
+  static constexpr bool shared = MHM_FAST && MHM_PARAMS_SMEM && NH <= 2;
+  static constexpr int min_blocks = shared ? 5 : MHM_CELL_MIN_BLOCKS;
 };
 
 // ---- one model step for one cell ---------------------------------------------------
@@ -221,8 +261,8 @@ __device__ __forceinline__ void accumulate_outputs(const uint32_t mask, double* 
 enum CellVariant { kGeneric = 0, kHourlyFeddes = 1, kHourlyJarvis = 2 };
 
 // returns total_runoff (mo_runoff.f90:271-272)
-template <int NH, int VARIANT, bool EMIT, bool OUT>
-__device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStates<NH>& s,
+template <int NH, int VARIANT, bool EMIT, bool OUT, class PARAMS>
+__device__ __forceinline__ double cascade_step(const PARAMS& p, CellStates<NH>& s,
                                                const double pet, const double temperature,
                                                const double prec, const int soil_case,
                                                const double evap_coeff,
@@ -236,21 +276,21 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
   {
     double aux = s.inter + prec;
     double ic;
-    if (aux >= p.maxInter) {
-      throughfall = aux - p.maxInter;
-      ic = p.maxInter;
+    if (aux >= PX(maxInter)) {
+      throughfall = aux - PX(maxInter);
+      ic = PX(maxInter);
     } else {
       throughfall = 0.0;
       ic = aux;
     }
     double ev;
-    if (p.maxInter > kEps) {
+    if (PX(maxInter) > kEps) {
 #if MHM_FAST
       // x**(2/3) = x * x**(-1/3); x = 0 is the common dry-canopy case
-      const double x = ic * p.inv_maxInter;
+      const double x = ic * PX(inv_maxInter);
       ev = (x == 0.0) ? 0.0 : pet * fm::pow23_pos(x);
 #else
-      ev = pet * pow(ic / p.maxInter, kTwoThird);
+      ev = pet * pow(ic / PX(maxInter), kTwoThird);
 #endif
     } else {
       ev = 0.0;
@@ -271,7 +311,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
   // ---- snow_accum_melt, mo_snow_accum_melt.f90:117-156 ----
   double prec_effect;
   {
-    const bool warm = temperature > p.tthr;
+    const bool warm = temperature > PX(tthr);
     double snow, rain, melt, dd;
     if (warm) {
       snow = 0.0;
@@ -280,14 +320,14 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
       snow = throughfall;
       rain = 0.0;
     }
-    if (prec <= p.ddthr) {
-      dd = p.ddnop_c + p.ddinc * prec;
+    if (prec <= PX(ddthr)) {
+      dd = PX(ddnop_c) + PX(ddinc) * prec;
     } else {
-      dd = p.ddmax_c;
+      dd = PX(ddmax_c);
     }
     if (warm) {
       if (s.snowpack > 0.0) {
-        double aux = dd * (temperature - p.tthr);
+        double aux = dd * (temperature - PX(tthr));
         if (aux > s.snowpack) {
           melt = s.snowpack;
           s.snowpack = 0.0;
@@ -315,21 +355,21 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
   double runoff_sealed = 0.0, infil_last = 0.0;
   {
     double aet_sealed = 0.0;
-    if (p.fSealed > 0.0) {
+    if (PX(fSealed) > 0.0) {
       double tmp = s.sealed + prec_effect;
       double st;
-      if (tmp > p.sealedThr) {
-        runoff_sealed = tmp - p.sealedThr;
-        st = p.sealedThr;
+      if (tmp > PX(sealedThr)) {
+        runoff_sealed = tmp - PX(sealedThr);
+        st = PX(sealedThr);
       } else {
         runoff_sealed = 0.0;
         st = tmp;
       }
-      if (p.sealedThr > kEps) {
+      if (PX(sealedThr) > kEps) {
 #if MHM_FAST
-        aet_sealed = (pet * inv_evap_coeff - aet_canopy) * (st * p.inv_sealedThr);
+        aet_sealed = (pet * inv_evap_coeff - aet_canopy) * (st * PX(inv_sealedThr));
 #else
-        aet_sealed = (pet / evap_coeff - aet_canopy) * (st / p.sealedThr);
+        aet_sealed = (pet / evap_coeff - aet_canopy) * (st / PX(sealedThr));
 #endif
         if (aet_sealed < 0.0) aet_sealed = 0.0;
       } else {
@@ -365,7 +405,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
       bool need[NH];
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) {
-        need[hh] = wet && s.sm[hh] > kEps && !(s.sm[hh] > p.SAT[hh]);
+        need[hh] = wet && s.sm[hh] > kEps && !(s.sm[hh] > PH(SAT, hh));
         const unsigned m = __ballot_sync(0xffffffffu, need[hh]);
         slot[hh] = base + __popc(m & lt);
         base += __popc(m);
@@ -374,7 +414,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
       if (base != 0) {  // warp-uniform
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh)
-          if (need[hh]) warp_tasks[slot[hh]] = make_double2(s.sm[hh] * p.inv_SAT[hh], p.EXPN[hh]);
+          if (need[hh]) warp_tasks[slot[hh]] = make_double2(s.sm[hh] * PH(inv_SAT, hh), PH(EXPN, hh));
         __syncwarp();
         for (unsigned k = lane; k < base; k += 32u) {
           const double2 tk = warp_tasks[k];
@@ -391,7 +431,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) {
       double sm = s.sm[hh];
-      const double sat = p.SAT[hh];
+      const double sat = PH(SAT, hh);
       double inf;
       if (hh != 0) prec_effec_soil = infil_last;
       if (sm > sat) {
@@ -416,7 +456,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
 #else
         double frac_runoff;
         if (sm > kEps) {
-          frac_runoff = exp(p.EXPN[hh] * log(sm / sat));
+          frac_runoff = exp(PH(EXPN, hh) * log(sm / sat));
         } else {
           frac_runoff = 0.0;
         }
@@ -440,26 +480,26 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
                           : VARIANT == kHourlyJarvis ? false
                                                      : (soil_case == 1 || soil_case == 4);
       if (feddes) {  // feddes_et_reduction :353-361
-        if (sm >= p.FC[hh]) {
-          stress = p.fRoots[hh];
-        } else if (sm > p.WP[hh]) {
+        if (sm >= PH(FC, hh)) {
+          stress = PH(fRoots, hh);
+        } else if (sm > PH(WP, hh)) {
 #if MHM_FAST
-          stress = p.fRoots[hh] * (sm - p.WP[hh]) * p.inv_FCWP[hh];
+          stress = PH(fRoots, hh) * (sm - PH(WP, hh)) * PH(inv_FCWP, hh);
 #else
-          stress = p.fRoots[hh] * (sm - p.WP[hh]) / (p.FC[hh] - p.WP[hh]);
+          stress = PH(fRoots, hh) * (sm - PH(WP, hh)) / (PH(FC, hh) - PH(WP, hh));
 #endif
         } else {
           stress = 0.0;
         }
       } else {  // jarvis_et_reduction :431-444 (cases 2, 3)
-        double th = (sm - p.WP[hh]) / (sat - p.WP[hh]);
+        double th = (sm - PH(WP, hh)) / (sat - PH(WP, hh));
         if (th < 0.0) th = 0.0;
         if (th > 1.0) th = 1.0;
         stress = 0.0;
-        if (th >= p.jarvis_c1) {
-          stress = p.fRoots[hh];
-        } else if (th < p.jarvis_c1) {
-          stress = p.fRoots[hh] * (th / p.jarvis_c1);
+        if (th >= PX(jarvis_c1)) {
+          stress = PH(fRoots, hh);
+        } else if (th < PX(jarvis_c1)) {
+          stress = PH(fRoots, hh) * (th / PX(jarvis_c1));
         }
       }
       a = a * stress;
@@ -482,22 +522,22 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
   double fast = 0.0, slow = 0.0;
   {
     double us = s.unsat + infil_last;
-    if (us > p.unsatThr) fast = fmin(p.k0r * (us - p.unsatThr), us - kEps);
+    if (us > PX(unsatThr)) fast = fmin(PX(k0r) * (us - PX(unsatThr)), us - kEps);
     us = us - fast;
     if (us > kEps) {
 #if MHM_FAST
-      slow = fmin(p.k1r * fm::pow_tab(tab, us, 1.0 + p.alpha), us - kEps);
+      slow = fmin(PX(k1r) * fm::pow_tab(tab, us, 1.0 + PX(alpha)), us - kEps);
 #else
-      slow = fmin(p.k1r * pow(us, 1.0 + p.alpha), us - kEps);
+      slow = fmin(PX(k1r) * pow(us, 1.0 + PX(alpha)), us - kEps);
 #endif
     }
     us = us - slow;
-    double perc = p.kpr * us;
+    double perc = PX(kpr) * us;
     if (us > perc) {
       us = us - perc;
-      s.sat = s.sat + perc * p.karst;
+      s.sat = s.sat + perc * PX(karst);
     } else {
-      s.sat = s.sat + us * p.karst;
+      s.sat = s.sat + us * PX(karst);
       us = 0.0;
     }
     s.unsat = us;
@@ -508,7 +548,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
   // ---- runoff_sat_zone :204-210 ----
   double baseflow;
   if (s.sat > 0.0) {
-    baseflow = p.k2r * s.sat;
+    baseflow = PX(k2r) * s.sat;
     s.sat = s.sat - baseflow;
   } else {
     baseflow = 0.0;
@@ -517,7 +557,7 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
   emit(MHM_F_BASEFLOW, baseflow);
   // ---- L1_total_runoff :271-272 ----
   const double total_runoff =
-      ((baseflow + slow + fast) * (1.0 - p.fSealed)) + (runoff_sealed * p.fSealed);
+      ((baseflow + slow + fast) * (1.0 - PX(fSealed))) + (runoff_sealed * PX(fSealed));
   emit(MHM_F_TOTAL_RUNOFF, total_runoff);
   return total_runoff;
 }
@@ -529,8 +569,8 @@ __device__ __forceinline__ double cascade_step(const CellParams<NH>& p, CellStat
 // balance (canopy / snow / sealed store / soil horizons / reservoirs) overlap in the pipeline
 // instead of being serialised by branch reconvergence.  Every value equals the branch form's
 // (a discarded side may be inf/NaN, never the selected one); the powers keep warp-uniform skips.
-template <int NH, int VARIANT, bool EMIT>
-__device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, CellStates<NH>& s,
+template <int NH, int VARIANT, bool EMIT, class PARAMS>
+__device__ __forceinline__ double cascade_step_sel(const PARAMS& p, CellStates<NH>& s,
                                                    const double pet, const double temperature,
                                                    const double prec, const double inv_evap_coeff,
                                                    double2* warp_tasks, const fm::Tables& tab,
@@ -538,11 +578,11 @@ __device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, Cell
   constexpr bool kFeddes = VARIANT == kHourlyFeddes;
   // ---- canopy_interc ----
   const double aux = s.inter + prec;
-  const bool over = aux >= p.maxInter;
-  const double throughfall = over ? aux - p.maxInter : 0.0;
-  const double ic0 = over ? p.maxInter : aux;
-  const double x = ic0 * p.inv_maxInter;
-  const bool has = (p.maxInter > kEps) && (x != 0.0);
+  const bool over = aux >= PX(maxInter);
+  const double throughfall = over ? aux - PX(maxInter) : 0.0;
+  const double ic0 = over ? PX(maxInter) : aux;
+  const double x = ic0 * PX(inv_maxInter);
+  const bool has = (PX(maxInter) > kEps) && (x != 0.0);
   double ev = 0.0;
   if (__any_sync(0xffffffffu, has)) ev = has ? pet * fm::pow23_pos(has ? x : 1.0) : 0.0;
   ev = ev < 0.0 ? 0.0 : ev;
@@ -553,10 +593,10 @@ __device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, Cell
   emit(MHM_F_AETCANOPY, aet_canopy);
 
   // ---- snow_accum_melt ----
-  const bool warm = temperature > p.tthr;
+  const bool warm = temperature > PX(tthr);
   const double snow = warm ? 0.0 : throughfall, rain = warm ? throughfall : 0.0;
-  const double dd = (prec <= p.ddthr) ? p.ddnop_c + p.ddinc * prec : p.ddmax_c;
-  const double pot = dd * (temperature - p.tthr);
+  const double dd = (prec <= PX(ddthr)) ? PX(ddnop_c) + PX(ddinc) * prec : PX(ddmax_c);
+  const double pot = dd * (temperature - PX(tthr));
   const bool pack = s.snowpack > 0.0, all = pot > s.snowpack;
   const double melt_w = pack ? (all ? s.snowpack : pot) : 0.0;
   const double pack_w = pack ? (all ? 0.0 : s.snowpack - pot) : 0.0;
@@ -570,14 +610,14 @@ __device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, Cell
   emit(MHM_F_PREEFFECT, prec_effect);
 
   // ---- sealed store ----
-  const bool sealed_on = p.fSealed > 0.0;
+  const bool sealed_on = PX(fSealed) > 0.0;
   const double tmp_s = s.sealed + prec_effect;
-  const bool spill = tmp_s > p.sealedThr;
-  const double rs_on = spill ? tmp_s - p.sealedThr : 0.0;
-  const double st0 = spill ? p.sealedThr : tmp_s;
-  double ae = (pet * inv_evap_coeff - aet_canopy) * (st0 * p.inv_sealedThr);
+  const bool spill = tmp_s > PX(sealedThr);
+  const double rs_on = spill ? tmp_s - PX(sealedThr) : 0.0;
+  const double st0 = spill ? PX(sealedThr) : tmp_s;
+  double ae = (pet * inv_evap_coeff - aet_canopy) * (st0 * PX(inv_sealedThr));
   ae = ae < 0.0 ? 0.0 : ae;
-  ae = (p.sealedThr > kEps) ? ae : DBL_MAX;
+  ae = (PX(sealedThr) > kEps) ? ae : DBL_MAX;
   const bool more_s = st0 > ae;
   const double aet_sealed = sealed_on ? (more_s ? ae : st0) : 0.0;
   const double runoff_sealed = sealed_on ? rs_on : 0.0;
@@ -596,7 +636,7 @@ __device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, Cell
     bool need[NH];
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) {
-      need[hh] = wet && s.sm[hh] > kEps && !(s.sm[hh] > p.SAT[hh]);
+      need[hh] = wet && s.sm[hh] > kEps && !(s.sm[hh] > PH(SAT, hh));
       const unsigned m = __ballot_sync(0xffffffffu, need[hh]);
       slot[hh] = base + __popc(m & lt);
       base += __popc(m);
@@ -605,7 +645,7 @@ __device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, Cell
     if (base != 0) {  // warp-uniform
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh)
-        if (need[hh]) warp_tasks[slot[hh]] = make_double2(s.sm[hh] * p.inv_SAT[hh], p.EXPN[hh]);
+        if (need[hh]) warp_tasks[slot[hh]] = make_double2(s.sm[hh] * PH(inv_SAT, hh), PH(EXPN, hh));
       __syncwarp();
       for (unsigned k = lane; k < base; k += 32u) {
         const double2 tk = warp_tasks[k];
@@ -623,7 +663,7 @@ __device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, Cell
   double infil_last = 0.0, aet_pos_sum = 0.0;
 #pragma unroll
   for (int hh = 0; hh < NH; ++hh) {
-    const double sm0 = s.sm[hh], sat = p.SAT[hh];
+    const double sm0 = s.sm[hh], sat = PH(SAT, hh);
     const double pe = hh == 0 ? prec_effect : infil_last;
     const bool oversat = sm0 > sat;
     const double tmp = pe * (1.0 - frac_pre[hh]);
@@ -636,13 +676,13 @@ __device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, Cell
     if (hh != 0) a = a - aet_pos_sum;
     double stress;
     if (kFeddes) {
-      const double part = p.fRoots[hh] * (sm1 - p.WP[hh]) * p.inv_FCWP[hh];
-      stress = sm1 >= p.FC[hh] ? p.fRoots[hh] : (sm1 > p.WP[hh] ? part : 0.0);
+      const double part = PH(fRoots, hh) * (sm1 - PH(WP, hh)) * PH(inv_FCWP, hh);
+      stress = sm1 >= PH(FC, hh) ? PH(fRoots, hh) : (sm1 > PH(WP, hh) ? part : 0.0);
     } else {
-      double th = (sm1 - p.WP[hh]) / (sat - p.WP[hh]);
+      double th = (sm1 - PH(WP, hh)) / (sat - PH(WP, hh));
       th = th < 0.0 ? 0.0 : th;
       th = th > 1.0 ? 1.0 : th;
-      stress = th >= p.jarvis_c1 ? p.fRoots[hh] : (th < p.jarvis_c1 ? p.fRoots[hh] * (th / p.jarvis_c1) : 0.0);
+      stress = th >= PX(jarvis_c1) ? PH(fRoots, hh) : (th < PX(jarvis_c1) ? PH(fRoots, hh) * (th / PX(jarvis_c1)) : 0.0);
     }
     a = a * stress;
     a = a < 0.0 ? 0.0 : a;
@@ -657,25 +697,25 @@ __device__ __forceinline__ double cascade_step_sel(const CellParams<NH>& p, Cell
 
   // ---- runoff_unsat_zone ----
   double us = s.unsat + infil_last;
-  const double fast = us > p.unsatThr ? fmin(p.k0r * (us - p.unsatThr), us - kEps) : 0.0;
+  const double fast = us > PX(unsatThr) ? fmin(PX(k0r) * (us - PX(unsatThr)), us - kEps) : 0.0;
   us = us - fast;
   const bool wetu = us > kEps;
-  const double pw = fm::pow_tab(tab, wetu ? us : 1.0, 1.0 + p.alpha);
-  const double slow = wetu ? fmin(p.k1r * pw, us - kEps) : 0.0;
+  const double pw = fm::pow_tab(tab, wetu ? us : 1.0, 1.0 + PX(alpha));
+  const double slow = wetu ? fmin(PX(k1r) * pw, us - kEps) : 0.0;
   us = us - slow;
-  const double perc = p.kpr * us;
+  const double perc = PX(kpr) * us;
   const bool gt = us > perc;
-  s.sat = s.sat + (gt ? perc : us) * p.karst;
+  s.sat = s.sat + (gt ? perc : us) * PX(karst);
   s.unsat = gt ? us - perc : 0.0;
   emit(MHM_F_FASTRUNOFF, fast);
   emit(MHM_F_SLOWRUNOFF, slow);
   emit(MHM_F_PERCOL, perc);
   // ---- runoff_sat_zone ----
   const bool pos = s.sat > 0.0;
-  const double baseflow = pos ? p.k2r * s.sat : 0.0;
+  const double baseflow = pos ? PX(k2r) * s.sat : 0.0;
   s.sat = pos ? s.sat - baseflow : 0.0;
   emit(MHM_F_BASEFLOW, baseflow);
-  const double total_runoff = ((baseflow + slow + fast) * (1.0 - p.fSealed)) + (runoff_sealed * p.fSealed);
+  const double total_runoff = ((baseflow + slow + fast) * (1.0 - PX(fSealed))) + (runoff_sealed * PX(fSealed));
   emit(MHM_F_TOTAL_RUNOFF, total_runoff);
   return total_runoff;
 }
@@ -693,7 +733,7 @@ struct CellCursor {
 };
 
 template <int NH, int VARIANT, bool OUT>
-__global__ void __launch_bounds__(kCellThreads, MHM_CELL_MIN_BLOCKS)
+__global__ void __launch_bounds__(kCellThreads, ParamPlace<NH>::min_blocks)
 MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
   const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
@@ -729,15 +769,18 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 #pragma unroll
   for (int h = 0; h < NH; ++h) s.sm[h] = a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + c];
 
-  CellParams<NH> p;
+  constexpr bool kSharedParams = ParamPlace<NH>::shared;
+  __shared__ std::conditional_t<kSharedParams, CellParamsShared<NH>, EmptyParams> p_shared;
+  std::conditional_t<kSharedParams, EmptyParams, CellParams<NH>> p_regs;
+  auto& p = pick_ref<kSharedParams>(p_shared, p_regs);
   // parameters that never change during a run
-  p.karst = a.P[MHM_P_KARSTLOSS][mc];
-  p.jarvis_c1 = a.P[MHM_P_JARVIS_C1][mc];
-  p.unsatThr = a.P[MHM_P_UNSATTHRESH][mc];
-  p.sealedThr = a.P[MHM_P_SEALEDTHRESH][mc];
+  PX(karst) = a.P[MHM_P_KARSTLOSS][mc];
+  PX(jarvis_c1) = a.P[MHM_P_JARVIS_C1][mc];
+  PX(unsatThr) = a.P[MHM_P_UNSATTHRESH][mc];
+  PX(sealedThr) = a.P[MHM_P_SEALEDTHRESH][mc];
 #if MHM_FAST
-  p.inv_sealedThr = 1.0 / p.sealedThr;
-  p.inv_jc1 = 1.0 / p.jarvis_c1;
+  PX(inv_sealedThr) = 1.0 / PX(sealedThr);
+  PX(inv_jc1) = 1.0 / PX(jarvis_c1);
 #endif
   CellCursor cu;
   cu.cur_y = -1;
@@ -770,48 +813,48 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     if (y != cu.cur_y) {  // land-cover scene changed (new year): mo_mhm_interface_run.f90:626-628
       cu.cur_y = y;
       const size_t o1 = ((size_t)member * a.nLC + y) * n + c;  // (n, 1, nLC) arrays
-      p.fSealed = a.P[MHM_P_FSEALED][o1];
-      p.alpha = a.P[MHM_P_ALPHA][o1];
-      p.ddinc = a.P[MHM_P_DEGDAYINC][o1];
-      p.ddmax_c = a.P[MHM_P_DEGDAYMAX][o1] * a.c2TSTu;    // mo_mhm.f90:463
-      p.ddnop_c = a.P[MHM_P_DEGDAYNOPRE][o1] * a.c2TSTu;  // mo_mhm.f90:464
-      p.ddthr = (p.ddmax_c - p.ddnop_c) / p.ddinc;        // mo_snow_accum_melt.f90:127
-      p.k0r = a.c2TSTu / a.P[MHM_P_KFASTFLOW][o1];        // mo_mhm.f90:484
-      p.k1r = a.c2TSTu / a.P[MHM_P_KSLOWFLOW][o1];
-      p.kpr = a.c2TSTu / a.P[MHM_P_KPERCO][o1];
-      p.k2r = a.c2TSTu / a.P[MHM_P_KBASEFLOW][o1];        // mo_mhm.f90:488
-      p.tthr = a.P[MHM_P_TEMPTHRESH][o1];
+      PX(fSealed) = a.P[MHM_P_FSEALED][o1];
+      PX(alpha) = a.P[MHM_P_ALPHA][o1];
+      PX(ddinc) = a.P[MHM_P_DEGDAYINC][o1];
+      PX(ddmax_c) = a.P[MHM_P_DEGDAYMAX][o1] * a.c2TSTu;    // mo_mhm.f90:463
+      PX(ddnop_c) = a.P[MHM_P_DEGDAYNOPRE][o1] * a.c2TSTu;  // mo_mhm.f90:464
+      PX(ddthr) = (PX(ddmax_c) - PX(ddnop_c)) / PX(ddinc);        // mo_snow_accum_melt.f90:127
+      PX(k0r) = a.c2TSTu / a.P[MHM_P_KFASTFLOW][o1];        // mo_mhm.f90:484
+      PX(k1r) = a.c2TSTu / a.P[MHM_P_KSLOWFLOW][o1];
+      PX(kpr) = a.c2TSTu / a.P[MHM_P_KPERCO][o1];
+      PX(k2r) = a.c2TSTu / a.P[MHM_P_KBASEFLOW][o1];        // mo_mhm.f90:488
+      PX(tthr) = a.P[MHM_P_TEMPTHRESH][o1];
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
         const size_t oh = (((size_t)member * a.nLC + y) * NH + h) * n + c;  // (n, nH, nLC)
-        p.fRoots[h] = a.P[MHM_P_FROOTS][oh];
-        p.FC[h] = a.P[MHM_P_SOILMOISTFC][oh];
-        p.SAT[h] = a.P[MHM_P_SOILMOISTSAT][oh];
-        p.EXPN[h] = a.P[MHM_P_SOILMOISTEXP][oh];
-        p.WP[h] = a.P[MHM_P_WILTINGPOINT][oh];
+        PH(fRoots, h) = a.P[MHM_P_FROOTS][oh];
+        PH(FC, h) = a.P[MHM_P_SOILMOISTFC][oh];
+        PH(SAT, h) = a.P[MHM_P_SOILMOISTSAT][oh];
+        PH(EXPN, h) = a.P[MHM_P_SOILMOISTEXP][oh];
+        PH(WP, h) = a.P[MHM_P_WILTINGPOINT][oh];
 #if MHM_FAST
-        p.inv_SAT[h] = 1.0 / p.SAT[h];
-        p.inv_FCWP[h] = 1.0 / (p.FC[h] - p.WP[h]);
+        PH(inv_SAT, h) = 1.0 / PH(SAT, h);
+        PH(inv_FCWP, h) = 1.0 / (PH(FC, h) - PH(WP, h));
 #endif
       }
       cu.cur_l = -1;  // petLAIcorFactor / aeroResist also depend on yId
       if (t == 0 && a.tt_first == 1 && !a.read_states) {  // mo_mhm.f90:448-450
 #pragma unroll
-        for (int h = 0; h < NH; ++h) s.sm[h] = 0.5 * p.FC[h];
+        for (int h = 0; h < NH; ++h) s.sm[h] = 0.5 * PH(FC, h);
       }
     }
     if (il != cu.cur_l) {  // LAI step changed: mo_common_datetime_type.f90:135-155
       cu.cur_l = il;
-      p.maxInter = a.P[MHM_P_MAXINTER][((size_t)member * a.nLAI + il) * n + c];
+      PX(maxInter) = a.P[MHM_P_MAXINTER][((size_t)member * a.nLAI + il) * n + c];
 #if MHM_FAST
-      p.inv_maxInter = 1.0 / p.maxInter;
+      PX(inv_maxInter) = 1.0 / PX(maxInter);
 #endif
       if (a.pet_case == -1) {
-        p.petFac = a.P[MHM_P_PETLAICORFACTOR][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + c];
+        PX(petFac) = a.P[MHM_P_PETLAICORFACTOR][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + c];
       } else if (a.pet_case == 0 || a.pet_case == 1) {
-        p.petFac = a.P[MHM_P_FASP][mc];
+        PX(petFac) = a.P[MHM_P_FASP][mc];
       } else {
-        p.petFac = 1.0;
+        PX(petFac) = 1.0;
       }
     }
 
@@ -823,11 +866,11 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     // ---- get_corrected_pet :1053-1119 ----
     double pet;
     if (kHourlyPetIn || a.pet_case <= 0) {
-      pet = p.petFac * raw_pet;
+      pet = PX(petFac) * raw_pet;
     } else if (a.pet_case == 1) {
       const double tmx = a.met[MHM_M_TMAX][(size_t)(row - a.met_first[MHM_M_TMAX]) * n + c];
       const double tmn = a.met[MHM_M_TMIN][(size_t)(row - a.met_first[MHM_M_TMIN]) * n + c];
-      pet = p.petFac * pet_hargreaves(a.P[MHM_P_HARSAMCOEFF][mc], raw_temp, tmx, tmn,
+      pet = PX(petFac) * pet_hargreaves(a.P[MHM_P_HARSAMCOEFF][mc], raw_temp, tmx, tmn,
                                       a.P[MHM_P_LATITUDE][mc], si.doy);
     } else if (a.pet_case == 2) {
       const double rn = a.met[MHM_M_NETRAD][(size_t)(row - a.met_first[MHM_M_NETRAD]) * n + c];

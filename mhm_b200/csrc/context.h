@@ -78,8 +78,6 @@ struct Domain {
   bool has_time = false;
   TimeAxis axis;
   std::vector<StepIdx> h_idx;  // steps 1..nTimeSteps
-  StepIdx* d_idx = nullptr;
-  StepIdx* d_idx_one = nullptr;  // scratch for the per-step seam
 
   // total-runoff history of the last block, device [steps][member][nCells]
   double* runoff_hist = nullptr;
