@@ -208,6 +208,44 @@ def forcing(out, mask1, pick, sim_start, n_days, pet_case):
         out["forcing/" + key] = a
 
 
+def make_case_optimised(case, sim_start, n_days, warming_days, lc_years, cases):
+    """a calibration check case: no mHM restart is written, the saved discharge belongs to the
+    final run with the optimiser's best parameter set (output_save/FinalParam.out, 15 digits).
+    The fixture holds forcing, that gamma, the network / final routing state and Qsim; the L1
+    parameters have to come from MPR."""
+    cdir = os.path.join(REF, "check", case)
+    sav = os.path.join(cdir, "output_save")
+    mrm = h5lite.H5File(os.path.join(sav, "b1_mRM_restart_001.nc"))
+    ref00 = h5lite.H5File(os.path.join(REF, "check", "case_00", "output_save", "b1_mHM_restart_001.nc"))
+    mask1 = ref00["L1_domain_mask"].read() != 0
+    pick = lambda a: np.ascontiguousarray(a[..., mask1])
+    out = {"cases": np.array(cases, dtype=np.int32), "mask1": mask1,
+           "L1_lat": pick(ref00["L1_domain_lat"].read()), "horizon_bnds": ref00["L1_SoilHorizons_bnds"].read()}
+    network(out, mrm, pick, cdir)
+    forcing(out, mask1, pick, sim_start, n_days, cases[1])
+    q = h5lite.H5File(os.path.join(sav, "b1_discharge.nc"))
+    for k in q.keys():
+        if k.startswith("Qsim_"):
+            out["Qsim/" + k[5:]] = q[k].read()
+    txt = np.loadtxt(os.path.join(sav, "b1_daily_discharge.out"), skiprows=1)
+    out["Qsim_text"] = txt[:, 5::2]
+    # best parameter set: second line of FinalParam.out = objective followed by all parameters
+    with open(os.path.join(sav, "FinalParam.out")) as f:
+        names = f.readline().split()
+        vals = [float(x) for x in f.readline().split()]
+    assert names[0] == "OF" and len(names) == len(vals)
+    _, pm = gamma_vector(os.path.join(cdir, "mhm_parameter.nml"), cases)
+    assert pm[2, 8] == len(vals) - 1, (pm[2], len(vals))
+    out["gamma"], out["processMatrix"] = np.array(vals[1:]), pm
+    out["rout_param"] = out["gamma"][pm[2, 7] - pm[1, 7]: pm[2, 7]]
+    out["time"] = np.array([sim_start.toordinal(), n_days, warming_days])
+    out["lc_years"] = np.array(lc_years, dtype=np.int32)
+    path = os.path.join(HERE, case + ".npz")
+    np.savez_compressed(path, **out)
+    print("%s: optimised run, %d parameters, %d forcing days, %.0f kB" % (case, len(vals) - 1, n_days,
+                                                                        os.path.getsize(path) / 1e3))
+
+
 if __name__ == "__main__":
     D = datetime.date
     LC = lambda y0, ny: [y0] + [1 if y <= 1990 else 2 for y in range(y0, y0 + ny)]
@@ -222,6 +260,8 @@ if __name__ == "__main__":
     # soil moisture case 3 (Jarvis, FC-dependent roots) / 4 (Feddes, FC-dependent roots) + LAI-corrected PET
     make_case("case_10", D(1990, 1, 1), 181 + 365, 181, LC(1990, 2), (3, -1, 1))
     make_case("case_12", D(1990, 1, 1), 181 + 365, 181, LC(1990, 2), (4, -1, 1))
+    # DDS calibration with Penman-Monteith PET (processCase(5) = 3): final run with the best set
+    make_case_optimised("case_03", D(1990, 1, 1), 181 + 365, 181, LC(1990, 2), (1, 3, 1))
     # case_04: six domains; 1, 2, 4, 5 use the test domain (3 and 6 need forcing files that
     # are not in the tree).  2: L1 12 km under L11 24 km; 5: L1 = L11 = 12 km
     e = lambda a, b, w: (a - datetime.timedelta(days=w), (b - a).days + 1 + w, w)

@@ -106,7 +106,7 @@ def load_mpr(case, init_lowres_level):
     db = {k[5:]: z0[k] for k in z0.files if k.startswith("soil/")}
     db["nSoil"], db["maxHor"] = int(db["nSoil"]), int(db["maxHor"])
     db["is_present"] = z0["is_present"]
-    nH = zc["param/L1_soilMoistSat"].shape[1]
+    nH = zc["param/L1_soilMoistSat"].shape[1] if "param/L1_soilMoistSat" in zc.files else zc["horizon_bnds"].shape[0]
     hd = np.array(zc["horizon_bnds"][:, 1], dtype=np.float64)
     hd[nH - 1] = float(db.pop("HorizonDepth_last"))
     prob = {"nrows0": mask0.shape[1], "ncols0": mask0.shape[0], "nL0": n0,
@@ -119,5 +119,6 @@ def load_mpr(case, init_lowres_level):
             "processMatrix": zc["processMatrix"], "soil_case": soil_case, "pet_case": pet_case}
     ref = {k[6:]: zc[k] for k in zc.files if k.startswith("param/")}
     ref["mask1"] = mask1
-    ref["L1_areaCell_km2"] = zc["L1_areaCell_km2"]
+    if "L1_areaCell_km2" in zc.files:
+        ref["L1_areaCell_km2"] = zc["L1_areaCell_km2"]
     return prob, ref

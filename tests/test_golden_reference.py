@@ -158,3 +158,61 @@ def test_oracle_reproduces_reference_gridded_outputs(case):
     assert set(W[0][1]) == set(outs["fields"])
     for key, want in outs["fields"].items():
         parity.assert_bit_exact(W[0][1][key], want[0], "%s output %s" % (case, key))
+
+
+# ---- Penman-Monteith PET (processCase(5) = 3): the final run of a DDS calibration -------------
+def _case03(init_lowres_level, run_mpr):
+    """check/case_03: gamma = the optimiser's best set (FinalParam.out, 15 digits); the L1
+    parameters come from MPR on the raw test-basin inputs, forcing incl. net radiation, vapour
+    pressure and wind speed from the reference's files"""
+    mprob, _ = golden_case.load_mpr("case_03", init_lowres_level)
+    params = run_mpr(mprob)
+    z = np.load(golden_case.HERE + "/golden/case_03.npz")
+    # golden_case.load needs param/* entries: build the problem by hand from the MPR output
+    import datetime
+    from mhm_b200 import synth
+    n = mprob["nL1"]
+    ordinal0, n_days, warming = [int(x) for x in z["time"]]
+    d0 = datetime.date.fromordinal(ordinal0)
+    lc = z["lc_years"]
+    prob = {"nH": 2, "nLAI": 12, "nLC": 2, "timestep_h": 1, "hourly": False, "soil_case": 1, "pet_case": 3,
+            "rout_case": 1, "read_weights": False, "nCells": n, "nTstepForcingDay": 1,
+            "processMatrix": z["processMatrix"],
+            "time": {"jul_start": synth.JUL_1990_01_01 + (d0 - datetime.date(1990, 1, 1)).days,
+                     "nTimeSteps": n_days * 24, "warming_days": warming, "timeStep_LAI_input": 0,
+                     "lc_year_start": int(lc[0]), "LCyearId": np.asarray(lc[1:], dtype=np.int32)}}
+    full = synth.make_params(np.random.default_rng(0), n, 2, 12, 2, 3)
+    P = {k: np.ascontiguousarray(v) for k, v in params.items()}
+    P["latitude"] = z["L1_lat"][None, None, :]
+    for k, v in full.items():
+        P.setdefault(k, v)
+    prob["params"] = P
+    prob["forcing"] = {k[8:]: np.ascontiguousarray(z[k]) for k in z.files if k.startswith("forcing/")}
+    prob["horizon_depth"] = np.ascontiguousarray(z["horizon_bnds"][:, 1])
+    prob["states0"] = synth.default_states(n, 2, prob["horizon_depth"])
+    z0 = np.load(golden_case.HERE + "/golden/case_00.npz")   # same basin, same network
+    net_prob, _ = golden_case.load("case_00")
+    net = dict(net_prob["net"])
+    net["rout_param"] = z["rout_param"]
+    prob["net"] = net
+    prob["inflowQ"] = np.zeros((0, n_days))
+    ref = {"Qsim": np.stack([z[k] for k in z.files if k.startswith("Qsim/")]), "warming_days": warming,
+           "final": {k[6:]: z[k] for k in z.files if k.startswith("final/")}}
+    assert np.array_equal(z["net/L11_netPerm"], z0["net/L11_netPerm"])
+    return prob, ref
+
+
+def test_oracle_reproduces_penman_monteith_run():
+    """MPR (aerodynamic + bulk surface resistance) -> PET case 3 -> cascade -> routing against the
+    discharge of the reference's final calibration run: pins the FORCES constants cp0, rho0 and
+    Psychro, which test_pet.pf fixes only to 1e-3.  gamma is known to 15 digits only."""
+    import orc_mpr
+
+    prob, ref = _case03(orc_mpr.init_lowres_level, orc_mpr.run_mpr)
+    o = orc_run.OracleRun(prob)
+    o.run(1, prob["time"]["nTimeSteps"])
+    q = golden_case.daily_mean(o.mRM_runoff, ref["warming_days"])
+    worst = parity.assert_close(q, ref["Qsim"], "case_03 daily discharge", rtol=1e-10, atol=0.0)
+    for ours, theirs in (("L11_qTIN", "L11_qTIN"), ("L11_qTR", "L11_qTR"), ("L11_C1", "L11_C1"), ("L11_C2", "L11_C2")):
+        parity.assert_close(o.R[ours], ref["final"][theirs], "case_03 " + theirs, rtol=1e-10)
+    print("case_03: daily discharge max rel diff %.2e" % worst)

@@ -64,3 +64,33 @@ def test_raw_inputs_to_discharge(case, res1, res11):
         for (var, hor), want in outs["fields"].items():
             parity.assert_close(dom.get_output(0, var, hor + 1 if hor >= 0 else 0), want[0], "%s output %d" % (case, var))
         print("%s from raw inputs: daily discharge max rel diff %.2e, states %.2e" % (case, wq, worst))
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_penman_monteith_calibration_run(mode):
+    """check/case_03 (PET processCase 3, final run of a DDS calibration): MPR incl. aerodynamic
+    and bulk surface resistance, Penman-Monteith prologue, cascade and routing on the device
+    against the reference's saved discharge"""
+    from test_golden_reference import _case03
+    from mhm_b200 import driver
+
+    def device_mpr(mprob):
+        with interface.Context() as c:
+            c.set_math_mode("strict")
+            dom = c.register_domain(1, mprob["nL1"], mprob["nH"], mprob["nLAI"], mprob["nLC"], mprob["processMatrix"])
+            synth_mpr.set_mpr_inputs(dom, mprob)
+            synth_mpr.mpr_eval(dom, mprob["param"])
+            out = {}
+            for name in synth_mpr.outputs_for(1, 3):
+                d2, d3 = synth_mpr.MPR_OUTPUTS[name](mprob["nH"], mprob["nLAI"], mprob["nLC"])
+                out[name] = dom.get_param(name, d2, d3)
+            return out
+
+    prob, ref = _case03(synth_mpr.init_lowres_level, device_mpr)
+    with interface.Context() as ctx:
+        ctx.set_math_mode(mode)
+        dom = driver.setup_domain(ctx, 1, prob)
+        dom.run_steps(1, prob["time"]["nTimeSteps"])
+        q = golden_case.daily_mean(dom.get_runoff(), ref["warming_days"])
+        worst = parity.assert_close(q, ref["Qsim"], "case_03 daily discharge (%s)" % mode, rtol=parity.RTOL_Q)
+        print("case_03[%s]: daily discharge max rel diff %.2e" % (mode, worst))
