@@ -29,6 +29,12 @@ namespace mhm {
 #ifndef MHM_FAST
 #define MHM_FAST 0
 #endif
+#ifndef MHM_CELL_SMEM_BLOCKS
+#define MHM_CELL_SMEM_BLOCKS 5
+#endif
+#ifndef MHM_TABLES_GLOBAL
+#define MHM_TABLES_GLOBAL 0
+#endif
 #ifndef MHM_PARAMS_SMEM
 #define MHM_PARAMS_SMEM 1
 #endif
@@ -116,7 +122,7 @@ struct CellParams {
   double maxInter;
   double petFac;  // petLAIcorFactor (case -1) or fAsp (case 0, 1)
 #if MHM_FAST
-  double inv_maxInter, inv_sealedThr, inv_SAT[NH], inv_FCWP[NH], inv_jc1;
+  double inv_maxInter, inv_sealedThr, inv_SAT[NH], inv_FCWP[NH];
 #endif
 };
 
@@ -134,7 +140,7 @@ struct CellParamsShared {
   double maxInter[kCellThreads];
   double petFac[kCellThreads];
   double inv_maxInter[kCellThreads], inv_sealedThr[kCellThreads], inv_SAT[NH][kCellThreads],
-      inv_FCWP[NH][kCellThreads], inv_jc1[kCellThreads];
+      inv_FCWP[NH][kCellThreads];
 };
 // one access syntax for both stores: a member is a double (registers) or a column (shared)
 __device__ __forceinline__ double& pcol(double& x) { return x; }
@@ -154,7 +160,7 @@ __device__ __forceinline__ auto& pick_ref(A& a, B& b) {
 template <int NH>
 struct ParamPlace {
   static constexpr bool shared = MHM_FAST && MHM_PARAMS_SMEM && NH <= 2;
-  static constexpr int min_blocks = shared ? 5 : MHM_CELL_MIN_BLOCKS;
+  static constexpr int min_blocks = shared ? MHM_CELL_SMEM_BLOCKS : MHM_CELL_MIN_BLOCKS;
 };
 
 // ---- one model step for one cell ---------------------------------------------------
@@ -739,6 +745,9 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
 #if MHM_FAST
   __shared__ double2 sh_tasks[kCellThreads * NH];
+#if MHM_TABLES_GLOBAL
+  const fm::Tables& sh_tab = fm::d_tables;  // served from L1
+#else
   __shared__ fm::Tables sh_tab;  // log / exp tables of fastmath.cuh, 4 KB
   {
     static_assert(sizeof(fm::Tables) == 256 * sizeof(double2), "table layout");
@@ -747,6 +756,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     for (int i = threadIdx.x; i < 256; i += kCellThreads) dst[i] = src[i];
     __syncthreads();
   }
+#endif
   double2* const warp_tasks = sh_tasks + (threadIdx.x >> 5) * (32 * NH);
   // out-of-range lanes of the last tile stay alive (warp collectives) on a valid cell
   const bool live = cell < a.nCells;
@@ -780,7 +790,6 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   PX(sealedThr) = a.P[MHM_P_SEALEDTHRESH][mc];
 #if MHM_FAST
   PX(inv_sealedThr) = 1.0 / PX(sealedThr);
-  PX(inv_jc1) = 1.0 / PX(jarvis_c1);
 #endif
   CellCursor cu;
   cu.cur_y = -1;
