@@ -269,6 +269,45 @@ int mhm_cuda_get_output_windows(mhm_cuda_context *ctx, int32_t iDomain, int32_t 
 int mhm_cuda_get_output(mhm_cuda_context *ctx, int32_t iDomain, int32_t member, int32_t window,
                         int32_t variable, int32_t horizon, double *out);
 
+/* ---------------------------------------------------------------------------------
+ * A10  calibration aggregates and BFI sums, accumulated on the device while blocks of steps run.
+ * Replaces, for run_steps, `call mhm_interface_run_update_optisim(etOptiSim, twsOptiSim, ...,
+ * smOptiSim)` (mHM/mo_mhm_interface_run.f90:745-861, called from mo_mhm_eval.f90:144) and the
+ * BFI sums of mo_mhm_interface_run.f90:630-636.  The container optidata_sim (FORCES v0.6.0
+ * mo_optimization_types, not vendored in the reference tree) is reproduced: dataSim starts at
+ * zero; for every step of the evaluation period, in this order, the open slot is closed when
+ * the step's date increment raised is_new_day / _month / _year (timeStepInput -1 / -2 / -3:
+ * soil moisture and TWS are divided by the number of values added, ET only moves on), then
+ * the step's value is added unless it is the run's last step:
+ *   soil moisture  sum(soilMoist(:, 1:nSoilHorizons_sm_input)) / sum(soilMoistSat(:, 1:n, yId))
+ *   ET             sum(aETSoil) * fNotSealed + aETCanopy + aETSealed * fSealed
+ *   TWS            inter + snowPack + sealSTW + unsatSTW + satSTW, then + soilMoist(:, h) per horizon
+ * nTime = size(dataObs, 2).  Neutrons are out of scope.  BFI: per member, sum over the steps
+ * with tIndex_out > 0 of sum(L1_baseflow * CellArea) / nCells and the same for L1_total_runoff
+ * (summed per cell over time first; <= 1e-13 relative to the reference's order).
+ * --------------------------------------------------------------------------------- */
+typedef struct mhm_optisim_config {
+  int32_t sm_on;
+  int32_t sm_timeStepInput;
+  int32_t sm_nTime;
+  int32_t nSoilHorizons_sm_input;
+  int32_t et_on;
+  int32_t et_timeStepInput;
+  int32_t et_nTime;
+  int32_t tws_on;
+  int32_t tws_timeStepInput;
+  int32_t tws_nTime;
+  int32_t bfi_on;
+} mhm_optisim_config;
+int mhm_cuda_set_optisim(mhm_cuda_context *ctx, int32_t iDomain, const mhm_optisim_config *cfg);
+/* which: 0 soil moisture, 1 ET, 2 TWS; dataSim(:, 1:nTime) of one member into the Fortran array
+ * base(ld, nTime) starting at row offset */
+int mhm_cuda_get_optisim(mhm_cuda_context *ctx, int32_t iDomain, int32_t member, int32_t which,
+                         double *base, int64_t ld, int64_t offset);
+/* cellArea = level1(iDomain)%CellArea, host, [nCells] */
+int mhm_cuda_get_bfi_sums(mhm_cuda_context *ctx, int32_t iDomain, int32_t member,
+                          const double *cellArea, double *qBF_sum, double *qT_sum);
+
 /* keep host module globals coherent (pybind get%L1_variable, restart writing): bind once,
  * then mhm_cuda_sync_to_host copies every bound state/flux of every member 0 array back */
 int mhm_cuda_bind_host_state(mhm_cuda_context *ctx, int32_t iDomain, int32_t state_id,

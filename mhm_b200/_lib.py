@@ -42,6 +42,10 @@ class MprL0Inputs(C.Structure):
     _fields_ = _cstruct.parse_struct(HEADER, "mpr_l0_inputs")
 
 
+class OptisimConfig(C.Structure):
+    _fields_ = _cstruct.parse_struct(HEADER, "mhm_optisim_config")
+
+
 class MprSoilDb(C.Structure):
     _fields_ = _cstruct.parse_struct(HEADER, "mpr_soil_db")
 
@@ -102,6 +106,9 @@ def load():
         "mrm_cuda_export_outflow": [vp, i32, vp, i32],
         "mrm_cuda_import_outflow": [vp, i32, vp, i32],
         "mhm_cuda_get_output_windows": [vp, i32, pi, pi, i32],
+        "mhm_cuda_set_optisim": [vp, i32, C.POINTER(OptisimConfig)],
+        "mhm_cuda_get_optisim": [vp, i32, i32, i32, pd, i64, i64],
+        "mhm_cuda_get_bfi_sums": [vp, i32, i32, pd, pd, pd],
         "mhm_cuda_get_output": [vp, i32, i32, i32, i32, i32, pd],
         "mrm_cuda_set_network": [vp, i32, C.POINTER(Network)],
         "mrm_routing_order": [i32, i32, pi, pi, pi, pi],

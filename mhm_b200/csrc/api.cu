@@ -71,6 +71,8 @@ static void free_domain(Domain* d) {
   cudaFree(d->runoff_hist);
   cudaFree(d->out_acc);
   cudaFree(d->out_win);
+  for (int w = 0; w < 3; ++w) cudaFree(d->opt_data[w]);
+  cudaFree(d->bfi_acc);
   if (d->rt) routing_free(d->rt);
   if (d->mpr) mpr_free(d->mpr);
   delete d;
@@ -759,6 +761,36 @@ __global__ void out_finalize_kernel(double* __restrict__ acc, double* __restrict
   }
 }
 
+// ---- calibration aggregates: optidata_sim of FORCES mo_optimization_types, restated ------------
+__global__ void optisim_average_kernel(double* __restrict__ col, size_t per, double counter) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < per) col[i] = col[i] / counter;
+}
+static inline bool optisim_flag(int32_t timeStepInput, int8_t fl) {
+  return (timeStepInput == -1 && (fl & 1)) || (timeStepInput == -2 && (fl & 2)) ||
+         (timeStepInput == -3 && (fl & 4));
+}
+static bool optisim_closes(const Domain* d, int8_t fl) {
+  for (int w = 0; w < 3; ++w)
+    if (d->opt_on[w] && optisim_flag(d->opt_ts[w], fl)) return true;
+  return false;
+}
+// average_per_timestep (soil moisture, TWS) / increment_counter (ET) of a step whose date flags are fl
+static int optisim_close(mhm_cuda_context* ctx, Domain* d, int8_t fl) {
+  const size_t per = (size_t)d->cfg.nMembers * (size_t)d->cfg.nCells;
+  for (int w = 0; w < 3; ++w) {
+    if (!d->opt_on[w] || !optisim_flag(d->opt_ts[w], fl)) continue;
+    if (w != 1 && d->opt_avg_ts[w] <= d->opt_ntime[w]) {
+      optisim_average_kernel<<<(unsigned)((per + 255) / 256), 256, 0, ctx->stream>>>(
+          d->opt_data[w] + (size_t)(d->opt_avg_ts[w] - 1) * per, per, (double)d->opt_avg_cnt[w]);
+      MHM_CUDA_OK(cudaGetLastError());
+    }
+    d->opt_avg_ts[w] += 1;
+    d->opt_avg_cnt[w] = 0;
+  }
+  return 0;
+}
+
 // One block of model steps = a sequence of launches of at most kIdxInline steps: the calendar
 // of a launch travels inside the kernel arguments (constant bank), states are re-read at each
 // launch.  With gridded outputs on, a launch also ends where an output window closes.
@@ -768,6 +800,8 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
   double* const hist0 = a.runoff_hist;
   const size_t per_slot = (size_t)d->cfg.nMembers * (size_t)d->cfg.nCells;
   const bool outputs = block_mode && d->out_mask != 0;  // the per-step seam leaves outputs to the host
+  const bool optisim = block_mode && (d->opt_on[0] || d->opt_on[1] || d->opt_on[2]);
+  const bool aggregates = optisim || (block_mode && d->bfi_on);
   ctx->stat_begin(kStatCell);
   int rc = 0;
   int64_t launches = 0;
@@ -775,24 +809,56 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
     int32_t nb = total - t0 < kIdxInline ? total - t0 : kIdxInline;
     bool closes = false;
     a.out_mask = 0;
-    if (outputs) {
+    a.agg_mask = 0;
+    if (optisim) {
+      // update_optisim (mo_mhm_interface_run.f90:776-857) runs after the step: a slot is closed
+      // (average / increment_counter) BEFORE the step's own value is added, and the run's last
+      // step adds nothing.  A launch therefore ends in front of every such step.
+      const int32_t tt = tt0 + t0;
+      if (out_active(d, tt))
+        if (int r2 = optisim_close(ctx, d, d->h_idx[(size_t)tt - 1].flags)) return r2;
+      for (int32_t t = 1; t < nb; ++t) {
+        const int32_t tn = tt + t;
+        if (out_active(d, tn) && (optisim_closes(d, d->h_idx[(size_t)tn - 1].flags) || tn == d->axis.nTimeSteps)) {
+          nb = t;
+          break;
+        }
+      }
+    }
+    if (outputs || aggregates) {
       int32_t first = nb;
       for (int32_t t = 0; t < nb; ++t) {
         const int32_t tt = tt0 + t0 + t;
         if (out_active(d, tt) && first == nb) first = t;
         a.out_yid[t] = (int8_t)(tt < d->axis.nTimeSteps ? d->h_idx[(size_t)tt].yId
                                                         : d->h_idx[(size_t)tt - 1].yId);
-        if (out_writes(d, tt)) {
+        if (outputs && out_writes(d, tt)) {
           nb = t + 1;
           closes = true;
           break;
         }
       }
       if (first < nb) {
-        a.out_mask = d->out_mask;
         a.out_first = first;
-        a.out_acc = d->out_acc;
-        d->out_counter += nb - first;
+        if (outputs) {
+          a.out_mask = d->out_mask;
+          a.out_acc = d->out_acc;
+          d->out_counter += nb - first;
+        }
+        if (d->bfi_on && block_mode) {
+          a.agg_mask |= 8u;
+          a.bfi_acc = d->bfi_acc;
+        }
+        if (optisim && tt0 + t0 + first != d->axis.nTimeSteps) {  // [first, nb) never holds the last step otherwise
+          const size_t per = (size_t)d->cfg.nMembers * (size_t)d->cfg.nCells;
+          for (int w = 0; w < 3; ++w) {
+            if (!d->opt_on[w] || d->opt_avg_ts[w] > d->opt_ntime[w]) continue;
+            a.agg_mask |= 1u << w;
+            a.agg_col[w] = d->opt_data[w] + (size_t)(d->opt_avg_ts[w] - 1) * per;
+            if (w != 1) d->opt_avg_cnt[w] += nb - first;  // average_add
+          }
+          a.agg_nhor_sm = d->opt_nhor_sm;
+        }
       }
     }
     a.nSteps = nb;
@@ -861,6 +927,88 @@ int mhm_cuda_set_outputs(mhm_cuda_context* ctx, int32_t iDomain, const int32_t* 
     MHM_CUDA_OK(cudaMalloc(&d->out_acc, bytes));
     MHM_CUDA_OK(cudaMemsetAsync(d->out_acc, 0, bytes, ctx->stream));
   }
+  return 0;
+}
+
+int mhm_cuda_set_optisim(mhm_cuda_context* ctx, int32_t iDomain, const mhm_optisim_config* cfg) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(cfg, "set_optisim: null config");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  const size_t per = (size_t)d->cfg.nMembers * (size_t)d->cfg.nCells;
+  const int32_t on[3] = {cfg->sm_on, cfg->et_on, cfg->tws_on};
+  const int32_t ts[3] = {cfg->sm_timeStepInput, cfg->et_timeStepInput, cfg->tws_timeStepInput};
+  const int32_t nt[3] = {cfg->sm_nTime, cfg->et_nTime, cfg->tws_nTime};
+  for (int w = 0; w < 3; ++w) {
+    if (on[w]) {
+      MHM_REQUIRE(ts[w] >= -3 && ts[w] <= -1, "set_optisim: timeStepInput must be -1, -2 or -3 (got %d)", ts[w]);
+      MHM_REQUIRE(nt[w] >= 1, "set_optisim: nTime must be positive");
+    }
+  }
+  MHM_REQUIRE(!cfg->sm_on || (cfg->nSoilHorizons_sm_input >= 1 && cfg->nSoilHorizons_sm_input <= d->cfg.nHorizons),
+              "set_optisim: nSoilHorizons_sm_input %d outside 1..%d", cfg->nSoilHorizons_sm_input,
+              d->cfg.nHorizons);  // mo_mhm_read_config.f90:189
+  for (int w = 0; w < 3; ++w) {
+    cudaFree(d->opt_data[w]);
+    d->opt_data[w] = nullptr;
+    d->opt_on[w] = on[w] != 0;
+    d->opt_ts[w] = ts[w];
+    d->opt_ntime[w] = on[w] ? nt[w] : 0;
+    d->opt_avg_ts[w] = 1;  // optidata_sim%init
+    d->opt_avg_cnt[w] = 0;
+    if (on[w]) {
+      MHM_CUDA_OK(cudaMalloc(&d->opt_data[w], (size_t)nt[w] * per * sizeof(double)));
+      MHM_CUDA_OK(cudaMemsetAsync(d->opt_data[w], 0, (size_t)nt[w] * per * sizeof(double), ctx->stream));
+    }
+  }
+  d->opt_nhor_sm = cfg->nSoilHorizons_sm_input;
+  cudaFree(d->bfi_acc);
+  d->bfi_acc = nullptr;
+  d->bfi_on = cfg->bfi_on != 0;
+  if (d->bfi_on) {
+    MHM_CUDA_OK(cudaMalloc(&d->bfi_acc, 2 * per * sizeof(double)));
+    MHM_CUDA_OK(cudaMemsetAsync(d->bfi_acc, 0, 2 * per * sizeof(double), ctx->stream));
+  }
+  return 0;
+}
+
+int mhm_cuda_get_optisim(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, int32_t which,
+                         double* base, int64_t ld, int64_t offset) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(base && member >= 0 && member < d->cfg.nMembers && which >= 0 && which < 3 && d->opt_on[which],
+              "get_optisim: bad member, or aggregate %d is not enabled", which);
+  const size_t n = (size_t)d->cfg.nCells, per = n * (size_t)d->cfg.nMembers;
+  MHM_REQUIRE(ld >= (int64_t)n && offset >= 0 && offset + (int64_t)n <= ld, "get_optisim: bad ld/offset");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaMemcpy2DAsync(base + offset, (size_t)ld * sizeof(double), d->opt_data[which] + (size_t)member * n,
+                                per * sizeof(double), n * sizeof(double), (size_t)d->opt_ntime[which],
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int mhm_cuda_get_bfi_sums(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, const double* cellArea,
+                          double* qBF_sum, double* qT_sum) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  MHM_REQUIRE(d->bfi_on && cellArea && qBF_sum && qT_sum && member >= 0 && member < d->cfg.nMembers,
+              "get_bfi_sums: BFI sums are not enabled, or bad arguments");
+  const size_t n = (size_t)d->cfg.nCells, per = n * (size_t)d->cfg.nMembers;
+  std::vector<double> h(2 * n);
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  MHM_CUDA_OK(cudaMemcpyAsync(h.data(), d->bfi_acc + (size_t)member * n, n * sizeof(double),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  MHM_CUDA_OK(cudaMemcpyAsync(h.data() + n, d->bfi_acc + per + (size_t)member * n, n * sizeof(double),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  // sum over the evaluation period of sum(q * CellArea) / nCells, summed per cell first
+  double sb = 0.0, st = 0.0;
+  for (size_t k = 0; k < n; ++k) sb += h[k] * cellArea[k];
+  for (size_t k = 0; k < n; ++k) st += h[n + k] * cellArea[k];
+  *qBF_sum = sb / (double)n;
+  *qT_sum = st / (double)n;
   return 0;
 }
 

@@ -35,6 +35,9 @@ namespace mhm {
 #ifndef MHM_TABLES_GLOBAL
 #define MHM_TABLES_GLOBAL 0
 #endif
+#ifndef MHM_QUAD_STORE
+#define MHM_QUAD_STORE 0  // measured on B200: the 4x unrolled time loop is 15 % slower
+#endif
 #ifndef MHM_PARAMS_SMEM
 #define MHM_PARAMS_SMEM 1
 #endif
@@ -259,6 +262,47 @@ __device__ __forceinline__ void accumulate_outputs(const uint32_t mask, double* 
   }
   if (on(20)) add(f.v[MHM_F_PREEFFECT]);
   if (on(21)) add(f.v[MHM_F_MELT]);
+}
+
+// mhm_interface_run_update_optisim (mo_mhm_interface_run.f90:776-857): the step's soil-moisture
+// fraction of the first nhor_sm horizons, total evapotranspiration and total water storage are
+// added to the open dataSim column (optidata_sim%add); BFI sums (:630-636) per cell, the host
+// applies the cell areas.  Same scene (after the date increment) as the gridded outputs.
+template <int NH>
+__device__ __forceinline__ void accumulate_aggregates(const uint32_t mask, const int nhor_sm,
+                                                      double* const* col, double* bfi,
+                                                      const size_t mc, const size_t per_slot,
+                                                      const FluxCapture& f, const CellStates<NH>& s,
+                                                      const double fS, const double* sat_o) {
+  if (mask & 1u) {  // :785-786
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+      if (h < nhor_sm) a = a + s.sm[h];
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+      if (h < nhor_sm) b = b + sat_o[h];
+    col[0][mc] = col[0][mc] + a / b;
+  }
+  if (mask & 2u) {  // :827-830
+    const double fNS = 1.0 - fS;
+    double a = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) a = a + f.aet_soil[h];
+    const double t1 = a * fNS, t2 = f.v[MHM_F_AETSEALED] * fS;
+    col[1][mc] = col[1][mc] + ((t1 + f.v[MHM_F_AETCANOPY]) + t2);
+  }
+  if (mask & 4u) {  // :850-854: average_add of the five stores, then add per horizon
+    double acc = col[2][mc];
+    acc = acc + ((((s.inter + s.snowpack) + s.sealed) + s.unsat) + s.sat);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) acc = acc + s.sm[h];
+    col[2][mc] = acc;
+  }
+  if (mask & 8u) {
+    bfi[mc] = bfi[mc] + f.v[MHM_F_BASEFLOW];
+    bfi[per_slot + mc] = bfi[per_slot + mc] + f.v[MHM_F_TOTAL_RUNOFF];
+  }
 }
 
 // kernel variants: the generic one takes every process selection at run time; the two
@@ -728,6 +772,11 @@ __device__ __forceinline__ double cascade_step_sel(const PARAMS& p, CellStates<N
 #endif
 
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldg(p); }
+// four consecutive doubles, 32-byte aligned: one 256-bit store (sm_100: STG.E.256)
+__device__ __forceinline__ void st_sector(double* p, double v0, double v1, double v2, double v3) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v0), "d"(v1), "d"(v2), "d"(v3)
+               : "memory");
+}
 
 // everything of the time loop that lives across steps besides states and parameters
 struct CellCursor {
@@ -814,8 +863,10 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const size_t qtile_stride = ((size_t)a.nMembers * a.qout_E) << 3;
 
   // one model step; EMIT is a compile-time tag so that steps 1..n-1 carry no flux stores
-  auto step = [&](auto emit_tag, const int t) {
+  // STORE = false: the caller collects the node runoff of four steps and writes one 32-byte sector
+  auto step = [&](auto emit_tag, auto store_tag, const int t) -> double {
     constexpr bool EMIT = decltype(emit_tag)::value;
+    constexpr bool STORE = decltype(store_tag)::value;
     const StepIdx si = a.idx_in[t];  // kernel-parameter space: uniform constant loads
     const int y = si.yId - 1, il = si.iLAI - 1, month = si.month - 1;
 
@@ -970,28 +1021,54 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 #pragma unroll
         for (int h = 0; h < NH; ++h)
           sat_o[h] = a.P[MHM_P_SOILMOISTSAT][(((size_t)member * a.nLC + yo) * NH + h) * n + c];
-        accumulate_outputs<NH>(a.out_mask, a.out_acc + mc, hist_stride, cap, s, fS, sat_o);
+        if (a.out_mask) accumulate_outputs<NH>(a.out_mask, a.out_acc + mc, hist_stride, cap, s, fS, sat_o);
+        if (a.agg_mask)
+          accumulate_aggregates<NH>(a.agg_mask, a.agg_nhor_sm, a.agg_col, a.bfi_acc, mc, hist_stride, cap, s,
+                                    fS, sat_o);
       }
     }
     if (cu.hist) {
       if (live) __stcs(cu.hist, total_runoff);
       cu.hist += hist_stride;
     }
+    double v = 0.0;
     if (qout) {
-      const int st = a.qout_step0 + t;
       const double r = 0.0 + total_runoff;
-      double v = a.qout_map_flag ? (0.0 + r * qarea) : r * qarea;
+      v = a.qout_map_flag ? (0.0 + r * qarea) : r * qarea;
 #if MHM_FAST
       v = v * a.qout_scale;
 #else
       v = v * 1000.0 / a.qout_tst;
 #endif
-      if (live) qout[(size_t)(st >> 3) * qtile_stride + (size_t)(st & 7)] = v;
+      if (STORE) {
+        const int st = a.qout_step0 + t;
+        if (live) qout[(size_t)(st >> 3) * qtile_stride + (size_t)(st & 7)] = v;
+      }
     }
+    return v;
   };
 
-  for (int t = 0; t < a.nSteps - 1; ++t) step(std::false_type{}, t);
-  step(std::true_type{}, a.nSteps - 1);
+  // Steps 1..n-1 carry no flux stores.  In the specialised fast variants four consecutive steps
+  // whose node runoff shares one 32-byte half of a history tile run back to back and leave with
+  // a single 256-bit store (full DRAM sectors instead of four partial ones).
+  constexpr bool kQuad = MHM_FAST && MHM_QUAD_STORE && VARIANT != kGeneric && !OUT;
+  const bool quad_ok = kQuad && qout != nullptr;
+  const int n_last = a.nSteps - 1;
+  for (int t = 0; t < n_last;) {
+    const int st = a.qout_step0 + t;
+    if (quad_ok && (st & 3) == 0 && t + 4 <= n_last) {
+      const double v0 = step(std::false_type{}, std::false_type{}, t);
+      const double v1 = step(std::false_type{}, std::false_type{}, t + 1);
+      const double v2 = step(std::false_type{}, std::false_type{}, t + 2);
+      const double v3 = step(std::false_type{}, std::false_type{}, t + 3);
+      if (live) st_sector(qout + (size_t)(st >> 3) * qtile_stride + (size_t)(st & 7), v0, v1, v2, v3);
+      t += 4;
+    } else {
+      step(std::false_type{}, std::true_type{}, t);
+      ++t;
+    }
+  }
+  step(std::true_type{}, std::true_type{}, n_last);
 
   // ---- write back states ----
   if (live) {

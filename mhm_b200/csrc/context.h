@@ -95,6 +95,14 @@ struct Domain {
   size_t out_win_cap = 0;
   std::vector<int32_t> out_win_tt;      // model step that closed each window
 
+  // calibration aggregates (mhm_cuda_set_optisim): 0 soil moisture, 1 evapotranspiration, 2 TWS
+  bool opt_on[3] = {};
+  int32_t opt_ts[3] = {}, opt_ntime[3] = {}, opt_nhor_sm = 0;
+  int32_t opt_avg_ts[3] = {1, 1, 1}, opt_avg_cnt[3] = {};  // optidata_sim averageTimestep / averageCounter
+  double* opt_data[3] = {};             // dataSim, [time][member][nCells]
+  bool bfi_on = false;
+  double* bfi_acc = nullptr;            // [2][member][nCells]: sums of baseflow, total runoff
+
   Routing* rt = nullptr;
   MprState* mpr = nullptr;
   int32_t last_yId = 1;  // scene of the last executed step (routing parameters, per-step seam)

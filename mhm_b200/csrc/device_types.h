@@ -8,7 +8,10 @@ namespace mhm {
 
 constexpr int kCellThreads = 128;
 constexpr int kMaxHorizons = 8;
-constexpr int kIdxInline = 64;  // model steps per cell-kernel launch (calendar rides in the arguments)
+#ifndef MHM_IDX_INLINE
+#define MHM_IDX_INLINE 128
+#endif
+constexpr int kIdxInline = MHM_IDX_INLINE;  // model steps per cell-kernel launch (calendar rides in the arguments)
 
 // per-step calendar indices, 16 bytes (one LDG.128, warp-uniform)
 struct alignas(16) StepIdx {
@@ -55,6 +58,13 @@ struct CellArgs {
   int32_t out_first;                  // first step of the launch with tIndex_out > 0
   double* out_acc;
   int8_t out_yid[kIdxInline];         // land-cover scene the driver holds after each step
+  // calibration aggregates (mo_mhm_interface_run.f90:745-861) and BFI sums (:630-636): every step
+  // t >= out_first adds to the open dataSim column of bit 0 soil moisture, bit 1 evapotranspiration,
+  // bit 2 total water storage; bit 3 adds baseflow / total runoff to bfi_acc [2][member][nCells]
+  uint32_t agg_mask;
+  int32_t agg_nhor_sm;                // nSoilHorizons_sm_input
+  double* agg_col[3];                 // [member][nCells]
+  double* bfi_acc;
   MeteoTables tab;
 };
 

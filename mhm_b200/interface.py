@@ -357,6 +357,34 @@ class Domain:
         check(self.L.mhm_cuda_get_output(self.h, self.id, member, window, variable, horizon, _pd(out)))
         return out
 
+    def set_optisim(self, sm=None, et=None, tws=None, bfi=False):
+        """calibration aggregates of mhm_interface_run_update_optisim: sm = (timeStepInput, nTime,
+        nSoilHorizons_sm_input), et / tws = (timeStepInput, nTime); bfi switches the BFI sums on"""
+        c = _lib.OptisimConfig()
+        if sm is not None:
+            c.sm_on, c.sm_timeStepInput, c.sm_nTime, c.nSoilHorizons_sm_input = 1, int(sm[0]), int(sm[1]), int(sm[2])
+        if et is not None:
+            c.et_on, c.et_timeStepInput, c.et_nTime = 1, int(et[0]), int(et[1])
+        if tws is not None:
+            c.tws_on, c.tws_timeStepInput, c.tws_nTime = 1, int(tws[0]), int(tws[1])
+        c.bfi_on = int(bool(bfi))
+        self._opt_ntime = {"sm": c.sm_nTime, "et": c.et_nTime, "tws": c.tws_nTime}
+        check(self.L.mhm_cuda_set_optisim(self.h, self.id, C.byref(c)))
+
+    def get_optisim(self, which, member=0):
+        """dataSim of 'sm' | 'et' | 'tws' as (nTime, nCells) = Fortran (nCells, nTime)"""
+        out = np.zeros((self._opt_ntime[which], self.nCells))
+        check(self.L.mhm_cuda_get_optisim(self.h, self.id, member, ("sm", "et", "tws").index(which), _pd(out),
+                                          self.nCells, 0))
+        return out
+
+    def get_bfi_sums(self, cell_area, member=0):
+        """(BFI_qBF_sum, BFI_qT_sum) of mo_mhm_interface_run.f90:630-636"""
+        a = np.ascontiguousarray(cell_area, dtype=np.float64)
+        qb, qt = C.c_double(), C.c_double()
+        check(self.L.mhm_cuda_get_bfi_sums(self.h, self.id, member, _pd(a), C.byref(qb), C.byref(qt)))
+        return qb.value, qt.value
+
     def keep_runoff_history(self, keep=True):
         check(self.L.mhm_cuda_keep_runoff_history(self.h, self.id, int(keep)))
 

@@ -852,15 +852,85 @@ static void write_output(orc_domain *d, int32_t tt, const orc_dt *s) {
   d->out_counter = 0;
 }
 
+/* ---- optidata_sim of FORCES mo_optimization_types (restated, see header) ---------------- */
+static double *opt_data(orc_domain *d, int32_t w) { return w == 0 ? d->opt_sm : (w == 1 ? d->opt_et : d->opt_tws); }
+static int32_t opt_flag(int32_t timeStepInput, const orc_dt *s) {
+  if (timeStepInput == -1) return s->is_new_day;
+  if (timeStepInput == -2) return s->is_new_month;
+  if (timeStepInput == -3) return s->is_new_year;
+  return 0;
+}
+static void opt_add(orc_domain *d, int32_t w, const double *data1d) { /* dataSim(:, averageTimestep) += */
+  const size_t n = (size_t)d->nCells, col = (size_t)d->opt_avg_ts[w] - 1;
+  double *x = opt_data(d, w);
+  int32_t k;
+  if ((int32_t)col >= d->opt_ntime[w]) return;
+  for (k = 0; k < d->nCells; k++) x[col * n + k] = x[col * n + k] + data1d[k];
+}
+static void opt_average(orc_domain *d, int32_t w) { /* divide by the counter, next slot, counter = 0 */
+  const size_t n = (size_t)d->nCells, col = (size_t)d->opt_avg_ts[w] - 1;
+  double *x = opt_data(d, w);
+  int32_t k;
+  if ((int32_t)col < d->opt_ntime[w])
+    for (k = 0; k < d->nCells; k++) x[col * n + k] = x[col * n + k] / (double)d->opt_avg_cnt[w];
+  d->opt_avg_ts[w] += 1;
+  d->opt_avg_cnt[w] = 0;
+}
+
+/* mhm_interface_run_update_optisim, mo_mhm_interface_run.f90:745-861 (neutrons out of scope);
+ * s is the date AFTER the increment of step tt, s->yId the land-cover scene held then */
+static void update_optisim(orc_domain *d, int32_t tt, const orc_dt *s, double *tmp) {
+  const size_t n = (size_t)d->nCells;
+  const int32_t nH = d->nH, y = s->yId - 1;
+  int32_t k, h;
+  if (tt - d->warming_days * d->nTstepDay <= 0) return;
+  if (d->opt_on[0]) { /* :776-791 */
+    if (opt_flag(d->opt_timestep[0], s)) opt_average(d, 0); /* average_per_timestep */
+    if (tt != d->nTimeSteps) {
+      for (k = 0; k < d->nCells; k++) {
+        double a = 0.0, b = 0.0;
+        for (h = 0; h < d->opt_nhor_sm; h++) a = a + d->soilMoist[(size_t)h * n + k];
+        for (h = 0; h < d->opt_nhor_sm; h++) b = b + d->soilMoistSat[((size_t)y * nH + h) * n + k];
+        tmp[k] = a / b;
+      }
+      opt_add(d, 0, tmp); /* average_add = add + counter */
+      d->opt_avg_cnt[0] += 1;
+    }
+  }
+  if (d->opt_on[1]) { /* :817-833 */
+    if (opt_flag(d->opt_timestep[1], s)) d->opt_avg_ts[1] += 1; /* increment_counter */
+    if (tt != d->nTimeSteps) {
+      for (k = 0; k < d->nCells; k++) {
+        const double fS = d->fSealed[(size_t)y * n + k], fNS = 1.0 - fS;
+        double a = 0.0;
+        for (h = 0; h < nH; h++) a = a + d->aETSoil[(size_t)h * n + k];
+        tmp[k] = a * fNS + d->aETCanopy[k] + d->aETSealed[k] * fS;
+      }
+      opt_add(d, 1, tmp);
+    }
+  }
+  if (d->opt_on[2]) { /* :840-857 */
+    if (opt_flag(d->opt_timestep[2], s)) opt_average(d, 2);
+    if (tt != d->nTimeSteps) {
+      for (k = 0; k < d->nCells; k++)
+        tmp[k] = d->inter[k] + d->snowPack[k] + d->sealSTW[k] + d->unsatSTW[k] + d->satSTW[k];
+      opt_add(d, 2, tmp);
+      d->opt_avg_cnt[2] += 1;
+      for (h = 0; h < nH; h++) opt_add(d, 2, d->soilMoist + (size_t)h * n);
+    }
+  }
+}
+
 int32_t orc_run(orc_domain *d, int32_t tt_first, int32_t tt_last) {
   orc_dt s;
   int32_t tt, k, g, jj;
   const int32_t per = (int32_t)lround(24.0 / (double)d->nTstepForcingDay);
   double tsRoutFactor = 1.0, tsRoutFactorIn = 1.0;
   int32_t timestep_rout = d->timestep_h, doRoute;
-  double *qAcc = 0;
+  double *qAcc = 0, *opt_tmp = 0;
 
   if (d->do_routing) qAcc = (double *)malloc(sizeof(double) * (size_t)d->nNodes);
+  if (d->opt_on[0] || d->opt_on[1] || d->opt_on[2]) opt_tmp = (double *)malloc(sizeof(double) * (size_t)d->nCells);
   dt_init(d, &s);
   for (tt = 1; tt <= tt_last; tt++) {
     int32_t iMeteoTS;
@@ -926,8 +996,17 @@ int32_t orc_run(orc_domain *d, int32_t tt_first, int32_t tt_last) {
     }
     dt_increment(d, &s); /* :623 */
     if (s.is_new_year && tt < d->nTimeSteps) s.yId = lc_yid(d, s.year); /* :626-628 */
+    if (tt >= tt_first && d->bfi_on && tt - d->warming_days * d->nTstepDay > 0) { /* :630-636 */
+      double sb = 0.0, st = 0.0;
+      for (k = 0; k < d->nCells; k++) sb = sb + d->baseflow[k] * d->L1_areaCell[k];
+      for (k = 0; k < d->nCells; k++) st = st + d->total_runoff[k] * d->L1_areaCell[k];
+      d->bfi_qBF_sum = d->bfi_qBF_sum + sb / (double)d->nCells;
+      d->bfi_qT_sum = d->bfi_qT_sum + st / (double)d->nCells;
+    }
     if (tt >= tt_first) write_output(d, tt, &s);                        /* mo_mhm_eval.f90:141 */
+    if (tt >= tt_first && opt_tmp) update_optisim(d, tt, &s, opt_tmp);  /* mo_mhm_eval.f90:144 */
   }
+  free(opt_tmp);
   free(qAcc);
   return 0;
 }

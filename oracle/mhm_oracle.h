@@ -286,6 +286,27 @@ typedef struct orc_domain {
   double *out_acc;
   double *out_win;
   int32_t *out_win_tt;
+  /* calibration aggregates: mhm_interface_run_update_optisim (mo_mhm_interface_run.f90:745-861),
+   * index 0 = soil moisture, 1 = evapotranspiration, 2 = total water storage.  The container
+   * type optidata_sim lives in FORCES v0.6.0 mo_optimization_types (un-vendored, absent from
+   * /root/reference): its published behaviour is restated in the .c (init: dataSim = 0,
+   * averageTimestep = 1, averageCounter = 0; add; average; average_add; increment_counter;
+   * average_per_timestep) -- PARITY UNPINNED for that part, no reference output holds dataSim.
+   * opt_timestep = timeStepInput (-1 daily, -2 monthly, -3 yearly); opt_sm/et/tws = dataSim,
+   * Fortran (nCells, opt_ntime[i]). */
+  int32_t opt_on[3];
+  int32_t opt_timestep[3];
+  int32_t opt_ntime[3];
+  int32_t opt_nhor_sm;
+  int32_t opt_avg_ts[3];
+  int32_t opt_avg_cnt[3];
+  double *opt_sm;
+  double *opt_et;
+  double *opt_tws;
+  /* BFI sums of the evaluation period (mo_mhm_interface_run.f90:630-636) */
+  int32_t bfi_on;
+  double bfi_qBF_sum;
+  double bfi_qT_sum;
 } orc_domain;
 
 /* number of per-cell records written per step into flux_history (see .c) */

@@ -40,9 +40,13 @@ S2FIELD = {"L1_inter": "inter", "L1_snowPack": "snowPack", "L1_sealSTW": "sealST
 class OracleRun:
     """Owns the numpy buffers behind an orc_domain and exposes results by reference name."""
 
-    def __init__(self, prob, params=None, history=False, num_threads=1, outputs=None, max_windows=64):
+    def __init__(self, prob, params=None, history=False, num_threads=1, outputs=None, max_windows=64,
+                 optisim=None, bfi=False, cell_area=None):
         """outputs = (outputFlxState[21], timeStep_model_outputs) switches the gridded output
-        accumulation on; results in self.out_windows() after run()"""
+        accumulation on; results in self.out_windows() after run().
+        optisim = {"sm": (timeStepInput, nTime, nSoilHorizons_sm_input), "et": (timeStepInput, nTime),
+        "tws": (timeStepInput, nTime)} switches the calibration aggregates on (self.opt[...] =
+        dataSim as (nTime, nCells)); bfi=True the BFI sums (d.bfi_qBF_sum / d.bfi_qT_sum)."""
         self.prob = prob
         self.keep = []
         d = self.d = orc.OrcDomain()
@@ -157,6 +161,22 @@ class OracleRun:
             d.out_win_tt = self._i(self.out_win_tt)
             self.out_win_tt = self.keep[-1]
             d.out_max_windows = max_windows
+
+        self.opt = {}
+        for w, key in enumerate(("sm", "et", "tws")):
+            d.opt_avg_ts[w] = 1  # optidata_sim%init
+            if optisim and key in optisim:
+                cfg = optisim[key]
+                d.opt_on[w], d.opt_timestep[w], d.opt_ntime[w] = 1, int(cfg[0]), int(cfg[1])
+                if key == "sm":
+                    d.opt_nhor_sm = int(cfg[2])
+                ptr = self._d(np.zeros((int(cfg[1]), n)))
+                self.opt[key] = self.keep[-1]
+                setattr(d, "opt_" + key, ptr)
+        if bfi:
+            d.bfi_on = 1
+            if net is None:
+                d.L1_areaCell = self._d(cell_area)
 
     def _d(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
