@@ -97,6 +97,14 @@ module mo_mhm_cuda
     real(c_double) :: fracSealed_CityArea
   end type mpr_soil_db
 
+  !> calibration aggregates + BFI sums (mhm_cuda_set_optisim)
+  type, bind(C) :: mhm_optisim_config
+    integer(c_int32_t) :: sm_on = 0, sm_timeStepInput = -1, sm_nTime = 0, nSoilHorizons_sm_input = 1
+    integer(c_int32_t) :: et_on = 0, et_timeStepInput = -1, et_nTime = 0
+    integer(c_int32_t) :: tws_on = 0, tws_timeStepInput = -1, tws_nTime = 0
+    integer(c_int32_t) :: bfi_on = 0
+  end type mhm_optisim_config
+
   interface
     integer(c_int) function mhm_cuda_init(device, ctx) bind(C, name = 'mhm_cuda_init')
       import
@@ -357,6 +365,27 @@ module mo_mhm_cuda
       type(c_ptr), value :: ctx, out
       integer(c_int32_t), value :: iDomain, member, window, variable, horizon
     end function
+    ! ---- A10: calibration aggregates (update_optisim) and BFI sums -------------------------
+    integer(c_int) function mhm_cuda_set_optisim(ctx, iDomain, cfg) bind(C, name = 'mhm_cuda_set_optisim')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      type(mhm_optisim_config), intent(in) :: cfg
+    end function
+    integer(c_int) function mhm_cuda_get_optisim(ctx, iDomain, member, which, base, ld, offset) &
+        bind(C, name = 'mhm_cuda_get_optisim')
+      import
+      type(c_ptr), value :: ctx, base                  !< c_loc(xxOptiSim(iDomain)%dataSim)
+      integer(c_int32_t), value :: iDomain, member, which
+      integer(c_int64_t), value :: ld, offset
+    end function
+    integer(c_int) function mhm_cuda_get_bfi_sums(ctx, iDomain, member, cellArea, qBF_sum, qT_sum) &
+        bind(C, name = 'mhm_cuda_get_bfi_sums')
+      import
+      type(c_ptr), value :: ctx, cellArea              !< c_loc(level1(iDomain)%CellArea)
+      integer(c_int32_t), value :: iDomain, member
+      real(c_double), intent(out) :: qBF_sum, qT_sum
+    end function
     ! ---- sub-catchment sharding (one domain over several GPUs / MPI ranks) -----------------
     integer(c_int) function mrm_partition_subcatchments(nNodes, nLinks, fromN, toN, netPerm, nParts, part_of_node) &
         bind(C, name = 'mrm_partition_subcatchments')
@@ -404,9 +433,10 @@ module mo_mhm_cuda
             mpr_cuda_l0_fractional_cover, mpr_cuda_set_l0, mpr_cuda_set_soildb, mpr_cuda_eval, &
             mhm_cuda_get_param, mhm_cuda_states_default_init, mhm_cuda_set_outputs, &
             mhm_cuda_get_output_windows, mhm_cuda_get_output, mrm_partition_subcatchments, &
+            mhm_cuda_set_optisim, mhm_cuda_get_optisim, mhm_cuda_get_bfi_sums, &
             mrm_cuda_set_deferred, mrm_cuda_route_pending, mrm_cuda_export_outflow, mrm_cuda_import_outflow, &
             mrm_routing_order, mhm_cuda_set_meteo_l2, mrm_net_init, mrm_net_l1_l11_mapping
-  public :: mpr_l0_inputs, mpr_soil_db
+  public :: mpr_l0_inputs, mpr_soil_db, mhm_optisim_config
 
 contains
 
