@@ -428,6 +428,8 @@ typedef struct mrm_net_inputs {
   const int32_t *LCover0;        /* L0_LCover (nCells0, nLCoverScene) */
   int32_t nLCoverScene;
   int32_t LCClassImp;            /* 2 in mrm_init (mo_mrm_init.f90:258) */
+  int32_t routingCase;           /* processMatrix(8, 1): 2 / 3 raise the link lengths to their 40th
+                                    percentile (L11_stream_features :1440-1446); 0 / 1: as computed */
 } mrm_net_inputs;
 typedef struct mrm_net_outputs {
   int32_t nCells0;
@@ -455,8 +457,30 @@ typedef struct mrm_net_outputs {
   double *aFloodPlain;           /* L11_aFloodPlain (nNodes) or null: no flood plains */
   double *nLinkFracFPimp;        /* L11_nLinkFracFPimp (nNodes, nLCoverScene) or null */
   int32_t *floodPlain0;          /* L0_floodPlain packed (nCells0) or null */
+  int32_t *streamNet0;           /* L0_streamNet packed (nCells0) or null (needs the flood plains) */
 } mrm_net_outputs;
 int mrm_net_init(const mrm_net_inputs *in, mrm_net_outputs *out);
+/* L11_flow_accumulation (mRM/mo_mrm_net_startup.f90:2022-2163, called from mrm_init
+ * mo_mrm_init.f90:224): L11_fAcc [km2] from L11_fDir and level11%cellarea [m2], both packed
+ * (nNodes); mask11 is Fortran (nrows11, ncols11) 0/1.  Linear time, no recursion. */
+int mrm_net_flow_accumulation(int32_t nrows11, int32_t ncols11, const int32_t *mask11,
+                              const int32_t *fDir11, const double *cellarea11, double *fAcc11);
+/* L11_calc_celerity (mRM/mo_mrm_net_startup.f90:2212-2423, called from mrm_update_param
+ * mo_mrm_mpr.f90:302 for processCase(8) = 3): L0_slope [%] and L0_streamNet packed (nCells0),
+ * the link locations of mrm_net_init, param(1) = slope_factor; fills L11_celerity (nNodes, valid
+ * for the links) and, if not null, L0_celerity (nCells0). */
+int mrm_net_calc_celerity(int32_t nrows0, int32_t ncols0, const int32_t *mask0, const int32_t *fDir0,
+                          const int32_t *streamNet0, const double *slope0, int32_t nNodes,
+                          int32_t nLinks, const int32_t *netPerm, const int32_t *fRow,
+                          const int32_t *fCol, const int32_t *tRow, const int32_t *tCol,
+                          double slope_factor, double *celerity11, double *celerity0);
+/* mrm_update_param (mRM/mo_mrm_mpr.f90:241-329): travel time K = L11_length / celerity
+ * (processCase(8) = 2: celerity_stride 0, one constant; 3: stride 1, L11_celerity), routing step
+ * L11_TSrout from given_TS (mo_mrm_constants.F90:42-46), Muskingum C1 / C2 (nNodes) for
+ * mrm_cuda_set_c1c2. */
+int mrm_net_update_param(int32_t nNodes, int32_t nOutlets, const double *L11_length,
+                         const double *celerity, int32_t celerity_stride, double *C1, double *C2,
+                         double *TSrout);
 /* L11_L1_mapping (mRM/mo_mrm_net_startup.f90:61-166): masks are Fortran (nrows, ncols) 0/1 */
 int mrm_net_l1_l11_mapping(int32_t nrows1, int32_t ncols1, const int32_t *mask1, double cellsize1,
                            int32_t nrows11, int32_t ncols11, const int32_t *mask11, double cellsize11,

@@ -427,6 +427,24 @@ extern "C" int mrm_net_init(const mrm_net_inputs* in, mrm_net_outputs* out) {
   }
   if (do_fp && out->floodPlain0)
     for (int c = 0; c < nCells0; ++c) out->floodPlain0[c] = flood0[g0.at(coor0i[(size_t)c], coor0j[(size_t)c])];
+  if (do_fp && out->streamNet0)
+    for (int c = 0; c < nCells0; ++c) out->streamNet0[c] = stream0[g0.at(coor0i[(size_t)c], coor0j[(size_t)c])];
+  // routing with a celerity (cases 2 and 3): no link shorter than the 40th percentile of the
+  // lengths :1440-1446 (FORCES mo_percentile, inverse empirical CDF: the ceiling(0.4 n)-th
+  // smallest); the merge also overwrites the nodata entries of the outlets
+  if ((in->routingCase == 2 || in->routingCase == 3) && nNodes > 1 && in->elev0) {
+    std::vector<double> v;
+    for (int k = 0; k < nNodes; ++k)
+      if (out->length[k] >= 0.0) v.push_back(out->length[k]);
+    if (v.size() > 2) {
+      size_t kk = (size_t)ceil((double)v.size() * 40.0 / 100.0);
+      kk = std::min(std::max(kk, (size_t)1), v.size());
+      std::nth_element(v.begin(), v.begin() + (kk - 1), v.end());
+      const double p40 = v[kk - 1];
+      for (int k = 0; k < nNodes; ++k)
+        if (!(out->length[k] > p40)) out->length[k] = p40;
+    }
+  }
   // ---- L11_fraction_sealed_floodplain :1510-1564 (loops to nLinks + 1 like the reference) ----
   if (do_fp && out->nLinkFracFPimp && in->LCover0 && in->nLCoverScene > 0) {
     std::vector<double> imp((size_t)nNodes + 1);
@@ -487,5 +505,180 @@ extern "C" int mrm_net_l1_l11_mapping(int32_t nrows1, int32_t ncols1, const int3
   n = 0;
   for (size_t a = 0; a < on11.size(); ++a)
     if (mask11[a]) L11_L1_Id[n++] = on11[a];
+  return 0;
+}
+
+// L11_flow_accumulation :2022-2163: area draining through every L11 cell [km2].  The reference
+// recurses from every sink and adds the finished sums of the inflowing neighbours in the order
+// E, SE, S, SW, W, NW, N, NE of its tests; here every cell's inflowing neighbours are listed in
+// that order once and the cells are finished in an explicit post-order walk (no recursion, O(N)),
+// which performs the same additions in the same order.
+extern "C" int mrm_net_flow_accumulation(int32_t nrows11, int32_t ncols11, const int32_t* mask11,
+                                         const int32_t* fDir11, const double* cellarea11, double* fAcc11) {
+  MHM_REQUIRE(nrows11 >= 1 && ncols11 >= 1 && mask11 && fDir11 && cellarea11 && fAcc11,
+              "mrm_net_flow_accumulation: bad arguments");
+  const Grid2 g{nrows11, ncols11};
+  const size_t ng = (size_t)nrows11 * ncols11;
+  std::vector<int32_t> fd(ng, kNoData);
+  std::vector<double> acc(ng, -9999.0);
+  const double to_km2 = (double)1.e-6f;  // the reference's literal 1.e-6 is default real
+  {
+    size_t k = 0;
+    for (size_t a = 0; a < ng; ++a)
+      if (mask11[a]) {
+        fd[a] = fDir11[k];
+        acc[a] = cellarea11[k] * to_km2;
+        ++k;
+      }
+  }
+  static const int di[8] = {0, 1, 1, 1, 0, -1, -1, -1}, dj[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+  static const int32_t code[8] = {16, 32, 64, 128, 1, 2, 4, 8};
+  struct Frame {
+    int i, j, next;
+  };
+  std::vector<Frame> stack;
+  for (int jj = 1; jj <= g.nc; ++jj)
+    for (int ii = 1; ii <= g.nr; ++ii) {
+      if (fd[g.at(ii, jj)] != 0) continue;
+      stack.push_back({ii, jj, 0});
+      while (!stack.empty()) {
+        Frame& f = stack.back();
+        if (f.next > 0) {  // the neighbour visited last is finished: add it
+          const int q = f.next - 1;
+          acc[g.at(f.i, f.j)] = acc[g.at(f.i, f.j)] + acc[g.at(f.i + di[q], f.j + dj[q])];
+        }
+        int q = f.next;
+        for (; q < 8; ++q) {
+          const int ni = f.i + di[q], nj = f.j + dj[q];
+          if (g.inside(ni, nj) && fd[g.at(ni, nj)] == code[q]) break;
+        }
+        if (q == 8) {
+          stack.pop_back();
+          continue;
+        }
+        f.next = q + 1;
+        const Frame child{f.i + di[q], f.j + dj[q], 0};
+        MHM_REQUIRE(stack.size() <= ng, "mrm_net_flow_accumulation: flow directions form a cycle");
+        stack.push_back(child);
+      }
+    }
+  size_t k = 0;
+  for (size_t a = 0; a < ng; ++a)
+    if (mask11[a]) fAcc11[k++] = acc[a];
+  return 0;
+}
+
+namespace {
+// FORCES mo_percentile::median (un-vendored, v0.6.0): middle element, or the mean of the two
+// middle elements for an even count
+double median_of(std::vector<double>& v) {
+  const size_t n = v.size();
+  std::nth_element(v.begin(), v.begin() + n / 2, v.end());
+  const double hi = v[n / 2];
+  if (n % 2 == 1) return hi;
+  const double lo = *std::max_element(v.begin(), v.begin() + n / 2);
+  return 0.5 * (lo + hi);
+}
+}  // namespace
+
+// L11_calc_celerity :2212-2423: celerity = slope_factor * sqrt(slope) of every L0 stream cell,
+// harmonic mean along each link's L0 path (from-cell .. to-cell inclusive).  Slopes [%] are
+// floored at 0.1; over the stream cells steeper than that floor, values above median + 2.25 *
+// MAD / 0.6745 are cut back to this bound (FORCES mo_mad::mad with tout = 'u', mval = 0.1; the
+// library is not vendored -- this reading is the one that reproduces check/case_13's discharge).
+extern "C" int mrm_net_calc_celerity(int32_t nrows0, int32_t ncols0, const int32_t* mask0, const int32_t* fDir0,
+                                     const int32_t* streamNet0, const double* slope0, int32_t nNodes,
+                                     int32_t nLinks, const int32_t* netPerm, const int32_t* fRow,
+                                     const int32_t* fCol, const int32_t* tRow, const int32_t* tCol,
+                                     double slope_factor, double* celerity11, double* celerity0) {
+  MHM_REQUIRE(nrows0 >= 1 && ncols0 >= 1 && mask0 && fDir0 && streamNet0 && slope0 && nNodes >= 1 &&
+                  nLinks >= 0 && nLinks <= nNodes && netPerm && fRow && fCol && tRow && tCol && celerity11,
+              "mrm_net_calc_celerity: bad arguments");
+  const Grid2 g0{nrows0, ncols0};
+  const size_t n0g = (size_t)nrows0 * ncols0;
+  std::vector<int32_t> cell_of(n0g, -1);  // packed index of every valid L0 cell
+  int32_t nCells0 = 0;
+  for (size_t a = 0; a < n0g; ++a)
+    if (mask0[a]) cell_of[a] = nCells0++;
+  if (celerity0)
+    for (int c = 0; c < nCells0; ++c) celerity0[c] = -9999.0;
+  if (nNodes <= 1) {
+    for (int k = 0; k < nNodes; ++k) celerity11[k] = 1.0;
+    return 0;
+  }
+  std::vector<double> slope((size_t)nCells0);
+  for (int c = 0; c < nCells0; ++c) slope[(size_t)c] = slope0[c] < 0.1 ? 0.1 : slope0[c];
+  {
+    // mad(arr, z = 2.25, mask = stream cells, tout = 'u', mval = 0.1): entries equal to mval are
+    // missing values and stay out of the statistics; larger outliers are cut back to the bound
+    size_t n_stream = 0;
+    std::vector<double> s;
+    for (int c = 0; c < nCells0; ++c)
+      if (streamNet0[c] != kNoData) {
+        ++n_stream;
+        if (slope[(size_t)c] != 0.1) s.push_back(slope[(size_t)c]);
+      }
+    if (n_stream > 1 && !s.empty()) {
+      std::vector<double> w(s);
+      const double med = median_of(w);
+      for (size_t k = 0; k < s.size(); ++k) w[k] = fabs(s[k] - med);
+      const double bound = med + median_of(w) * 2.25 / 0.6745;
+      for (int c = 0; c < nCells0; ++c)
+        if (streamNet0[c] != kNoData && slope[(size_t)c] != 0.1 && slope[(size_t)c] > bound) slope[(size_t)c] = bound;
+    }
+  }
+  for (int k = 0; k < nNodes; ++k) celerity11[k] = -9999.0;
+  for (int rr = 0; rr < nLinks; ++rr) {
+    const int ii = netPerm[rr] - 1;
+    MHM_REQUIRE(ii >= 0 && ii < nNodes, "mrm_net_calc_celerity: netPerm(%d) = %d", rr + 1, ii + 1);
+    int fr = fRow[ii], fc = fCol[ii];
+    MHM_REQUIRE(g0.inside(fr, fc) && g0.inside(tRow[ii], tCol[ii]) && cell_of[g0.at(fr, fc)] >= 0,
+                "mrm_net_calc_celerity: link %d lies outside the L0 grid", ii + 1);
+    const size_t to = g0.at(tRow[ii], tCol[ii]);
+    double rsum = 0.0;  // sum(1 / stack(:)) in element order
+    size_t count = 0;
+    for (;;) {
+      const size_t a = g0.at(fr, fc);
+      const int32_t c = cell_of[a];
+      MHM_REQUIRE(c >= 0 && count <= n0g, "mrm_net_calc_celerity: link %d never reaches its end", ii + 1);
+      const double cel = slope_factor * sqrt(slope[(size_t)c] / 100.0);
+      if (celerity0) celerity0[c] = cel;
+      rsum = rsum + 1.0 / cel;
+      ++count;
+      if (a == to) break;
+      move_down(fDir0[c], fr, fc);
+      MHM_REQUIRE(g0.inside(fr, fc), "mrm_net_calc_celerity: link %d leaves the L0 grid", ii + 1);
+    }
+    celerity11[ii] = (double)count / rsum;
+  }
+  return 0;
+}
+
+// mrm_update_param, mRM/mo_mrm_mpr.f90:241-329: K = length / celerity (processCase(8) = 2: one
+// constant, celerity_stride 0; = 3: L11_celerity, stride 1), routing step = the entry of given_TS
+// (mo_mrm_constants.F90:42-46) at or below the shortest travel time, then C1 / C2.
+extern "C" int mrm_net_update_param(int32_t nNodes, int32_t nOutlets, const double* L11_length,
+                                    const double* celerity, int32_t celerity_stride, double* C1, double* C2,
+                                    double* TSrout) {
+  MHM_REQUIRE(nNodes >= 1 && nOutlets >= 0 && nOutlets < nNodes && L11_length && celerity && C1 && C2 && TSrout &&
+                  (celerity_stride == 0 || celerity_stride == 1),
+              "mrm_net_update_param: bad arguments");
+  static const double given_TS[19] = {60.0,   120.0,  180.0,   240.0,   300.0,   360.0,   600.0,
+                                      720.0,  900.0,  1200.0,  1800.0,  3600.0,  7200.0,  10800.0,
+                                      14400.0, 21600.0, 28800.0, 43200.0, 86400.0};
+  const double xi = 0.0;  // abs(rout_space_weight)
+  std::vector<double> K((size_t)nNodes);
+  for (int i = 0; i < nNodes; ++i) K[(size_t)i] = L11_length[i] / celerity[(size_t)i * celerity_stride];
+  const double kmin = *std::min_element(K.begin(), K.begin() + (nNodes - nOutlets));
+  // FORCES mo_utils::locate: last index with given_TS <= kmin (bisection); below the table -> 1
+  int ind = (int)(std::upper_bound(given_TS, given_TS + 19, kmin) - given_TS);
+  if (kmin == given_TS[18]) ind = 18;
+  if (ind < 1) ind = 1;
+  const double ts = given_TS[ind - 1];
+  for (int i = 0; i < nNodes; ++i) {
+    C1[i] = ts / (K[(size_t)i] * (1.0 - xi) + 0.5 * ts);
+    C2[i] = 1.0 - C1[i] * K[(size_t)i] / ts;
+  }
+  *TSrout = ts;
   return 0;
 }

@@ -345,6 +345,28 @@ module mo_mhm_cuda
       real(c_double), value :: cellsize1, cellsize11
       type(c_ptr), value :: mask1, mask11, L1_L11_Id, L11_L1_Id
     end function
+    ! L11_flow_accumulation (mo_mrm_net_startup.f90:2022), L11_calc_celerity (:2212) and
+    ! mrm_update_param (mo_mrm_mpr.f90:241) for the celerity-based routing cases 2 and 3
+    integer(c_int) function mrm_net_flow_accumulation(nrows11, ncols11, mask11, fDir11, cellarea11, fAcc11) &
+        bind(C, name = 'mrm_net_flow_accumulation')
+      import
+      integer(c_int32_t), value :: nrows11, ncols11
+      type(c_ptr), value :: mask11, fDir11, cellarea11, fAcc11
+    end function
+    integer(c_int) function mrm_net_calc_celerity(nrows0, ncols0, mask0, fDir0, streamNet0, slope0, nNodes, nLinks, &
+        netPerm, fRow, fCol, tRow, tCol, slope_factor, celerity11, celerity0) bind(C, name = 'mrm_net_calc_celerity')
+      import
+      integer(c_int32_t), value :: nrows0, ncols0, nNodes, nLinks
+      type(c_ptr), value :: mask0, fDir0, streamNet0, slope0, netPerm, fRow, fCol, tRow, tCol, celerity11, celerity0
+      real(c_double), value :: slope_factor
+    end function
+    integer(c_int) function mrm_net_update_param(nNodes, nOutlets, L11_length, celerity, celerity_stride, C1, C2, &
+        TSrout) bind(C, name = 'mrm_net_update_param')
+      import
+      integer(c_int32_t), value :: nNodes, nOutlets, celerity_stride
+      type(c_ptr), value :: L11_length, celerity, C1, C2
+      real(c_double), intent(out) :: TSrout
+    end function
     ! ---- A10: gridded outputs accumulated on the device ------------------------------------
     integer(c_int) function mhm_cuda_set_outputs(ctx, iDomain, outputFlxState, timeStep_model_outputs) &
         bind(C, name = 'mhm_cuda_set_outputs')
@@ -435,7 +457,8 @@ module mo_mhm_cuda
             mhm_cuda_get_output_windows, mhm_cuda_get_output, mrm_partition_subcatchments, &
             mhm_cuda_set_optisim, mhm_cuda_get_optisim, mhm_cuda_get_bfi_sums, &
             mrm_cuda_set_deferred, mrm_cuda_route_pending, mrm_cuda_export_outflow, mrm_cuda_import_outflow, &
-            mrm_routing_order, mhm_cuda_set_meteo_l2, mrm_net_init, mrm_net_l1_l11_mapping
+            mrm_routing_order, mhm_cuda_set_meteo_l2, mrm_net_init, mrm_net_l1_l11_mapping, &
+            mrm_net_flow_accumulation, mrm_net_calc_celerity, mrm_net_update_param
   public :: mpr_l0_inputs, mpr_soil_db, mhm_optisim_config
 
 contains

@@ -130,6 +130,28 @@ void orc_reg_rout(const double *param5, int32_t nLinks, int32_t nSlope, const do
 double orc_mrm_update_param_case2(int32_t nNodes, int32_t nOutlets, const double *length,
                                   double celerity, double *C1, double *C2);
 
+/* ---- routing case 3 (river-slope celerity): literal restatements, test infrastructure ---- */
+/* L0_streamNet as left by L11_stream_features (mRM/mo_mrm_net_startup.f90:1370-1412) and the
+ * 40th-percentile floor of the link lengths for cases 2/3 (:1440-1446).  2-D index (i, j) of a
+ * Fortran (nrows0, ncols0) array is at [(j-1)*nrows0 + i-1]; fDir0 / id0 / streamNet0 are 2-D. */
+void orc_stream_net(int32_t nrows0, int32_t ncols0, const int32_t *fDir0_2d, int32_t nLinks,
+                    const int32_t *netPerm, const int32_t *fRow, const int32_t *fCol,
+                    const int32_t *tRow, const int32_t *tCol, int32_t *streamNet0_2d);
+void orc_length_floor(int32_t nNodes, double *length);
+/* FORCES mo_mad::mad(arr, z, mask, tout='u', mval) (un-vendored; semantics pinned by check/case_13) */
+void orc_mad_upper(int32_t n, double *arr, double z, const int32_t *mask, double mval);
+/* L11_calc_celerity (mRM/mo_mrm_net_startup.f90:2212-2423); slope0 / streamNet0 packed */
+void orc_calc_celerity(int32_t nrows0, int32_t ncols0, const int32_t *mask0_2d, const int32_t *fDir0_2d,
+                       const int32_t *streamNet0_packed, const double *slope0_packed, int32_t nNodes,
+                       int32_t nLinks, const int32_t *netPerm, const int32_t *fRow, const int32_t *fCol,
+                       const int32_t *tRow, const int32_t *tCol, double param, double *celerity11);
+/* mrm_update_param, processCase 3 (mRM/mo_mrm_mpr.f90:298-321); returns TSrout */
+double orc_mrm_update_param_case3(int32_t nNodes, int32_t nOutlets, const double *length,
+                                  const double *celerity11, double *C1, double *C2);
+/* L11_flow_accumulation (mRM/mo_mrm_net_startup.f90:2022-2163), recursive like the reference */
+void orc_flow_accumulation(int32_t nrows11, int32_t ncols11, const int32_t *mask11_2d,
+                           const int32_t *fDir11_packed, const double *cellarea11_packed, double *fAcc11_packed);
+
 /* ---- one domain, everything the time loop touches ---------------------------- */
 typedef struct orc_domain {
   /* sizes */

@@ -86,13 +86,16 @@ def gamma_vector(par_nml, cases):
 
 
 def make_case(case, sim_start, n_days, warming_days, lc_years, cases=(1, 0, 1), out_prefix="b1",
-              restart_id="001", name=None):
-    """cases = processCase(3) soil moisture, (5) PET, (8) routing of the check case's mhm.nml"""
+              restart_id="001", name=None, net_from=None):
+    """cases = processCase(3) soil moisture, (5) PET, (8) routing of the check case's mhm.nml.
+    net_from: the check case saved no mRM restart; the (identical) river network comes from that
+    case's restart, without its final routing state and Muskingum parameters."""
     cdir = os.path.join(REF, "check", case)
     sav = os.path.join(cdir, "output_save")
     mhm = h5lite.H5File(os.path.join(sav, "%s_mHM_restart_%s.nc" % (out_prefix, restart_id)))
     routing = cases[2] != 0
-    mrm = h5lite.H5File(os.path.join(sav, "%s_mRM_restart_%s.nc" % (out_prefix, restart_id))) if routing else None
+    mrm_dir = sav if net_from is None else os.path.join(REF, "check", net_from, "output_save")
+    mrm = h5lite.H5File(os.path.join(mrm_dir, "%s_mRM_restart_%s.nc" % (out_prefix, restart_id))) if routing else None
     out = {"cases": np.array(cases, dtype=np.int32)}
     mask1 = mhm["L1_domain_mask"].read() != 0           # nc (y, x) == Fortran (x, y), x fastest
     # restart masks: 1 = valid?  check against the cell count below
@@ -122,14 +125,21 @@ def make_case(case, sim_start, n_days, warming_days, lc_years, cases=(1, 0, 1), 
     out["L1_lat"] = pick(mhm["L1_domain_lat"].read())
     if routing:
         network(out, mrm, pick, cdir)
+        if net_from is not None:
+            for k in [k for k in out if k.startswith("final/L11_")] + ["net/L11_TSrout", "net/ProcessMatrix"]:
+                del out[k]
+            out["net_from"] = np.array(net_from)
+        if cases[2] == 3:
+            out["slope_factor"] = gamma_group(os.path.join(cdir, "mhm_parameter.nml"), "routing3")
     forcing(out, mask1, pick, sim_start, n_days, cases[1])
     if routing:
         q = h5lite.H5File(os.path.join(sav, "%s_discharge.nc" % out_prefix))
         for k in q.keys():
             if k.startswith("Qsim_"):
                 out["Qsim/" + k[5:]] = q[k].read()
-        txt = np.loadtxt(os.path.join(sav, "%s_daily_discharge.out" % out_prefix), skiprows=1)
-        out["Qsim_text"] = txt[:, 5::2]
+        if os.path.exists(os.path.join(sav, "%s_daily_discharge.out" % out_prefix)):
+            txt = np.loadtxt(os.path.join(sav, "%s_daily_discharge.out" % out_prefix), skiprows=1)
+            out["Qsim_text"] = txt[:, 5::2]
     # gridded outputs of the run (mhm_outputs.nml: outputFlxState, timeStep_model_outputs)
     fs = os.path.join(sav, "%s_mHM_Fluxes_States.nc" % out_prefix)
     if os.path.exists(fs):
@@ -260,6 +270,9 @@ if __name__ == "__main__":
     # soil moisture case 3 (Jarvis, FC-dependent roots) / 4 (Feddes, FC-dependent roots) + LAI-corrected PET
     make_case("case_10", D(1990, 1, 1), 181 + 365, 181, LC(1990, 2), (3, -1, 1))
     make_case("case_12", D(1990, 1, 1), 181 + 365, 181, LC(1990, 2), (4, -1, 1))
+    # routing case 3 (celerity from the river slope) + river temperature (not part of the path);
+    # the run saved no mRM restart: same domain and routing resolution as case_00
+    make_case("case_13", D(1990, 1, 1), 181 + 365, 181, LC(1990, 2), (1, 0, 3), net_from="case_00")
     # DDS calibration with Penman-Monteith PET (processCase(5) = 3): final run with the best set
     make_case_optimised("case_03", D(1990, 1, 1), 181 + 365, 181, LC(1990, 2), (1, 3, 1))
     # case_04: six domains; 1, 2, 4, 5 use the test domain (3 and 6 need forcing files that

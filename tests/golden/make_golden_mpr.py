@@ -173,7 +173,7 @@ def main():
     out = {"fDir0": fdir, "fAcc0": facc, "gaugeLoc0": gauges, "elev0": pick(dem),
            "xllcorner0": hdr["xllcorner"], "yllcorner0": hdr["yllcorner"],
            "mask0": mask0, "cellsize0": hdr["cellsize"], "geoUnit0": geo, "soilId0": soil, "LCover0": lc,
-           "Asp0": aspect, "slope_emp0": emp, "y0": pick(rst["L0_domain_lat"].read()), "LAI0": LAI0,
+           "Asp0": aspect, "slope0": slope, "slope_emp0": emp, "y0": pick(rst["L0_domain_lat"].read()), "LAI0": LAI0,
            "GeoUnitList": np.array(gl, dtype=np.int32), "GeoUnitKar": np.array(gk, dtype=np.int32),
            "is_present": present, "fracSealed_CityArea": 0.6, "tillageDepth": 200.0}
     for k, v in db.items():

@@ -73,13 +73,18 @@ def load(case):
            "InflowGaugeHeadwater": np.zeros(0, np.int32), "nInflowTotal": 0, "processCase": rout_case,
            "L11_length": z["net/L11_length"], "L11_slope": z["net/L11_slope"],
            "L11_nLinkFracFPimp": z["net/L11_nLinkFracFPimp"], "rout_param": z["rout_param"],
-           "TSrout": int(z["net/L11_TSrout"][0]), "celerity": float(z["celerity"][0])}
+           "TSrout": int(z["net/L11_TSrout"][0]) if "net/L11_TSrout" in z.files else 0,
+           "celerity": float(z["celerity"][0])}
+    if rout_case == 3:   # link locations on the L0 grid and the slope factor for L11_calc_celerity
+        for k in ("fRow", "fCol", "tRow", "tCol"):
+            net[k] = z["net/L11_" + k]
+        net["slope_factor"] = float(z["slope_factor"][0])
     net = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in net.items()}
     prob["net"] = net
     prob["inflowQ"] = np.zeros((0, n_days))
     ref = {"final": {k[6:]: z[k] for k in z.files if k.startswith("final/")},
            "Qsim": np.stack([z[k] for k in z.files if k.startswith("Qsim/")]),
-           "Qsim_text": z["Qsim_text"].T, "warming_days": warming, "n_days": n_days, "outputs": outs}
+           "Qsim_text": z["Qsim_text"].T if "Qsim_text" in z.files else None, "warming_days": warming, "n_days": n_days, "outputs": outs}
     return prob, ref
 
 

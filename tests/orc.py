@@ -123,6 +123,16 @@ def lib():
         L.orc_reg_rout.restype = None
         L.orc_mrm_update_param_case2.argtypes = [i, i, pd, d, pd, pd]
         L.orc_mrm_update_param_case2.restype = d
+        L.orc_stream_net.argtypes = [i, i, pi, i, pi, pi, pi, pi, pi, pi]
+        L.orc_stream_net.restype = None
+        L.orc_length_floor.argtypes = [i, pd]
+        L.orc_length_floor.restype = None
+        L.orc_calc_celerity.argtypes = [i, i, pi, pi, pi, pd, i, i, pi, pi, pi, pi, pi, d, pd]
+        L.orc_calc_celerity.restype = None
+        L.orc_mrm_update_param_case3.argtypes = [i, i, pd, pd, pd, pd]
+        L.orc_mrm_update_param_case3.restype = d
+        L.orc_flow_accumulation.argtypes = [i, i, pi, pi, pd, pd]
+        L.orc_flow_accumulation.restype = None
         L.orc_flux_record_size.argtypes = [i]
         L.orc_flux_record_size.restype = i
         L.orc_run.argtypes = [C.POINTER(OrcDomain), i, i]

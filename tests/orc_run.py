@@ -228,3 +228,30 @@ def case23_params(net):
                                       float(net["celerity"]), orc.dptr(C1), orc.dptr(C2))
     net["C1"], net["C2"], net["TSrout"] = C1, C2, ts
     return net
+
+
+def case3_params(net, z0):
+    """routing case 3 for a golden network: L0_streamNet, floored link lengths, L11_celerity from
+    the L0 slopes (z0 = tests/golden/test_domain_l0.npz), then C1 / C2 / TSrout like
+    mrm_update_param.  Everything through the oracle's restatements."""
+    L = orc.lib()
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    mask0 = i32(z0["mask0"])                     # numpy (ncols0, nrows0) == Fortran (nrows0, ncols0)
+    ncols0, nrows0 = mask0.shape
+    fdir2 = np.full(mask0.shape, -9999, dtype=np.int32)
+    fdir2[mask0 != 0] = z0["fDir0"]
+    nn, nl = net["nNodes"], net["nNodes"] - net["nOutlets"]
+    loc = [i32(net[k]) for k in ("netPerm", "fRow", "fCol", "tRow", "tCol")]
+    sn2 = np.zeros(mask0.shape, dtype=np.int32)
+    L.orc_stream_net(nrows0, ncols0, orc.iptr(fdir2), nl, *[orc.iptr(a) for a in loc], orc.iptr(sn2))
+    stream = np.ascontiguousarray(sn2[mask0 != 0])
+    length = np.array(net["L11_length"], dtype=np.float64)
+    L.orc_length_floor(nn, orc.dptr(length))
+    cel = np.zeros(nn)
+    slope0 = np.ascontiguousarray(z0["slope0"], dtype=np.float64)
+    L.orc_calc_celerity(nrows0, ncols0, orc.iptr(mask0), orc.iptr(fdir2), orc.iptr(stream), orc.dptr(slope0), nn, nl,
+                        *[orc.iptr(a) for a in loc], float(net["slope_factor"]), orc.dptr(cel))
+    C1, C2 = np.zeros(nn), np.zeros(nn)
+    ts = L.orc_mrm_update_param_case3(nn, net["nOutlets"], orc.dptr(length), orc.dptr(cel), orc.dptr(C1), orc.dptr(C2))
+    net.update(C1=C1, C2=C2, TSrout=ts, L11_length=length, L11_celerity=cel, streamNet0=stream)
+    return net

@@ -22,7 +22,7 @@ import golden_case
 import orc_run
 import parity
 
-CASES = ["case_00", "case_02", "case_09", "case_10", "case_12",
+CASES = ["case_00", "case_02", "case_09", "case_10", "case_12", "case_13",
          "case_04_b1", "case_04_b2", "case_04_b4", "case_04_b5"]
 STATES = ["L1_inter", "L1_snowPack", "L1_sealSTW", "L1_unsatSTW", "L1_satSTW", "L1_soilMoist"]
 FLUXES = ["L1_aETCanopy", "L1_aETSealed", "L1_baseflow", "L1_fastRunoff", "L1_melt", "L1_percol",
@@ -37,6 +37,11 @@ def _load(case):
     if prob["rout_case"] == 2:
         orc_run.case23_params(prob["net"])   # mrm_update_param (constant celerity) -> C1, C2, TSrout
         assert prob["net"]["TSrout"] == int(np.load(golden_case.HERE + "/golden/%s.npz" % case)["net/L11_TSrout"][0])
+    if prob["rout_case"] == 3:
+        # check/case_13: celerity from the L0 river slopes (L11_calc_celerity incl. FORCES mad),
+        # link-length floor, mrm_update_param -- the run saved no mRM restart, its daily
+        # discharge pins all of it
+        orc_run.case3_params(prob["net"], np.load(golden_case.HERE + "/golden/test_domain_l0.npz"))
     return prob, ref
 
 
@@ -52,12 +57,14 @@ def test_oracle_reproduces_reference_run(case):
     if prob["net"] is None:
         return
     for ours, theirs in ROUT.items():
-        parity.assert_bit_exact(o.R[ours], ref["final"][theirs], "%s %s" % (case, theirs))
+        if theirs in ref["final"]:
+            parity.assert_bit_exact(o.R[ours], ref["final"][theirs], "%s %s" % (case, theirs))
     q = golden_case.daily_mean(o.mRM_runoff, ref["warming_days"])
     # the daily mean is a sum of 24 values: summation order of the Fortran `sum` intrinsic
     # (gfortran may vectorise it) is the only freedom left -> 4 ulp
     worst = parity.assert_close(q, ref["Qsim"], case + " daily discharge", rtol=1e-15, atol=0.0)
-    assert np.abs(q - ref["Qsim_text"]).max() < 0.6e-7, "7-decimal text table"
+    if ref["Qsim_text"] is not None:
+        assert np.abs(q - ref["Qsim_text"]).max() < 0.6e-7, "7-decimal text table"
     print("%s: daily discharge max rel diff %.2e over %d days" % (case, worst, q.shape[1]))
 
 

@@ -66,6 +66,54 @@ def test_raw_inputs_to_discharge(case, res1, res11):
         print("%s from raw inputs: daily discharge max rel diff %.2e, states %.2e" % (case, wq, worst))
 
 
+def test_raw_inputs_to_discharge_celerity_routing():
+    """check/case_13 (routing processCase 3): river network, link-length floor, L11_calc_celerity
+    and mrm_update_param from the raw grids, MPR + cascade + adaptive-step routing on the device,
+    against the reference's daily discharge and final states"""
+    case = "case_13"
+    z0 = np.load(golden_case.HERE + "/golden/test_domain_l0.npz")
+    zc = np.load(golden_case.HERE + "/golden/%s.npz" % case)
+    prob_ref, ref = golden_case.load(case)
+    mprob, _ = golden_case.load_mpr(case, synth_mpr.init_lowres_level)
+    cs0 = float(z0["cellsize0"])
+    n0 = int(z0["mask0"].sum())
+    g1 = mprob["grid"]
+    g11 = synth_mpr.init_lowres_level(z0["mask0"], cs0, 24000.0, np.full(n0, cs0 * cs0))
+    net0 = netinit.net_init(z0["mask0"], z0["fDir0"], z0["fAcc0"], z0["elev0"], cs0, g11, z0["gaugeLoc0"], [398],
+                            LCover0=z0["LCover0"], routingCase=3)
+    l1_l11, _ = netinit.l1_l11_mapping(g1, 24000.0, g11, 24000.0)
+    nn, nl = g11["nCells1"], net0["nLinks"]
+    cel11, _ = netinit.calc_celerity(z0["mask0"], z0["fDir0"], z0["slope0"], net0, float(zc["slope_factor"][0]))
+    c1, c2, ts = netinit.update_param(net0["length"], cel11, nn - nl)
+    net = {"nNodes": nn, "nOutlets": nn - nl, "map_flag": 1, "fromN": net0["fromN"], "toN": net0["toN"],
+           "netPerm": net0["netPerm"], "L1_L11_Id": l1_l11, "L11_L1_Id": np.ones(nn, dtype=np.int32),
+           "L1_areaCell": g1["cellArea1"] * 1e-6, "L11_areaCell": g11["cellArea1"] * 1e-6,
+           "gaugeNodeList": net0["gaugeNodeList"], "gaugeIndexList": np.array([1], dtype=np.int32),
+           "nGaugesTotal": 1, "processCase": 3}
+    for mode in ("strict", "fast"):
+        with interface.Context() as ctx:
+            ctx.set_math_mode(mode)
+            dom = ctx.register_domain(1, g1["nCells1"], mprob["nH"], mprob["nLAI"], mprob["nLC"], mprob["processMatrix"])
+            synth_mpr.set_mpr_inputs(dom, mprob)
+            dom.set_meteo_config(prob_ref["pet_case"], 1, False, False, synth.FNIGHT_PREC, synth.FNIGHT_PET,
+                                 synth.FNIGHT_TEMP, synth.EVAP_COEFF)
+            dom.set_time(prob_ref["time"])
+            synth_mpr.mpr_eval(dom, mprob["param"])
+            dom.states_default_init(np.array([200.0, 1000.0]))
+            for var in ("pre", "temp", "pet"):
+                dom.set_meteo(var, prob_ref["forcing"][var])
+            dom.set_network(net)
+            dom.set_c1c2(c1, c2, ts)
+            dom.run_steps(1, prob_ref["time"]["nTimeSteps"])
+            q = golden_case.daily_mean(dom.get_runoff(), ref["warming_days"])
+            wq = parity.assert_close(q, ref["Qsim"], case + " daily discharge", rtol=parity.RTOL_Q)
+            worst = 0.0
+            for name in ("L1_inter", "L1_snowPack", "L1_sealSTW", "L1_unsatSTW", "L1_satSTW", "L1_soilMoist"):
+                worst = max(worst, parity.assert_close(dom.get_variable(name), ref["final"][name], case + " " + name))
+            print("%s[%s] from raw inputs (TSrout %g s): daily discharge max rel diff %.2e, states %.2e" % (
+                case, mode, ts, wq, worst))
+
+
 @pytest.mark.parametrize("mode", ["strict", "fast"])
 def test_penman_monteith_calibration_run(mode):
     """check/case_03 (PET processCase 3, final run of a DDS calibration): MPR incl. aerodynamic

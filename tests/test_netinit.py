@@ -78,3 +78,73 @@ def test_network_init_scales_linearly_and_feeds_the_routing():
     ok = down < 0
     assert (pos[np.where(ok, 0, down)][~ok] > pos[~ok]).all()   # a link is routed before the link below it
     assert (r["length"][:nl] > 0).all() and (r["slope"][:nl] >= 0.0001).all()
+
+
+def _test_basin(res11=24000.0, routingCase=1):
+    z0 = np.load(golden_case.HERE + "/golden/test_domain_l0.npz")
+    n0 = int(z0["mask0"].sum())
+    g = synth_mpr.init_lowres_level(z0["mask0"], float(z0["cellsize0"]), res11, np.full(n0, float(z0["cellsize0"]) ** 2))
+    r = netinit.net_init(z0["mask0"], z0["fDir0"], z0["fAcc0"], z0["elev0"], float(z0["cellsize0"]), g,
+                         z0["gaugeLoc0"], [398], xll=float(z0["xllcorner0"]), yll=float(z0["yllcorner0"]),
+                         LCover0=z0["LCover0"], routingCase=routingCase)
+    return z0, g, r
+
+
+def test_flow_accumulation_equals_reference_restart():
+    """L11_flow_accumulation against L11_fAcc of the reference's mRM restart files (24 and 12 km)"""
+    for case, res11 in (("case_00", 24000.0), ("case_04_b5", 12000.0)):
+        z0, g, r = _test_basin(res11)
+        zc = np.load(golden_case.HERE + "/golden/%s.npz" % case)
+        facc = netinit.flow_accumulation(g, r["fDir11"])
+        assert np.array_equal(facc, zc["net/L11_fAcc"]), case
+
+
+def test_celerity_routing_parameters_equal_reference_and_oracle():
+    """routing cases 2 and 3 from the raw grids: link-length floor, mrm_update_param and
+    L11_calc_celerity.  Case 2 against the reference's restart file of check/case_09 (length, C1,
+    C2, TSrout bit-identical); case 3 against the oracle's literal restatement (which
+    check/case_13's discharge pins, tests/test_golden_reference.py)."""
+    import orc_run
+
+    z0, g, r = _test_basin(routingCase=2)
+    z9 = np.load(golden_case.HERE + "/golden/case_09.npz")
+    nn, nl = g["nCells1"], r["nLinks"]
+    assert np.array_equal(r["length"], z9["net/L11_length"])          # floored at the 40th percentile
+    c1, c2, ts = netinit.update_param(r["length"], float(z9["celerity"][0]), nn - nl)
+    assert ts == float(z9["net/L11_TSrout"][0])
+    assert np.array_equal(c1[:nl], z9["final/L11_C1"][:nl]) and np.array_equal(c2[:nl], z9["final/L11_C2"][:nl])
+
+    z0, g, r3 = _test_basin(routingCase=3)
+    prob, _ = golden_case.load("case_13")
+    onet = orc_run.case3_params(prob["net"], z0)                      # oracle: from the reference's link locations
+    assert np.array_equal(r3["streamNet0"], onet["streamNet0"])
+    assert np.array_equal(r3["length"], onet["L11_length"])
+    cel11, cel0 = netinit.calc_celerity(z0["mask0"], z0["fDir0"], z0["slope0"], r3, onet["slope_factor"])
+    assert np.array_equal(cel11[:nl], onet["L11_celerity"][:nl])
+    on_stream = r3["streamNet0"] > 0
+    assert (cel0[on_stream] > 0).all() and (cel0[~on_stream] == -9999.0).all()
+    c1, c2, ts = netinit.update_param(r3["length"], np.where(cel11 > 0, cel11, -9999.0), nn - nl)
+    assert ts == onet["TSrout"] == 7200.0
+    assert np.array_equal(c1[:nl], onet["C1"][:nl]) and np.array_equal(c2[:nl], onet["C2"][:nl])
+
+
+def test_flow_accumulation_linear_on_a_deep_network():
+    """a 600 x 500 synthetic grid (chains thousands of cells deep): the explicit post-order walk
+    equals a topological-order sum and needs no recursion"""
+    rng = np.random.default_rng(3)
+    ny, nx = 500, 600                              # numpy (ncols, nrows)
+    codes = rng.choice(np.array([4, 2, 8], dtype=np.int32), size=(ny, nx))   # all move the first index up
+    codes[0, codes[0] == 8] = 4
+    codes[-1, codes[-1] == 2] = 4
+    codes[:, -1] = 0                               # sinks on the last row of the first index
+    mask = np.ones((ny, nx), dtype=np.int32)
+    area = rng.integers(1, 5, ny * nx).astype(np.float64) * 1.0e6
+    g = {"mask1": mask, "nrows1": nx, "ncols1": ny, "nCells1": ny * nx, "cellArea1": area}
+    got = netinit.flow_accumulation(g, codes.ravel()).reshape(ny, nx)
+    f = float(np.float32(1.e-6))
+    acc = area.reshape(ny, nx) * f
+    for i in range(nx - 1):                        # integers x f: every partial sum is exact enough to compare closely
+        for dj, c in ((0, 4), (1, 2), (-1, 8)):
+            src = np.nonzero(codes[:, i] == c)[0]
+            np.add.at(acc[:, i + 1], src + dj, acc[src, i])
+    assert np.allclose(got, acc, rtol=1e-12, atol=0.0)
