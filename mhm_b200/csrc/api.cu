@@ -861,6 +861,32 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
         }
       }
     }
+    // uniform calendar: the specialised kernels drop their per-step calendar work when all steps
+    // of a launch share yId / iLAI / month and read consecutive meteo rows; a launch ends where
+    // the calendar turns (about once a month)
+    a.uniform_calendar = 0;
+    if (block_mode && ctx->uniform_calendar && !a.out_mask && !a.agg_mask && a.is_hourly && a.pet_case <= 0) {
+      const StepIdx& f = idx[t0];
+      int32_t t = 1;
+      for (; t < nb; ++t) {
+        const StepIdx& g = idx[t0 + t];
+        if (g.yId != f.yId || g.iLAI != f.iLAI || g.month != f.month || g.iMeteoTS != f.iMeteoTS + t) break;
+      }
+      if (t == nb || t >= 8) {  // a change in the first steps: one short general launch instead
+        nb = t;
+        closes = false;
+        a.uniform_calendar = 1;
+      } else {
+        for (t = 1; t < nb; ++t) {  // ... that ends where the uniform stretch begins
+          const StepIdx &g = idx[t0 + t], &h = idx[t0 + t - 1];
+          if (g.yId != h.yId || g.iLAI != h.iLAI || g.month != h.month) {
+            nb = t;
+            closes = false;
+            break;
+          }
+        }
+      }
+    }
     a.nSteps = nb;
     a.tt_first = tt0 + t0;
     a.write_fluxes = (wf && t0 + nb >= total) ? 1 : 0;
@@ -1084,6 +1110,7 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
   if (!d) return 1;
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
   if (int rc = ensure_calendar(ctx, d)) return rc;
+  ctx->uniform_calendar = getenv("MHM_CUDA_NO_UNIFORM_CALENDAR") == nullptr;
   MHM_REQUIRE(tt_first >= 1 && n_steps >= 1 && tt_first + n_steps - 1 <= d->axis.nTimeSteps,
               "run_steps: steps %d..%d outside 1..%d", tt_first, tt_first + n_steps - 1,
               d->axis.nTimeSteps);

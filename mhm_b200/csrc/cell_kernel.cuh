@@ -785,9 +785,13 @@ struct CellCursor {
   double raw_pre, raw_temp, raw_pet;
   const double *ppre, *ptemp, *ppet;  // this cell in forcing row cur_row
   double* hist;                       // this cell/member in the total-runoff row of step t
+  double* qp;                         // this cell's node in the tiled node-runoff history, step qst
+  int qst;
 };
 
-template <int NH, int VARIANT, bool OUT>
+// UNIFORM: every step of the launch has the yId / iLAI / month of its first step and the forcing
+// rows advance by one per step (CellArgs::uniform_calendar, specialised variants only)
+template <int NH, int VARIANT, bool OUT, bool UNIFORM = false>
 __global__ void __launch_bounds__(kCellThreads, ParamPlace<NH>::min_blocks)
 MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
@@ -861,16 +865,18 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     qarea = a.cell_area[c];
   }
   const size_t qtile_stride = ((size_t)a.nMembers * a.qout_E) << 3;
+  cu.qst = a.qout_step0;
+  cu.qp = qout ? qout + (size_t)(cu.qst >> 3) * qtile_stride + (size_t)(cu.qst & 7) : nullptr;
 
   // one model step; EMIT is a compile-time tag so that steps 1..n-1 carry no flux stores
   // STORE = false: the caller collects the node runoff of four steps and writes one 32-byte sector
   auto step = [&](auto emit_tag, auto store_tag, const int t) -> double {
     constexpr bool EMIT = decltype(emit_tag)::value;
     constexpr bool STORE = decltype(store_tag)::value;
-    const StepIdx si = a.idx_in[t];  // kernel-parameter space: uniform constant loads
+    const StepIdx si = a.idx_in[UNIFORM ? 0 : t];  // kernel-parameter space: uniform constant loads
     const int y = si.yId - 1, il = si.iLAI - 1, month = si.month - 1;
 
-    if (y != cu.cur_y) {  // land-cover scene changed (new year): mo_mhm_interface_run.f90:626-628
+    if ((!UNIFORM || t == 0) && y != cu.cur_y) {  // land-cover scene changed (new year): mo_mhm_interface_run.f90:626-628
       cu.cur_y = y;
       const size_t o1 = ((size_t)member * a.nLC + y) * n + c;  // (n, 1, nLC) arrays
       PX(fSealed) = a.P[MHM_P_FSEALED][o1];
@@ -903,7 +909,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
         for (int h = 0; h < NH; ++h) s.sm[h] = 0.5 * PH(FC, h);
       }
     }
-    if (il != cu.cur_l) {  // LAI step changed: mo_common_datetime_type.f90:135-155
+    if ((!UNIFORM || t == 0) && il != cu.cur_l) {  // LAI step changed: mo_common_datetime_type.f90:135-155
       cu.cur_l = il;
       PX(maxInter) = a.P[MHM_P_MAXINTER][((size_t)member * a.nLAI + il) * n + c];
 #if MHM_FAST
@@ -979,17 +985,26 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 
     // the next step's forcing row is requested before this step's arithmetic
     if (t + 1 < a.nSteps) {
-      const long long nrow = (long long)a.idx_in[t + 1].iMeteoTS;
-      if (nrow != row) {
-        const size_t adv = (size_t)(nrow - row) * n;
-        cu.cur_row = nrow;
-        cu.ppre += adv;
-        cu.ptemp += adv;
+      if constexpr (UNIFORM) {  // consecutive rows
+        cu.ppre += n;
+        cu.ptemp += n;
+        cu.ppet += n;
         cu.raw_pre = ldg_stream(cu.ppre);
         cu.raw_temp = ldg_stream(cu.ptemp);
-        if (kHourlyPetIn || a.pet_case <= 0) {
-          cu.ppet += adv;
-          cu.raw_pet = ldg_stream(cu.ppet);
+        cu.raw_pet = ldg_stream(cu.ppet);
+      } else {
+        const long long nrow = (long long)a.idx_in[t + 1].iMeteoTS;
+        if (nrow != row) {
+          const size_t adv = (size_t)(nrow - row) * n;
+          cu.cur_row = nrow;
+          cu.ppre += adv;
+          cu.ptemp += adv;
+          cu.raw_pre = ldg_stream(cu.ppre);
+          cu.raw_temp = ldg_stream(cu.ptemp);
+          if (kHourlyPetIn || a.pet_case <= 0) {
+            cu.ppet += adv;
+            cu.raw_pet = ldg_stream(cu.ppet);
+          }
         }
       }
     }
@@ -1040,9 +1055,10 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 #else
       v = v * 1000.0 / a.qout_tst;
 #endif
-      if (STORE) {
-        const int st = a.qout_step0 + t;
-        if (live) qout[(size_t)(st >> 3) * qtile_stride + (size_t)(st & 7)] = v;
+      if (STORE) {  // tiled history [step / 8][member][lane][step % 8]: running pointer
+        if (live) *cu.qp = v;
+        ++cu.qst;
+        cu.qp += (cu.qst & 7) ? (size_t)1 : qtile_stride - 7;
       }
     }
     return v;
@@ -1063,6 +1079,8 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       const double v3 = step(std::false_type{}, std::false_type{}, t + 3);
       if (live) st_sector(qout + (size_t)(st >> 3) * qtile_stride + (size_t)(st & 7), v0, v1, v2, v3);
       t += 4;
+      cu.qst = st + 4;
+      cu.qp = qout + (size_t)(cu.qst >> 3) * qtile_stride + (size_t)(cu.qst & 7);
     } else {
       step(std::false_type{}, std::true_type{}, t);
       ++t;

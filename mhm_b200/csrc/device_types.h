@@ -36,6 +36,10 @@ struct CellArgs {
   int32_t nCells, nMembers, nSteps, tt_first;
   int32_t nLC, nLAI;
   int32_t soil_case, pet_case, is_hourly, read_weights, read_states, write_fluxes;
+  // the launch's steps share yId / iLAI / month and read consecutive meteo rows (set by the host,
+  // which cuts launches where the calendar turns): the specialised kernels then drop the per-step
+  // calendar work
+  int32_t uniform_calendar;
   double nTstepDay_dp, c2TSTu;
   StepIdx idx_in[kIdxInline];         // calendar of the launch's steps: constant-bank loads
   const double* met[MHM_M_COUNT];     // device, [rows][nCells]

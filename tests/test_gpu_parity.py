@@ -263,3 +263,31 @@ def test_fused_node_runoff_equals_separate_runoff_accumulation(ctx):
     dom.run_steps(1, nT)
     parity.assert_close(dom.get_runoff(), o.mRM_runoff, "gauge discharge (fast, fused)", rtol=parity.RTOL_Q)
     ctx.set_math_mode("strict")
+
+
+def test_uniform_calendar_launches_equal_general_launches(ctx, monkeypatch):
+    """Hourly forcing, fast mode: launches whose steps share yId / iLAI / month run the kernel
+    variant without per-step calendar work and end where the calendar turns.  40 days from
+    1 January cross a month; states, last-step fluxes and the gauge series are bit-identical to
+    the general kernels (MHM_CUDA_NO_UNIFORM_CALENDAR) and agree with the oracle."""
+    prob = synth.make_problem(nx=24, ny=14, n_days=40, hourly=True)
+    nT = prob["time"]["nTimeSteps"]
+    o = orc_run.OracleRun(prob)
+    o.run(1, nT)
+    ctx.set_math_mode("fast")
+    res = {}
+    for key in ("uniform", "general"):
+        if key == "general":
+            monkeypatch.setenv("MHM_CUDA_NO_UNIFORM_CALENDAR", "1")
+        dom = fresh(ctx, prob)
+        dom.run_steps(1, 100)          # uneven calls: the node-runoff tiles are entered mid-way
+        dom.run_steps(101, nT - 100)
+        res[key] = {name: dom.get_variable(name) for name in STATES + FLUXES}
+        res[key]["q"] = dom.get_runoff()
+    monkeypatch.delenv("MHM_CUDA_NO_UNIFORM_CALENDAR")
+    for name in res["uniform"]:
+        parity.assert_bit_exact(res["uniform"][name], res["general"][name], name + " uniform vs general launches")
+    parity.assert_close(res["uniform"]["q"], o.mRM_runoff, "gauge discharge", rtol=parity.RTOL_Q)
+    for name in STATES:
+        parity.assert_close(res["uniform"][name], o.S[name], name)
+    ctx.set_math_mode("strict")
