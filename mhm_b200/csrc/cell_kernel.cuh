@@ -35,9 +35,6 @@ namespace mhm {
 #ifndef MHM_TABLES_GLOBAL
 #define MHM_TABLES_GLOBAL 0
 #endif
-#ifndef MHM_QUAD_STORE
-#define MHM_QUAD_STORE 0  // measured on B200: the 4x unrolled time loop is 15 % slower
-#endif
 #ifndef MHM_PARAMS_SMEM
 #define MHM_PARAMS_SMEM 1
 #endif
@@ -772,12 +769,6 @@ __device__ __forceinline__ double cascade_step_sel(const PARAMS& p, CellStates<N
 #endif
 
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldg(p); }
-// four consecutive doubles, 32-byte aligned: one 256-bit store (sm_100: STG.E.256)
-__device__ __forceinline__ void st_sector(double* p, double v0, double v1, double v2, double v3) {
-  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v0), "d"(v1), "d"(v2), "d"(v3)
-               : "memory");
-}
-
 // everything of the time loop that lives across steps besides states and parameters
 struct CellCursor {
   int cur_y, cur_l;
@@ -865,7 +856,9 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     qarea = a.cell_area[c];
   }
   const size_t qtile_stride = ((size_t)a.nMembers * a.qout_E) << 3;
-  cu.qst = a.qout_step0;
+  // the history is stored skewed: step e of a node sits in slot e + (position of the node in its
+  // routing segment), the slot the routing pipeline touches in the same sub-step for all lanes
+  cu.qst = a.qout_step0 + (qout ? (int)a.cell_skew[c] : 0);
   cu.qp = qout ? qout + (size_t)(cu.qst >> 3) * qtile_stride + (size_t)(cu.qst & 7) : nullptr;
 
   // one model step; EMIT is a compile-time tag so that steps 1..n-1 carry no flux stores
@@ -1064,28 +1057,10 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     return v;
   };
 
-  // Steps 1..n-1 carry no flux stores.  In the specialised fast variants four consecutive steps
-  // whose node runoff shares one 32-byte half of a history tile run back to back and leave with
-  // a single 256-bit store (full DRAM sectors instead of four partial ones).
-  constexpr bool kQuad = MHM_FAST && MHM_QUAD_STORE && VARIANT != kGeneric && !OUT;
-  const bool quad_ok = kQuad && qout != nullptr;
+  // Steps 1..n-1 carry no flux stores (a 4x unrolled loop with one 256-bit node-runoff store per
+  // four steps was measured 15 % slower on B200).
   const int n_last = a.nSteps - 1;
-  for (int t = 0; t < n_last;) {
-    const int st = a.qout_step0 + t;
-    if (quad_ok && (st & 3) == 0 && t + 4 <= n_last) {
-      const double v0 = step(std::false_type{}, std::false_type{}, t);
-      const double v1 = step(std::false_type{}, std::false_type{}, t + 1);
-      const double v2 = step(std::false_type{}, std::false_type{}, t + 2);
-      const double v3 = step(std::false_type{}, std::false_type{}, t + 3);
-      if (live) st_sector(qout + (size_t)(st >> 3) * qtile_stride + (size_t)(st & 7), v0, v1, v2, v3);
-      t += 4;
-      cu.qst = st + 4;
-      cu.qp = qout + (size_t)(cu.qst >> 3) * qtile_stride + (size_t)(cu.qst & 7);
-    } else {
-      step(std::false_type{}, std::true_type{}, t);
-      ++t;
-    }
-  }
+  for (int t = 0; t < n_last; ++t) step(std::false_type{}, std::true_type{}, t);
   step(std::true_type{}, std::true_type{}, n_last);
 
   // ---- write back states ----

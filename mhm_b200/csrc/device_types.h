@@ -50,10 +50,12 @@ struct CellArgs {
   double* F[MHM_F_COUNT];             // device, [member][(nH)][nCells]
   double* runoff_hist;                // device, [nSteps][member][nCells] or null
   // routing input produced in place (one cell per node, one model step per routing event):
-  // node runoff qOUT of L11_runoff_acc in the tiled layout [step/8][member][lane][step%8]
+  // node runoff qOUT of L11_runoff_acc in the tiled layout [slot/8][member][lane][slot%8],
+  // slot = step + cell_skew
   double* qout_hist;                  // null: not fused
   const int32_t* cell_lane;           // [nCells] routing lane of the cell's node
   const double* cell_area;            // [nCells] area factor (mo_mrm_pre_routing.f90:125/:141)
+  const int8_t* cell_skew;            // [nCells] position of the cell's node in its routing segment (history slot shift)
   int32_t qout_step0, qout_E, qout_map_flag;
   double qout_tst, qout_scale;        // seconds per model step; 1000 / tst
   // gridded outputs (mo_write_fluxes_states.f90:283-438): bit v = outputFlxState(v), slots in

@@ -62,6 +62,13 @@ static_assert(sizeof(LaneMeta) == 32, "LaneMeta must be 32 bytes");
 // by 8 steps: [step / 8][member][lane][step % 8]; a node's 8 consecutive steps are one
 // 64-byte run and neighbouring lanes are neighbouring runs.
 constexpr int kHistTile = 8;
+// The node-runoff history (qout_hist) is stored SKEWED: event e of lane p sits in slot
+// e + skew(p), skew = position of the node in its segment (0..31).  In sub-step d of macro step
+// S the routing pipeline works on event kWin * S + d - skew, i.e. on slot kWin * S + d for every
+// lane: the lanes of a warp read the same aligned slots and the lean kernel fetches the kWin
+// values of a macro step with one 256-bit load per lane (with unskewed storage every 8-byte
+// load touched 32 different 64-byte runs and the L1 tag stage bounded the kernel).
+constexpr int kHistPad = 40;  // slots past the last event: largest skew + window overshoot
 __host__ __device__ __forceinline__ size_t hidx(int step, int M, int E, int m, int p) {
   return ((((size_t)(step >> 3) * M + m) * E + p) << 3) + (size_t)(step & 7);
 }
@@ -87,6 +94,8 @@ struct Routing {
   int32_t E = 0;                 // lanes = nodes + padding
   std::vector<int32_t> lvl_ptr;  // lane range per segment level (multiples of 32)
   std::vector<int32_t> lvl_ku, lvl_mem;  // per level: upstream slots in use, any memory tributary
+  std::vector<int32_t> lvl_plain;        // per level: no ghost / zeroed-outflow lanes, <= kMetaUps inflowing links
+  bool lean_ok = true;                   // MHM_CUDA_NO_LEAN_ROUTING (diagnostics) forces the general kernel
   std::vector<int32_t> gaugeIndexList, gaugeNodeList, inflowIndexList, inflowHeadwater,
       inflowNodeList;
   // device topology (shared by members)
@@ -109,6 +118,7 @@ struct Routing {
   bool pend_fused = false;
   int32_t last_n = 0;               // steps of the last routed block (export)
   int32_t* d_cell_entry = nullptr;  // [nCells1] lane of the cell's node
+  int8_t* d_cell_skew = nullptr;    // [nCells1] position of that node in its segment
   double* d_cell_area = nullptr;    // [nCells1] area factor of mo_mrm_pre_routing.f90:125/:141
   // per member state, device [M][...]
   double *C1 = nullptr, *C2 = nullptr, *qOUT = nullptr, *qMod = nullptr;
@@ -148,7 +158,7 @@ void routing_free(Routing* rt) {
   if (!rt) return;
   void* ptrs[] = {rt->meta, rt->up_ptr, rt->up_pos, rt->node_lane, rt->cell_ptr, rt->cell_idx,
                   rt->L11_L1_Id, rt->d_inflow_node, rt->d_inflow_index, rt->d_inflow_head,
-                  rt->L1_area, rt->L11_area, rt->d_gauge_col, rt->d_gauge_slot, rt->d_cell_entry, rt->d_ghost_lane, rt->d_export_lane,
+                  rt->L1_area, rt->L11_area, rt->d_gauge_col, rt->d_gauge_slot, rt->d_cell_entry, rt->d_cell_skew, rt->d_ghost_lane, rt->d_export_lane,
                   rt->d_cell_area, rt->C1, rt->C2, rt->qOUT, rt->qMod, rt->qTIN, rt->qTR,
                   rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry, rt->gauge_hist,
                   rt->qout_hist, rt->qtr_hist, rt->qmod_g, rt->d_inflow_val, rt->d_events};
@@ -268,9 +278,10 @@ __global__ void __launch_bounds__(128) qout_kernel(const QoutArgs a) {
     if (lm.flags & kEntInflow) v = apply_inflow(a, node, ev, v);
     q[d] = v;
   }
-  double2* dst = reinterpret_cast<double2*>(a.qout_hist + hidx(tile * kHistTile, a.M, a.E, m, p));
+  const int skew = lm.flags >> 16;  // skewed slots: two neighbouring runs of this lane
 #pragma unroll
-  for (int d = 0; d < kHistTile / 2; ++d) dst[d] = make_double2(q[2 * d], q[2 * d + 1]);
+  for (int d = 0; d < kHistTile; ++d)
+    if (tile * kHistTile + d < a.nEvents) a.qout_hist[hidx(tile * kHistTile + d + skew, a.M, a.E, m, p)] = q[d];
 }
 
 // Same for the common one-cell-per-node case with one model step per event: a thread takes one
@@ -300,9 +311,10 @@ qout_cell_kernel(const QoutArgs a, const int32_t* __restrict__ cell_entry,
     if (lm.flags & kEntInflow) v = apply_inflow(a, lm.node, ev, v);
     q[d] = v;
   }
-  double2* dst = reinterpret_cast<double2*>(a.qout_hist + hidx(tile * kHistTile, a.M, a.E, m, p));
+  const int skew = lm.flags >> 16;
 #pragma unroll
-  for (int d = 0; d < kHistTile / 2; ++d) dst[d] = make_double2(q[2 * d], q[2 * d + 1]);
+  for (int d = 0; d < kHistTile; ++d)
+    if (tile * kHistTile + d < a.nEvents) a.qout_hist[hidx(tile * kHistTile + d + skew, a.M, a.E, m, p)] = q[d];
 }
 
 // carry = (carry) + sum of the block's not yet routed runoff
@@ -392,7 +404,8 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
       const bool in = valid && r >= 0 && r < nRS;
       const int rs = a.rs0 + r;                       // absolute sub-step within the block
       const int ev = RL1 ? a.ev0 + r : a.ev0 + r / rl;  // its event
-      const size_t oq = (size_t)(ev >> 3) * tile_stride + (size_t)(ev & 7);
+      const int evs = ev + skew;  // skewed slot of the node-runoff history
+      const size_t oq = (size_t)(evs >> 3) * tile_stride + (size_t)(evs & 7);
       const size_t ot = (size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7);
       qo[d] = (in && !ghost) ? a.qout_hist[oq + lane_off] : 0.0;
       if (MEM) {
@@ -458,6 +471,124 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
         tr[lm.node] = qtr1;
         tr[a.nNodes + lm.node] = qtr1;
       }
+    }
+    a.qMod[(size_t)m * a.nNodes + lm.node] = qmod;
+    a.qOUT[(size_t)m * a.nNodes + lm.node] = qout;
+  }
+}
+
+// Lean form of route_chain_kernel for the levels that need none of its options: one routing
+// step per event with history indices rs == ev, more than one node, no ghost sources, no zeroed
+// outflows, at most kMetaUps inflowing links per lane (Routing::lvl_plain).  Same operations in
+// the same order -> bit-identical.  The node runoff of a macro step arrives with one 256-bit
+// load per lane (skewed storage, see kHistPad); for the routed-outflow history every lane
+// carries one running byte offset (its own row; tributary rows are a constant distance away)
+// that moves by 8 bytes per routing step and by a tile at a tile end, instead of rebuilding
+// tiled addresses per step.
+template <int KU, bool MEM>
+__global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_lean_kernel(const ChainArgs a) {
+  const int p = a.lane0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.lane1) return;
+  const int m = blockIdx.y;
+  const LaneMeta lm = a.meta[p];
+  const bool valid = lm.flags & kEntValid, is_link = lm.flags & kEntLink;
+  const bool add_qout = lm.flags & kEntAddQout, write_hist = lm.flags & kEntWriteHist;
+  const int nup = (lm.flags >> 8) & 0xff, skew = lm.flags >> 16;
+  const int nRS = a.ev1 - a.ev0;
+  const int lmax = __reduce_max_sync(0xffffffffu, valid ? skew + 1 : 0);
+  double c1 = 0.0, c2 = 0.0;
+  if (is_link) {
+    c1 = a.C1[(size_t)m * a.nNodes + lm.link];
+    c2 = a.C2[(size_t)m * a.nNodes + lm.link];
+  }
+  double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
+  double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
+  double qtin1 = 0.0, qtr1 = 0.0, qout = 0.0, last_q = 0.0, qmod = 0.0;
+  if (valid) {
+    qtin1 = tin[lm.node];
+    qtr1 = tr[lm.node];
+  }
+  // byte offset of (step e, this lane) in a tiled history; e starts before the block for the
+  // lanes that wait for their predecessors (never dereferenced there)
+  const long long tile_bytes = (long long)a.M * a.E * kHistTile * (long long)sizeof(double);
+  int e = a.ev0 - skew;
+  long long off = (long long)(e >> 3) * tile_bytes +
+                  (((long long)m * a.E + p) * kHistTile + (e & 7)) * (long long)sizeof(double);
+  long long up_delta[MEM ? KU : 1];  // tributary row - own row
+  bool up_mem[MEM ? KU : 1];
+  if (MEM) {
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+      up_mem[u] = u < nup && lm.up[u] != kUpShuffle;
+      up_delta[u] = up_mem[u] ? ((long long)lm.up[u] - p) * kHistTile * (long long)sizeof(double) : 0;
+    }
+  }
+  char* const qtr_b = reinterpret_cast<char*>(a.qtr_hist);
+  double* const qg = lm.gslot >= 0 ? a.qmod_g + (size_t)m * a.nGslots + lm.gslot : nullptr;
+  const size_t qg_stride = (size_t)a.M * a.nGslots;
+  const int nMacro = (nRS + lmax - 1 + kWin - 1) / kWin;
+  // node runoff: skewed slots ev0 + kWin * S + d, the same for all lanes; ev0 is a multiple of
+  // kWin (host), so the kWin slots of a macro step are one aligned 32-byte half of a run
+  static_assert(kWin == 4, "the lean kernel loads one 4-slot window per macro step");
+  int slot = a.ev0;
+  const double* qo_p = a.qout_hist + (size_t)(slot >> 3) * (size_t)(tile_bytes / (long long)sizeof(double)) +
+                       ((size_t)m * a.E + p) * kHistTile + (size_t)(slot & 7);
+  int r = -skew;  // routing step (relative to ev0) of sub-step 0 of the macro step
+  for (int S = 0; S < nMacro; ++S, r += kWin) {
+    double qo[kWin], t[MEM ? KU : 1][kWin];
+    long long wr[kWin];
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(qo[0]), "=d"(qo[1]), "=d"(qo[2]), "=d"(qo[3])
+                 : "l"(qo_p));
+    // (an L2 prefetch of the window four macro steps ahead was measured 4 % slower on B200)
+    qo_p += (slot & 4) ? (size_t)(tile_bytes / (long long)sizeof(double)) - 4 : (size_t)4;
+    slot += kWin;
+    {
+      long long o = off;
+      int ee = e;
+#pragma unroll
+      for (int d = 0; d < kWin; ++d) {
+        if (MEM) {
+          const bool in = valid && (unsigned)(r + d) < (unsigned)nRS;
+#pragma unroll
+          for (int u = 0; u < KU; ++u)
+            t[u][d] = (in && up_mem[u]) ? *reinterpret_cast<const double*>(qtr_b + o + up_delta[u]) : 0.0;
+        }
+        wr[d] = o;
+        o += ((ee & 7) == 7) ? tile_bytes - 7 * (long long)sizeof(double) : (long long)sizeof(double);
+        ++ee;
+      }
+      off = o;
+      e = ee;
+    }
+#pragma unroll
+    for (int d = 0; d < kWin; ++d) {
+      const double from_prev = __shfl_up_sync(0xffffffffu, last_q, 1);
+      if (valid && (unsigned)(r + d) < (unsigned)nRS) {
+        qout = qo[d];
+        double q_in = 0.0;  // :428, then upstream links in netPerm order :457
+#pragma unroll
+        for (int u = 0; u < KU; ++u)
+          if (u < nup) q_in = q_in + ((!MEM || !up_mem[u]) ? from_prev : t[u][d]);
+        if (add_qout) q_in = q_in + qout;  // :441 / :466-467
+        if (is_link) {
+          const double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
+          if (write_hist) *reinterpret_cast<double*>(qtr_b + wr[d]) = q;
+          qtr1 = q;
+          last_q = q;
+        }
+        qtin1 = q_in;
+        qmod = q_in;  // (0 + q) / 1, :263,:281
+        if (qg) qg[(size_t)(a.ev0 + r + d) * qg_stride] = qmod;
+      }
+    }
+  }
+  if (valid && nRS > 0) {
+    tin[lm.node] = qtin1;
+    tin[a.nNodes + lm.node] = qtin1;
+    if (is_link) {
+      tr[lm.node] = qtr1;
+      tr[a.nNodes + lm.node] = qtr1;
     }
     a.qMod[(size_t)m * a.nNodes + lm.node] = qmod;
     a.qOUT[(size_t)m * a.nNodes + lm.node] = qout;
@@ -712,10 +843,12 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
   // per level: how many of the kMetaUps slots are in use, and whether any is read from memory
   rt->lvl_ku.assign(rt->lvl_ptr.size() - 1, 1);
   rt->lvl_mem.assign(rt->lvl_ptr.size() - 1, 0);
+  rt->lvl_plain.assign(rt->lvl_ptr.size() - 1, 1);
   for (size_t l = 0; l + 1 < rt->lvl_ptr.size(); ++l)
     for (int p = rt->lvl_ptr[l]; p < rt->lvl_ptr[l + 1]; ++p) {
       const LaneMeta& lm = meta[(size_t)p];
       if (!(lm.flags & kEntValid)) continue;
+      if ((lm.flags & (kEntGhost | kEntZeroOut)) || ((lm.flags >> 8) & 0xff) > kMetaUps) rt->lvl_plain[l] = 0;
       const int nup = std::min((lm.flags >> 8) & 0xff, kMetaUps);
       rt->lvl_ku[l] = std::max(rt->lvl_ku[l], nup);
       for (int u = 0; u < nup; ++u)
@@ -796,14 +929,17 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     }
     if (ok) {
       std::vector<int32_t> ce((size_t)n1);
+      std::vector<int8_t> cs((size_t)n1);
       std::vector<double> ca((size_t)n1);
       for (int k = 0; k < n1; ++k) {
         const int nd = node_of_cell[(size_t)k];
         MHM_REQUIRE(!is_ghost[(size_t)nd], "set_network: L1 cell %d maps to a ghost node", k + 1);
         ce[(size_t)k] = lane_of[(size_t)nd];
+        cs[(size_t)k] = (int8_t)(meta[(size_t)lane_of[(size_t)nd]].flags >> 16);
         ca[(size_t)k] = rt->map_flag ? net->L1_areaCell[k] : net->L11_areaCell[nd];
       }
       if (int rc = upload(&rt->d_cell_entry, ce, st)) return rc;
+      if (int rc = upload(&rt->d_cell_skew, cs, st)) return rc;
       if (int rc = upload(&rt->d_cell_area, ca, st)) return rc;
       rt->bijective = true;
     }
@@ -880,7 +1016,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
     RS += e.rout_loop;
   }
   if (int rc = ensure(&rt->d_events, &rt->ev_cap, (size_t)nEv, st)) return rc;
-  if (int rc = ensure(&rt->qout_hist, &rt->qout_cap, hist_size(nEv, M, E), st)) return rc;
+  if (int rc = ensure(&rt->qout_hist, &rt->qout_cap, hist_size(nEv + kHistPad, M, E), st)) return rc;
   if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(RS, M, E), st)) return rc;
   if (int rc = ensure(&rt->qmod_g, &rt->qmodg_cap, (size_t)nEv * M * std::max(1, rt->nGslots), st))
     return rc;
@@ -955,6 +1091,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
     MHM_CUDA_OK(cudaGetLastError());
   }
 
+  rt->lean_ok = getenv("MHM_CUDA_NO_LEAN_ROUTING") == nullptr;
   for (const Segment& sg : segs) {
     if (int rc = ensure_c1c2(ctx, rt, sg.yId, timestep_rout)) return rc;
     ChainArgs ca{};
@@ -994,7 +1131,16 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
   else if (ku == 2) MHM_CHAIN(R, 2, true);               \
   else if (ku == 3) MHM_CHAIN(R, 3, true);               \
   else MHM_CHAIN(R, 4, true)
-      if (rl == 1) {
+      const bool lean = rl == 1 && ca.rs0 == ca.ev0 && ca.ev0 % kWin == 0 && !ca.single_node && rt->lvl_plain[l] && rt->lean_ok;
+      if (lean) {
+#define MHM_LEAN(K, Mm) route_chain_lean_kernel<K, Mm><<<grid, threads, 0, st>>>(ca)
+        if (!mem) MHM_LEAN(1, false);
+        else if (ku <= 1) MHM_LEAN(1, true);
+        else if (ku == 2) MHM_LEAN(2, true);
+        else if (ku == 3) MHM_LEAN(3, true);
+        else MHM_LEAN(4, true);
+#undef MHM_LEAN
+      } else if (rl == 1) {
         MHM_CHAIN_K(true);
       } else {
         MHM_CHAIN_K(false);
@@ -1034,9 +1180,10 @@ bool routing_fuse_qout(mhm_cuda_context* ctx, Domain* d, int32_t n_steps, CellAr
   if (!rt || !rt->bijective || rt->nInflowGauges > 0 || rt->nInflowTotal > 0 || d->keep_runoff_hist ||
       routing_accumulates(d, rt) || getenv("MHM_CUDA_NO_ALIGNED") || getenv("MHM_CUDA_NO_FUSED_QOUT"))
     return false;
-  if (ensure(&rt->qout_hist, &rt->qout_cap, hist_size(n_steps, rt->M, rt->E), ctx->stream)) return false;
+  if (ensure(&rt->qout_hist, &rt->qout_cap, hist_size(n_steps + kHistPad, rt->M, rt->E), ctx->stream)) return false;
   a->qout_hist = rt->qout_hist;
   a->cell_lane = rt->d_cell_entry;
+  a->cell_skew = rt->d_cell_skew;
   a->cell_area = rt->d_cell_area;
   a->qout_step0 = 0;
   a->qout_E = rt->E;

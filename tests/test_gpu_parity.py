@@ -291,3 +291,29 @@ def test_uniform_calendar_launches_equal_general_launches(ctx, monkeypatch):
     for name in STATES:
         parity.assert_close(res["uniform"][name], o.S[name], name)
     ctx.set_math_mode("strict")
+
+
+def test_lean_routing_kernel_equals_general_kernel(ctx, monkeypatch):
+    """Levels without ghost sources / zeroed outflows run route_chain_lean_kernel (running
+    offsets into the tiled histories); MHM_CUDA_NO_LEAN_ROUTING forces the general kernel.
+    Gauge series and the routing state must be bit-identical, and equal the serial sweep."""
+    prob = synth.make_problem(nx=70, ny=45, n_days=3, hourly=True, n_gauges=5)
+    nT = prob["time"]["nTimeSteps"]
+    o = orc_run.OracleRun(prob)
+    o.run(1, nT)
+    ctx.set_math_mode("strict")
+    res = {}
+    for key in ("lean", "general"):
+        if key == "general":
+            monkeypatch.setenv("MHM_CUDA_NO_LEAN_ROUTING", "1")
+        dom = fresh(ctx, prob)
+        dom.run_steps(1, 29)       # blocks that start and end inside history tiles
+        dom.run_steps(30, nT - 29)
+        res[key] = {k: dom.get_routing_state(k) for k in ("L11_qTIN", "L11_qTR", "L11_qMod", "L11_qOUT")}
+        res[key]["q"] = dom.get_runoff()
+    monkeypatch.delenv("MHM_CUDA_NO_LEAN_ROUTING")
+    for k in res["lean"]:
+        parity.assert_bit_exact(res["lean"][k], res["general"][k], k + " lean vs general routing kernel")
+    for k in ("L11_qTIN", "L11_qTR", "L11_qMod", "L11_qOUT"):   # the cells' runoff differs in the last bits
+        parity.assert_close(res["lean"][k], o.R[k], k + " vs serial sweep", rtol=parity.RTOL_Q)
+    parity.assert_close(res["lean"]["q"], o.mRM_runoff, "gauge discharge", rtol=parity.RTOL_Q)
