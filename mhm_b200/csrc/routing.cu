@@ -68,7 +68,7 @@ constexpr int kHistTile = 8;
 // lane: the lanes of a warp read the same aligned slots and the lean kernel fetches the kWin
 // values of a macro step with one 256-bit load per lane (with unskewed storage every 8-byte
 // load touched 32 different 64-byte runs and the L1 tag stage bounded the kernel).
-constexpr int kHistPad = 40;  // slots past the last event: largest skew + window overshoot
+constexpr int kHistPad = 48;  // slots past the last event: largest skew + window overshoot
 __host__ __device__ __forceinline__ size_t hidx(int step, int M, int E, int m, int p) {
   return ((((size_t)(step >> 3) * M + m) * E + p) << 3) + (size_t)(step & 7);
 }
@@ -508,9 +508,76 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_lean_ke
     qtin1 = tin[lm.node];
     qtr1 = tr[lm.node];
   }
+  const long long tile_bytes = (long long)a.M * a.E * kHistTile * (long long)sizeof(double);
+  if (!MEM && lmax == 1 && (a.ev0 & (kHistTile - 1)) == 0 && __all_sync(0xffffffffu, !valid || nup == 0)) {
+    // A warp of single-node segments (every level ends with them; on the headwater level these
+    // are the leaves of the network, more than a third of all nodes): no lane waits for another
+    // one, so every lane streams its own runs -- one 64-byte run of node runoff in, eight
+    // Muskingum steps, one 64-byte run of routed outflow out; the next run is requested before
+    // the current one is worked on.
+    const size_t tile_elems = (size_t)(tile_bytes / (long long)sizeof(double));
+    const size_t row = (size_t)(a.ev0 >> 3) * tile_elems + ((size_t)m * a.E + p) * kHistTile;
+    const double* qp = a.qout_hist + row;
+    double* hp = a.qtr_hist + row;
+    double* const qg1 = lm.gslot >= 0 ? a.qmod_g + ((size_t)a.ev0 * a.M + m) * a.nGslots + lm.gslot : nullptr;
+    const bool store = valid && is_link && write_hist;
+    double nx[kHistTile];
+    auto load_run = [&](const double* src) {
+      asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                   : "=d"(nx[0]), "=d"(nx[1]), "=d"(nx[2]), "=d"(nx[3]) : "l"(src));
+      asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                   : "=d"(nx[4]), "=d"(nx[5]), "=d"(nx[6]), "=d"(nx[7]) : "l"(src + 4));
+    };
+    load_run(qp);
+    for (int r0 = 0; r0 < nRS; r0 += kHistTile) {
+      double v[kHistTile], o[kHistTile];
+#pragma unroll
+      for (int d = 0; d < kHistTile; ++d) v[d] = nx[d];
+      qp += tile_elems;
+      if (r0 + kHistTile < nRS) load_run(qp);
+#pragma unroll
+      for (int d = 0; d < kHistTile; ++d) {
+        o[d] = 0.0;
+        if (valid && r0 + d < nRS) {
+          qout = v[d];
+          double q_in = 0.0;                 // a segment head on this level has no inflowing link
+          if (add_qout) q_in = q_in + qout;  // :441 / :466-467
+          if (is_link) {
+            const double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
+            o[d] = q;
+            qtr1 = q;
+          }
+          qtin1 = q_in;
+          qmod = q_in;
+          if (qg1) qg1[(size_t)(r0 + d) * (size_t)a.M * a.nGslots] = qmod;
+        }
+      }
+      if (store) {
+        if (r0 + kHistTile <= nRS) {
+          asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(hp), "d"(o[0]), "d"(o[1]), "d"(o[2]), "d"(o[3]) : "memory");
+          asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(hp + 4), "d"(o[4]), "d"(o[5]), "d"(o[6]), "d"(o[7]) : "memory");
+        } else {
+#pragma unroll
+          for (int d = 0; d < kHistTile; ++d)
+            if (r0 + d < nRS) hp[d] = o[d];
+        }
+      }
+      hp += tile_elems;
+    }
+    if (valid && nRS > 0) {
+      tin[lm.node] = qtin1;
+      tin[a.nNodes + lm.node] = qtin1;
+      if (is_link) {
+        tr[lm.node] = qtr1;
+        tr[a.nNodes + lm.node] = qtr1;
+      }
+      a.qMod[(size_t)m * a.nNodes + lm.node] = qmod;
+      a.qOUT[(size_t)m * a.nNodes + lm.node] = qout;
+    }
+    return;
+  }
   // byte offset of (step e, this lane) in a tiled history; e starts before the block for the
   // lanes that wait for their predecessors (never dereferenced there)
-  const long long tile_bytes = (long long)a.M * a.E * kHistTile * (long long)sizeof(double);
   int e = a.ev0 - skew;
   long long off = (long long)(e >> 3) * tile_bytes +
                   (((long long)m * a.E + p) * kHistTile + (e & 7)) * (long long)sizeof(double);
