@@ -195,6 +195,14 @@ MHM_HD double pow23_pos(double x) {
   }
   return pow23_core(x);
 }
+// pow23_pos for 0 < x <= 1e30 without a branch (the same values): the rescaling of tiny
+// arguments is selected instead of skipped, so the call can sit inside straight-line code
+MHM_HD double pow23_sel(double x) {
+  int k = ((hi_word(x) >> 20) - 1023) / 3;
+  k = x < 1.0e-30 ? k : 0;  // k = 0: both scale factors are exactly 1
+  const double m = x * make_double((1023 - 3 * k) << 20, 0);
+  return pow23_core(m) * make_double((1023 + 2 * k) << 20, 0);
+}
 MHM_HD double pow23_core(double x) {
 #if defined(__CUDA_ARCH__)
   float l, r0;
