@@ -1137,7 +1137,8 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     // Measured on B200: +8 % (5.18e10 -> 5.60e10 cell-steps/s).  Not better: evaluating the
     // infiltration powers per lane without warp compaction (straight-line, but 23 more fp64
     // operations per lane-step: -7 %), and a deeper pipeline that also starts those powers for
-    // step t+1 right after the horizons of step t (equal).
+    // step t+1 right after the horizons of step t (per lane: equal; warp-compacted with the
+    // reservoirs of step t and stage A of step t+2 inside the round's block: -3 %).
     if (n_last > 0) {
       const int month = a.idx_in[0].month - 1;
       const double inv_ec = a.tab.inv_evap_coeff[month];

@@ -485,8 +485,11 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
 // carries one running byte offset (its own row; tributary rows are a constant distance away)
 // that moves by 8 bytes per routing step and by a tile at a tile end, instead of rebuilding
 // tiled addresses per step.
+#ifndef MHM_LEAN_MIN_BLOCKS
+#define MHM_LEAN_MIN_BLOCKS 5  // measured on B200: 4 -> 20.9 ms, 5 -> 19.2, 6 -> 19.1 (spills), 8 -> 20.6 per 96-step block
+#endif
 template <int KU, bool MEM>
-__global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_lean_kernel(const ChainArgs a) {
+__global__ void __launch_bounds__(128, MHM_LEAN_MIN_BLOCKS) route_chain_lean_kernel(const ChainArgs a) {
   const int p = a.lane0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.lane1) return;
   const int m = blockIdx.y;
