@@ -265,12 +265,14 @@ def test_fused_node_runoff_equals_separate_runoff_accumulation(ctx):
     ctx.set_math_mode("strict")
 
 
-def test_uniform_calendar_launches_equal_general_launches(ctx, monkeypatch):
-    """Hourly forcing, fast mode: launches whose steps share yId / iLAI / month run the kernel
-    variant without per-step calendar work and end where the calendar turns.  40 days from
-    1 January cross a month; states, last-step fluxes and the gauge series are bit-identical to
-    the general kernels (MHM_CUDA_NO_UNIFORM_CALENDAR) and agree with the oracle."""
-    prob = synth.make_problem(nx=24, ny=14, n_days=40, hourly=True)
+@pytest.mark.parametrize("soil_case,pet_case,nH", [(1, -1, 2), (2, 0, 3), (4, -1, 1), (3, 0, 2)])
+def test_uniform_calendar_launches_equal_general_launches(ctx, monkeypatch, soil_case, pet_case, nH):
+    """Hourly forcing, fast mode: launches whose steps share yId / iLAI / month run the
+    software-pipelined kernel variant without per-step calendar work and end where the calendar
+    turns.  40 days from 1 January cross a month; states, last-step fluxes and the gauge series
+    are bit-identical to the general kernels (MHM_CUDA_NO_UNIFORM_CALENDAR) and agree with the
+    oracle -- Feddes and Jarvis, parameters in shared memory (nH <= 2) and in registers."""
+    prob = synth.make_problem(nx=24, ny=14, n_days=40, hourly=True, soil_case=soil_case, pet_case=pet_case, nH=nH)
     nT = prob["time"]["nTimeSteps"]
     o = orc_run.OracleRun(prob)
     o.run(1, nT)
