@@ -153,6 +153,7 @@ int mhm_cuda_init(int device, mhm_cuda_context** out) {
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0)
     ctx->block_bytes = (size_t)((double)total_b * 0.45);
   if (const char* s = getenv("MHM_CUDA_BLOCK_BYTES")) ctx->block_bytes = (size_t)atoll(s);
+  MHM_CUDA_OK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   *out = ctx;
   return 0;
 }

@@ -129,6 +129,7 @@ struct mhm_cuda_context {
   std::vector<mhm::TimedLaunch> pending;
   std::vector<cudaEvent_t> ev_pool;
   size_t block_bytes = (size_t)24 << 30;  // memory budget of per-block history buffers
+  int sm_count = 148;                      // streaming multiprocessors of the device
   bool uniform_calendar = true;            // MHM_CUDA_NO_UNIFORM_CALENDAR (diagnostics) switches it off
 
   // bracket a kernel launch with events when timing is enabled

@@ -488,8 +488,8 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
 #ifndef MHM_LEAN_MIN_BLOCKS
 #define MHM_LEAN_MIN_BLOCKS 5  // measured on B200: 4 -> 20.9 ms, 5 -> 19.2, 6 -> 19.1 (spills), 8 -> 20.6 per 96-step block
 #endif
-template <int KU, bool MEM>
-__global__ void __launch_bounds__(128, MHM_LEAN_MIN_BLOCKS) route_chain_lean_kernel(const ChainArgs a) {
+template <int KU, bool MEM, bool PF>
+__global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain_lean_kernel(const ChainArgs a) {
   const int p = a.lane0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.lane1) return;
   const int m = blockIdx.y;
@@ -603,54 +603,75 @@ __global__ void __launch_bounds__(128, MHM_LEAN_MIN_BLOCKS) route_chain_lean_ker
   int slot = a.ev0;
   const double* qo_p = a.qout_hist + (size_t)(slot >> 3) * (size_t)(tile_bytes / (long long)sizeof(double)) +
                        ((size_t)m * a.E + p) * kHistTile + (size_t)(slot & 7);
-  int r = -skew;  // routing step (relative to ev0) of sub-step 0 of the macro step
-  for (int S = 0; S < nMacro; ++S, r += kWin) {
+  struct Window {
     double qo[kWin], t[MEM ? KU : 1][kWin];
     long long wr[kWin];
+  };
+  // loads of the macro step whose sub-step 0 is routing step r_ (advances the running offsets)
+  auto load_window = [&](Window& w, const int r_) {
     asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
-                 : "=d"(qo[0]), "=d"(qo[1]), "=d"(qo[2]), "=d"(qo[3])
+                 : "=d"(w.qo[0]), "=d"(w.qo[1]), "=d"(w.qo[2]), "=d"(w.qo[3])
                  : "l"(qo_p));
     // (an L2 prefetch of the window four macro steps ahead was measured 4 % slower on B200)
     qo_p += (slot & 4) ? (size_t)(tile_bytes / (long long)sizeof(double)) - 4 : (size_t)4;
     slot += kWin;
-    {
-      long long o = off;
-      int ee = e;
+    long long o = off;
+    int ee = e;
 #pragma unroll
-      for (int d = 0; d < kWin; ++d) {
-        if (MEM) {
-          const bool in = valid && (unsigned)(r + d) < (unsigned)nRS;
+    for (int d = 0; d < kWin; ++d) {
+      if (MEM) {
+        const bool in = valid && (unsigned)(r_ + d) < (unsigned)nRS;
 #pragma unroll
-          for (int u = 0; u < KU; ++u)
-            t[u][d] = (in && up_mem[u]) ? *reinterpret_cast<const double*>(qtr_b + o + up_delta[u]) : 0.0;
-        }
-        wr[d] = o;
-        o += ((ee & 7) == 7) ? tile_bytes - 7 * (long long)sizeof(double) : (long long)sizeof(double);
-        ++ee;
+        for (int u = 0; u < KU; ++u)
+          w.t[u][d] = (in && up_mem[u]) ? *reinterpret_cast<const double*>(qtr_b + o + up_delta[u]) : 0.0;
       }
-      off = o;
-      e = ee;
+      w.wr[d] = o;
+      o += ((ee & 7) == 7) ? tile_bytes - 7 * (long long)sizeof(double) : (long long)sizeof(double);
+      ++ee;
     }
+    off = o;
+    e = ee;
+  };
+  auto route_window = [&](const Window& w, const int r_) {
 #pragma unroll
     for (int d = 0; d < kWin; ++d) {
       const double from_prev = __shfl_up_sync(0xffffffffu, last_q, 1);
-      if (valid && (unsigned)(r + d) < (unsigned)nRS) {
-        qout = qo[d];
+      if (valid && (unsigned)(r_ + d) < (unsigned)nRS) {
+        qout = w.qo[d];
         double q_in = 0.0;  // :428, then upstream links in netPerm order :457
 #pragma unroll
         for (int u = 0; u < KU; ++u)
-          if (u < nup) q_in = q_in + ((!MEM || !up_mem[u]) ? from_prev : t[u][d]);
+          if (u < nup) q_in = q_in + ((!MEM || !up_mem[u]) ? from_prev : w.t[u][d]);
         if (add_qout) q_in = q_in + qout;  // :441 / :466-467
         if (is_link) {
           const double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
-          if (write_hist) *reinterpret_cast<double*>(qtr_b + wr[d]) = q;
+          if (write_hist) *reinterpret_cast<double*>(qtr_b + w.wr[d]) = q;
           qtr1 = q;
           last_q = q;
         }
         qtin1 = q_in;
         qmod = q_in;  // (0 + q) / 1, :263,:281
-        if (qg) qg[(size_t)(a.ev0 + r + d) * qg_stride] = qmod;
+        if (qg) qg[(size_t)(a.ev0 + r_ + d) * qg_stride] = qmod;
       }
+    }
+  };
+  int r = -skew;  // routing step (relative to ev0) of sub-step 0 of the macro step
+  if (PF) {
+    // narrow levels (less than one wave of CTAs): nothing hides the load latency of a macro
+    // step, so the next window is requested before the current one is routed (the tributary
+    // series were written by earlier launches)
+    Window cur, nxt;
+    load_window(nxt, r);
+    for (int S = 0; S < nMacro; ++S, r += kWin) {
+      cur = nxt;
+      if (S + 1 < nMacro) load_window(nxt, r + kWin);
+      route_window(cur, r);
+    }
+  } else {
+    for (int S = 0; S < nMacro; ++S, r += kWin) {
+      Window w;
+      load_window(w, r);
+      route_window(w, r);
     }
   }
   if (valid && nRS > 0) {
@@ -1203,12 +1224,16 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
   else MHM_CHAIN(R, 4, true)
       const bool lean = rl == 1 && ca.rs0 == ca.ev0 && ca.ev0 % kWin == 0 && !ca.single_node && rt->lvl_plain[l] && rt->lean_ok;
       if (lean) {
-#define MHM_LEAN(K, Mm) route_chain_lean_kernel<K, Mm><<<grid, threads, 0, st>>>(ca)
-        if (!mem) MHM_LEAN(1, false);
-        else if (ku <= 1) MHM_LEAN(1, true);
-        else if (ku == 2) MHM_LEAN(2, true);
-        else if (ku == 3) MHM_LEAN(3, true);
-        else MHM_LEAN(4, true);
+        // less than one wave of CTAs: the variant that keeps the next window's loads in flight
+        const bool pf = (size_t)grid.x * grid.y <= (size_t)ctx->sm_count * MHM_LEAN_MIN_BLOCKS;
+#define MHM_LEAN(K, Mm)                                                      \
+  if (pf) route_chain_lean_kernel<K, Mm, true><<<grid, threads, 0, st>>>(ca); \
+  else route_chain_lean_kernel<K, Mm, false><<<grid, threads, 0, st>>>(ca)
+        if (!mem) { MHM_LEAN(1, false); }
+        else if (ku <= 1) { MHM_LEAN(1, true); }
+        else if (ku == 2) { MHM_LEAN(2, true); }
+        else if (ku == 3) { MHM_LEAN(3, true); }
+        else { MHM_LEAN(4, true); }
 #undef MHM_LEAN
       } else if (rl == 1) {
         MHM_CHAIN_K(true);
