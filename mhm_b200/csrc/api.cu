@@ -844,6 +844,7 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
         if (outputs) {
           a.out_mask = d->out_mask;
           a.out_acc = d->out_acc;
+          a.out_nslots = d->out_nslots;
           d->out_counter += nb - first;
         }
         if (d->bfi_on && block_mode) {

@@ -207,14 +207,19 @@ struct FluxEmitter {
 // output variable to the open window, slots in the order of the reference's `ii = ii + 1`
 // blocks.  fS / fNS / sat_o belong to the land-cover scene the driver holds after the step's
 // date increment (mo_mhm_interface_run.f90:623-628, 690-696).
+// The open window's sums of a (cell, member) live in a per-thread array for the whole launch
+// (loaded before its first step, written back after its last): the additions happen in the same
+// order as with one read-modify-write of global memory per step and slot, without the trips.
+constexpr int kOutSlotsMax = 64;  // mhm_cuda_set_outputs rejects more
 template <int NH>
-__device__ __forceinline__ void accumulate_outputs(const uint32_t mask, double* ap, const size_t stride,
+__device__ __forceinline__ void accumulate_outputs(const uint32_t mask, double* acc,
                                                    const FluxCapture& f, const CellStates<NH>& s,
                                                    const double fS, const double* sat_o) {
   const double fNS = 1.0 - fS;  // L1_fNotSealed, mo_mhm_interface_run.f90:238-239
+  int k = 0;
   auto add = [&](double v) {
-    *ap = *ap + v;  // OutputVariable%updateVariable, mo_nc_output.f90:140-149
-    ap += stride;
+    acc[k] = acc[k] + v;  // OutputVariable%updateVariable, mo_nc_output.f90:140-149
+    ++k;
   };
   auto on = [&](int v) { return (mask >> v) & 1u; };
   if (on(1)) add(s.inter);
@@ -626,11 +631,11 @@ __device__ __forceinline__ double cascade_step(const PARAMS& p, CellStates<NH>& 
 struct StageA {
   double prec_effect, pet_left, runoff_sealed;  // pet_left = pet - aet_canopy
 };
-template <int NH, int VARIANT, bool EMIT, bool STRAIGHT, class PARAMS>
+template <int NH, int VARIANT, bool EMIT, bool STRAIGHT, class PARAMS, class EM>
 __device__ __forceinline__ StageA cascade_stage_a_sel(const PARAMS& p, CellStates<NH>& s,
                                                       const double pet, const double temperature,
                                                       const double prec, const double inv_evap_coeff,
-                                                      const FluxEmitter<EMIT, false>& emit) {
+                                                      const EM& emit) {
   // ---- canopy_interc ----
   const double aux = s.inter + prec;
   const bool over = aux >= PX(maxInter);
@@ -734,10 +739,10 @@ __device__ __forceinline__ void cascade_stage_b1_sel(const PARAMS& p, const Cell
 
 }
 
-template <int NH, int VARIANT, bool EMIT, class PARAMS>
+template <int NH, int VARIANT, bool EMIT, class PARAMS, class EM>
 __device__ __forceinline__ double cascade_horizons_sel(const PARAMS& p, CellStates<NH>& s, const StageA& in,
                                                        const double (&frac_pre)[NH],
-                                                       const FluxEmitter<EMIT, false>& emit) {
+                                                       const EM& emit) {
   constexpr bool kFeddes = VARIANT == kHourlyFeddes;
   const double prec_effect = in.prec_effect;
   // ---- soil horizons ----
@@ -778,10 +783,10 @@ __device__ __forceinline__ double cascade_horizons_sel(const PARAMS& p, CellStat
   return infil_last;
 }
 
-template <int NH, int VARIANT, bool EMIT, class PARAMS>
+template <int NH, int VARIANT, bool EMIT, class PARAMS, class EM>
 __device__ __forceinline__ double cascade_reservoirs_sel(const PARAMS& p, CellStates<NH>& s, const double infil_last,
                                                          const double runoff_sealed, const fm::Tables& tab,
-                                                         const FluxEmitter<EMIT, false>& emit) {
+                                                         const EM& emit) {
   // ---- runoff_unsat_zone ----
   double us = s.unsat + infil_last;
   const double fast = us > PX(unsatThr) ? fmin(PX(k0r) * (us - PX(unsatThr)), us - kEps) : 0.0;
@@ -807,20 +812,20 @@ __device__ __forceinline__ double cascade_reservoirs_sel(const PARAMS& p, CellSt
   return total_runoff;
 }
 
-template <int NH, int VARIANT, bool EMIT, class PARAMS>
+template <int NH, int VARIANT, bool EMIT, class PARAMS, class EM>
 __device__ __forceinline__ double cascade_stage_b2_sel(const PARAMS& p, CellStates<NH>& s, const StageA& in,
                                                        const double (&frac_pre)[NH], const fm::Tables& tab,
-                                                       const FluxEmitter<EMIT, false>& emit) {
+                                                       const EM& emit) {
   const double infil_last = cascade_horizons_sel<NH, VARIANT, EMIT>(p, s, in, frac_pre, emit);
   return cascade_reservoirs_sel<NH, VARIANT, EMIT>(p, s, infil_last, in.runoff_sealed, tab, emit);
 }
 
-template <int NH, int VARIANT, bool EMIT, class PARAMS>
+template <int NH, int VARIANT, bool EMIT, class PARAMS, class EM>
 __device__ __forceinline__ double cascade_step_sel(const PARAMS& p, CellStates<NH>& s,
                                                    const double pet, const double temperature,
                                                    const double prec, const double inv_evap_coeff,
                                                    double2* warp_tasks, const fm::Tables& tab,
-                                                   const FluxEmitter<EMIT, false>& emit) {
+                                                   const EM& emit) {
   const StageA sa = cascade_stage_a_sel<NH, VARIANT, EMIT, false>(p, s, pet, temperature, prec, inv_evap_coeff, emit);
   double frac_pre[NH];
   cascade_stage_b1_sel<NH, VARIANT, EMIT>(p, s, sa.prec_effect, warp_tasks, tab, frac_pre);
@@ -921,6 +926,14 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   cu.qst = a.qout_step0 + (qout ? (int)a.cell_skew[c] : 0);
   cu.qp = qout ? qout + (size_t)(cu.qst >> 3) * qtile_stride + (size_t)(cu.qst & 7) : nullptr;
 
+  // gridded outputs: the open window of this (cell, member), see accumulate_outputs
+  double out_acc_l[OUT ? kOutSlotsMax : 1];
+  int out_y = -1;
+  double out_fS = 0.0, out_sat[NH];
+  if (OUT) {
+    if (a.out_mask && live)
+      for (int k = 0; k < a.out_nslots; ++k) out_acc_l[k] = a.out_acc[(size_t)k * hist_stride + mc];
+  }
   // parameters of the step's land-cover scene / LAI step, reloaded when they change (with a
   // uniform calendar: at the launch's first step only)
   auto load_params = [&](const int t) {
@@ -1072,7 +1085,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 
 #if MHM_FAST && MHM_SELECT_FORM
     double total_runoff;
-    if constexpr (VARIANT != kGeneric && !OUT) {
+    if constexpr (VARIANT != kGeneric) {
       total_runoff = cascade_step_sel<NH, VARIANT, EMIT>(p, s, pet_calc, temp_calc, prec_calc,
                                                          a.tab.inv_evap_coeff[month], warp_tasks, sh_tab, emit);
     } else {
@@ -1092,15 +1105,17 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     if (OUT) {
       if (live && t >= a.out_first) {
         const int yo = a.out_yid[t] - 1;
-        const double fS = a.P[MHM_P_FSEALED][((size_t)member * a.nLC + yo) * n + c];
-        double sat_o[NH];
+        if (yo != out_y) {  // scene the driver holds after the step's date increment
+          out_y = yo;
+          out_fS = a.P[MHM_P_FSEALED][((size_t)member * a.nLC + yo) * n + c];
 #pragma unroll
-        for (int h = 0; h < NH; ++h)
-          sat_o[h] = a.P[MHM_P_SOILMOISTSAT][(((size_t)member * a.nLC + yo) * NH + h) * n + c];
-        if (a.out_mask) accumulate_outputs<NH>(a.out_mask, a.out_acc + mc, hist_stride, cap, s, fS, sat_o);
+          for (int h = 0; h < NH; ++h)
+            out_sat[h] = a.P[MHM_P_SOILMOISTSAT][(((size_t)member * a.nLC + yo) * NH + h) * n + c];
+        }
+        if (a.out_mask) accumulate_outputs<NH>(a.out_mask, out_acc_l, cap, s, out_fS, out_sat);
         if (a.agg_mask)
           accumulate_aggregates<NH>(a.agg_mask, a.agg_nhor_sm, a.agg_col, a.bfi_acc, mc, hist_stride, cap, s,
-                                    fS, sat_o);
+                                    out_fS, out_sat);
       }
     }
     if (cu.hist) {
@@ -1191,6 +1206,10 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   }
   step(std::true_type{}, std::true_type{}, n_last);
 
+  if (OUT) {
+    if (a.out_mask && live)
+      for (int k = 0; k < a.out_nslots; ++k) a.out_acc[(size_t)k * hist_stride + mc] = out_acc_l[k];
+  }
   // ---- write back states ----
   if (live) {
     a.S[MHM_S_INTER][mc] = s.inter;

@@ -62,6 +62,7 @@ struct CellArgs {
   // the order of mHM_updateDataset; out_acc [slot][member][nCells] is the open window
   uint32_t out_mask;
   int32_t out_first;                  // first step of the launch with tIndex_out > 0
+  int32_t out_nslots;                 // slots of out_acc in use
   double* out_acc;
   int8_t out_yid[kIdxInline];         // land-cover scene the driver holds after each step
   // calibration aggregates (mo_mhm_interface_run.f90:745-861) and BFI sums (:630-636): every step
