@@ -207,19 +207,19 @@ struct FluxEmitter {
 // output variable to the open window, slots in the order of the reference's `ii = ii + 1`
 // blocks.  fS / fNS / sat_o belong to the land-cover scene the driver holds after the step's
 // date increment (mo_mhm_interface_run.f90:623-628, 690-696).
-// The open window's sums of a (cell, member) live in a per-thread array for the whole launch
-// (loaded before its first step, written back after its last): the additions happen in the same
-// order as with one read-modify-write of global memory per step and slot, without the trips.
-constexpr int kOutSlotsMax = 64;  // mhm_cuda_set_outputs rejects more
+// The open window's sums of a (cell, member) live in (dynamic) shared memory for the whole
+// launch, one conflict-free column per thread ([slot][thread]; loaded before the launch's first
+// step, written back after its last): the additions happen in the same order as with one
+// read-modify-write of global memory per step and slot, without the trips to L2 (a per-thread
+// local array does not help: the parameter store leaves the L1 too small to hold it).
 template <int NH>
 __device__ __forceinline__ void accumulate_outputs(const uint32_t mask, double* acc,
                                                    const FluxCapture& f, const CellStates<NH>& s,
                                                    const double fS, const double* sat_o) {
   const double fNS = 1.0 - fS;  // L1_fNotSealed, mo_mhm_interface_run.f90:238-239
-  int k = 0;
   auto add = [&](double v) {
-    acc[k] = acc[k] + v;  // OutputVariable%updateVariable, mo_nc_output.f90:140-149
-    ++k;
+    *acc = *acc + v;  // OutputVariable%updateVariable, mo_nc_output.f90:140-149
+    acc += kCellThreads;
   };
   auto on = [&](int v) { return (mask >> v) & 1u; };
   if (on(1)) add(s.inter);
@@ -927,12 +927,13 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   cu.qp = qout ? qout + (size_t)(cu.qst >> 3) * qtile_stride + (size_t)(cu.qst & 7) : nullptr;
 
   // gridded outputs: the open window of this (cell, member), see accumulate_outputs
-  double out_acc_l[OUT ? kOutSlotsMax : 1];
+  extern __shared__ double out_sh[];  // [out_nslots][kCellThreads], OUT launches only
+  double* const out_acc_l = out_sh + threadIdx.x;
   int out_y = -1;
   double out_fS = 0.0, out_sat[NH];
   if (OUT) {
     if (a.out_mask && live)
-      for (int k = 0; k < a.out_nslots; ++k) out_acc_l[k] = a.out_acc[(size_t)k * hist_stride + mc];
+      for (int k = 0; k < a.out_nslots; ++k) out_acc_l[k * kCellThreads] = a.out_acc[(size_t)k * hist_stride + mc];
   }
   // parameters of the step's land-cover scene / LAI step, reloaded when they change (with a
   // uniform calendar: at the launch's first step only)
@@ -1208,7 +1209,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 
   if (OUT) {
     if (a.out_mask && live)
-      for (int k = 0; k < a.out_nslots; ++k) a.out_acc[(size_t)k * hist_stride + mc] = out_acc_l[k];
+      for (int k = 0; k < a.out_nslots; ++k) a.out_acc[(size_t)k * hist_stride + mc] = out_acc_l[k * kCellThreads];
   }
   // ---- write back states ----
   if (live) {
