@@ -96,6 +96,7 @@ struct Routing {
   std::vector<int32_t> lvl_ku, lvl_mem;  // per level: upstream slots in use, any memory tributary
   std::vector<int32_t> lvl_plain;        // per level: no ghost / zeroed-outflow lanes, <= kMetaUps inflowing links
   bool lean_ok = true;                   // MHM_CUDA_NO_LEAN_ROUTING (diagnostics) forces the general kernel
+  size_t pf_waves = 1;                   // levels of up to this many waves of CTAs run the prefetching variant
   std::vector<int32_t> gaugeIndexList, gaugeNodeList, inflowIndexList, inflowHeadwater,
       inflowNodeList;
   // device topology (shared by members)
@@ -1183,6 +1184,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
   }
 
   rt->lean_ok = getenv("MHM_CUDA_NO_LEAN_ROUTING") == nullptr;
+  if (const char* w = getenv("MHM_CUDA_LEAN_PF_WAVES")) rt->pf_waves = (size_t)atoll(w);
   for (const Segment& sg : segs) {
     if (int rc = ensure_c1c2(ctx, rt, sg.yId, timestep_rout)) return rc;
     ChainArgs ca{};
@@ -1225,7 +1227,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
       const bool lean = rl == 1 && ca.rs0 == ca.ev0 && ca.ev0 % kWin == 0 && !ca.single_node && rt->lvl_plain[l] && rt->lean_ok;
       if (lean) {
         // less than one wave of CTAs: the variant that keeps the next window's loads in flight
-        const bool pf = (size_t)grid.x * grid.y <= (size_t)ctx->sm_count * MHM_LEAN_MIN_BLOCKS;
+        const bool pf = (size_t)grid.x * grid.y <= (size_t)ctx->sm_count * MHM_LEAN_MIN_BLOCKS * rt->pf_waves;
 #define MHM_LEAN(K, Mm)                                                      \
   if (pf) route_chain_lean_kernel<K, Mm, true><<<grid, threads, 0, st>>>(ca); \
   else route_chain_lean_kernel<K, Mm, false><<<grid, threads, 0, st>>>(ca)
