@@ -443,6 +443,113 @@ module mo_mhm_cuda
       integer(c_int32_t), value :: nNodes, nLinks
       type(c_ptr), value :: fromN, toN, rOrder, netPerm
     end function
+    ! ---- entry points without a call site of their own in the patched driver: teardown, math mode,
+    ! ---- zero-copy forcing, diagnostics, host-side integer maps and the calendar
+    integer(c_int) function mhm_cuda_unregister_domain(ctx, iDomain) bind(C, name = 'mhm_cuda_unregister_domain')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+    end function
+    type(c_ptr) function mhm_cuda_version() bind(C, name = 'mhm_cuda_version')
+      import
+    end function
+    !> mode 0 = strict (reference operation order, libdevice), 1 = fast (tables, FMA contraction)
+    integer(c_int) function mhm_cuda_set_math_mode(ctx, mode) bind(C, name = 'mhm_cuda_set_math_mode')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: mode
+    end function
+    integer(c_int) function mhm_cuda_synchronize(ctx) bind(C, name = 'mhm_cuda_synchronize')
+      import
+      type(c_ptr), value :: ctx
+    end function
+    !> dev: device address of a [n_steps][nCells] chunk owned by the caller (no copy)
+    integer(c_int) function mhm_cuda_set_meteo_device(ctx, iDomain, var, dev, first_step, n_steps) &
+        bind(C, name = 'mhm_cuda_set_meteo_device')
+      import
+      type(c_ptr), value :: ctx, dev
+      integer(c_int32_t), value :: iDomain, var
+      integer(c_int64_t), value :: first_step, n_steps
+    end function
+    integer(c_int) function mhm_cuda_get_meteo(ctx, iDomain, var, out, ld, first_step, n_steps) &
+        bind(C, name = 'mhm_cuda_get_meteo')
+      import
+      type(c_ptr), value :: ctx, out
+      integer(c_int32_t), value :: iDomain, var
+      integer(c_int64_t), value :: ld, first_step, n_steps
+    end function
+    integer(c_int) function mhm_cuda_keep_runoff_history(ctx, iDomain, keep) &
+        bind(C, name = 'mhm_cuda_keep_runoff_history')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain, keep
+    end function
+    integer(c_int) function mhm_cuda_get_runoff_history(ctx, iDomain, member, out, ld) &
+        bind(C, name = 'mhm_cuda_get_runoff_history')
+      import
+      type(c_ptr), value :: ctx, out
+      integer(c_int32_t), value :: iDomain, member
+      integer(c_int64_t), value :: ld
+    end function
+    integer(c_int) function mhm_cuda_event_record(ctx, slot) bind(C, name = 'mhm_cuda_event_record')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: slot
+    end function
+    integer(c_int) function mhm_cuda_event_elapsed_ms(ctx, a, b, ms) bind(C, name = 'mhm_cuda_event_elapsed_ms')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: a, b
+      real(c_double), intent(out) :: ms
+    end function
+    integer(c_int) function mhm_cuda_kernel_stats(ctx, which, ms, launches) bind(C, name = 'mhm_cuda_kernel_stats')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: which
+      real(c_double), intent(out) :: ms
+      integer(c_int64_t), intent(out) :: launches
+    end function
+    integer(c_int) function mhm_cuda_kernel_stats_reset(ctx, enable_timing) &
+        bind(C, name = 'mhm_cuda_kernel_stats_reset')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: enable_timing
+    end function
+    integer(c_int) function mhm_cuda_measure_dfma_peak(ctx, dfma_per_s) bind(C, name = 'mhm_cuda_measure_dfma_peak')
+      import
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: dfma_per_s
+    end function
+    integer(c_int) function mpr_cuda_grid_destroy(ctx, grid) bind(C, name = 'mpr_cuda_grid_destroy')
+      import
+      type(c_ptr), value :: ctx, grid
+    end function
+    integer(c_int) function mpr_cuda_upscale_geometric_mean(ctx, grid, nodata, L0_data, L1_out) &
+        bind(C, name = 'mpr_cuda_upscale_geometric_mean')
+      import
+      type(c_ptr), value :: ctx, grid, L0_data, L1_out
+      real(c_double), value :: nodata
+    end function
+    !> init_lowres_level (mo_grid.f90) without a device: masks and bounds as c_loc of the caller's arrays
+    integer(c_int) function mhm_grid_init_lowres_level(nrows0, ncols0, mask0, cellArea0, cellsize0, &
+        target_resolution, nrows1, ncols1, nCells1, mask1, cellCoor, cellArea1, upper_bound, lower_bound, &
+        left_bound, right_bound, n_subcells, lowres_id_on_highres) bind(C, name = 'mhm_grid_init_lowres_level')
+      import
+      integer(c_int32_t), value :: nrows0, ncols0
+      type(c_ptr), value :: mask0, cellArea0
+      real(c_double), value :: cellsize0, target_resolution
+      integer(c_int32_t), intent(out) :: nrows1, ncols1, nCells1
+      type(c_ptr), value :: mask1, cellCoor, cellArea1, upper_bound, lower_bound, left_bound, right_bound, &
+                            n_subcells, lowres_id_on_highres
+    end function
+    !> the per-step calendar of mhm_interface_run_do_time_step for steps tt_first .. tt_first+n_steps-1
+    integer(c_int) function mhm_time_indices(cfg, timestep_h, nTstepForcingDay, tt_first, n_steps, out) &
+        bind(C, name = 'mhm_time_indices')
+      import
+      type(mhm_time_config), intent(in) :: cfg
+      integer(c_int32_t), value :: timestep_h, nTstepForcingDay, tt_first, n_steps
+      type(mhm_step_index), intent(out) :: out(*)
+    end function
   end interface
 
   public :: mhm_cuda_init, mhm_cuda_finalize, mhm_cuda_register_domain, mhm_cuda_set_param, &
@@ -458,7 +565,13 @@ module mo_mhm_cuda
             mhm_cuda_set_optisim, mhm_cuda_get_optisim, mhm_cuda_get_bfi_sums, &
             mrm_cuda_set_deferred, mrm_cuda_route_pending, mrm_cuda_export_outflow, mrm_cuda_import_outflow, &
             mrm_routing_order, mhm_cuda_set_meteo_l2, mrm_net_init, mrm_net_l1_l11_mapping, &
-            mrm_net_flow_accumulation, mrm_net_calc_celerity, mrm_net_update_param
+            mrm_net_flow_accumulation, mrm_net_calc_celerity, mrm_net_update_param, &
+            mhm_cuda_unregister_domain, mhm_cuda_version, mhm_cuda_set_math_mode, mhm_cuda_synchronize, &
+            mhm_cuda_set_meteo_device, mhm_cuda_get_meteo, mhm_cuda_keep_runoff_history, &
+            mhm_cuda_get_runoff_history, mhm_cuda_event_record, mhm_cuda_event_elapsed_ms, &
+            mhm_cuda_kernel_stats, mhm_cuda_kernel_stats_reset, mhm_cuda_measure_dfma_peak, &
+            mpr_cuda_grid_destroy, mpr_cuda_upscale_geometric_mean, mhm_grid_init_lowres_level, &
+            mhm_time_indices
   public :: mpr_l0_inputs, mpr_soil_db, mhm_optisim_config
 
 contains

@@ -21,6 +21,33 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in L.mhm_cuda_version()
 
 
+def test_fortran_module_binds_every_declared_symbol():
+    """mhm_b200/fortran/mo_mhm_cuda.F90 carries one bind(C) interface per entry point of the
+    header, made public (mhm_cuda_last_error stays private behind mhm_cuda_check)"""
+    import re
+
+    src = open(os.path.join(os.path.dirname(_lib.HEADER), "..", "mhm_b200", "fortran", "mo_mhm_cuda.F90")).read()
+    bound = set(re.findall(r"bind\(C,\s*name\s*=\s*'(\w+)'\)", src))
+    public = set()
+    for stmt in re.findall(r"^\s*public\s*::((?:.*&\s*\n)*.*)$", src, flags=re.M):
+        public |= set(re.findall(r"\w+", stmt))
+    names = _cstruct.declared_functions(_lib.HEADER)
+    assert len(names) > 40
+    for n in names:
+        assert n in bound, "mo_mhm_cuda.F90 has no bind(C) interface for %s" % n
+        assert n in public or n == "mhm_cuda_last_error", "%s is not public in mo_mhm_cuda.F90" % n
+    assert bound <= set(names), "bind(C) names unknown to the header: %s" % sorted(bound - set(names))
+    # same number of arguments on both sides
+    hdr = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER).read(), flags=re.S)
+    joined = re.sub(r"&\s*\n\s*", "", src)
+    for n in names:
+        c = re.search(r"\b%s\s*\(([^;{}]*?)\)\s*;" % n, hdr).group(1).strip()
+        f = re.search(r"function\s+%s\s*\(([^)]*)\)" % n, joined).group(1).strip()
+        nc = 0 if c in ("", "void") else c.count(",") + 1
+        nf = 0 if f == "" else f.count(",") + 1
+        assert nc == nf, "%s: %d arguments in the header, %d in mo_mhm_cuda.F90" % (n, nc, nf)
+
+
 def test_no_gpu_means_error_not_fallback():
     import torch
 
