@@ -48,6 +48,39 @@ def test_fortran_module_binds_every_declared_symbol():
         assert nc == nf, "%s: %d arguments in the header, %d in mo_mhm_cuda.F90" % (n, nc, nf)
 
 
+def test_fortran_derived_types_match_header_structs():
+    """every `type, bind(C)` of mo_mhm_cuda.F90 has the header struct's components: same names,
+    same order, same size in bytes"""
+    import re
+
+    src = open(os.path.join(os.path.dirname(_lib.HEADER), "..", "mhm_b200", "fortran", "mo_mhm_cuda.F90")).read()
+    src = re.sub(r"&\s*\n\s*", "", src)
+    kind_bytes = {"c_int8_t": 1, "c_int16_t": 2, "c_int32_t": 4, "c_int": 4, "c_int64_t": 8, "c_double": 8}
+    types = re.findall(r"type, bind\(C\) :: (\w+)\n(.*?)end type", src, flags=re.S)
+    assert len(types) >= 8
+    for name, body in types:
+        comps = []
+        for line in body.splitlines():
+            line = line.split("!")[0]
+            if "::" not in line:
+                continue
+            decl, rest = line.split("::", 1)
+            if "c_ptr" in decl:
+                size = C.sizeof(C.c_void_p)
+            else:
+                size = kind_bytes[re.search(r"\((\w+)\)", decl).group(1)]
+            dim = re.search(r"dimension\((\d+)\)", decl)
+            for c in re.split(r",(?![^(]*\))", rest):
+                c = c.split("=")[0].strip()
+                if not c:
+                    continue
+                own = re.search(r"\((\d+)\)", c)
+                n = int(own.group(1)) if own else int(dim.group(1)) if dim else 1
+                comps.append((re.sub(r"\(.*\)", "", c).lower(), size * n))
+        fields = [(f.lower(), C.sizeof(t)) for f, t in _cstruct.parse_struct(_lib.HEADER, name)]
+        assert comps == fields, "%s differs between mo_mhm_cuda.F90 and the header" % name
+
+
 def test_no_gpu_means_error_not_fallback():
     import torch
 
