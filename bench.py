@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--nx", type=int, default=1180)
     ap.add_argument("--ny", type=int, default=1000)
     ap.add_argument("--members", type=int, default=32, help="ensemble members per GPU")
-    ap.add_argument("--block-hours", type=int, default=96)
+    ap.add_argument("--block-hours", type=int, default=128)
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-routing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
