@@ -33,6 +33,16 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+# The one JSON line goes to the process's original stdout; everything else that writes to file
+# descriptor 1 during the run (NCCL prints its version there) is sent to stderr.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj, flush=True):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -361,7 +371,7 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.finalize()
     if world > 1:
         dist.barrier()
@@ -402,7 +412,7 @@ def run_mpr(args):
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     ms = out["fast"]
-    print(json.dumps({
+    emit(({
         "metric": "MPR L0 cells/s (gamma -> all L1 effective parameters)", "value": prob["nL0"] / (ms * 1e-3),
         "unit": "L0 cells/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "dtype": "f64", "data": "synthetic",
@@ -469,7 +479,7 @@ def run_shard(args):
     if rank == 0:
         n = prob["nCells"]
         sh = run.sub["shard"]
-        print(json.dumps({
+        emit(({
             "metric": "L1 cell-timesteps/s", "value": float(n) * M * T * K / wall, "unit": "cell-timesteps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": wall * 1e3 / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -536,7 +546,7 @@ def run_reference(args):
     v = prob["nCells"] * hours * args.steps / total
     sample = ("%d cells x 1 member x %d hourly steps per step; oracle/ restatement of the reference "
               "(Fortran original not buildable here)" % (prob["nCells"], hours))
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "L1 cell-timesteps/s", "value": v, "unit": "cell-timesteps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
