@@ -192,6 +192,33 @@ int mhm_cuda_get_meteo(mhm_cuda_context *ctx, int32_t iDomain, int32_t var, doub
                        int64_t first_step, int64_t n_steps);
 int mhm_cuda_set_meteo_device(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,
                               const double *dev, int64_t first_step, int64_t n_steps);
+/* ---------------------------------------------------------------------------------
+ * the GPUs of one box, one process (MPI rank) per GPU -- the reference distributes whole domains
+ * over ranks (common/mo_common_read_config.F90:416-437, common/mo_common_MPI_tools.F90:39-69).
+ * The library owns an NCCL communicator: rank 0 calls mhm_cuda_comm_unique_id, the caller carries
+ * the 128 opaque bytes to every rank (MPI_Bcast in the Fortran driver), then every rank calls
+ * mhm_cuda_comm_init.  nranks = 1 needs no NCCL library.  libnccl.so.2 is opened at run time.
+ * --------------------------------------------------------------------------------- */
+#define MHM_CUDA_UNIQUE_ID_BYTES 128
+int mhm_cuda_comm_unique_id(char *id128);
+int mhm_cuda_comm_init(mhm_cuda_context *ctx, int32_t nranks, int32_t rank, const char *id128);
+int mhm_cuda_comm_finalize(mhm_cuda_context *ctx);
+int mhm_cuda_comm_info(mhm_cuda_context *ctx, int32_t *nranks, int32_t *rank, int32_t *nccl_version);
+/* Forcing SHARED by all ranks (ensemble members / calibration parameter sets of ONE domain spread
+ * over the GPUs, BASELINE config 5): like mhm_cuda_set_meteo_async, but every rank copies only its
+ * own 1/nranks of the chunk's meteo steps from host memory -- rows first_row .. first_row+n_rows-1
+ * (0-based, within the chunk) as mhm_cuda_meteo_shared_rows tells; the other rows of `base` are
+ * never read and need not be valid -- and the ranks all-gather the chunk over NVLink on the upload
+ * stream.  Collective: every rank of the communicator must call it with the same var / first_step /
+ * n_steps, in the same order.  is_f32: `base` holds float32 (NetCDF forcing is usually stored so;
+ * mo_read_nc.f90 widens on read): half the host and NVLink bytes, widened to float64 on the device. */
+int mhm_cuda_meteo_shared_rows(int64_t n_steps, int32_t nranks, int32_t rank, int64_t *first_row,
+                               int64_t *n_rows);
+int mhm_cuda_set_meteo_shared(mhm_cuda_context *ctx, int32_t iDomain, int32_t var, const void *base,
+                              int32_t is_f32, int64_t ld, int64_t offset, int64_t first_step,
+                              int64_t n_steps);
+/* host bytes of forcing this process has copied to the device for the domain so far (measurement) */
+int mhm_cuda_meteo_h2d_bytes(mhm_cuda_context *ctx, int32_t iDomain, int64_t *bytes);
 /* L1_pre_weights / L1_temp_weights / L1_pet_weights (nCellsTot, 12, 24); var = PRE/TEMP/PET */
 int mhm_cuda_set_meteo_weights(mhm_cuda_context *ctx, int32_t iDomain, int32_t var,
                                const double *base, int64_t ld, int64_t offset);

@@ -86,6 +86,13 @@ def load():
         "mhm_cuda_set_meteo": [vp, i32, i32, pd, i64, i64, i64, i64],
         "mhm_cuda_set_meteo_async": [vp, i32, i32, pd, i64, i64, i64, i64],
         "mhm_cuda_set_meteo_device": [vp, i32, i32, vp, i64, i64],
+        "mhm_cuda_comm_unique_id": [C.c_char_p],
+        "mhm_cuda_comm_init": [vp, i32, i32, C.c_char_p],
+        "mhm_cuda_comm_finalize": [vp],
+        "mhm_cuda_comm_info": [vp, pi, pi, pi],
+        "mhm_cuda_meteo_shared_rows": [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)],
+        "mhm_cuda_set_meteo_shared": [vp, i32, i32, vp, i32, i64, i64, i64, i64],
+        "mhm_cuda_meteo_h2d_bytes": [vp, i32, C.POINTER(i64)],
         "mhm_cuda_set_meteo_weights": [vp, i32, i32, pd, i64, i64],
         "mhm_cuda_set_time": [vp, i32, C.POINTER(TimeConfig)],
         "mhm_time_indices": [C.POINTER(TimeConfig), i32, i32, i32, i32, C.POINTER(StepIndex)],

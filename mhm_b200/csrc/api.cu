@@ -2,6 +2,7 @@
 // calendar, and the drivers of the fused cell kernel (per-step seam and time blocks).
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <mutex>
 
 #include "context.h"
@@ -68,6 +69,7 @@ static void free_domain(Domain* d) {
     if (d->met_ready[v]) cudaEventDestroy(d->met_ready[v]);
   }
   for (auto& p : d->weights) cudaFree(p);
+  cudaFree(d->met_f32);
   cudaFree(d->runoff_hist);
   cudaFree(d->out_acc);
   cudaFree(d->out_win);
@@ -164,6 +166,7 @@ int mhm_cuda_finalize(mhm_cuda_context* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->domains) free_domain(kv.second);
+  mhm_cuda_comm_finalize(ctx);
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
   for (auto& t : ctx->pending) {
     cudaEventDestroy(t.a);
@@ -187,18 +190,22 @@ int mhm_cuda_register_domain(mhm_cuda_context* ctx, int32_t iDomain, const mhm_d
               "register_domain: nLAI/nLCscenes/nMembers must be >= 1");
   MHM_REQUIRE(cfg->processMatrix && cfg->nProcesses >= 8,
               "register_domain: processMatrix with >= 8 rows required");
+  MHM_REQUIRE(cfg->nLCscenes <= 32767 && cfg->nLAI <= 32767, "register_domain: nLCscenes / nLAI above 32767");
+  // processMatrix(3,1), (5,1), (8,1)
+  const int soil_case = cfg->processMatrix[2], pet_case = cfg->processMatrix[4];
+  MHM_REQUIRE(soil_case >= 1 && soil_case <= 4, "soil moisture processCase %d unsupported", soil_case);
+  MHM_REQUIRE(pet_case >= -1 && pet_case <= 3, "PET processCase %d unsupported", pet_case);
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
-  auto* d = new Domain();
+  // owned until registration succeeded: an early return frees the domain and its device memory
+  std::unique_ptr<Domain, void (*)(Domain*)> own(new Domain(), free_domain);
+  Domain* d = own.get();
   d->id = iDomain;
   d->cfg = *cfg;
   d->processMatrix.assign(cfg->processMatrix, cfg->processMatrix + (size_t)cfg->nProcesses * 3);
   d->cfg.processMatrix = d->processMatrix.data();
-  d->soil_case = d->processMatrix[2];  // processMatrix(3,1)
-  d->pet_case = d->processMatrix[4];   // processMatrix(5,1)
-  d->rout_case = d->processMatrix[7];  // processMatrix(8,1)
-  MHM_REQUIRE(d->soil_case >= 1 && d->soil_case <= 4, "soil moisture processCase %d unsupported",
-              d->soil_case);
-  MHM_REQUIRE(d->pet_case >= -1 && d->pet_case <= 3, "PET processCase %d unsupported", d->pet_case);
+  d->soil_case = soil_case;
+  d->pet_case = pet_case;
+  d->rout_case = d->processMatrix[7];
   const size_t n = (size_t)cfg->nCells, M = (size_t)cfg->nMembers;
   for (int s = 0; s < MHM_S_COUNT; ++s) {
     const size_t sz = M * state_rows(d, s) * n * sizeof(double);
@@ -211,7 +218,7 @@ int mhm_cuda_register_domain(mhm_cuda_context* ctx, int32_t iDomain, const mhm_d
     MHM_CUDA_OK(cudaMemsetAsync(d->F[f], 0, sz, ctx->stream));
   }
   MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  ctx->domains[iDomain] = d;
+  ctx->domains[iDomain] = own.release();
   return 0;
 }
 
@@ -383,6 +390,7 @@ static int meteo_upload(mhm_cuda_context* ctx, Domain* d, int var, const double*
   d->met[var] = d->met_buf[var][nb];
   d->met_first[var] = first_step;
   d->met_n[var] = n_steps;
+  d->met_h2d_bytes += need * sizeof(double);
   return 0;
 }
 
@@ -831,7 +839,7 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
       for (int32_t t = 0; t < nb; ++t) {
         const int32_t tt = tt0 + t0 + t;
         if (out_active(d, tt) && first == nb) first = t;
-        a.out_yid[t] = (int8_t)(tt < d->axis.nTimeSteps ? d->h_idx[(size_t)tt].yId
+        a.out_yid[t] = (int16_t)(tt < d->axis.nTimeSteps ? d->h_idx[(size_t)tt].yId
                                                         : d->h_idx[(size_t)tt - 1].yId);
         if (outputs && out_writes(d, tt)) {
           nb = t + 1;

@@ -72,6 +72,9 @@ struct Domain {
   cudaEvent_t met_ready[MHM_M_COUNT] = {};  // upload finished (copy stream)
   cudaEvent_t met_free[MHM_M_COUNT][2] = {};  // last run reading the buffer finished (main stream)
   bool met_ready_set[MHM_M_COUNT] = {}, met_free_set[MHM_M_COUNT][2] = {};
+  float* met_f32 = nullptr;       // staging of float32-on-the-wire chunks (mhm_cuda_set_meteo_shared)
+  size_t met_f32cap = 0;
+  size_t met_h2d_bytes = 0;       // host bytes this process copied for forcing (measurement)
   double* weights[3] = {};
 
   // time axis
@@ -131,6 +134,9 @@ struct mhm_cuda_context {
   size_t block_bytes = (size_t)24 << 30;  // memory budget of per-block history buffers
   int sm_count = 148;                      // streaming multiprocessors of the device
   bool uniform_calendar = true;            // MHM_CUDA_NO_UNIFORM_CALENDAR (diagnostics) switches it off
+  // the GPUs of one box, one process each (comm.cu): NCCL communicator owned by the library
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
 
   // bracket a kernel launch with events when timing is enabled
   void stat_begin(int which);
@@ -151,4 +157,8 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
 bool routing_is_deferred(const Domain* d);
 bool routing_defer_block(Domain* d, int32_t tt_first, int32_t n_steps, bool fused);
 bool routing_fuse_qout(mhm_cuda_context* ctx, Domain* d, int32_t n_steps, CellArgs* a);
+// comm.cu: one grouped NCCL exchange of doubles; send_counts / recv_counts are per peer rank, the
+// pieces consecutive in `send` / `recv` by ascending rank; enqueued on `st`
+int comm_send_recv(mhm_cuda_context* ctx, const double* send, const size_t* send_counts, double* recv,
+                   const size_t* recv_counts, cudaStream_t st);
 }  // namespace mhm

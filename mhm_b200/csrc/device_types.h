@@ -64,7 +64,7 @@ struct CellArgs {
   int32_t out_first;                  // first step of the launch with tIndex_out > 0
   int32_t out_nslots;                 // slots of out_acc in use
   double* out_acc;
-  int8_t out_yid[kIdxInline];         // land-cover scene the driver holds after each step
+  int16_t out_yid[kIdxInline];        // land-cover scene the driver holds after each step (StepIdx::yId's type)
   // calibration aggregates (mo_mhm_interface_run.f90:745-861) and BFI sums (:630-636): every step
   // t >= out_first adds to the open dataSim column of bit 0 soil moisture, bit 1 evapotranspiration,
   // bit 2 total water storage; bit 3 adds baseflow / total runoff to bfi_acc [2][member][nCells]

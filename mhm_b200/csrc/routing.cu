@@ -130,7 +130,8 @@ struct Routing {
   double *d_length = nullptr, *d_slope = nullptr, *d_fFPimp = nullptr;  // fFPimp [M][nLC][nNodes]
   double ssMax = 0.0, ssMax_global = 0.0;  // ssMax_global: maxval(slope) of the unsharded domain
   int32_t nLC = 1;
-  double TSrout = 0.0;  // case 2/3 [s]
+  double TSrout = 0.0;  // case 2/3 [s]: the members' common value, settled when a block is routed
+  std::vector<double> TSrout_m;  // per member, as given to mrm_cuda_set_c1c2 (0 = not set)
   // inflow series, host (nDays, nInflowTotal) Fortran layout
   std::vector<double> inflowQ;
   int64_t nDays = 0;
@@ -1057,10 +1058,14 @@ static int alloc_zero(double** p, size_t n, cudaStream_t st) {
 
 // make sure every member's C1/C2 belong to land-cover scene yId (case 1: reg_rout is
 // re-evaluated by the reference on every call with the current scene's fFPimp)
-static int ensure_c1c2(mhm_cuda_context* ctx, Routing* rt, int yId, double timestep_rout) {
+static int ensure_c1c2(mhm_cuda_context* ctx, const Domain* d, Routing* rt, int yId, double timestep_rout) {
   if (rt->rout_case != 1 || rt->nNodes <= 1) return 0;
+  // restart run: the reference skips reg_rout (mo_mrm_routing.f90:211 `.not. read_states`) and
+  // routes with the restart file's L11_C1 / L11_C2 -- they must have come through mrm_cuda_set_c1c2
+  // (or mrm_cuda_set_state), whatever mrm_cuda_set_reg_rout was given
+  if (d->cfg.read_states) return 0;
   for (int m = 0; m < rt->M; ++m) {
-    if (rt->param5[(size_t)m].empty()) continue;  // C1/C2 supplied (read_states)
+    if (rt->param5[(size_t)m].empty()) continue;  // C1/C2 supplied
     if (rt->c1c2_yId[(size_t)m] == yId) continue;
     const std::vector<double>& g = rt->param5[(size_t)m];
     const int nl = rt->nLinks;
@@ -1186,7 +1191,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
   rt->lean_ok = getenv("MHM_CUDA_NO_LEAN_ROUTING") == nullptr;
   if (const char* w = getenv("MHM_CUDA_LEAN_PF_WAVES")) rt->pf_waves = (size_t)atoll(w);
   for (const Segment& sg : segs) {
-    if (int rc = ensure_c1c2(ctx, rt, sg.yId, timestep_rout)) return rc;
+    if (int rc = ensure_c1c2(ctx, d, rt, sg.yId, timestep_rout)) return rc;
     ChainArgs ca{};
     ca.ev0 = sg.ev0;
     ca.ev1 = sg.ev1;
@@ -1256,7 +1261,6 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
     MHM_CUDA_OK(cudaGetLastError());
   }
   ctx->stat_end(kStatRouting, launched);
-  (void)d;
   return 0;
 }
 
@@ -1297,6 +1301,20 @@ int routing_run_block(mhm_cuda_context* ctx, Domain* d, int32_t tt_first, int32_
               "routing: time axis changed after mrm_cuda_set_network");
   const int nTstepDay = 24 / d->cfg.timestep_h;
   const int nT = d->axis.nTimeSteps;
+  if (rt->rout_case != 1) {
+    // the members of a domain are routed side by side on one schedule, so they must share the
+    // adaptive routing step mrm_update_param derived for them (mo_mrm_mpr.f90:294-321); checked
+    // here and not in set_c1c2, because every evaluation of a calibration run sets all members anew
+    double ts = 0.0;
+    for (int m = 0; m < rt->M; ++m) {
+      const double v = rt->TSrout_m[(size_t)m];
+      MHM_REQUIRE(v > 0.0, "routing: mrm_cuda_set_c1c2 has not been called for member %d", m);
+      MHM_REQUIRE(ts == 0.0 || ts == v,
+                  "routing: members of one domain must share L11_TSrout (member %d: %g, others: %g)", m, v, ts);
+      ts = v;
+    }
+    rt->TSrout = ts;
+  }
   if (rt->inflow_acc.size() != (size_t)rt->nInflowTotal) rt->inflow_acc.assign((size_t)rt->nInflowTotal, 0.0);
   auto inflow_at = [&](int g, int day) -> double {  // InflowGauge%Q(day, g), 1-based day
     if (rt->inflowQ.empty()) return 0.0;
@@ -1567,6 +1585,7 @@ int mrm_cuda_set_network(mhm_cuda_context* ctx, int32_t iDomain, const mrm_netwo
   MHM_CUDA_OK(cudaStreamSynchronize(st));
   rt->param5.assign(M, {});
   rt->c1c2_yId.assign(M, -1);
+  rt->TSrout_m.assign(M, 0.0);
   d->rt = rt;
   return 0;
 }
@@ -1613,8 +1632,6 @@ int mrm_cuda_set_c1c2(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, co
   MHM_REQUIRE(rt, "set_c1c2: no network set");
   MHM_REQUIRE(member >= 0 && member < rt->M && C1 && C2, "set_c1c2: bad arguments");
   MHM_REQUIRE(rt->rout_case == 1 || TSrout > 0.0, "set_c1c2: L11_TSrout must be > 0 for case 2/3");
-  MHM_REQUIRE(rt->rout_case == 1 || rt->TSrout == 0.0 || rt->TSrout == TSrout,
-              "set_c1c2: members of one domain must share L11_TSrout (%g vs %g)", rt->TSrout, TSrout);
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
   const size_t nn = (size_t)rt->nNodes;
   MHM_CUDA_OK(cudaMemcpyAsync(rt->C1 + (size_t)member * nn, C1, nn * sizeof(double),
@@ -1623,7 +1640,10 @@ int mrm_cuda_set_c1c2(mhm_cuda_context* ctx, int32_t iDomain, int32_t member, co
                               cudaMemcpyHostToDevice, ctx->stream));
   MHM_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   rt->param5[(size_t)member].clear();
-  if (rt->rout_case != 1) rt->TSrout = TSrout;
+  if (rt->rout_case != 1) {
+    rt->TSrout_m[(size_t)member] = TSrout;
+    rt->TSrout = TSrout;  // settled (and checked across members) when the next block is routed
+  }
   return 0;
 }
 

@@ -9,10 +9,11 @@ METEO_BY_CASE = {-1: ["pet"], 0: ["pet"], 1: ["tmin", "tmax"], 2: ["netrad"],
                  3: ["netrad", "absvappress", "windspeed"]}
 
 
-def setup_domain(ctx, iDomain, prob, nMembers=1, member_params=None, upload_forcing=True):
+def setup_domain(ctx, iDomain, prob, nMembers=1, member_params=None, upload_forcing=True,
+                 read_states=False):
     n, nH, nLAI, nLC = prob["nCells"], prob["nH"], prob["nLAI"], prob["nLC"]
     dom = ctx.register_domain(iDomain, n, nH, nLAI, nLC, prob["processMatrix"],
-                              timestep_h=prob["timestep_h"], read_states=False, nMembers=nMembers)
+                              timestep_h=prob["timestep_h"], read_states=read_states, nMembers=nMembers)
     dom.set_meteo_config(prob["pet_case"], prob["nTstepForcingDay"], prob["hourly"],
                          prob["read_weights"], synth.FNIGHT_PREC, synth.FNIGHT_PET,
                          synth.FNIGHT_TEMP, synth.EVAP_COEFF)

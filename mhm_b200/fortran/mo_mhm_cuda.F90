@@ -191,6 +191,48 @@ module mo_mhm_cuda
       integer(c_int32_t), value :: iDomain, var
       integer(c_int64_t), value :: ld, offset, first_step, n_steps
     end function
+    !> rank 0 creates the 128-byte id; broadcast it (MPI_Bcast of 128 characters), then every rank
+    !! calls mhm_cuda_comm_init(ctx, nproc, rank, id)
+    integer(c_int) function mhm_cuda_comm_unique_id(id128) bind(C, name = 'mhm_cuda_comm_unique_id')
+      import
+      character(kind = c_char), dimension(128), intent(out) :: id128
+    end function
+    integer(c_int) function mhm_cuda_comm_init(ctx, nranks, rank, id128) bind(C, name = 'mhm_cuda_comm_init')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: nranks, rank
+      character(kind = c_char), dimension(128), intent(in) :: id128
+    end function
+    integer(c_int) function mhm_cuda_comm_finalize(ctx) bind(C, name = 'mhm_cuda_comm_finalize')
+      import
+      type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function mhm_cuda_comm_info(ctx, nranks, rank, nccl_version) bind(C, name = 'mhm_cuda_comm_info')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), intent(out) :: nranks, rank, nccl_version
+    end function
+    integer(c_int) function mhm_cuda_meteo_shared_rows(n_steps, nranks, rank, first_row, n_rows) &
+        bind(C, name = 'mhm_cuda_meteo_shared_rows')
+      import
+      integer(c_int64_t), value :: n_steps
+      integer(c_int32_t), value :: nranks, rank
+      integer(c_int64_t), intent(out) :: first_row, n_rows
+    end function
+    !> forcing shared by all ranks: each rank uploads 1/nranks of the chunk, NCCL all-gather
+    integer(c_int) function mhm_cuda_set_meteo_shared(ctx, iDomain, var, base, is_f32, ld, offset, first_step, &
+        n_steps) bind(C, name = 'mhm_cuda_set_meteo_shared')
+      import
+      type(c_ptr), value :: ctx, base
+      integer(c_int32_t), value :: iDomain, var, is_f32
+      integer(c_int64_t), value :: ld, offset, first_step, n_steps
+    end function
+    integer(c_int) function mhm_cuda_meteo_h2d_bytes(ctx, iDomain, bytes) bind(C, name = 'mhm_cuda_meteo_h2d_bytes')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      integer(c_int64_t), intent(out) :: bytes
+    end function
     integer(c_int) function mhm_cuda_set_meteo_weights(ctx, iDomain, var, base, ld, offset) &
         bind(C, name = 'mhm_cuda_set_meteo_weights')
       import
@@ -571,7 +613,8 @@ module mo_mhm_cuda
             mhm_cuda_get_runoff_history, mhm_cuda_event_record, mhm_cuda_event_elapsed_ms, &
             mhm_cuda_kernel_stats, mhm_cuda_kernel_stats_reset, mhm_cuda_measure_dfma_peak, &
             mpr_cuda_grid_destroy, mpr_cuda_upscale_geometric_mean, mhm_grid_init_lowres_level, &
-            mhm_time_indices
+            mhm_time_indices, mhm_cuda_comm_unique_id, mhm_cuda_comm_init, mhm_cuda_comm_finalize, &
+            mhm_cuda_comm_info, mhm_cuda_meteo_shared_rows, mhm_cuda_set_meteo_shared, mhm_cuda_meteo_h2d_bytes
   public :: mpr_l0_inputs, mpr_soil_db, mhm_optisim_config
 
 contains

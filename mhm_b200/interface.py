@@ -123,6 +123,14 @@ def routing_order(nNodes, fromN, toN, nLinks=None):
     return rOrder, netPerm
 
 
+def shared_rows(n_steps, nranks, rank):
+    """(first_row, n_rows) of a shared forcing chunk that `rank` copies from its host (host only)"""
+    L = _lib.load()
+    a, b = C.c_int64(), C.c_int64()
+    check(L.mhm_cuda_meteo_shared_rows(n_steps, nranks, rank, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 def time_indices(time_cfg, timestep_h, nTstepForcingDay, tt_first, n_steps):
     """per-step calendar indices as the library derives them (host only)"""
     L = _lib.load()
@@ -198,6 +206,27 @@ class Context:
         check(self.L.mhm_cuda_measure_dfma_peak(self.h, C.byref(v)))
         return v.value
 
+    # ---- the GPUs of one box (comm.cu) ---------------------------------------------------
+    def comm_init(self, dist=None):
+        """library-owned NCCL communicator over the ranks of torch.distributed `dist` (the unique id
+        travels through dist.broadcast_object_list, like MPI_Bcast in the Fortran driver)"""
+        if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+            check(self.L.mhm_cuda_comm_init(self.h, 1, 0, None))
+            return 1, 0
+        world, rank = dist.get_world_size(), dist.get_rank()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            check(self.L.mhm_cuda_comm_unique_id(buf))
+        box = [buf.raw]
+        dist.broadcast_object_list(box, src=0)
+        check(self.L.mhm_cuda_comm_init(self.h, world, rank, box[0]))
+        return world, rank
+
+    def comm_info(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.L.mhm_cuda_comm_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"nranks": a.value, "rank": b.value, "nccl_version": c.value}
+
     def finalize(self):
         if self.h:
             check(self.L.mhm_cuda_finalize(self.h))
@@ -220,13 +249,23 @@ class Domain:
         self.nTimeSteps = 0
 
     # ---- parameters / states / fluxes ------------------------------------------------
-    def set_param(self, name, arr, member=0):
+    # `ld` / `offset`: the array is the module-global one of ALL domains (leading dimension
+    # nCellsTot, this domain's first cell at offset = s1 - 1), like the sections
+    # L1_fSealed(s1:e1, 1, yId) the Fortran driver passes (mo_mhm_interface_run.f90:394-457)
+    def _glob(self, arr, ld, offset, n=None):
+        n = self.nCells if n is None else n
+        ld = arr.shape[-1] if ld is None else ld
+        assert arr.shape[-1] == ld and offset >= 0 and offset + n <= ld, (arr.shape, ld, offset, n)
+        return ld
+
+    def set_param(self, name, arr, member=0, ld=None, offset=0):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         if arr.ndim == 1:
             arr = arr.reshape(1, 1, -1)
-        dim3, dim2, n = arr.shape
+        dim3, dim2, _ = arr.shape
+        ld = self._glob(arr, ld, offset)
         check(self.L.mhm_cuda_set_param(self.h, self.id, member, PARAM[PARAM_NAMES[name]], _pd(arr),
-                                        n, 0, dim2, dim3))
+                                        ld, offset, dim2, dim3))
 
     def get_param(self, name, dim2, dim3, member=0):
         out = np.zeros((dim3, dim2, self.nCells))
@@ -234,23 +273,43 @@ class Domain:
                                         self.nCells, 0, dim2, dim3))
         return out
 
-    def set_state(self, name, arr, member=0):
+    def set_state(self, name, arr, member=0, ld=None, offset=0):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
+        ld = self._glob(arr, ld, offset)
         check(self.L.mhm_cuda_set_state(self.h, self.id, member, STATE[STATE_NAMES[name]], _pd(arr),
-                                        self.nCells, 0))
+                                        ld, offset))
 
-    def get_state(self, name, member=0):
-        out = np.zeros((self.nH, self.nCells)) if name == "L1_soilMoist" else np.zeros(self.nCells)
+    def get_state(self, name, member=0, out=None, offset=0):
+        if out is None:
+            out = np.zeros((self.nH, self.nCells)) if name == "L1_soilMoist" else np.zeros(self.nCells)
+        ld = self._glob(out, None, offset)
         check(self.L.mhm_cuda_get_state(self.h, self.id, member, STATE[STATE_NAMES[name]], _pd(out),
-                                        self.nCells, 0))
+                                        ld, offset))
         return out
 
-    def get_flux(self, name, member=0):
+    def get_flux(self, name, member=0, out=None, offset=0):
         two = name in ("L1_aETSoil", "L1_infilSoil")
-        out = np.zeros((self.nH, self.nCells)) if two else np.zeros(self.nCells)
+        if out is None:
+            out = np.zeros((self.nH, self.nCells)) if two else np.zeros(self.nCells)
+        ld = self._glob(out, None, offset)
         check(self.L.mhm_cuda_get_flux(self.h, self.id, member, FLUX[FLUX_NAMES[name]], _pd(out),
-                                       self.nCells, 0))
+                                       ld, offset))
         return out
+
+    # host coherence (pybind get%L1_variable, restart writers): bind the module globals once,
+    # sync_to_host then refreshes this domain's section of every bound array (member 0)
+    def bind_host_state(self, name, arr, offset=0):
+        assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
+        ld = self._glob(arr, None, offset)
+        check(self.L.mhm_cuda_bind_host_state(self.h, self.id, STATE[STATE_NAMES[name]], _pd(arr), ld, offset))
+
+    def bind_host_flux(self, name, arr, offset=0):
+        assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
+        ld = self._glob(arr, None, offset)
+        check(self.L.mhm_cuda_bind_host_flux(self.h, self.id, FLUX[FLUX_NAMES[name]], _pd(arr), ld, offset))
+
+    def sync_to_host(self):
+        check(self.L.mhm_cuda_sync_to_host(self.h, self.id))
 
     def get_variable(self, name, member=0):
         """pybind get%L1_variable equivalent"""
@@ -282,11 +341,12 @@ class Domain:
             mc.evap_coeff[m] = evap_coeff[m]
         check(self.L.mhm_cuda_set_meteo_config(self.h, self.id, C.byref(mc)))
 
-    def set_meteo(self, var, arr, first_step=1):
+    def set_meteo(self, var, arr, first_step=1, ld=None, offset=0):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
-        assert arr.ndim == 2 and arr.shape[1] == self.nCells
+        assert arr.ndim == 2
+        ld = self._glob(arr, ld, offset)
         check(self.L.mhm_cuda_set_meteo(self.h, self.id, METEO[METEO_NAMES[var]], _pd(arr),
-                                        self.nCells, 0, first_step, arr.shape[0]))
+                                        ld, offset, first_step, arr.shape[0]))
 
     def set_meteo_l2(self, var, data2, mask2, cellsize2, mask1, cellsize1, first_step=1):
         """level-2 chunk, numpy (n_steps, ncols2, nrows2) float64 or float32 == Fortran
@@ -307,22 +367,34 @@ class Domain:
                                         first_step, n_steps))
         return out
 
-    def set_meteo_host_ptr(self, var, ptr, ld, first_step, n_steps, async_copy=False):
+    def set_meteo_host_ptr(self, var, ptr, ld, first_step, n_steps, async_copy=False, offset=0):
         """upload from a raw host pointer (e.g. pinned torch tensor .data_ptr()); async_copy:
         return before the copy has finished (double buffered, own stream)"""
         fn = self.L.mhm_cuda_set_meteo_async if async_copy else self.L.mhm_cuda_set_meteo
-        check(fn(self.h, self.id, METEO[METEO_NAMES[var]], C.cast(ptr, C.POINTER(C.c_double)), ld, 0,
+        check(fn(self.h, self.id, METEO[METEO_NAMES[var]], C.cast(ptr, C.POINTER(C.c_double)), ld, offset,
                  first_step, n_steps))
+
+    def set_meteo_shared(self, var, ptr, ld, first_step, n_steps, is_f32=False, offset=0):
+        """forcing shared by all ranks of the context's communicator: this rank copies only its rows
+        (shared_rows) from the host pointer, the rest arrives by NCCL all-gather"""
+        check(self.L.mhm_cuda_set_meteo_shared(self.h, self.id, METEO[METEO_NAMES[var]], C.c_void_p(ptr),
+                                               int(is_f32), ld, offset, first_step, n_steps))
+
+    def meteo_h2d_bytes(self):
+        b = C.c_int64()
+        check(self.L.mhm_cuda_meteo_h2d_bytes(self.h, self.id, C.byref(b)))
+        return b.value
 
     def set_meteo_device(self, var, dev_ptr, first_step, n_steps):
         check(self.L.mhm_cuda_set_meteo_device(self.h, self.id, METEO[METEO_NAMES[var]],
                                                C.c_void_p(dev_ptr), first_step, n_steps))
 
-    def set_meteo_weights(self, var, arr):
+    def set_meteo_weights(self, var, arr, ld=None, offset=0):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
-        assert arr.shape == (24, 12, self.nCells)
+        assert arr.shape[:2] == (24, 12)
+        ld = self._glob(arr, ld, offset)
         check(self.L.mhm_cuda_set_meteo_weights(self.h, self.id, METEO[METEO_NAMES[var]], _pd(arr),
-                                                self.nCells, 0))
+                                                ld, offset))
 
     def set_time(self, time_cfg):
         tc, keep = _time_config(time_cfg)
@@ -447,16 +519,20 @@ class Domain:
         Q = np.ascontiguousarray(Q, dtype=np.float64)  # numpy (nInflowTotal, nDays)
         check(self.L.mrm_cuda_set_inflow(self.h, self.id, _pd(Q), Q.shape[1]))
 
-    def set_routing_state(self, name, arr, member=0):
+    def set_routing_state(self, name, arr, member=0, offset=0):
+        """L11_* module globals: (nNodesTot) or (nNodesTot, 2); offset = s11 - 1"""
         arr = np.ascontiguousarray(arr, dtype=np.float64)
+        ld = self._glob(arr, None, offset, self.nNodes)
         check(self.L.mrm_cuda_set_state(self.h, self.id, member, MRM_STATE[MRM_STATE_NAMES[name]],
-                                        _pd(arr), self.nNodes, 0))
+                                        _pd(arr), ld, offset))
 
-    def get_routing_state(self, name, member=0):
+    def get_routing_state(self, name, member=0, out=None, offset=0):
         two = name in ("L11_qTIN", "L11_qTR")
-        out = np.zeros((2, self.nNodes)) if two else np.zeros(self.nNodes)
+        if out is None:
+            out = np.zeros((2, self.nNodes)) if two else np.zeros(self.nNodes)
+        ld = self._glob(out, None, offset, self.nNodes)
         check(self.L.mrm_cuda_get_state(self.h, self.id, member, MRM_STATE[MRM_STATE_NAMES[name]],
-                                        _pd(out), self.nNodes, 0))
+                                        _pd(out), ld, offset))
         return out
 
     def route(self, tt, yId, timestep_rout, tsRoutFactorIn, RunToRout=None, InflowDischarge=None):

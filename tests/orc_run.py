@@ -41,7 +41,7 @@ class OracleRun:
     """Owns the numpy buffers behind an orc_domain and exposes results by reference name."""
 
     def __init__(self, prob, params=None, history=False, num_threads=1, outputs=None, max_windows=64,
-                 optisim=None, bfi=False, cell_area=None):
+                 optisim=None, bfi=False, cell_area=None, read_states=False):
         """outputs = (outputFlxState[21], timeStep_model_outputs) switches the gridded output
         accumulation on; results in self.out_windows() after run().
         optisim = {"sm": (timeStepInput, nTime, nSoilHorizons_sm_input), "et": (timeStepInput, nTime),
@@ -53,7 +53,7 @@ class OracleRun:
         n, nH = prob["nCells"], prob["nH"]
         d.nCells, d.nH, d.nLAI, d.nLC = n, nH, prob["nLAI"], prob["nLC"]
         d.pc_soil, d.pc_pet = prob["soil_case"], prob["pet_case"]
-        d.read_states = 0
+        d.read_states = int(read_states)  # mo_mhm.f90:448-450, mo_mrm_routing.f90:211
         d.timestep_h = prob["timestep_h"]
         d.nTstepDay = 24 // prob["timestep_h"]
         t = prob["time"]
