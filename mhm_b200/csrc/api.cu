@@ -875,7 +875,9 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
     // of a launch share yId / iLAI / month and read consecutive meteo rows; a launch ends where
     // the calendar turns (about once a month)
     a.uniform_calendar = 0;
-    if (block_mode && ctx->uniform_calendar && !a.out_mask && !a.agg_mask && a.is_hourly && a.pet_case <= 0) {
+    // (the uniform kernels index a launch's forcing rows with 32 bits)
+    if (block_mode && ctx->uniform_calendar && !a.out_mask && !a.agg_mask && a.is_hourly && a.pet_case <= 0 &&
+        (uint64_t)kIdxInline * (uint64_t)a.nCells < ((uint64_t)1 << 32)) {
       const StepIdx& f = idx[t0];
       int32_t t = 1;
       for (; t < nb; ++t) {

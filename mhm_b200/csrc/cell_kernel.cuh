@@ -44,6 +44,12 @@ namespace mhm {
 #ifndef MHM_CELL_PIPELINE
 #define MHM_CELL_PIPELINE 1  // uniform-calendar launches: stage A of step t+1 beside stage B of step t
 #endif
+#ifndef MHM_CELL_PIPE3
+#define MHM_CELL_PIPE3 0  // uniform-calendar launches: three steps in flight (0: two; measured 10 % faster on B200)
+#endif
+#ifndef MHM_POW_COMPACT
+#define MHM_POW_COMPACT 1  // infiltration powers of a warp compacted through shared memory (0: per lane)
+#endif
 #ifndef MHM_CELL_MIN_BLOCKS
 #define MHM_CELL_MIN_BLOCKS 4
 #endif
@@ -158,8 +164,12 @@ __device__ __forceinline__ auto& pick_ref(A& a, B& b) {
   if constexpr (FIRST) return a;
   else return b;
 }
-// fast build, up to 2 soil horizons (43 KB of shared memory per CTA): parameters in shared
-// memory, 84 registers, 5 CTAs/SM; otherwise in registers, 128 registers, 4 CTAs/SM
+// fast build, up to 2 soil horizons: parameters in shared memory (specialised variants: 15 pairs,
+// the 4 read most often in registers -- 96 registers, 29 KB of shared memory, 5 CTAs/SM; measured
+// on B200 in cell-steps/s: all pairs in shared memory at 80 registers / 6 CTAs 6.68e10, 4 pairs in
+// registers at 96 / 5 CTAs 6.93e10, 12 pairs at 128 / 4 CTAs 6.73e10, all 15 at 128 / 4 6.35e10: the
+// kernel sits where the shared-memory data pipe (98 % busy with every pair in shared memory) and
+// the latency the resident warps can hide meet); otherwise in registers, 128 registers, 4 CTAs/SM
 template <int NH>
 struct ParamPlace {
   static constexpr bool shared = MHM_FAST && MHM_PARAMS_SMEM && NH <= 2;
@@ -185,6 +195,7 @@ struct FluxCapture {
 
 template <bool EMIT, bool OUT = false>
 struct FluxEmitter {
+  static constexpr bool kEmit = EMIT, kOut = OUT;
   double* const* F;
   size_t mc, n, mh;  // member*n + cell; nCells; (member*NH)*n + cell
   bool on;
@@ -618,12 +629,101 @@ __device__ __forceinline__ double cascade_step(const PARAMS& p, CellStates<NH>& 
 }
 
 #if MHM_FAST
-// Select form of cascade_step for the specialised fast variants: the same arithmetic written as
-// straight-line code with selects instead of branches (both sides of every small `if` are a
-// couple of operations and free of side effects), so that the independent parts of the water
-// balance (canopy / snow / sealed store / soil horizons / reservoirs) overlap in the pipeline
-// instead of being serialised by branch reconvergence.  Every value equals the branch form's
-// (a discarded side may be inf/NaN, never the selected one); the powers keep warp-uniform skips.
+// (a < b) ? x : y and friends as setp + selp: written in PTX because the compiler recognises
+// `a < b ? a : b` as fmin / fmax, whose sm_100 expansion (DSETP.MIN + NaN fix-up) costs six
+// instructions instead of three.  NaN compares false, like in the C expression.
+__device__ __forceinline__ double sel_lt(double a, double b, double x, double y) {
+  double r;
+  asm("{\n\t.reg .pred q;\n\tsetp.lt.f64 q, %1, %2;\n\tselp.f64 %0, %3, %4, q;\n\t}" : "=d"(r) : "d"(a), "d"(b), "d"(x), "d"(y));
+  return r;
+}
+__device__ __forceinline__ double sel_gt(double a, double b, double x, double y) {
+  double r;
+  asm("{\n\t.reg .pred q;\n\tsetp.gt.f64 q, %1, %2;\n\tselp.f64 %0, %3, %4, q;\n\t}" : "=d"(r) : "d"(a), "d"(b), "d"(x), "d"(y));
+  return r;
+}
+__device__ __forceinline__ double min_sel(double a, double b) { return sel_lt(a, b, a, b); }  // NaN a -> b
+__device__ __forceinline__ double pos_part(double a) { return sel_gt(a, 0.0, a, 0.0); }       // NaN -> 0
+#endif
+
+#if MHM_FAST
+// ---- select form of the cascade for the specialised fast variants ------------------------------
+// The same water balance as cascade_step, written as straight-line code for the instruction issue
+// port: the fused kernel issues ~3 instructions per fp64 instruction, so every select pair, every
+// address computation and every parameter load counts.  Three means:
+//  * exact floating-point identities instead of select pairs.  x - x = +0, x +- 0 = x and
+//    a - (c - b) = a + (b - c) hold bit for bit, so "the rest" of a min() is one subtraction
+//    (throughfall = aux - min(aux, maxInter); rain = throughfall - snow; unsat = us - min(us, perc) ...)
+//    and the masked sums of the reference become plain sums of terms that are exactly zero;
+//  * conditions that can only be false for a vanishing value are dropped: sat_storage > 0
+//    (k2 * 0 = 0, 0 - 0 = 0), snow_pack > 0 (min(pot, 0) = 0), the positive-part mask of the aET
+//    sum (aET >= 0).  Precondition of the fast mode: states and fluxes of the model are not
+//    negative (the model keeps them so itself; strict mode is literal and has no precondition);
+//  * parameters live in shared memory as PAIRS that are used together: one 128-bit load each.
+// Values: identical to the branch form except where a reciprocal is hoisted or FMA-contracted
+// differently (<= a few ulp per step; tests hold fast mode to 1e-9 against the oracle).
+//
+// Feddes and Jarvis share the code: both reduce the root water uptake to
+//   aET_h = max(0, (pet_h * fRoots_h) * min(1, (sm_h - WP_h) * inv_range_h))
+// with inv_range = 1 / (FC - WP) (Feddes, mo_soil_moisture.f90:353-361: sm >= FC <=> factor >= 1)
+// or 1 / ((SAT - WP) * jarvis_c1) (Jarvis, :431-444: theta >= c1 <=> factor >= 1).
+// Pair ids, ordered by how much shared-memory traffic a register copy saves: the first
+// PairStore::kRegPairs ids live in registers, the rest in shared memory (the kernel is bound by the
+// shared-memory data pipe: ~110 wavefronts per warp-step when every pair is re-read from there).
+// Horizon h's pairs: pid_sat(h) first (read twice per step), the others at the end.
+template <int NH>
+struct PairIds {
+  static constexpr int kSat0 = 0;             // SAT, 1 / SAT                       x NH
+  static constexpr int kSeal2 = NH;           // fSealed, 1 - fSealed               (stage A and runoff)
+  static constexpr int kDdBase = NH + 1;      // ddmax * c2TSTu, c2TSTu / kBaseFlow  (snow; baseflow)
+  static constexpr int kPetTthr = NH + 2;     // petFac [iLAI, yId], tempThresh [yId]
+  static constexpr int kMaxInter = NH + 3;    // maxInter, 1 / maxInter (0 when maxInter <= eps: no canopy evaporation)
+  static constexpr int kDd = NH + 4;          // ddnoprec * c2TSTu, ddinc
+  static constexpr int kSeal = NH + 5;        // sealedThr, 1 / sealedThr (+inf when sealedThr <= eps: everything evaporates)
+  static constexpr int kUnsat = NH + 6;       // unsatThr, c2TSTu / kFastFlow
+  static constexpr int kSlow = NH + 7;        // c2TSTu / kSlowFlow, 1 + alpha
+  static constexpr int kPerc = NH + 8;        // c2TSTu / kPerco, karstLoss
+  static constexpr int kExpWp0 = NH + 9;      // EXPN, WP                           x NH
+  static constexpr int kRoot0 = 2 * NH + 9;   // fRoots, inv_range (see above)      x NH
+  static constexpr int kCount = 3 * NH + 9;
+};
+#ifndef MHM_PARAM_REG_PAIRS
+#define MHM_PARAM_REG_PAIRS 4  // pairs kept in registers when the rest is in shared memory (see ParamPlace)
+#endif
+// SHARED_STORE: pairs >= kRegPairs in shared memory, one conflict-free 16-byte column per thread;
+// otherwise everything in registers (more than two horizons)
+template <int NH, bool SHARED_STORE>
+struct PairStore {
+  static constexpr bool kShared = SHARED_STORE;
+  static constexpr int kRegPairs = SHARED_STORE ? (MHM_PARAM_REG_PAIRS < PairIds<NH>::kCount ? MHM_PARAM_REG_PAIRS
+                                                                                              : PairIds<NH>::kCount)
+                                                : PairIds<NH>::kCount;
+  static constexpr int kSmemPairs = PairIds<NH>::kCount - kRegPairs;
+  struct Smem {
+    double2 q[kSmemPairs > 0 ? kSmemPairs : 1][kCellThreads];
+  };
+  double2 r[kRegPairs > 0 ? kRegPairs : 1];
+  Smem* sm;
+  __device__ __forceinline__ double2 get(int k) const { return k < kRegPairs ? r[k] : sm->q[k - kRegPairs][threadIdx.x]; }
+  // a pair of another thread's column (shared-memory pairs only)
+  __device__ __forceinline__ double2 get_of(int k, unsigned tid) const { return sm->q[k - kRegPairs][tid]; }
+  __device__ __forceinline__ void set(int k, double x, double y) {
+    if (k < kRegPairs) r[k] = make_double2(x, y);
+    else sm->q[k - kRegPairs][threadIdx.x] = make_double2(x, y);
+  }
+  __device__ __forceinline__ void setx(int k, double x) {
+    if (k < kRegPairs) r[k].x = x;
+    else sm->q[k - kRegPairs][threadIdx.x].x = x;
+  }
+  __device__ __forceinline__ void sety(int k, double y) {
+    if (k < kRegPairs) r[k].y = y;
+    else sm->q[k - kRegPairs][threadIdx.x].y = y;
+  }
+};
+#define PID PairIds<NH>
+#define P2(k_) p.get(PID::k_)
+#define PH2(k_, h_) p.get(PID::k_ + (h_))
+
 // What stage A (canopy, snow, sealed store: everything that needs the step's forcing) hands to
 // stage B (soil horizons, unsaturated and saturated zone).  Stage A touches only the states
 // inter / snowpack / sealed, stage B only soil moisture / unsat / sat, so stage A of step t+1
@@ -631,45 +731,34 @@ __device__ __forceinline__ double cascade_step(const PARAMS& p, CellStates<NH>& 
 struct StageA {
   double prec_effect, pet_left, runoff_sealed;  // pet_left = pet - aet_canopy
 };
-template <int NH, int VARIANT, bool EMIT, bool STRAIGHT, class PARAMS, class EM>
-__device__ __forceinline__ StageA cascade_stage_a_sel(const PARAMS& p, CellStates<NH>& s,
-                                                      const double pet, const double temperature,
-                                                      const double prec, const double inv_evap_coeff,
-                                                      const EM& emit) {
-  // ---- canopy_interc ----
+template <int NH, bool EMIT, class PARAMS, class EM>
+__device__ __forceinline__ StageA cascade_stage_a_sel(const PARAMS& p, CellStates<NH>& s, const double pet,
+                                                      const double temperature, const double prec,
+                                                      const double inv_evap_coeff, const EM& emit) {
+  // ---- canopy_interc, mo_canopy_interc.f90:105-131 ----
+  const double2 mi = P2(kMaxInter);
   const double aux = s.inter + prec;
-  const bool over = aux >= PX(maxInter);
-  const double throughfall = over ? aux - PX(maxInter) : 0.0;
-  const double ic0 = over ? PX(maxInter) : aux;
-  const double x = ic0 * PX(inv_maxInter);
-  const bool has = (PX(maxInter) > kEps) && (x != 0.0);
-  double ev = 0.0;
-  if (STRAIGHT) {  // no warp-uniform skip, no range branch: one basic block
-    double pw = fm::pow23_sel(has ? x : 1.0);
-#if defined(__CUDA_ARCH__)
-    asm volatile("" : "+d"(pw));  // keeps the compiler from turning the select below into a branch around the power
-#endif
-    ev = has ? pet * pw : 0.0;
-  } else if (__any_sync(0xffffffffu, has)) {
-    ev = has ? pet * fm::pow23_pos(has ? x : 1.0) : 0.0;
-  }
-  ev = ev < 0.0 ? 0.0 : ev;
-  const bool more_c = ic0 > ev;
-  const double aet_canopy = more_c ? ev : ic0;
-  s.inter = more_c ? ic0 - ev : 0.0;
+  const double ic0 = min_sel(aux, mi.x);
+  const double throughfall = aux - ic0;          // aux - maxInter, or exactly 0
+  const double evr = pet * fm::pow23_nz(ic0 * mi.y);  // NaN for an empty canopy
+  const double ev = pos_part(evr);               // NaN, negative -> 0 (:118-121)
+  const double aet_canopy = min_sel(ev, ic0);
+  s.inter = ic0 - aet_canopy;                    // ic0 - ev, or exactly 0
   emit(MHM_F_THROUGHFALL, throughfall);
   emit(MHM_F_AETCANOPY, aet_canopy);
 
-  // ---- snow_accum_melt ----
-  const bool warm = temperature > PX(tthr);
-  const double snow = warm ? 0.0 : throughfall, rain = warm ? throughfall : 0.0;
-  const double dd = (prec <= PX(ddthr)) ? PX(ddnop_c) + PX(ddinc) * prec : PX(ddmax_c);
-  const double pot = dd * (temperature - PX(tthr));
-  const bool pack = s.snowpack > 0.0, all = pot > s.snowpack;
-  const double melt_w = pack ? (all ? s.snowpack : pot) : 0.0;
-  const double pack_w = pack ? (all ? 0.0 : s.snowpack - pot) : 0.0;
+  // ---- snow_accum_melt, mo_snow_accum_melt.f90:117-156 ----
+  const double2 pt = P2(kPetTthr), d2 = P2(kDd);
+  const bool warm = temperature > pt.y;
+  const double rain = warm ? throughfall : 0.0;
+  const double snow = throughfall - rain;        // exactly throughfall or 0
+  // min(ddnoprec + ddinc * prec, ddmax): the reference's test prec <= (ddmax - ddnoprec) / ddinc
+  // (:127) up to the rounding of that quotient
+  const double dd = min_sel(d2.x + d2.y * prec, P2(kDdBase).x);
+  const double pot = dd * (temperature - pt.y);
+  const double melt_w = sel_gt(pot, s.snowpack, s.snowpack, pot);  // snow_pack = 0 gives melt = 0
   const double melt = warm ? melt_w : 0.0;
-  s.snowpack = warm ? pack_w : s.snowpack + snow;
+  s.snowpack = s.snowpack + (snow - melt);       // one of the two terms is exactly 0
   const double prec_effect = melt + rain;
   emit(MHM_F_SNOW, snow);
   emit(MHM_F_RAIN, rain);
@@ -677,159 +766,245 @@ __device__ __forceinline__ StageA cascade_stage_a_sel(const PARAMS& p, CellState
   emit(MHM_F_DEGDAY, dd);
   emit(MHM_F_PREEFFECT, prec_effect);
 
-  // ---- sealed store ----
-  const bool sealed_on = PX(fSealed) > 0.0;
+  // ---- sealed store, mo_soil_moisture.f90:179-215 ----
+  const double2 se = P2(kSeal), fs = P2(kSeal2);
+  const bool sealed_on = fs.x > 0.0;
   const double tmp_s = s.sealed + prec_effect;
-  const bool spill = tmp_s > PX(sealedThr);
-  const double rs_on = spill ? tmp_s - PX(sealedThr) : 0.0;
-  const double st0 = spill ? PX(sealedThr) : tmp_s;
-  double ae = (pet * inv_evap_coeff - aet_canopy) * (st0 * PX(inv_sealedThr));
-  ae = ae < 0.0 ? 0.0 : ae;
-  ae = (PX(sealedThr) > kEps) ? ae : DBL_MAX;
-  const bool more_s = st0 > ae;
-  const double aet_sealed = sealed_on ? (more_s ? ae : st0) : 0.0;
-  const double runoff_sealed = sealed_on ? rs_on : 0.0;
-  s.sealed = sealed_on ? (more_s ? st0 - ae : 0.0) : s.sealed;
-  emit(MHM_F_RUNOFFSEAL, runoff_sealed);
-  emit(MHM_F_AETSEALED, aet_sealed);
-
+  const double st0 = sel_gt(tmp_s, se.x, se.x, tmp_s);
+  const double rs = tmp_s - st0;                 // tmp - sealedThr, or exactly 0
+  const double aer = (pet * inv_evap_coeff - aet_canopy) * (st0 * se.y);
+  const double ae = pos_part(aer);
+  const double aes = min_sel(ae, st0);
+  if (sealed_on) s.sealed = st0 - aes;           // st0 - ae, or exactly 0
+  if (EM::kEmit || EM::kOut) {
+    emit(MHM_F_RUNOFFSEAL, sealed_on ? rs : 0.0);
+    emit(MHM_F_AETSEALED, sealed_on ? aes : 0.0);
+  }
   StageA out;
   out.prec_effect = prec_effect;
   out.pet_left = pet - aet_canopy;
-  out.runoff_sealed = runoff_sealed;
+  out.runoff_sealed = rs;  // multiplied by fSealed = 0 where the reference has no sealed runoff
   return out;
 }
 
-template <int NH, int VARIANT, bool EMIT, class PARAMS>
-__device__ __forceinline__ void cascade_stage_b1_sel(const PARAMS& p, const CellStates<NH>& s,
-                                                     const double prec_effect, double2* warp_tasks,
-                                                     const fm::Tables& tab, double (&frac_pre)[NH]) {
-  // ---- infiltration powers of the warp, compacted (see cascade_step) ----
-  {
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt = (1u << lane) - 1u;
-    const bool wet = prec_effect != 0.0;
-    unsigned base = 0;
-    unsigned slot[NH];
-    bool need[NH];
-#pragma unroll
-    for (int hh = 0; hh < NH; ++hh) {
-      need[hh] = wet && s.sm[hh] > kEps && !(s.sm[hh] > PH(SAT, hh));
-      const unsigned m = __ballot_sync(0xffffffffu, need[hh]);
-      slot[hh] = base + __popc(m & lt);
-      base += __popc(m);
-      frac_pre[hh] = 0.0;
-    }
-    if (base != 0) {  // warp-uniform
-#pragma unroll
-      for (int hh = 0; hh < NH; ++hh)
-        if (need[hh]) warp_tasks[slot[hh]] = make_double2(s.sm[hh] * PH(inv_SAT, hh), PH(EXPN, hh));
-      __syncwarp();
-      for (unsigned k = lane; k < base; k += 32u) {
-        const double2 tk = warp_tasks[k];
-        warp_tasks[k].x = fm::pow_tab(tab, tk.x, tk.y);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int hh = 0; hh < NH; ++hh)
-        if (need[hh]) frac_pre[hh] = warp_tasks[slot[hh]].x;
-      __syncwarp();
-    }
+// The warp's list of pending powers.  With the parameters in shared memory an entry is the 8-byte
+// base plus one byte naming its source (lane | horizon << 5): the evaluating lane reads the exponent
+// from the source lane's parameter column.  576 bytes per warp instead of 1 KB -- together with the
+// 15 parameter pairs that is what lets a sixth CTA fit on the SM.  Otherwise (base, exponent) pairs.
+template <int NH, bool BY_SOURCE>
+struct WarpTasks;
+template <int NH>
+struct WarpTasks<NH, true> {
+  static constexpr bool kBySource = true;
+  double x[32 * NH];
+  unsigned char src[32 * NH];
+  template <class PARAMS>
+  __device__ __forceinline__ void put(const PARAMS&, unsigned k, double base, int hh) {
+    x[k] = base;
+    src[k] = (unsigned char)((threadIdx.x & 31u) | ((unsigned)hh << 5));
   }
+  template <class PARAMS>
+  __device__ __forceinline__ void eval(const PARAMS& p, unsigned k, const fm::Tables& tab) {
+    const unsigned sc = src[k];
+    const unsigned hh = (sc >> 5) < (unsigned)NH ? (sc >> 5) : 0u;  // (a stale entry must stay in range)
+    const double y = p.get_of(PID::kExpWp0 + hh, (threadIdx.x & ~31u) + (sc & 31u)).x;
+    x[k] = fm::pow_tab(tab, x[k], y);
+  }
+  __device__ __forceinline__ double result(unsigned k) const { return x[k]; }
+};
+template <int NH>
+struct WarpTasks<NH, false> {
+  static constexpr bool kBySource = false;
+  double2 xy[32 * NH];
+  template <class PARAMS>
+  __device__ __forceinline__ void put(const PARAMS& p, unsigned k, double base, int hh) {
+    xy[k] = make_double2(base, PH2(kExpWp0, hh).x);
+  }
+  template <class PARAMS>
+  __device__ __forceinline__ void eval(const PARAMS&, unsigned k, const fm::Tables& tab) {
+    const double2 tk = xy[k];
+    xy[k].x = fm::pow_tab(tab, tk.x, tk.y);
+  }
+  __device__ __forceinline__ double result(unsigned k) const { return xy[k].x; }
+};
 
-}
-
-template <int NH, int VARIANT, bool EMIT, class PARAMS, class EM>
-__device__ __forceinline__ double cascade_horizons_sel(const PARAMS& p, CellStates<NH>& s, const StageA& in,
-                                                       const double (&frac_pre)[NH],
-                                                       const EM& emit) {
-  constexpr bool kFeddes = VARIANT == kHourlyFeddes;
-  const double prec_effect = in.prec_effect;
-  // ---- soil horizons ----
-  double infil_last = 0.0, aet_pos_sum = 0.0;
+// infiltration powers of the warp, compacted (see cascade_step): frac_h = (sm_h / SAT_h) ** EXPN_h
+// for the (cell, horizon) pairs that receive water; 0 elsewhere.  (The reference's sm > eps test
+// is dropped: at sm = eps the power is below 1e-16 and 1 - frac rounds to the same 1.)
+template <int NH, class PARAMS, class TASKS>
+__device__ __forceinline__ void cascade_stage_b1_sel(const PARAMS& p, const CellStates<NH>& s,
+                                                     const double prec_effect, TASKS& wt,
+                                                     const fm::Tables& tab, double (&frac_pre)[NH]) {
+  const bool wet = prec_effect != 0.0;
+#if MHM_POW_COMPACT
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned base = 0;
+  unsigned slot[NH];
+  bool need[NH];
 #pragma unroll
   for (int hh = 0; hh < NH; ++hh) {
-    const double sm0 = s.sm[hh], sat = PH(SAT, hh);
-    const double pe = hh == 0 ? prec_effect : infil_last;
-    const bool oversat = sm0 > sat;
-    const double tmp = pe * (1.0 - frac_pre[hh]);
-    const bool fill = (sm0 + tmp) > sat;
-    const double inf = oversat ? pe : (fill ? pe + (sm0 - sat) : pe - tmp);
-    const double sm1 = oversat ? sm0 : (fill ? sat : sm0 + tmp);
-    infil_last = inf;
-    emit(MHM_F_INFILSOIL, hh, inf);
-    double a = in.pet_left;
-    if (hh != 0) a = a - aet_pos_sum;
-    double stress;
-    if (kFeddes) {
-      const double part = PH(fRoots, hh) * (sm1 - PH(WP, hh)) * PH(inv_FCWP, hh);
-      stress = sm1 >= PH(FC, hh) ? PH(fRoots, hh) : (sm1 > PH(WP, hh) ? part : 0.0);
-    } else {
-      double th = (sm1 - PH(WP, hh)) / (sat - PH(WP, hh));
-      th = th < 0.0 ? 0.0 : th;
-      th = th > 1.0 ? 1.0 : th;
-      stress = th >= PX(jarvis_c1) ? PH(fRoots, hh) : (th < PX(jarvis_c1) ? PH(fRoots, hh) * (th / PX(jarvis_c1)) : 0.0);
-    }
-    a = a * stress;
-    a = a < 0.0 ? 0.0 : a;
-    const bool more = sm1 > a;
-    const double a2 = more ? a : sm1 - kEps;
-    double sm2 = more ? sm1 - a : kEps;
-    sm2 = sm2 < kEps ? kEps : sm2;
-    emit(MHM_F_AETSOIL, hh, a2);
-    s.sm[hh] = sm2;
-    aet_pos_sum = a2 > 0.0 ? aet_pos_sum + a2 : aet_pos_sum;
+    need[hh] = wet && !(s.sm[hh] > PH2(kSat0, hh).x);
+    const unsigned m = __ballot_sync(0xffffffffu, need[hh]);
+    slot[hh] = base + __popc(m & lt);
+    base += __popc(m);
+    frac_pre[hh] = 0.0;
   }
-  return infil_last;
+  if (base != 0) {  // warp-uniform
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+      if (need[hh]) wt.put(p, slot[hh], s.sm[hh] * PH2(kSat0, hh).y, hh);
+    __syncwarp();
+    for (unsigned k = lane; k < base; k += 32u) wt.eval(p, k, tab);
+    __syncwarp();
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+      if (need[hh]) frac_pre[hh] = wt.result(slot[hh]);
+    __syncwarp();
+  }
+#else
+  // every lane evaluates its own powers (NH independent chains in straight-line code, no shared
+  // memory round trip); a warp without a wet lane skips them
+  (void)wt;
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) frac_pre[hh] = 0.0;
+  if (__any_sync(0xffffffffu, wet)) {
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      const double2 sa = PH2(kSat0, hh);
+      const double f = fm::pow_tab(tab, s.sm[hh] * sa.y, PH2(kExpWp0, hh).x);
+      frac_pre[hh] = (wet && !(s.sm[hh] > sa.x)) ? f : 0.0;
+    }
+  }
+#endif
 }
 
-template <int NH, int VARIANT, bool EMIT, class PARAMS, class EM>
+// The same compaction in three parts, so that independent work of the thread can be placed between
+// the warp barriers (the exchange through shared memory is a chain of four memory latencies):
+//   pow_post    : which (cell, horizon) pairs need a power; their entries into the warp's task
+//                 list; barrier
+//   pow_round0  : this lane evaluates task `lane` -- unconditionally (a lane without a task works
+//                 on a stale entry; pow_tab is safe for any bit pattern), so that the code is
+//                 straight-line and shares its basic block with whatever follows
+//   pow_collect : the rare further rounds (more than 32 tasks), barrier, results back, barrier
+template <int NH>
+struct PowTasks {
+  unsigned slot[NH], base;
+  bool need[NH];
+};
+template <int NH, class PARAMS, class TASKS>
+__device__ __forceinline__ void pow_post(const PARAMS& p, const CellStates<NH>& s, const double prec_effect,
+                                         TASKS& wt, PowTasks<NH>& pt) {
+  const unsigned lt = (1u << (threadIdx.x & 31u)) - 1u;
+  const bool wet = prec_effect != 0.0;
+  pt.base = 0;
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    const double2 sa = PH2(kSat0, hh);
+    pt.need[hh] = wet && !(s.sm[hh] > sa.x);
+    const unsigned m = __ballot_sync(0xffffffffu, pt.need[hh]);
+    pt.slot[hh] = pt.base + __popc(m & lt);
+    pt.base += __popc(m);
+    if (pt.need[hh]) wt.put(p, pt.slot[hh], s.sm[hh] * sa.y, hh);
+  }
+  __syncwarp();
+}
+template <class PARAMS, class TASKS>
+__device__ __forceinline__ void pow_round0(const PARAMS& p, TASKS& wt, const fm::Tables& tab) {
+  wt.eval(p, threadIdx.x & 31u, tab);
+}
+template <int NH, class PARAMS, class TASKS>
+__device__ __forceinline__ void pow_collect(const PARAMS& p, const PowTasks<NH>& pt, TASKS& wt,
+                                            const fm::Tables& tab, double (&frac_pre)[NH]) {
+  if (NH > 1 && pt.base > 32u) {  // warp-uniform
+    for (unsigned k = (threadIdx.x & 31u) + 32u; k < pt.base; k += 32u) wt.eval(p, k, tab);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    const double f = wt.result(pt.slot[hh]);
+    frac_pre[hh] = pt.need[hh] ? f : 0.0;
+  }
+  __syncwarp();
+}
+
+// soil horizons, mo_soil_moisture.f90:217-286; returns the infiltration leaving the last horizon
+template <int NH, class PARAMS, class EM>
+__device__ __forceinline__ double cascade_horizons_sel(const PARAMS& p, CellStates<NH>& s, const StageA& in,
+                                                       const double (&frac_pre)[NH], const EM& emit) {
+  double pe = in.prec_effect, aet_sum = 0.0;
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    const double2 sa = PH2(kSat0, hh), ew = PH2(kExpWp0, hh), rt = PH2(kRoot0, hh);
+    const double sm0 = s.sm[hh];
+    const double tmp = pe * (1.0 - frac_pre[hh]);
+    const double u = sm0 + tmp;
+    const double cap = sel_gt(sm0, sa.x, sm0, sa.x);  // an over-saturated horizon keeps its water (:226)
+    const bool fill = u > sa.x;                  // also true whenever sm0 > SAT (frac = 0, pe >= 0)
+    const double sm1 = fill ? cap : u;
+    const double d = fill ? cap - sm0 : tmp;     // water the horizon takes up
+    const double inf = pe - d;                   // pe + (sm0 - SAT) bit for bit, pe - tmp, or pe
+    emit(MHM_F_INFILSOIL, hh, inf);
+    const double A = hh == 0 ? in.pet_left : in.pet_left - aet_sum;
+    const double w = (sm1 - ew.y) * rt.y;
+    const double a = pos_part((A * rt.x) * sel_lt(w, 1.0, w, 1.0));  // <= 0 below the wilting point, :266 / :361
+    const double a2 = sm1 > a ? a : sm1 - kEps;
+    const double sm2 = sm1 - a2;                 // sm1 - a, or eps (0 for sm1 >> eps: floored next)
+    emit(MHM_F_AETSOIL, hh, a2);
+    s.sm[hh] = sel_lt(sm2, kEps, kEps, sm2);
+    aet_sum = hh == 0 ? a2 : aet_sum + a2;       // sum(aet(1:hh), aet > 0): aet >= 0 here
+    pe = inf;
+  }
+  return pe;
+}
+
+// unsaturated and saturated zone, total runoff: mo_runoff.f90:120-152, 204-210, 271-272
+template <int NH, class PARAMS, class EM>
 __device__ __forceinline__ double cascade_reservoirs_sel(const PARAMS& p, CellStates<NH>& s, const double infil_last,
                                                          const double runoff_sealed, const fm::Tables& tab,
                                                          const EM& emit) {
-  // ---- runoff_unsat_zone ----
+  const double2 un = P2(kUnsat), sl = P2(kSlow), pk = P2(kPerc), fs = P2(kSeal2);
   double us = s.unsat + infil_last;
-  const double fast = us > PX(unsatThr) ? fmin(PX(k0r) * (us - PX(unsatThr)), us - kEps) : 0.0;
+  const double f1 = un.y * (us - un.x), ue = us - kEps;
+  const double fmin1 = min_sel(f1, ue);
+  const double fast = us > un.x ? fmin1 : 0.0;
   us = us - fast;
-  const bool wetu = us > kEps;
-  const double pw = fm::pow_tab(tab, wetu ? us : 1.0, 1.0 + PX(alpha));
-  const double slow = wetu ? fmin(PX(k1r) * pw, us - kEps) : 0.0;
+  const double s1 = sl.x * fm::pow_tab(tab, us, sl.y), ue2 = us - kEps;  // garbage for us <= eps: discarded
+  const double smin1 = min_sel(s1, ue2);
+  const double slow = us > kEps ? smin1 : 0.0;
   us = us - slow;
-  const double perc = PX(kpr) * us;
-  const bool gt = us > perc;
-  s.sat = s.sat + (gt ? perc : us) * PX(karst);
-  s.unsat = gt ? us - perc : 0.0;
+  const double perc = pk.x * us;
+  const double q = sel_gt(us, perc, perc, us);   // what leaves the unsaturated zone downwards
+  s.sat = s.sat + q * pk.y;
+  s.unsat = us - q;                              // us - perc, or exactly 0
   emit(MHM_F_FASTRUNOFF, fast);
   emit(MHM_F_SLOWRUNOFF, slow);
   emit(MHM_F_PERCOL, perc);
-  // ---- runoff_sat_zone ----
-  const bool pos = s.sat > 0.0;
-  const double baseflow = pos ? PX(k2r) * s.sat : 0.0;
-  s.sat = pos ? s.sat - baseflow : 0.0;
+  const double baseflow = P2(kDdBase).y * s.sat;  // sat_storage = 0 gives 0 and leaves 0
+  s.sat = __dadd_rn(s.sat, -baseflow);
   emit(MHM_F_BASEFLOW, baseflow);
-  const double total_runoff = ((baseflow + slow + fast) * (1.0 - PX(fSealed))) + (runoff_sealed * PX(fSealed));
+  const double total_runoff = ((baseflow + slow + fast) * fs.y) + (runoff_sealed * fs.x);
   emit(MHM_F_TOTAL_RUNOFF, total_runoff);
   return total_runoff;
 }
 
-template <int NH, int VARIANT, bool EMIT, class PARAMS, class EM>
+template <int NH, bool EMIT, class PARAMS, class EM>
 __device__ __forceinline__ double cascade_stage_b2_sel(const PARAMS& p, CellStates<NH>& s, const StageA& in,
                                                        const double (&frac_pre)[NH], const fm::Tables& tab,
                                                        const EM& emit) {
-  const double infil_last = cascade_horizons_sel<NH, VARIANT, EMIT>(p, s, in, frac_pre, emit);
-  return cascade_reservoirs_sel<NH, VARIANT, EMIT>(p, s, infil_last, in.runoff_sealed, tab, emit);
+  const double infil_last = cascade_horizons_sel<NH>(p, s, in, frac_pre, emit);
+  return cascade_reservoirs_sel<NH>(p, s, infil_last, in.runoff_sealed, tab, emit);
 }
 
-template <int NH, int VARIANT, bool EMIT, class PARAMS, class EM>
-__device__ __forceinline__ double cascade_step_sel(const PARAMS& p, CellStates<NH>& s,
-                                                   const double pet, const double temperature,
-                                                   const double prec, const double inv_evap_coeff,
-                                                   double2* warp_tasks, const fm::Tables& tab,
-                                                   const EM& emit) {
-  const StageA sa = cascade_stage_a_sel<NH, VARIANT, EMIT, false>(p, s, pet, temperature, prec, inv_evap_coeff, emit);
+template <int NH, bool EMIT, class PARAMS, class TASKS, class EM>
+__device__ __forceinline__ double cascade_step_sel(const PARAMS& p, CellStates<NH>& s, const double pet,
+                                                   const double temperature, const double prec,
+                                                   const double inv_evap_coeff, TASKS& warp_tasks,
+                                                   const fm::Tables& tab, const EM& emit) {
+  const StageA sa = cascade_stage_a_sel<NH, EMIT>(p, s, pet, temperature, prec, inv_evap_coeff, emit);
   double frac_pre[NH];
-  cascade_stage_b1_sel<NH, VARIANT, EMIT>(p, s, sa.prec_effect, warp_tasks, tab, frac_pre);
-  return cascade_stage_b2_sel<NH, VARIANT, EMIT>(p, s, sa, frac_pre, tab, emit);
+  cascade_stage_b1_sel<NH>(p, s, sa.prec_effect, warp_tasks, tab, frac_pre);
+  return cascade_stage_b2_sel<NH, EMIT>(p, s, sa, frac_pre, tab, emit);
 }
 #endif
 
@@ -845,15 +1020,30 @@ struct CellCursor {
   int qst;
 };
 
-// UNIFORM: every step of the launch has the yId / iLAI / month of its first step and the forcing
-// rows advance by one per step (CellArgs::uniform_calendar, specialised variants only)
-template <int NH, int VARIANT, bool OUT, bool UNIFORM = false>
+// which parameter store a kernel variant uses
+template <int NH, int VARIANT>
+struct ParamStoreOf {
+#if MHM_FAST
+  static constexpr bool paired = VARIANT != kGeneric;  // specialised fast variants: select form
+#else
+  static constexpr bool paired = false;
+#endif
+};
+
+// FUSED (uniform launches only): the step's runoff goes to the routing's tiled node-runoff history
+// and nowhere else (true) / to the total-runoff history row and nowhere else (false) -- a block of
+// steps always has exactly one of the two sinks
+template <int NH, int VARIANT, bool OUT, bool UNIFORM = false, bool FUSED = false>
 __global__ void __launch_bounds__(kCellThreads, ParamPlace<NH>::min_blocks)
 MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
   const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
 #if MHM_FAST
-  __shared__ double2 sh_tasks[kCellThreads * NH];
+  // the warps' lists of pending infiltration powers
+  // (by source: the exponents must be in shared memory)
+  constexpr bool kTasksBySource = ParamStoreOf<NH, VARIANT>::paired && ParamPlace<NH>::shared &&
+                                  PairStore<NH, true>::kRegPairs <= PairIds<NH>::kExpWp0;
+  __shared__ WarpTasks<NH, kTasksBySource> sh_tasks[kCellThreads / 32];
 #if MHM_TABLES_GLOBAL
   const fm::Tables& sh_tab = fm::d_tables;  // served from L1
 #else
@@ -866,7 +1056,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     __syncthreads();
   }
 #endif
-  double2* const warp_tasks = sh_tasks + (threadIdx.x >> 5) * (32 * NH);
+  auto& warp_tasks = sh_tasks[threadIdx.x >> 5];
   // out-of-range lanes of the last tile stay alive (warp collectives) on a valid cell
   const bool live = cell < a.nCells;
   const int c = live ? cell : a.nCells - 1;
@@ -878,6 +1068,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const size_t n = (size_t)a.nCells;
   const size_t mc = (size_t)member * n + c;
   constexpr bool kHourlyPetIn = VARIANT != kGeneric;
+  constexpr bool kPaired = ParamStoreOf<NH, VARIANT>::paired;
 
   CellStates<NH> s;
   s.inter = a.S[MHM_S_INTER][mc];
@@ -889,16 +1080,34 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   for (int h = 0; h < NH; ++h) s.sm[h] = a.S[MHM_S_SOILMOIST][((size_t)member * NH + h) * n + c];
 
   constexpr bool kSharedParams = ParamPlace<NH>::shared;
-  __shared__ std::conditional_t<kSharedParams, CellParamsShared<NH>, EmptyParams> p_shared;
-  std::conditional_t<kSharedParams, EmptyParams, CellParams<NH>> p_regs;
-  auto& p = pick_ref<kSharedParams>(p_shared, p_regs);
-  // parameters that never change during a run
-  PX(karst) = a.P[MHM_P_KARSTLOSS][mc];
-  PX(jarvis_c1) = a.P[MHM_P_JARVIS_C1][mc];
-  PX(unsatThr) = a.P[MHM_P_UNSATTHRESH][mc];
-  PX(sealedThr) = a.P[MHM_P_SEALEDTHRESH][mc];
 #if MHM_FAST
-  PX(inv_sealedThr) = 1.0 / PX(sealedThr);
+  // specialised variants: parameter pairs, partly in registers, the rest in shared memory
+  using Pairs = PairStore<NH, kSharedParams>;
+  __shared__ std::conditional_t<kPaired && kSharedParams, typename Pairs::Smem, EmptyParams> pair_smem;
+  std::conditional_t<kPaired, Pairs, EmptyParams> pairs;
+  if constexpr (kPaired && kSharedParams) pairs.sm = &pair_smem;
+#else
+  EmptyParams pairs;
+#endif
+  // generic variant: one member per parameter, in shared memory or in registers
+  __shared__ std::conditional_t<!kPaired && kSharedParams, CellParamsShared<NH>, EmptyParams> p_shared;
+  std::conditional_t<!kPaired && !kSharedParams, CellParams<NH>, EmptyParams> p_regs;
+  auto& p = pick_ref<kPaired>(pairs, pick_ref<kSharedParams>(p_shared, p_regs));
+  // parameters that never change during a run
+  if constexpr (!kPaired) {
+    PX(karst) = a.P[MHM_P_KARSTLOSS][mc];
+    PX(jarvis_c1) = a.P[MHM_P_JARVIS_C1][mc];
+    PX(unsatThr) = a.P[MHM_P_UNSATTHRESH][mc];
+    PX(sealedThr) = a.P[MHM_P_SEALEDTHRESH][mc];
+#if MHM_FAST
+    PX(inv_sealedThr) = 1.0 / PX(sealedThr);
+#endif
+  }
+#if MHM_FAST
+  else {
+    const double thr = a.P[MHM_P_SEALEDTHRESH][mc];
+    p.set(PID::kSeal, thr, thr > kEps ? 1.0 / thr : __longlong_as_double(0x7ff0000000000000LL));
+  }
 #endif
   CellCursor cu;
   cu.cur_y = -1;
@@ -908,9 +1117,6 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   cu.ptemp = a.met[MHM_M_TEMP] + (size_t)(cu.cur_row - a.met_first[MHM_M_TEMP]) * n + c;
   cu.ppet = a.pet_case <= 0 ? a.met[MHM_M_PET] + (size_t)(cu.cur_row - a.met_first[MHM_M_PET]) * n + c
                             : nullptr;
-  cu.raw_pre = ldg_stream(cu.ppre);
-  cu.raw_temp = ldg_stream(cu.ptemp);
-  cu.raw_pet = cu.ppet ? ldg_stream(cu.ppet) : 0.0;
   cu.hist = a.runoff_hist ? a.runoff_hist + (size_t)member * n + c : nullptr;
   const size_t hist_stride = (size_t)a.nMembers * n;
   // fused L11_runoff_acc (mo_mrm_pre_routing.f90:110-141): this cell is the only one of its node
@@ -920,6 +1126,9 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     qout = a.qout_hist + (((size_t)member * a.qout_E + a.cell_lane[c]) << 3);
     qarea = a.cell_area[c];
   }
+#if MHM_FAST
+  const double qscale = qarea * a.qout_scale;  // node runoff = total runoff * area * 1000 / TST
+#endif
   const size_t qtile_stride = ((size_t)a.nMembers * a.qout_E) << 3;
   // the history is stored skewed: step e of a node sits in slot e + (position of the node in its
   // routing segment), the slot the routing pipeline touches in the same sub-step for all lanes
@@ -943,57 +1152,126 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     if ((!UNIFORM || t == 0) && y != cu.cur_y) {  // land-cover scene changed (new year): mo_mhm_interface_run.f90:626-628
       cu.cur_y = y;
       const size_t o1 = ((size_t)member * a.nLC + y) * n + c;  // (n, 1, nLC) arrays
-      PX(fSealed) = a.P[MHM_P_FSEALED][o1];
-      PX(alpha) = a.P[MHM_P_ALPHA][o1];
-      PX(ddinc) = a.P[MHM_P_DEGDAYINC][o1];
-      PX(ddmax_c) = a.P[MHM_P_DEGDAYMAX][o1] * a.c2TSTu;    // mo_mhm.f90:463
-      PX(ddnop_c) = a.P[MHM_P_DEGDAYNOPRE][o1] * a.c2TSTu;  // mo_mhm.f90:464
-      PX(ddthr) = (PX(ddmax_c) - PX(ddnop_c)) / PX(ddinc);        // mo_snow_accum_melt.f90:127
-      PX(k0r) = a.c2TSTu / a.P[MHM_P_KFASTFLOW][o1];        // mo_mhm.f90:484
-      PX(k1r) = a.c2TSTu / a.P[MHM_P_KSLOWFLOW][o1];
-      PX(kpr) = a.c2TSTu / a.P[MHM_P_KPERCO][o1];
-      PX(k2r) = a.c2TSTu / a.P[MHM_P_KBASEFLOW][o1];        // mo_mhm.f90:488
-      PX(tthr) = a.P[MHM_P_TEMPTHRESH][o1];
+      const double ddinc = a.P[MHM_P_DEGDAYINC][o1];
+      const double ddmax_c = a.P[MHM_P_DEGDAYMAX][o1] * a.c2TSTu;    // mo_mhm.f90:463
+      const double ddnop_c = a.P[MHM_P_DEGDAYNOPRE][o1] * a.c2TSTu;  // mo_mhm.f90:464
+      const double ddthr = (ddmax_c - ddnop_c) / ddinc;              // mo_snow_accum_melt.f90:127
+      const double k0r = a.c2TSTu / a.P[MHM_P_KFASTFLOW][o1];        // mo_mhm.f90:484
+      const double k1r = a.c2TSTu / a.P[MHM_P_KSLOWFLOW][o1];
+      const double kpr = a.c2TSTu / a.P[MHM_P_KPERCO][o1];
+      const double k2r = a.c2TSTu / a.P[MHM_P_KBASEFLOW][o1];        // mo_mhm.f90:488
+      if constexpr (!kPaired) {
+        PX(fSealed) = a.P[MHM_P_FSEALED][o1];
+        PX(alpha) = a.P[MHM_P_ALPHA][o1];
+        PX(ddinc) = ddinc;
+        PX(ddmax_c) = ddmax_c;
+        PX(ddnop_c) = ddnop_c;
+        PX(ddthr) = ddthr;
+        PX(k0r) = k0r;
+        PX(k1r) = k1r;
+        PX(kpr) = kpr;
+        PX(k2r) = k2r;
+        PX(tthr) = a.P[MHM_P_TEMPTHRESH][o1];
+      }
+#if MHM_FAST
+      else {
+        const double fS = a.P[MHM_P_FSEALED][o1];
+        p.set(PID::kSeal2, fS, 1.0 - fS);
+        p.set(PID::kDd, ddnop_c, ddinc);
+        p.set(PID::kDdBase, ddmax_c, k2r);
+        p.set(PID::kUnsat, a.P[MHM_P_UNSATTHRESH][mc], k0r);
+        p.set(PID::kSlow, k1r, 1.0 + a.P[MHM_P_ALPHA][o1]);
+        p.set(PID::kPerc, kpr, a.P[MHM_P_KARSTLOSS][mc]);
+        p.sety(PID::kPetTthr, a.P[MHM_P_TEMPTHRESH][o1]);
+      }
+#endif
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
         const size_t oh = (((size_t)member * a.nLC + y) * NH + h) * n + c;  // (n, nH, nLC)
-        PH(fRoots, h) = a.P[MHM_P_FROOTS][oh];
-        PH(FC, h) = a.P[MHM_P_SOILMOISTFC][oh];
-        PH(SAT, h) = a.P[MHM_P_SOILMOISTSAT][oh];
-        PH(EXPN, h) = a.P[MHM_P_SOILMOISTEXP][oh];
-        PH(WP, h) = a.P[MHM_P_WILTINGPOINT][oh];
+        const double FC = a.P[MHM_P_SOILMOISTFC][oh], SAT = a.P[MHM_P_SOILMOISTSAT][oh];
+        const double WP = a.P[MHM_P_WILTINGPOINT][oh];
+        if constexpr (!kPaired) {
+          PH(fRoots, h) = a.P[MHM_P_FROOTS][oh];
+          PH(FC, h) = FC;
+          PH(SAT, h) = SAT;
+          PH(EXPN, h) = a.P[MHM_P_SOILMOISTEXP][oh];
+          PH(WP, h) = WP;
 #if MHM_FAST
-        PH(inv_SAT, h) = 1.0 / PH(SAT, h);
-        PH(inv_FCWP, h) = 1.0 / (PH(FC, h) - PH(WP, h));
+          PH(inv_SAT, h) = 1.0 / SAT;
+          PH(inv_FCWP, h) = 1.0 / (FC - WP);
 #endif
+        }
+#if MHM_FAST
+        else {
+          const bool feddes = a.soil_case == 1 || a.soil_case == 4;
+          const double range = feddes ? FC - WP : (SAT - WP) * a.P[MHM_P_JARVIS_C1][mc];
+          p.set(PID::kSat0 + h, SAT, 1.0 / SAT);
+          p.set(PID::kExpWp0 + h, a.P[MHM_P_SOILMOISTEXP][oh], WP);
+          p.set(PID::kRoot0 + h, a.P[MHM_P_FROOTS][oh], 1.0 / range);
+        }
+#endif
+        if (t == 0 && a.tt_first == 1 && !a.read_states) s.sm[h] = 0.5 * FC;  // mo_mhm.f90:448-450
       }
       cu.cur_l = -1;  // petLAIcorFactor / aeroResist also depend on yId
-      if (t == 0 && a.tt_first == 1 && !a.read_states) {  // mo_mhm.f90:448-450
-#pragma unroll
-        for (int h = 0; h < NH; ++h) s.sm[h] = 0.5 * PH(FC, h);
-      }
     }
     if ((!UNIFORM || t == 0) && il != cu.cur_l) {  // LAI step changed: mo_common_datetime_type.f90:135-155
       cu.cur_l = il;
-      PX(maxInter) = a.P[MHM_P_MAXINTER][((size_t)member * a.nLAI + il) * n + c];
-#if MHM_FAST
-      PX(inv_maxInter) = 1.0 / PX(maxInter);
-#endif
+      const double maxInter = a.P[MHM_P_MAXINTER][((size_t)member * a.nLAI + il) * n + c];
+      double petFac = 1.0;
       if (a.pet_case == -1) {
-        PX(petFac) = a.P[MHM_P_PETLAICORFACTOR][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + c];
+        petFac = a.P[MHM_P_PETLAICORFACTOR][(((size_t)member * a.nLC + y) * a.nLAI + il) * n + c];
       } else if (a.pet_case == 0 || a.pet_case == 1) {
-        PX(petFac) = a.P[MHM_P_FASP][mc];
-      } else {
-        PX(petFac) = 1.0;
+        petFac = a.P[MHM_P_FASP][mc];
       }
+      if constexpr (!kPaired) {
+        PX(maxInter) = maxInter;
+#if MHM_FAST
+        PX(inv_maxInter) = 1.0 / maxInter;
+#endif
+        PX(petFac) = petFac;
+      }
+#if MHM_FAST
+      else {
+        p.set(PID::kMaxInter, maxInter, maxInter > kEps ? 1.0 / maxInter : 0.0);
+        p.setx(PID::kPetTthr, petFac);
+      }
+#endif
+    }
+  };
+  auto pet_factor = [&]() -> double {
+#if MHM_FAST
+    if constexpr (kPaired) return P2(kPetTthr).x;
+    else
+#endif
+      return PX(petFac);
+  };
+  // node runoff of L11_runoff_acc from the step's total runoff (fused routing input)
+  auto node_runoff = [&](const double total_runoff) -> double {
+#if MHM_FAST
+    return total_runoff * qscale;
+#else
+    const double r = 0.0 + total_runoff;
+    const double v = a.qout_map_flag ? (0.0 + r * qarea) : r * qarea;
+    return v * 1000.0 / a.qout_tst;
+#endif
+  };
+  // the step's total runoff goes to the history row and / or the tiled node-runoff history
+  auto put = [&](const double total_runoff) {
+    if (UNIFORM ? !FUSED : cu.hist != nullptr) {
+      if (live) __stcs(cu.hist, total_runoff);
+      cu.hist += hist_stride;
+    }
+    if (UNIFORM ? FUSED : qout != nullptr) {
+      const double v = node_runoff(total_runoff);
+      if (live) *cu.qp = v;
+      ++cu.qst;
+      cu.qp += (cu.qst & 7) ? (size_t)1 : qtile_stride - 7;
     }
   };
 
   // one model step; EMIT is a compile-time tag so that steps 1..n-1 carry no flux stores
-  // STORE = false: the caller collects the node runoff of four steps and writes one 32-byte sector
-  auto step = [&](auto emit_tag, auto store_tag, const int t) -> double {
+  auto step = [&](auto emit_tag, const int t) {
     constexpr bool EMIT = decltype(emit_tag)::value;
-    constexpr bool STORE = decltype(store_tag)::value;
     const StepIdx si = a.idx_in[UNIFORM ? 0 : t];  // kernel-parameter space: uniform constant loads
     const int y = si.yId - 1, il = si.iLAI - 1, month = si.month - 1;
 
@@ -1007,12 +1285,12 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     // ---- get_corrected_pet :1053-1119 ----
     double pet;
     if (kHourlyPetIn || a.pet_case <= 0) {
-      pet = PX(petFac) * raw_pet;
+      pet = pet_factor() * raw_pet;
     } else if (a.pet_case == 1) {
       const double tmx = a.met[MHM_M_TMAX][(size_t)(row - a.met_first[MHM_M_TMAX]) * n + c];
       const double tmn = a.met[MHM_M_TMIN][(size_t)(row - a.met_first[MHM_M_TMIN]) * n + c];
-      pet = PX(petFac) * pet_hargreaves(a.P[MHM_P_HARSAMCOEFF][mc], raw_temp, tmx, tmn,
-                                      a.P[MHM_P_LATITUDE][mc], si.doy);
+      pet = pet_factor() * pet_hargreaves(a.P[MHM_P_HARSAMCOEFF][mc], raw_temp, tmx, tmn,
+                                          a.P[MHM_P_LATITUDE][mc], si.doy);
     } else if (a.pet_case == 2) {
       const double rn = a.met[MHM_M_NETRAD][(size_t)(row - a.met_first[MHM_M_NETRAD]) * n + c];
       pet = pet_priestly(a.P[MHM_P_PRIETAYALPHA][((size_t)member * a.nLAI + il) * n + c],
@@ -1084,23 +1362,20 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       }
     }
 
-#if MHM_FAST && MHM_SELECT_FORM
     double total_runoff;
-    if constexpr (VARIANT != kGeneric) {
-      total_runoff = cascade_step_sel<NH, VARIANT, EMIT>(p, s, pet_calc, temp_calc, prec_calc,
-                                                         a.tab.inv_evap_coeff[month], warp_tasks, sh_tab, emit);
+#if MHM_FAST
+    if constexpr (kPaired) {
+      total_runoff = cascade_step_sel<NH, EMIT>(p, s, pet_calc, temp_calc, prec_calc,
+                                                a.tab.inv_evap_coeff[month], warp_tasks, sh_tab, emit);
     } else {
-      total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case,
-                                                          a.tab.evap_coeff[month], a.tab.inv_evap_coeff[month],
-                                                          warp_tasks, sh_tab, emit);
+      if constexpr (!kTasksBySource)
+        total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case,
+                                                            a.tab.evap_coeff[month], a.tab.inv_evap_coeff[month],
+                                                            warp_tasks.xy, sh_tab, emit);
     }
 #else
-    const double total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(
-        p, s, pet_calc, temp_calc, prec_calc, a.soil_case, a.tab.evap_coeff[month],
-#if MHM_FAST
-        a.tab.inv_evap_coeff[month], warp_tasks, sh_tab,
-#endif
-        emit);
+    total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case,
+                                                        a.tab.evap_coeff[month], emit);
 #endif
 
     if (OUT) {
@@ -1119,93 +1394,119 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
                                     out_fS, out_sat);
       }
     }
-    if (cu.hist) {
-      if (live) __stcs(cu.hist, total_runoff);
-      cu.hist += hist_stride;
-    }
-    double v = 0.0;
-    if (qout) {
-      const double r = 0.0 + total_runoff;
-      v = a.qout_map_flag ? (0.0 + r * qarea) : r * qarea;
-#if MHM_FAST
-      v = v * a.qout_scale;
-#else
-      v = v * 1000.0 / a.qout_tst;
-#endif
-      if (STORE) {  // tiled history [step / 8][member][lane][step % 8]: running pointer
-        if (live) *cu.qp = v;
-        ++cu.qst;
-        cu.qp += (cu.qst & 7) ? (size_t)1 : qtile_stride - 7;
-      }
-    }
-    return v;
+    put(total_runoff);
   };
 
-  // Steps 1..n-1 carry no flux stores (a 4x unrolled loop with one 256-bit node-runoff store per
-  // four steps was measured 15 % slower on B200).
   const int n_last = a.nSteps - 1;
-#if MHM_FAST && MHM_SELECT_FORM && MHM_CELL_PIPELINE
-  if constexpr (UNIFORM && VARIANT != kGeneric && !OUT) {
+#if MHM_FAST
+  if constexpr (UNIFORM && kPaired && !OUT) {
     // Software pipeline over the steps of a uniform-calendar launch: stage A of step t+1 (canopy,
     // snow, sealed store -- it needs only the forcing and three states stage B never touches)
     // is issued in the same basic block as stage B2 of step t (horizons, reservoirs), so the
     // two dependent fp64 chains overlap.  Same operations on the same values as step().
-    // Measured on B200: +8 % (5.18e10 -> 5.60e10 cell-steps/s).  Not better: evaluating the
-    // infiltration powers per lane without warp compaction (straight-line, but 23 more fp64
-    // operations per lane-step: -7 %), and a deeper pipeline that also starts those powers for
-    // step t+1 right after the horizons of step t (per lane: equal; warp-compacted with the
-    // reservoirs of step t and stage A of step t+2 inside the round's block: -3 %).
+    // The three forcing arrays are walked with ONE 32-bit index (row * nCells + cell, relative to
+    // the launch's first row; the host keeps nSteps * nCells below 2^32).
+    load_params(0);
+    const long long row0 = a.idx_in[0].iMeteoTS;
+    const double* bpre = a.met[MHM_M_PRE] + (size_t)(row0 - a.met_first[MHM_M_PRE]) * n;
+    const double* btemp = a.met[MHM_M_TEMP] + (size_t)(row0 - a.met_first[MHM_M_TEMP]) * n;
+    const double* bpet = a.met[MHM_M_PET] + (size_t)(row0 - a.met_first[MHM_M_PET]) * n;
+    // (opaque to the optimiser: base + 8 * index is then one IMAD.WIDE per load)
+    asm volatile("" : "+l"(bpre), "+l"(btemp), "+l"(bpet));
+    unsigned fi = (unsigned)c;
+    double nx_pre = ldg_stream(bpre + fi), nx_temp = ldg_stream(btemp + fi), nx_pet = ldg_stream(bpet + fi);
     if (n_last > 0) {
       const int month = a.idx_in[0].month - 1;
       const double inv_ec = a.tab.inv_evap_coeff[month];
       const FluxEmitter<false, false> noemit{a.F, mc, n, (size_t)member * NH * n + c, false, nullptr};
-      auto next_forcing = [&](double& pre, double& temp, double& pet) {
-        pre = cu.raw_pre;
-        temp = cu.raw_temp;
-        pet = PX(petFac) * cu.raw_pet;
-        cu.ppre += n;
-        cu.ptemp += n;
-        cu.ppet += n;
-        cu.raw_pre = ldg_stream(cu.ppre);
-        cu.raw_temp = ldg_stream(cu.ptemp);
-        cu.raw_pet = ldg_stream(cu.ppet);
+      // stage A of the next step: its forcing row is consumed, the row after it requested
+      auto stage_a_next = [&]() -> StageA {
+        const double pre = nx_pre, temp = nx_temp, pet = P2(kPetTthr).x * nx_pet;
+        fi += (unsigned)a.nCells;
+        nx_pre = ldg_stream(bpre + fi);
+        nx_temp = ldg_stream(btemp + fi);
+        nx_pet = ldg_stream(bpet + fi);
+        return cascade_stage_a_sel<NH, false>(p, s, pet, temp, pre, inv_ec, noemit);
       };
-      load_params(0);
-      double pre, temp, pet;
-      next_forcing(pre, temp, pet);  // step 0; row 1 requested (nSteps > 1)
-      StageA sa = cascade_stage_a_sel<NH, VARIANT, false, true>(p, s, pet, temp, pre, inv_ec, noemit);
-      auto put = [&](const double total_runoff) {
-        if (cu.hist) {
-          if (live) __stcs(cu.hist, total_runoff);
-          cu.hist += hist_stride;
-        }
-        if (qout) {
-          const double r = 0.0 + total_runoff;
-          double v = a.qout_map_flag ? (0.0 + r * qarea) : r * qarea;
-          v = v * a.qout_scale;
-          if (live) *cu.qp = v;
-          ++cu.qst;
-          cu.qp += (cu.qst & 7) ? (size_t)1 : qtile_stride - 7;
-        }
+#if MHM_CELL_PIPE3
+      // Three steps in flight.  With A = canopy / snow / sealed store, R = infiltration powers of
+      // the warp (compacted, a chain of shared-memory round trips), H = soil horizons, V = unsaturated
+      // and saturated zone + runoff, iteration t runs
+      //      R(t+1)  ||  V(t)  ||  A(t+2)      -- one basic block, three independent chains
+      //      H(t+1)
+      // R(t+1) needs A(t+1) and the soil moisture H(t) left; V(t) needs what H(t) let through; the
+      // three touch disjoint states.  Same operations on the same values as step().
+      const int L = n_last;                // steps 0 .. L-1 go through the pipeline
+      StageA sa0 = stage_a_next(), sa1;    // A(0), A(1)
+      if (L > 1) sa1 = stage_a_next();
+      double infil, rsl, frac_pre[NH];
+      PowTasks<NH> pt;
+      pow_post<NH>(p, s, sa0.prec_effect, warp_tasks, pt);  // R(0), H(0)
+      pow_round0(p, warp_tasks, sh_tab);
+      pow_collect<NH>(p, pt, warp_tasks, sh_tab, frac_pre);
+      infil = cascade_horizons_sel<NH>(p, s, sa0, frac_pre, noemit);
+      rsl = sa0.runoff_sealed;
+      // cur = A(t+1) on entry; nxt receives A(t+2)
+      auto iter = [&](auto with_a, const StageA& cur, StageA& nxt) {
+        pow_post<NH>(p, s, cur.prec_effect, warp_tasks, pt);
+        pow_round0(p, warp_tasks, sh_tab);
+        put(cascade_reservoirs_sel<NH>(p, s, infil, rsl, sh_tab, noemit));
+        if constexpr (decltype(with_a)::value) nxt = stage_a_next();
+        pow_collect<NH>(p, pt, warp_tasks, sh_tab, frac_pre);
+        infil = cascade_horizons_sel<NH>(p, s, cur, frac_pre, noemit);
+        rsl = cur.runoff_sealed;
       };
-      for (int t = 0; t + 1 < n_last; ++t) {
+      int t = 0;
+      for (; t + 3 < L; t += 2) {  // two iterations per trip: the hand-over of A costs no moves
+        iter(std::true_type{}, sa1, sa0);
+        iter(std::true_type{}, sa0, sa1);
+      }
+      if (t + 2 < L) {
+        iter(std::true_type{}, sa1, sa0);
+        sa1 = sa0;
+        ++t;
+      }
+      if (t + 1 < L) iter(std::false_type{}, sa1, sa0);  // H(L-1): no forcing row left for the pipeline
+      put(cascade_reservoirs_sel<NH>(p, s, infil, rsl, sh_tab, noemit));  // V(L-1)
+#else
+      // Two steps in flight: stage A of step t+1 is issued in the same basic block as the horizons
+      // and reservoirs of step t, so the two dependent fp64 chains overlap.
+      StageA sa = stage_a_next();
+      int t = 0;
+      for (; t + 2 < n_last; t += 2) {  // unrolled by two: the hand-over sa <- sb costs no moves
         double frac_pre[NH];
-        cascade_stage_b1_sel<NH, VARIANT, false>(p, s, sa.prec_effect, warp_tasks, sh_tab, frac_pre);
-        next_forcing(pre, temp, pet);  // step t+1; row t+2 <= n_last requested
-        const StageA sb = cascade_stage_a_sel<NH, VARIANT, false, true>(p, s, pet, temp, pre, inv_ec, noemit);
-        put(cascade_stage_b2_sel<NH, VARIANT, false>(p, s, sa, frac_pre, sh_tab, noemit));
+        cascade_stage_b1_sel<NH>(p, s, sa.prec_effect, warp_tasks, sh_tab, frac_pre);
+        const StageA sb = stage_a_next();
+        put(cascade_stage_b2_sel<NH, false>(p, s, sa, frac_pre, sh_tab, noemit));
+        cascade_stage_b1_sel<NH>(p, s, sb.prec_effect, warp_tasks, sh_tab, frac_pre);
+        sa = stage_a_next();
+        put(cascade_stage_b2_sel<NH, false>(p, s, sb, frac_pre, sh_tab, noemit));
+      }
+      for (; t + 1 < n_last; ++t) {
+        double frac_pre[NH];
+        cascade_stage_b1_sel<NH>(p, s, sa.prec_effect, warp_tasks, sh_tab, frac_pre);
+        const StageA sb = stage_a_next();  // step t+1; row t+2 <= n_last requested
+        put(cascade_stage_b2_sel<NH, false>(p, s, sa, frac_pre, sh_tab, noemit));
         sa = sb;
       }
       double frac_pre[NH];
-      cascade_stage_b1_sel<NH, VARIANT, false>(p, s, sa.prec_effect, warp_tasks, sh_tab, frac_pre);
-      put(cascade_stage_b2_sel<NH, VARIANT, false>(p, s, sa, frac_pre, sh_tab, noemit));  // step n_last - 1
+      cascade_stage_b1_sel<NH>(p, s, sa.prec_effect, warp_tasks, sh_tab, frac_pre);
+      put(cascade_stage_b2_sel<NH, false>(p, s, sa, frac_pre, sh_tab, noemit));  // step n_last - 1
+#endif
     }
+    // the launch's last step through the general path (it stores the fluxes)
+    cu.raw_pre = nx_pre;
+    cu.raw_temp = nx_temp;
+    cu.raw_pet = nx_pet;
   } else
 #endif
   {
-    for (int t = 0; t < n_last; ++t) step(std::false_type{}, std::true_type{}, t);
+    cu.raw_pre = ldg_stream(cu.ppre);
+    cu.raw_temp = ldg_stream(cu.ptemp);
+    cu.raw_pet = cu.ppet ? ldg_stream(cu.ppet) : 0.0;
+    for (int t = 0; t < n_last; ++t) step(std::false_type{}, t);
   }
-  step(std::true_type{}, std::true_type{}, n_last);
+  step(std::true_type{}, n_last);
 
   if (OUT) {
     if (a.out_mask && live)

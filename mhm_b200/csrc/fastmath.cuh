@@ -203,6 +203,10 @@ MHM_HD double pow23_sel(double x) {
   const double m = x * make_double((1023 - 3 * k) << 20, 0);
   return pow23_core(m) * make_double((1023 + 2 * k) << 20, 0);
 }
+// x ** (2/3) for x >= 1.2e-38 (single-precision seed in range), NaN below it (also for x = 0):
+// the canopy's relative storage is at most 1, and an evaporation of less than 1e-25 * pet is
+// discarded by the caller's `> 0` select together with the NaN
+MHM_HD double pow23_nz(double x) { return pow23_core(x); }
 MHM_HD double pow23_core(double x) {
 #if defined(__CUDA_ARCH__)
   float l, r0;
