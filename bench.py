@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-routing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-cells", type=int, default=100000)
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed legs")
     ap.add_argument("--cpu-hours", type=int, default=24)
     ap.add_argument("--mpr", action="store_true",
                     help="time mpr_eval (gamma -> all L1 effective parameters) on the per-GPU share of "
@@ -186,24 +186,101 @@ def build_problem(args, n_steps_total):
     return prob, rng
 
 
+def kernel_profile():
+    """profiles/cell_kernel_ncu.json: what only a profiler can count (fp64 instructions and useful
+    lane operations per cell-step, DRAM bytes per cell-step), valid for the kernel sources it names"""
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import cell_profile
+
+    path = os.path.join(ROOT, "profiles", "cell_kernel_ncu.json")
+    try:
+        prof = json.load(open(path))
+    except Exception as e:  # noqa: BLE001
+        return None, "profiles/cell_kernel_ncu.json unreadable: %s" % e
+    now = cell_profile.kernel_hash()
+    if prof.get("kernel_hash") != now:
+        return None, "profiles/cell_kernel_ncu.json is stale: captured for kernel sources %s, built from %s" % (
+            prof.get("kernel_hash"), now)
+    return prof, None
+
+
+class ParityChecker:
+    """bench.py checks what it times: member 0 of the rank against the CPU oracle (test
+    infrastructure, oracle/) -- a sample of cells through every step of both legs (states and the
+    last step's fluxes, <= 1e-9 relative), and the gauge discharge of the first chunk from a
+    full-domain oracle run (<= 1e-8 relative).  A mismatch raises: no number is printed."""
+
+    def __init__(self, prob, host_forcing, T, n_chunks, n_sample=2048):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import orc_run
+        import parity
+
+        self.orc_run, self.parity, self.prob, self.T = orc_run, parity, prob, T
+        n = prob["nCells"]
+        rng = np.random.default_rng(7)
+        self.cells = np.sort(rng.choice(n, size=min(n_sample, n), replace=False))
+        sub = dict(prob)
+        sub["nCells"] = len(self.cells)
+        sub["net"] = None
+        sub["params"] = {k: (np.ascontiguousarray(v[..., self.cells]) if k != "rout_param" else v)
+                         for k, v in prob["params"].items()}
+        sub["states0"] = {k: np.ascontiguousarray(v[..., self.cells]) for k, v in prob["states0"].items()}
+        chunk = {k: np.ascontiguousarray(v.numpy()[:, self.cells]) for k, v in host_forcing.items()}
+        sub["forcing"] = {k: np.ascontiguousarray(np.tile(v, (n_chunks, 1))) for k, v in chunk.items()}
+        self.sample = orc_run.OracleRun(sub, num_threads=os.cpu_count() or 1)
+        self.done = 0
+        self.worst = {"state": 0.0, "flux": 0.0, "gauge": None}
+        self.host_forcing = host_forcing
+
+    def check_cells(self, dom, tt_last, what):
+        o, P = self.sample, self.parity
+        o.run(self.done + 1, tt_last)
+        self.done = tt_last
+        for name in ("L1_inter", "L1_snowPack", "L1_sealSTW", "L1_unsatSTW", "L1_satSTW", "L1_soilMoist"):
+            got = dom.get_state(name, member=0)[..., self.cells]
+            self.worst["state"] = max(self.worst["state"], P.assert_close(got, o.S[name], "%s: %s" % (what, name)))
+        for name in ("L1_total_runoff", "L1_aETSoil", "L1_infilSoil", "L1_baseflow", "L1_slowRunoff", "L1_melt"):
+            got = dom.get_flux(name, member=0)[..., self.cells]
+            self.worst["flux"] = max(self.worst["flux"], P.assert_close(got, o.F[name], "%s: %s" % (what, name)))
+
+    def check_gauges(self, dom):
+        """gauge series of the first chunk: the whole domain through the oracle (cells + serial routing)"""
+        prob, T = self.prob, self.T
+        if prob["net"] is None:
+            return
+        full = dict(prob)
+        full["forcing"] = {k: v.numpy() for k, v in self.host_forcing.items()}
+        o = self.orc_run.OracleRun(full, num_threads=os.cpu_count() or 1)
+        o.run(1, T)
+        got = dom.get_runoff(1, T, member=0)[:, :T]
+        self.worst["gauge"] = self.parity.assert_close(got, o.mRM_runoff[:, :T], "gauge discharge of the first chunk",
+                                                       rtol=self.parity.RTOL_Q)
+        assert np.abs(o.mRM_runoff[:, :T]).max() > 0.0
+
+
 def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    local = local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    # the CPU baseline runs before any process group exists (no other rank spins in NCCL beside it)
+    cpu = cpu_baseline(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+
     import torch
     import torch.distributed as dist
 
     from mhm_b200 import driver, ensemble, interface, synth
 
-    rank = int(os.environ.get("RANK", 0))
-    local = local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, K, T, M = args.warmup, args.steps, args.block_hours, args.members
-    n_total = (2 * (W + K) + 1) * T
+    n_chunks = 2 * (W + K) + 1
+    n_total = n_chunks * T
     prob, rng = build_problem(args, n_total)
     n = prob["nCells"]
     ctx = interface.Context(local)
     ctx.set_math_mode(args.mode)
+    ctx.comm_init(dist if world > 1 else None)  # the library's own NCCL communicator (shared forcing)
     mrng = np.random.default_rng(1000 + rank)
     dom = driver.setup_domain(ctx, 1, prob, nMembers=1, upload_forcing=False) if M == 1 else None
     if dom is None:
@@ -222,13 +299,15 @@ def run_ours(args):
                 dom.set_state(name, arr, member=m)
             if prob["net"] is not None:
                 net = prob["net"]
-                dom.set_reg_rout(net["rout_param"] * mrng.uniform(0.95, 1.05, 5),
-                                 net["L11_length"][: net["nNodes"] - 1],
+                rp = net["rout_param"] if m == 0 else net["rout_param"] * mrng.uniform(0.95, 1.05, 5)
+                dom.set_reg_rout(rp, net["L11_length"][: net["nNodes"] - 1],
                                  net["L11_slope"][: net["nNodes"] - 1], net["L11_nLinkFracFPimp"],
                                  member=m)
-    # forcing chunk of T hours, generated on the device, mirrored into pinned host memory
+    # forcing chunk of T hours -- the SAME on every rank (the ranks run members of one domain) --
+    # generated on the device, mirrored into pinned host memory
     g = torch.Generator(device="cuda")
-    g.manual_seed(synth.SEED + rank)
+    g.manual_seed(synth.SEED)
+    torch.manual_seed(synth.SEED)
     hours = torch.arange(T, device="cuda", dtype=torch.float64)[:, None]
     wet = torch.rand((T, n), generator=g, device="cuda") < 0.2
     gam = torch.distributions.Gamma(torch.tensor(0.7, device="cuda", dtype=torch.float64),
@@ -239,11 +318,15 @@ def run_ours(args):
     pet = (torch.clamp(0.15 * torch.sin(np.pi * ((hours % 24) - 6.0) / 12.0), min=0.0)
            * (0.8 + 0.4 * torch.rand((T, n), generator=g, device="cuda", dtype=torch.float64)))
     dev = {"pre": pre.contiguous(), "temp": temp.contiguous(), "pet": pet.contiguous()}
+    if world > 1:  # bit-identical forcing on every rank, whatever the ranks' generators did
+        for v in dev.values():
+            dist.broadcast(v, src=0)
     host = {k: torch.empty((T, n), dtype=torch.float64, pin_memory=True).copy_(v) for k, v in dev.items()}
     torch.cuda.synchronize()
     nG = dom.nGaugesTotal
     q_host = np.zeros((M, max(nG, 1), prob["time"]["nTimeSteps"]))
     gathered = {}
+    checker = ParityChecker(prob, host, T, n_chunks) if (rank == 0 and not args.no_parity) else None
 
     def barrier():
         ctx.synchronize()
@@ -258,8 +341,10 @@ def run_ours(args):
         dom.run_steps(first, T)
 
     def upload(i):
+        # every rank copies 1/world of the chunk from its pinned host memory; the ranks all-gather
+        # the rest over NVLink on the library's upload stream (mhm_cuda_set_meteo_shared)
         for k, v in host.items():
-            dom.set_meteo_host_ptr(k, v.data_ptr(), n, i * T + 1, T, async_copy=True)
+            dom.set_meteo_shared(k, v.data_ptr(), n, i * T + 1, T)
 
     def step_e2e(i):
         # chunk i was uploaded while chunk i-1 was computing (double buffered in the library);
@@ -282,6 +367,7 @@ def run_ours(args):
             fn(i0 + i)
         barrier()
         ctx.kernel_stats_reset(True)
+        h2d0 = dom.meteo_h2d_bytes()
         sampler = ClockSampler(local)
         sampler.start()
         ctx.event_record(0)
@@ -293,17 +379,30 @@ def run_ours(args):
         wall = time.time() - wall0
         ms = ctx.event_elapsed_ms(0, 1)
         clocks = sampler.summary()
+        h2d = (dom.meteo_h2d_bytes() - h2d0) / K
         if world > 1:
             t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
-        return ms, wall, clocks
+        return ms, wall, clocks, h2d
 
-    ms_v, wall_v, clocks = timed(step_value, 0)
+    ms_v, wall_v, clocks, _ = timed(step_value, 0)
     cell_ms, cell_launches = ctx.kernel_stats(0)
     rout_ms, rout_launches = ctx.kernel_stats(1)
+    ctx.kernel_stats_reset(False)
+    parity = None
+    if checker is not None:
+        checker.check_cells(dom, (W + K) * T, "value leg")
+        checker.check_gauges(dom)
+    barrier()
     upload(W + K)
-    ms_e, wall_e, _ = timed(step_e2e, W + K)
+    ms_e, wall_e, clocks_e, h2d_per_step = timed(step_e2e, W + K)
+    if checker is not None:
+        checker.check_cells(dom, 2 * (W + K) * T, "e2e leg")
+        parity = {"checked": True, "member": 0, "cells_sampled": int(len(checker.cells)),
+                  "steps_checked": 2 * (W + K) * T, "max_rel_state": checker.worst["state"],
+                  "max_rel_flux": checker.worst["flux"], "gauge_max_rel_first_chunk": checker.worst["gauge"],
+                  "tolerance": {"cells": 1e-9, "gauges": 1e-8}}
     units_per_step = float(n) * M * T
     value = units_per_step * K * world / (ms_v * 1e-3)
     e2e_value = units_per_step * K * world / (wall_e)
@@ -315,23 +414,48 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         # algorithmic bytes per cell-step-member: forcing 24 B shared by M members
-        # + 8 B total runoff written for the routing
+        # + 8 B node runoff written for the routing
         bytes_per_unit = 24.0 / M + 8.0
         launches_cell = max(1, cell_launches)
         cell_avg_ms = cell_ms / launches_cell
         units_per_launch = units_per_step * K / launches_cell
-        achieved = units_per_launch * bytes_per_unit / (cell_avg_ms * 1e-3) / 1e9
+        cell_rate = units_per_launch / (cell_avg_ms * 1e-3)  # cell-steps/s inside the kernel
+        hbm_achieved = cell_rate * bytes_per_unit / 1e9
         dfma = ctx.measure_dfma_peak()
-        traffic = None
-        try:  # DRAM bytes per unit of the same kernel from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_cell_traffic.json")))
-            traffic = tj["dram_bytes_per_unit"] * units_per_launch / (cell_avg_ms * 1e-3) / 1e9
-        except Exception:
-            pass
-        # useful fp64 lane operations per unit (DFMA + DADD + DMUL, predicated on), same capture
-        fp64_ops_per_unit = 94.0
+        prof, stale = kernel_profile()
+        if stale:
+            sys.stderr.write("bench.py: WARNING: %s -- roofline.frac withheld\n" % stale)
+        sm_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        props = torch.cuda.get_device_properties(local)
+        # the fp64 pipe of an SM sub-partition takes one warp instruction every two cycles (16 lanes)
+        pipe_peak = props.multi_processor_count * 4 * sm_hz / 2.0
+        roof = {"bound": "fp64", "unit": "fp64 warp-instructions/s", "peak": pipe_peak,
+                "peak_source": "SMs x 4 sub-partitions x measured SM clock / 2 (consistent with the DFMA peak "
+                               "measured live: %.3e lane-FMA/s)" % dfma,
+                "kernel": "cell_block_kernel_%s<2, hourly, uniform, fused>" % args.mode,
+                "kernel_ms_per_launch": cell_avg_ms, "units_per_launch": units_per_launch,
+                "kernel_units_per_s": cell_rate, "kernel_share_of_step": cell_ms / ms_v,
+                "achieved": None, "frac": None, "traffic": None}
+        if prof is not None:
+            fp64_rate = prof["fp64_warp_instructions_per_warp_step"] * cell_rate / 32.0
+            roof.update({
+                "achieved": fp64_rate, "frac": fp64_rate / pipe_peak,
+                "frac_note": "fp64-pipe utilisation = fp64 warp instructions per warp-step (ncu capture of this "
+                             "build, profiles/cell_kernel_ncu.json) x warp-steps/s (timed here) / peak",
+                "ncu_fp64_pipe_frac": prof["fp64_pipe_pct"] / 100.0,
+                "ncu_issue_active_frac": prof["issue_active_pct"] / 100.0,
+                "ncu_lsu_data_pipe_frac": prof["lsu_data_pipe_pct"] / 100.0,
+                "useful_frac": prof["fp64_lane_ops_per_unit"] * cell_rate / dfma if dfma else None,
+                "fp64_lane_ops_per_unit": prof["fp64_lane_ops_per_unit"],
+                "dfma_peak_per_s": dfma,
+                "traffic": prof["dram_bytes_per_unit"] * cell_rate / 1e9, "traffic_unit": "GB/s",
+                "profile_kernel_hash": prof["kernel_hash"]})
+        else:
+            roof["stale_profile"] = stale
+        roof["hbm"] = {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                       "bytes_per_unit": bytes_per_unit, "peak_source": peak_src}
         out = {
             "metric": "L1 cell-timesteps/s", "value": value, "unit": "cell-timesteps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_v / K,
@@ -346,31 +470,23 @@ def run_ours(args):
                 "nH": 2, "l2_policy": "inputs larger than L2 (forcing chunk %.1f GB, states+params "
                                       "%.1f GB per step)" % (3 * T * n * 8 / 1e9, 88 * 8 * n * M / 1e9),
             },
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "cell_block_kernel_%s<2>" % args.mode,
-                "kernel_ms_per_launch": cell_avg_ms, "units_per_launch": units_per_launch,
-                "bytes_per_unit": bytes_per_unit,
-                "kernel_share_of_step": cell_ms / ms_v,
-            },
-            "roofline_fp64": {
-                "note": "the fused kernel is fp64-pipe bound (BASELINE.md 3); dfma_peak measured "
-                        "live by a dependent-chain-free DFMA loop",
-                "dfma_peak_per_s": dfma, "cell_kernel_units_per_s": units_per_launch / (cell_avg_ms * 1e-3),
-                "fp64_lane_ops_per_unit": fp64_ops_per_unit,
-                "achieved_lane_ops_per_s": fp64_ops_per_unit * units_per_launch / (cell_avg_ms * 1e-3),
-                "frac": fp64_ops_per_unit * units_per_launch / (cell_avg_ms * 1e-3) / dfma if dfma else None,
-            },
+            "roofline": roof,
             "routing": {"ms": rout_ms, "kernel_launches": rout_launches, "share_of_step": rout_ms / ms_v},
             "e2e": {"value": e2e_value, "unit": "cell-timesteps/s",
-                    "h2d_bytes_per_step": 3 * T * n * 8,
-                    "d2h_bytes_per_step": M * max(nG, 1) * T * 8, "ms_per_step": wall_e * 1e3 / K},
+                    "h2d_bytes_per_step": int(h2d_per_step),
+                    "h2d_note": "host bytes THIS rank copies per step: 1/%d of the shared forcing chunk; the rest "
+                                "arrives by NCCL all-gather over NVLink (mhm_cuda_set_meteo_shared)" % world
+                                if world > 1 else "the whole forcing chunk from pinned host memory",
+                    "forcing_chunk_bytes": 3 * T * n * 8,
+                    "d2h_bytes_per_step": M * max(nG, 1) * T * 8, "ms_per_step": wall_e * 1e3 / K,
+                    "clocks": clocks_e},
             "gpu_launches": int(cell_launches + rout_launches),
             "clocks": clocks,
+            "parity_checked": bool(parity),
+            "parity": parity,
         }
-        if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args)
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
         emit(out)
     ctx.finalize()
     if world > 1:
@@ -498,16 +614,17 @@ def run_shard(args):
 
 
 def cpu_problem(args):
-    """bounded sample of the bench workload for the CPU arm: the first ~cpu_cells cells of a
-    domain of the same kind, one member, cpu_hours model steps"""
-    from mhm_b200 import synth
-    from mhm_b200.interface import routing_order
+    """The CPU arms' workload: the SAME synthetic domain as the GPU arm (all %d x %d x 0.85 cells, the
+    same 1M-node river network and parameters) with one member and cpu_hours model steps.  Built
+    without the product library: the routing order comes from the oracle's own linear-time
+    restatement (oracle/mhm_oracle.c: orc_routing_order_linear)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
 
-    nx = int(round((args.cpu_cells / 0.85) ** 0.5 * 1.086))
-    ny = int(round(args.cpu_cells / 0.85 / nx))
-    prob = synth.make_problem(nx=nx, ny=ny, n_days=max(1, (args.cpu_hours + 23) // 24), hourly=True,
-                              routing=not args.no_routing, start=(1990, 6, 1),
-                              routing_order=routing_order)
+    from mhm_b200 import synth  # numpy only; libmhm_cuda.so is not loaded
+
+    prob = synth.make_problem(nx=args.nx, ny=args.ny, n_days=max(1, (args.cpu_hours + 23) // 24), hourly=True,
+                              routing=not args.no_routing, start=(1990, 6, 1), routing_order=orc.routing_order)
     return prob
 
 
@@ -528,7 +645,7 @@ def cpu_baseline(args):
     best = min(cpu_run(prob, hours, cores) for _ in range(2))
     return {"value": prob["nCells"] * hours / best, "unit": "cell-timesteps/s", "cores": cores,
             "kind": "port",
-            "sample": "%d cells x 1 member x %d hourly steps, OpenMP static over cells + serial "
+            "sample": "the full %d-cell domain x 1 member x %d hourly steps, OpenMP static over cells + serial "
                       "routing (reference loop structure), best of 2" % (prob["nCells"], hours)}
 
 
@@ -544,16 +661,18 @@ def run_reference(args):
     t = [cpu_run(prob, hours, cores) for _ in range(args.steps)]
     total = sum(t)
     v = prob["nCells"] * hours * args.steps / total
-    sample = ("%d cells x 1 member x %d hourly steps per step; oracle/ restatement of the reference "
-              "(Fortran original not buildable here)" % (prob["nCells"], hours))
+    sample = ("the full %d-cell domain x 1 member x %d hourly steps per step; oracle/ restatement of the reference "
+              "(Fortran original not buildable here), %d OpenMP threads" % (prob["nCells"], hours, cores))
+    assert "mhm_b200._lib" not in sys.modules or sys.modules["mhm_b200._lib"]._lib is None, \
+        "the reference arm must not load libmhm_cuda.so"
     emit(({
         "impl": "reference", "metric": "L1 cell-timesteps/s", "value": v, "unit": "cell-timesteps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE config 5 per-GPU share (synthetic ~1M-cell domain x 32 members per "
-                               "GPU, hourly forcing, Muskingum routing case 1), timed on a bounded sample: see "
-                               "cpu_baseline.sample",
+        "config": {"workload": "BASELINE config 5 per-GPU share (synthetic %d-cell domain, hourly forcing, Muskingum "
+                               "routing case 1 on the same %d-node network); the CPU arm steps ONE member, the GPU arm "
+                               "32 per GPU" % (prob["nCells"], prob["nCells"]),
                    "cells": prob["nCells"], "members_per_gpu": 1, "block_hours": hours},
         "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port",
                          "sample": sample},

@@ -156,6 +156,7 @@ int mhm_cuda_init(int device, mhm_cuda_context** out) {
     ctx->block_bytes = (size_t)((double)total_b * 0.45);
   if (const char* s = getenv("MHM_CUDA_BLOCK_BYTES")) ctx->block_bytes = (size_t)atoll(s);
   MHM_CUDA_OK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (const char* s = getenv("MHM_CUDA_LAUNCH_LOG")) ctx->launch_log = fopen(s, "w");
   *out = ctx;
   return 0;
 }
@@ -167,6 +168,7 @@ int mhm_cuda_finalize(mhm_cuda_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->domains) free_domain(kv.second);
   mhm_cuda_comm_finalize(ctx);
+  if (ctx->launch_log) fclose(ctx->launch_log);
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
   for (auto& t : ctx->pending) {
     cudaEventDestroy(t.a);
@@ -907,6 +909,8 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
     memcpy(a.idx_in, idx + t0, (size_t)nb * sizeof(StepIdx));
     rc = ctx->math_mode == 1 ? launch_cell_block_fast(a, d->cfg.nHorizons, ctx->stream)
                              : launch_cell_block_strict(a, d->cfg.nHorizons, ctx->stream);
+    if (ctx->launch_log)  // MHM_CUDA_LAUNCH_LOG: one line per cell-kernel launch (profiles/cell_profile.py)
+      fprintf(ctx->launch_log, "cell %d %d %d %d %d\n", a.tt_first, nb, a.nCells, a.nMembers, a.uniform_calendar);
     ++launches;
     if (rc == 0 && closes) {
       const size_t w = d->out_win_tt.size();

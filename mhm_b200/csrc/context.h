@@ -135,6 +135,7 @@ struct mhm_cuda_context {
   int sm_count = 148;                      // streaming multiprocessors of the device
   bool uniform_calendar = true;            // MHM_CUDA_NO_UNIFORM_CALENDAR (diagnostics) switches it off
   // the GPUs of one box, one process each (comm.cu): NCCL communicator owned by the library
+  FILE* launch_log = nullptr;              // MHM_CUDA_LAUNCH_LOG (diagnostics)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
 

@@ -1251,3 +1251,58 @@ int32_t orc_meteo_l2_to_l1(const double *data2, int32_t nr2, int32_t nc2, int32_
   free(cnt);
   return ncell;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * L11_routing_order, mRM/mo_mrm_net_startup.f90:765-842, in linear time.
+ * The reference numbers the headwater links 1..nHead in ascending link index (:779-803) and then
+ * sweeps the remaining links in ascending index over and over; a link is numbered in the first
+ * sweep in which all links entering its from-node carry a number already -- numbers given earlier
+ * in the SAME sweep count (:812-838).  So a link i whose inflowing links are J gets numbered in
+ *   pass(i) = max(1, max_{j in J} (pass(j) + (j > i)))       (headwater links: pass 0)
+ * and its number is the rank of (pass(i), i).  One topological walk (links leave every node at most
+ * once, so the link graph is a forest) and a counting sort by pass.
+ * --------------------------------------------------------------------------------------------- */
+int32_t orc_routing_order_linear(int32_t nNodes, int32_t nLinks, const int32_t *fromN, const int32_t *toN,
+                                 int32_t *rOrder, int32_t *netPerm) {
+  int32_t *out_link = (int32_t *)malloc(((size_t)nNodes + 1) * sizeof(int32_t));
+  int32_t *waiting = (int32_t *)calloc((size_t)nLinks + 1, sizeof(int32_t));
+  int32_t *pass = (int32_t *)calloc((size_t)nLinks + 1, sizeof(int32_t));
+  int32_t *stack = (int32_t *)malloc(((size_t)nLinks + 1) * sizeof(int32_t));
+  int32_t rc = 0, top = 0, seen = 0, maxpass = 0;
+  if (!out_link || !waiting || !pass || !stack) { rc = 2; goto done; }
+  for (int32_t nd = 0; nd <= nNodes; ++nd) out_link[nd] = -1;
+  for (int32_t i = 0; i < nLinks; ++i) out_link[fromN[i]] = i;
+  for (int32_t j = 0; j < nLinks; ++j) {        /* links entering the from-node of link d */
+    const int32_t d = out_link[toN[j]];
+    if (d >= 0 && d != j) waiting[d] += 1;
+  }
+  for (int32_t i = 0; i < nLinks; ++i)
+    if (waiting[i] == 0) stack[top++] = i;      /* headwater links */
+  while (top > 0) {
+    const int32_t j = stack[--top];
+    ++seen;
+    if (pass[j] > maxpass) maxpass = pass[j];
+    const int32_t d = out_link[toN[j]];
+    if (d < 0 || d == j) continue;
+    int32_t need = pass[j] + (j > d ? 1 : 0);
+    if (need < 1) need = 1;
+    if (need > pass[d]) pass[d] = need;
+    if (--waiting[d] == 0) stack[top++] = d;
+  }
+  if (seen != nLinks) { rc = 1; goto done; }    /* a cycle */
+  {
+    int32_t *first = (int32_t *)calloc((size_t)maxpass + 2, sizeof(int32_t));
+    if (!first) { rc = 2; goto done; }
+    for (int32_t i = 0; i < nLinks; ++i) first[pass[i] + 1] += 1;
+    for (int32_t s = 0; s <= maxpass; ++s) first[s + 1] += first[s];
+    for (int32_t i = 0; i < nLinks; ++i) {      /* ascending i inside a pass */
+      const int32_t r = first[pass[i]]++;
+      rOrder[i] = r + 1;
+      netPerm[r] = i + 1;
+    }
+    free(first);
+  }
+done:
+  free(out_link); free(waiting); free(pass); free(stack);
+  return rc;
+}

@@ -134,6 +134,12 @@ double orc_mrm_update_param_case2(int32_t nNodes, int32_t nOutlets, const double
 /* L0_streamNet as left by L11_stream_features (mRM/mo_mrm_net_startup.f90:1370-1412) and the
  * 40th-percentile floor of the link lengths for cases 2/3 (:1440-1446).  2-D index (i, j) of a
  * Fortran (nrows0, ncols0) array is at [(j-1)*nrows0 + i-1]; fDir0 / id0 / streamNet0 are 2-D. */
+/* L11_routing_order (mRM/mo_mrm_net_startup.f90:765-842) for networks too large for the
+ * reference's O(nLinks^2) sweeps: the same rOrder / netPerm in linear time.  Used by the CPU arms of
+ * bench.py to build the 1M-node network without touching the product library; checked against a
+ * loop-for-loop transcription of the reference on random forests (tests/test_oracle_run.py). */
+int32_t orc_routing_order_linear(int32_t nNodes, int32_t nLinks, const int32_t *fromN, const int32_t *toN,
+                                 int32_t *rOrder, int32_t *netPerm);
 void orc_stream_net(int32_t nrows0, int32_t ncols0, const int32_t *fDir0_2d, int32_t nLinks,
                     const int32_t *netPerm, const int32_t *fRow, const int32_t *fCol,
                     const int32_t *tRow, const int32_t *tCol, int32_t *streamNet0_2d);

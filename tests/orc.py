@@ -139,8 +139,24 @@ def lib():
         L.orc_run.restype = i
         L.orc_time_indices.argtypes = [C.POINTER(OrcDomain), i] + [pi] * 8
         L.orc_time_indices.restype = None
+        L.orc_routing_order_linear.argtypes = [i, i, pi, pi, pi, pi]
+        L.orc_routing_order_linear.restype = i
         _lib = L
     return _lib
+
+
+def routing_order(nNodes, fromN, toN, nLinks=None):
+    """L11_routing_order through the oracle's linear-time restatement: (rOrder, netPerm), padded to
+    nNodes like mhm_b200.interface.routing_order (which this replaces for the CPU arms of bench.py)"""
+    fromN = np.ascontiguousarray(fromN, dtype=np.int32)
+    toN = np.ascontiguousarray(toN, dtype=np.int32)
+    nLinks = len(fromN) if nLinks is None else nLinks
+    rOrder = np.full(nNodes, -9999, dtype=np.int32)
+    netPerm = np.full(nNodes, -9999, dtype=np.int32)
+    rc = lib().orc_routing_order_linear(nNodes, nLinks, iptr(fromN), iptr(toN), iptr(rOrder), iptr(netPerm))
+    if rc != 0:
+        raise ValueError("orc_routing_order_linear: %s" % ("the link graph has a cycle" if rc == 1 else "out of memory"))
+    return rOrder, netPerm
 
 
 def dptr(a):

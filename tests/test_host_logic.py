@@ -176,6 +176,27 @@ def test_routing_order_equals_literal_reference():
         assert np.array_equal(netPerm[:nl], p_ref), trial
 
 
+def test_oracle_linear_routing_order_equals_literal_reference():
+    """the oracle's own linear-time L11_routing_order (used by bench.py's CPU arms, which must not
+    touch the product library) against the loop-for-loop transcription, and against the library"""
+    import orc
+
+    rng = np.random.default_rng(23)
+    for trial in range(200):
+        n = int(rng.integers(2, 60))
+        fromN, toN = random_forest(rng, n)
+        r_ref, p_ref = literal_routing_order(n, fromN, toN)
+        rOrder, netPerm = orc.routing_order(n, fromN, toN)
+        assert np.array_equal(rOrder[: len(fromN)], r_ref), trial
+        assert np.array_equal(netPerm[: len(fromN)], p_ref), trial
+    net = synth.scheidegger_network(np.random.default_rng(2), 60, 40)
+    a = orc.routing_order(net["nNodes"], net["fromN"], net["toN"])
+    b = interface.routing_order(net["nNodes"], net["fromN"], net["toN"])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    with pytest.raises(ValueError):
+        orc.routing_order(3, np.array([1, 2, 3], dtype=np.int32), np.array([2, 3, 1], dtype=np.int32))
+
+
 def test_routing_order_scheidegger():
     rng = np.random.default_rng(3)
     net = synth.scheidegger_network(rng, 14, 9)
