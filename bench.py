@@ -488,6 +488,9 @@ def run_ours(args):
         if cpu is not None:
             out["cpu_baseline"] = cpu
         emit(out)
+    free_b, total_b = torch.cuda.mem_get_info()
+    sys.stderr.write("bench.py: rank %d device memory in use at the end: %.1f of %.1f GB\n" % (
+        rank, (total_b - free_b) / 1e9, total_b / 1e9))
     ctx.finalize()
     if world > 1:
         dist.barrier()
@@ -557,7 +560,7 @@ def run_shard(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    W, K, T, M = args.warmup, args.steps, min(args.block_hours, 48), args.members
+    W, K, T, M = args.warmup, args.steps, args.block_hours, args.members
     if (args.nx, args.ny) == (1180, 1000):
         args.nx, args.ny = 1000, 590  # ~500k cells at 85 % fill
     n_days = ((W + K) * T + 23) // 24
@@ -566,6 +569,7 @@ def run_shard(args):
     part = shard.partition(prob["net"], world)
     ctx = interface.Context(local)
     ctx.set_math_mode(args.mode)
+    ctx.comm_init(dist if world > 1 else None)  # the cut-link exchange runs inside the library (NCCL)
     run = shard.ShardedRun(ctx, prob, part, rank, world, dist if world > 1 else None, nMembers=M)
 
     def barrier():
@@ -583,6 +587,7 @@ def run_shard(args):
     t0 = time.time()
     for i in range(W, W + K):
         run.run_block(i * T + 1, T)
+    run.finish()
     barrier()
     wall = time.time() - t0
     clocks = sampler.summary()

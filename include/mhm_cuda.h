@@ -411,6 +411,20 @@ int mrm_partition_subcatchments(int32_t nNodes, int32_t nLinks, const int32_t *f
  * block have arrived. */
 int mrm_cuda_set_deferred(mhm_cuda_context *ctx, int32_t iDomain, int32_t deferred);
 int mrm_cuda_route_pending(mhm_cuda_context *ctx, int32_t iDomain);
+/* The same protocol with the exchange BELOW the C ABI (needs mhm_cuda_comm_init): the cut-link
+ * series travel by NCCL send / recv on the library's stream, no host synchronisation.
+ * mrm_cuda_set_exchange gives the plan -- send_links[r] / recv_links[r] = cut links whose series this
+ * shard sends to / receives from rank r; exportNodeList / ghostSourceNodeList of mrm_network must be
+ * grouped by peer rank in ascending rank order (and agree link by link with the peer's list).
+ * mrm_cuda_shard_run_steps advances one time block (n_steps must fit one block): a shard that only
+ * sends runs its cells, routes, sends; a shard that receives first receives and routes the block
+ * left pending by its previous call, sends on what it exports, and then runs this block's cells --
+ * it works one block behind its senders, so nobody waits for anybody's routing.  mrm_cuda_shard_flush
+ * routes the last pending block (call it once per level of receiving shards after the last block). */
+int mrm_cuda_set_exchange(mhm_cuda_context *ctx, int32_t iDomain, const int32_t *send_links,
+                          const int32_t *recv_links);
+int mrm_cuda_shard_run_steps(mhm_cuda_context *ctx, int32_t iDomain, int32_t tt_first, int32_t n_steps);
+int mrm_cuda_shard_flush(mhm_cuda_context *ctx, int32_t iDomain);
 /* routed outflow of the export nodes over the last routed block / of the ghost sources over the
  * pending block, DEVICE buffers laid out [member][node in list order][n_steps]; both are
  * enqueued on the library's stream (mhm_cuda_synchronize before handing the buffer to NCCL) */

@@ -109,6 +109,9 @@ def load():
         "mhm_cuda_set_meteo_l2": [vp, i32, i32, vp, i32, i32, i32, pi, d, i32, i32, pi, d, i64, i64],
         "mrm_partition_subcatchments": [i32, i32, pi, pi, pi, i32, pi],
         "mrm_cuda_set_deferred": [vp, i32, i32],
+        "mrm_cuda_set_exchange": [vp, i32, pi, pi],
+        "mrm_cuda_shard_run_steps": [vp, i32, i32, i32],
+        "mrm_cuda_shard_flush": [vp, i32],
         "mrm_cuda_route_pending": [vp, i32],
         "mrm_cuda_export_outflow": [vp, i32, vp, i32],
         "mrm_cuda_import_outflow": [vp, i32, vp, i32],

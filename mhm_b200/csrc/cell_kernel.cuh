@@ -47,6 +47,9 @@ namespace mhm {
 #ifndef MHM_CELL_PIPE3
 #define MHM_CELL_PIPE3 0  // uniform-calendar launches: three steps in flight (0: two; measured 10 % faster on B200)
 #endif
+#ifndef MHM_RESV_POW_POLY
+#define MHM_RESV_POW_POLY 0  // slow-interflow power without table look-ups (more fp64, no bank conflicts)
+#endif
 #ifndef MHM_POW_COMPACT
 #define MHM_POW_COMPACT 1  // infiltration powers of a warp compacted through shared memory (0: per lane)
 #endif
@@ -969,7 +972,11 @@ __device__ __forceinline__ double cascade_reservoirs_sel(const PARAMS& p, CellSt
   const double fmin1 = min_sel(f1, ue);
   const double fast = us > un.x ? fmin1 : 0.0;
   us = us - fast;
+#if MHM_RESV_POW_POLY
+  const double s1 = sl.x * fm::pow_pos(us, sl.y), ue2 = us - kEps;       // garbage for us <= eps: discarded
+#else
   const double s1 = sl.x * fm::pow_tab(tab, us, sl.y), ue2 = us - kEps;  // garbage for us <= eps: discarded
+#endif
   const double smin1 = min_sel(s1, ue2);
   const double slow = us > kEps ? smin1 : 0.0;
   us = us - slow;

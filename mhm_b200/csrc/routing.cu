@@ -118,6 +118,13 @@ struct Routing {
   int32_t pend_tt = 0, pend_n = 0;  // block whose cells ran but whose routing is pending
   bool pend_fused = false;
   int32_t last_n = 0;               // steps of the last routed block (export)
+  // cut-link exchange below the C ABI (mrm_cuda_set_exchange): links sent to / received from each
+  // rank; the export / ghost lists are grouped by peer rank.  Device tables per list entry: first
+  // link of its peer's piece, links in the piece, position inside the piece.
+  std::vector<int32_t> xsend, xrecv;
+  int32_t *d_xs_tab = nullptr, *d_xr_tab = nullptr;  // [3][nExport] / [3][nGhost]
+  double *xsend_buf = nullptr, *xrecv_buf = nullptr;
+  size_t xsend_cap = 0, xrecv_cap = 0;
   int32_t* d_cell_entry = nullptr;  // [nCells1] lane of the cell's node
   int8_t* d_cell_skew = nullptr;    // [nCells1] position of that node in its segment
   double* d_cell_area = nullptr;    // [nCells1] area factor of mo_mrm_pre_routing.f90:125/:141
@@ -162,7 +169,7 @@ void routing_free(Routing* rt) {
                   rt->L11_L1_Id, rt->d_inflow_node, rt->d_inflow_index, rt->d_inflow_head,
                   rt->L1_area, rt->L11_area, rt->d_gauge_col, rt->d_gauge_slot, rt->d_cell_entry, rt->d_cell_skew, rt->d_ghost_lane, rt->d_export_lane,
                   rt->d_cell_area, rt->C1, rt->C2, rt->qOUT, rt->qMod, rt->qTIN, rt->qTR,
-                  rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry, rt->gauge_hist,
+                  rt->d_length, rt->d_slope, rt->d_fFPimp, rt->carry, rt->gauge_hist, rt->d_xs_tab, rt->d_xr_tab, rt->xsend_buf, rt->xrecv_buf,
                   rt->qout_hist, rt->qtr_hist, rt->qmod_g, rt->d_inflow_val, rt->d_events};
   for (void* p : ptrs) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
@@ -1412,6 +1419,27 @@ __global__ void import_outflow_kernel(int nList, int M, int E, int T, const int3
   qtr_hist[hidx(t, M, E, m, lanes[e])] = in[((size_t)m * nList + e) * T + t];
 }
 
+// the same for the exchange buffers of mrm_cuda_shard_run_steps: one contiguous piece
+// [member][link of the piece][step] per peer rank, pieces in rank order
+__global__ void xchg_pack_kernel(int nList, int M, int E, int T, const int32_t* __restrict__ lanes,
+                                 const int32_t* __restrict__ tab, const double* __restrict__ qtr_hist,
+                                 double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y, m = blockIdx.z;
+  if (t >= T) return;
+  const size_t first = (size_t)tab[e], cnt = (size_t)tab[nList + e], loc = (size_t)tab[2 * nList + e];
+  out[(first * M + (size_t)m * cnt + loc) * T + t] = qtr_hist[hidx(t, M, E, m, lanes[e])];
+}
+__global__ void xchg_unpack_kernel(int nList, int M, int E, int T, const int32_t* __restrict__ lanes,
+                                   const int32_t* __restrict__ tab, const double* __restrict__ in,
+                                   double* __restrict__ qtr_hist) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y, m = blockIdx.z;
+  if (t >= T) return;
+  const size_t first = (size_t)tab[e], cnt = (size_t)tab[nList + e], loc = (size_t)tab[2 * nList + e];
+  qtr_hist[hidx(t, M, E, m, lanes[e])] = in[(first * M + (size_t)m * cnt + loc) * T + t];
+}
+
 int mrm_partition_subcatchments(int32_t nNodes, int32_t nLinks, const int32_t* fromN,
                                 const int32_t* toN, const int32_t* netPerm, int32_t nParts,
                                 int32_t* part_of_node) {
@@ -1520,6 +1548,103 @@ int mrm_cuda_import_outflow(mhm_cuda_context* ctx, int32_t iDomain, const double
       rt->nGhost, rt->M, rt->E, n_steps, rt->d_ghost_lane, dev_in, rt->qtr_hist);
   MHM_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// ---- sub-catchment sharding with the exchange below the C ABI --------------------------------
+static std::vector<int32_t> piece_table(const std::vector<int32_t>& counts, int32_t n_list) {
+  std::vector<int32_t> tab((size_t)3 * n_list);
+  int32_t e = 0, first = 0;
+  for (int32_t c : counts) {
+    for (int32_t k = 0; k < c; ++k, ++e) {
+      tab[(size_t)e] = first;
+      tab[(size_t)n_list + e] = c;
+      tab[(size_t)2 * n_list + e] = k;
+    }
+    first += c;
+  }
+  return tab;
+}
+
+int mrm_cuda_set_exchange(mhm_cuda_context* ctx, int32_t iDomain, const int32_t* send_links,
+                          const int32_t* recv_links) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  Routing* rt = d->rt;
+  MHM_REQUIRE(rt && send_links && recv_links, "set_exchange: no network set, or null plan");
+  MHM_REQUIRE(ctx->nranks == 1 || ctx->nccl_comm, "set_exchange: no communicator (mhm_cuda_comm_init)");
+  rt->xsend.assign(send_links, send_links + ctx->nranks);
+  rt->xrecv.assign(recv_links, recv_links + ctx->nranks);
+  int64_t ns = 0, nr = 0;
+  for (int r = 0; r < ctx->nranks; ++r) {
+    MHM_REQUIRE(send_links[r] >= 0 && recv_links[r] >= 0 && (r != ctx->rank || (send_links[r] == 0 && recv_links[r] == 0)),
+                "set_exchange: bad plan entry for rank %d", r);
+    ns += send_links[r];
+    nr += recv_links[r];
+  }
+  MHM_REQUIRE(ns == rt->nExport && nr == rt->nGhost,
+              "set_exchange: the plan sends %lld / receives %lld links, the network has %d exports / %d ghost sources",
+              (long long)ns, (long long)nr, rt->nExport, rt->nGhost);
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  if (int rc = upload(&rt->d_xs_tab, piece_table(rt->xsend, rt->nExport), ctx->stream)) return rc;
+  if (int rc = upload(&rt->d_xr_tab, piece_table(rt->xrecv, rt->nGhost), ctx->stream)) return rc;
+  rt->deferred = true;
+  rt->pend_n = 0;
+  return 0;
+}
+
+// receive the ghost series of the pending block, route it, send the export series on
+static int shard_route_pending(mhm_cuda_context* ctx, Domain* d) {
+  Routing* rt = d->rt;
+  const int32_t n = rt->pend_n, tt = rt->pend_tt;
+  if (n <= 0) return 0;
+  rt->pend_n = 0;
+  const int N = ctx->nranks, M = rt->M;
+  std::vector<size_t> cnt((size_t)N);
+  if (rt->nGhost > 0) {
+    for (int r = 0; r < N; ++r) cnt[(size_t)r] = (size_t)rt->xrecv[(size_t)r] * M * n;
+    if (int rc = ensure(&rt->xrecv_buf, &rt->xrecv_cap, (size_t)rt->nGhost * M * n, ctx->stream)) return rc;
+    if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(n, M, rt->E), ctx->stream)) return rc;
+    if (int rc = comm_send_recv(ctx, nullptr, nullptr, rt->xrecv_buf, cnt.data(), ctx->stream)) return rc;
+    xchg_unpack_kernel<<<dim3((n + 63) / 64, rt->nGhost, M), 64, 0, ctx->stream>>>(
+        rt->nGhost, M, rt->E, n, rt->d_ghost_lane, rt->d_xr_tab, rt->xrecv_buf, rt->qtr_hist);
+    MHM_CUDA_OK(cudaGetLastError());
+  }
+  if (int rc = routing_run_block(ctx, d, tt, n, rt->pend_fused)) return rc;
+  if (rt->nExport > 0) {
+    for (int r = 0; r < N; ++r) cnt[(size_t)r] = (size_t)rt->xsend[(size_t)r] * M * n;
+    if (int rc = ensure(&rt->xsend_buf, &rt->xsend_cap, (size_t)rt->nExport * M * n, ctx->stream)) return rc;
+    xchg_pack_kernel<<<dim3((n + 63) / 64, rt->nExport, M), 64, 0, ctx->stream>>>(
+        rt->nExport, M, rt->E, n, rt->d_export_lane, rt->d_xs_tab, rt->qtr_hist, rt->xsend_buf);
+    MHM_CUDA_OK(cudaGetLastError());
+    if (int rc = comm_send_recv(ctx, rt->xsend_buf, cnt.data(), nullptr, nullptr, ctx->stream)) return rc;
+  }
+  return 0;
+}
+
+int mrm_cuda_shard_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first, int32_t n_steps) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  Routing* rt = d->rt;
+  MHM_REQUIRE(rt && rt->deferred && (int)rt->xsend.size() == ctx->nranks,
+              "shard_run_steps: mrm_cuda_set_exchange has not been called");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  // a shard that receives works one block behind its senders: it routes the block whose ghost
+  // series were sent during the senders' previous call, then runs this block's cells -- nobody waits
+  if (rt->nGhost > 0)
+    if (int rc = shard_route_pending(ctx, d)) return rc;
+  if (int rc = mhm_cuda_run_steps(ctx, iDomain, tt_first, n_steps)) return rc;  // cells; routing pending
+  if (rt->nGhost == 0)
+    if (int rc = shard_route_pending(ctx, d)) return rc;
+  return 0;
+}
+
+int mrm_cuda_shard_flush(mhm_cuda_context* ctx, int32_t iDomain) {
+  Domain* d = find_domain(ctx, iDomain);
+  if (!d) return 1;
+  Routing* rt = d->rt;
+  MHM_REQUIRE(rt && rt->deferred, "shard_flush: the domain is not sharded");
+  MHM_CUDA_OK(cudaSetDevice(ctx->device));
+  return shard_route_pending(ctx, d);
 }
 
 int mrm_routing_order(int32_t nNodes, int32_t nLinks, const int32_t* fromN, const int32_t* toN,

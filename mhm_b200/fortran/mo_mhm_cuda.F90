@@ -233,6 +233,25 @@ module mo_mhm_cuda
       integer(c_int32_t), value :: iDomain
       integer(c_int64_t), intent(out) :: bytes
     end function
+    !> sub-catchment sharding with the NCCL exchange inside the library
+    integer(c_int) function mrm_cuda_set_exchange(ctx, iDomain, send_links, recv_links) &
+        bind(C, name = 'mrm_cuda_set_exchange')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+      integer(c_int32_t), dimension(*), intent(in) :: send_links, recv_links
+    end function
+    integer(c_int) function mrm_cuda_shard_run_steps(ctx, iDomain, tt_first, n_steps) &
+        bind(C, name = 'mrm_cuda_shard_run_steps')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain, tt_first, n_steps
+    end function
+    integer(c_int) function mrm_cuda_shard_flush(ctx, iDomain) bind(C, name = 'mrm_cuda_shard_flush')
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int32_t), value :: iDomain
+    end function
     integer(c_int) function mhm_cuda_set_meteo_weights(ctx, iDomain, var, base, ld, offset) &
         bind(C, name = 'mhm_cuda_set_meteo_weights')
       import
@@ -614,7 +633,8 @@ module mo_mhm_cuda
             mhm_cuda_kernel_stats, mhm_cuda_kernel_stats_reset, mhm_cuda_measure_dfma_peak, &
             mpr_cuda_grid_destroy, mpr_cuda_upscale_geometric_mean, mhm_grid_init_lowres_level, &
             mhm_time_indices, mhm_cuda_comm_unique_id, mhm_cuda_comm_init, mhm_cuda_comm_finalize, &
-            mhm_cuda_comm_info, mhm_cuda_meteo_shared_rows, mhm_cuda_set_meteo_shared, mhm_cuda_meteo_h2d_bytes
+            mhm_cuda_comm_info, mhm_cuda_meteo_shared_rows, mhm_cuda_set_meteo_shared, mhm_cuda_meteo_h2d_bytes, &
+            mrm_cuda_set_exchange, mrm_cuda_shard_run_steps, mrm_cuda_shard_flush
   public :: mpr_l0_inputs, mpr_soil_db, mhm_optisim_config
 
 contains

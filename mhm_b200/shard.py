@@ -95,8 +95,10 @@ def extract(prob, part, rank):
     gsel = [g for g, nd in enumerate(np.asarray(net["gaugeNodeList"]) - 1) if own[nd]]
     area11 = np.zeros(nn_loc)
     area11[:n_local] = np.asarray(net["L11_areaCell"])[owned_nodes]
-    nl_glob = nl
-    sl = np.asarray(net["L11_slope"])[:nl_glob]
+    # reg_rout's maxval(slope(:)) runs over L11_slope(s11:e11-1), i.e. nNodes - 1 entries of the WHOLE
+    # domain -- with several outlets that is more than its links (mRM/mo_mrm_mpr.f90:97,
+    # mHM/mo_mhm_interface_run.f90:577)
+    sl = np.asarray(net["L11_slope"])[: max(nn - 1, 0)]
     lnet = {
         "nNodes": nn_loc, "nOutlets": nn_loc - len(links), "nCells1": len(cells), "map_flag": 1,
         "fromN": f_loc, "toN": t_loc, "netPerm": p_loc,
@@ -139,22 +141,53 @@ def extract(prob, part, rank):
 class ShardedRun:
     """one shard per rank; `dist` = torch.distributed (NCCL on GPUs) or None with world size 1"""
 
-    def __init__(self, ctx, prob, part, rank, world, dist=None, device=None, nMembers=1):
+    def __init__(self, ctx, prob, part, rank, world, dist=None, device=None, nMembers=1, member_params=None,
+                 native=None):
+        """native: the exchange runs inside the library (mrm_cuda_set_exchange / mrm_cuda_shard_run_steps,
+        NCCL on the library's stream, shard 0 one block behind); default when the context owns a
+        communicator of `world` ranks.  Otherwise torch.distributed send / recv from Python."""
         import torch
 
         from . import driver
 
         self.torch, self.dist, self.rank, self.world, self.ctx = torch, dist, rank, world, ctx
         self.sub = extract(prob, part, rank)
-        self.dom = driver.setup_domain(ctx, 1, self.sub, nMembers=nMembers)
-        check(ctx.L.mrm_cuda_set_deferred(ctx.h, 1, 1))
+        cells = self.sub["shard"]["cells"]
+        sub_mp = None
+        if member_params is not None:
+            sub_mp = [{k: (np.ascontiguousarray(v[..., cells]) if k not in CELL_KEYS_SKIP else v)
+                       for k, v in P.items()} for P in member_params]
+        self.dom = driver.setup_domain(ctx, 1, self.sub, nMembers=nMembers, member_params=sub_mp)
+        if native is None:
+            native = world > 1 and ctx.comm_info()["nranks"] == world
+        self.native = native
+        if native:
+            sh = self.sub["shard"]
+            send = np.zeros(world, dtype=np.int32)
+            recv = np.zeros(world, dtype=np.int32)
+            if rank == 0:
+                recv[: len(sh["recv_counts"])] = sh["recv_counts"]
+                recv[0] = 0
+            else:
+                send[0] = sh["n_export"]
+            check(ctx.L.mrm_cuda_set_exchange(ctx.h, 1, _pi(send), _pi(recv)))
+        else:
+            check(ctx.L.mrm_cuda_set_deferred(ctx.h, 1, 1))
         self.M = nMembers
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def finish(self):
+        """route what is still pending (native exchange: shard 0 works one block behind)"""
+        if getattr(self, "native", False):
+            check(self.ctx.L.mrm_cuda_shard_flush(self.ctx.h, 1))
 
     def run_block(self, tt_first, n_steps):
         """cells of the block everywhere, then routing: shards 1.. first, shard 0 after the
         outflow series of all cut links have arrived"""
         t, L, ctx, sh = self.torch, self.ctx.L, self.ctx, self.sub["shard"]
+        if getattr(self, "native", False):
+            check(L.mrm_cuda_shard_run_steps(ctx.h, 1, tt_first, n_steps))
+            return
         self.dom.run_steps(tt_first, n_steps)
         if self.rank != 0:
             check(L.mrm_cuda_route_pending(ctx.h, 1))
