@@ -58,6 +58,11 @@ def parse():
     ap.add_argument("--no-routing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed legs")
+    ap.add_argument("--full-run", action="store_true",
+                    help="the north-star run: --hours model hours (default one year) of the whole domain x members, "
+                         "streamed forcing, default monthly outputs, checked against the oracle")
+    ap.add_argument("--hours", type=int, default=8760)
+    ap.add_argument("--no-outputs", action="store_true", help="--full-run without gridded outputs")
     ap.add_argument("--cpu-hours", type=int, default=24)
     ap.add_argument("--mpr", action="store_true",
                     help="time mpr_eval (gamma -> all L1 effective parameters) on the per-GPU share of "
@@ -498,6 +503,184 @@ def run_ours(args):
     return out
 
 
+DEFAULT_OUTPUTS = [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 1, 1, 1]  # the reference's mhm_outputs.nml
+
+
+def run_full(args):
+    """The north-star run: the whole ~1M-cell domain x `members` per GPU through `--hours` model hours
+    (default one year, hourly), forcing STREAMED from pinned host memory chunk by chunk (three distinct
+    128-hour chunks -- warm, cold with snow, mild -- cycled, so consecutive chunks differ), across
+    month / LAI / year / land-cover-scene boundaries, with the reference's default mhm_outputs.nml
+    (monthly windows, 19 variables = 22 fields) accumulated on the device and every closed window of
+    member 0 fetched.  Checked against the oracle: a sample of cells through ALL steps (final states
+    and every monthly window) and the gauge discharge of the first 256 hours from a full-domain run."""
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    import torch
+    import torch.distributed as dist
+
+    from mhm_b200 import interface, synth
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    T, M, H = args.block_hours, args.members, args.hours
+    prob, rng = build_problem(args, H)
+    n = prob["nCells"]
+    ctx = interface.Context(local)
+    ctx.set_math_mode(args.mode)
+    ctx.comm_init(dist if world > 1 else None)
+    mrng = np.random.default_rng(1000 + rank)
+    dom = ctx.register_domain(1, n, 2, 12, 2, prob["processMatrix"], timestep_h=1, nMembers=M)
+    dom.set_meteo_config(-1, 24, True, False, synth.FNIGHT_PREC, synth.FNIGHT_PET, synth.FNIGHT_TEMP,
+                         synth.EVAP_COEFF)
+    dom.set_time(prob["time"])
+    net = prob["net"]
+    dom.set_network(net)
+    for m in range(M):
+        for name, arr in member_params(prob["params"], mrng, m).items():
+            dom.set_param(name, arr, member=m)
+        for name, arr in prob["states0"].items():
+            dom.set_state(name, arr, member=m)
+        rp = net["rout_param"] if m == 0 else net["rout_param"] * mrng.uniform(0.95, 1.05, 5)
+        dom.set_reg_rout(rp, net["L11_length"][: net["nNodes"] - 1], net["L11_slope"][: net["nNodes"] - 1],
+                         net["L11_nLinkFracFPimp"], member=m)
+    outputs = None if args.no_outputs else (DEFAULT_OUTPUTS, -2)
+    if outputs:
+        dom.set_outputs(*outputs)
+    # three distinct forcing chunks in pinned host memory (the same on every rank)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(synth.SEED)
+    torch.manual_seed(synth.SEED)
+    hours = torch.arange(T, device="cuda", dtype=torch.float64)[:, None]
+    host = []
+    for c, (t_mean, p_wet) in enumerate(((14.0, 0.2), (-3.0, 0.3), (6.0, 0.1))):
+        wet = torch.rand((T, n), generator=g, device="cuda") < p_wet
+        gam = torch.distributions.Gamma(torch.tensor(0.7, device="cuda", dtype=torch.float64),
+                                        torch.tensor(1.0 / 1.6, device="cuda", dtype=torch.float64))
+        pre = torch.where(wet, gam.sample((T, n)), torch.zeros((), device="cuda", dtype=torch.float64))
+        temp = (t_mean + 4.0 * torch.sin(2 * np.pi * (hours % 24) / 24.0)
+                + 2.0 * torch.randn((T, n), generator=g, device="cuda", dtype=torch.float64))
+        pet = (torch.clamp(0.15 * torch.sin(np.pi * ((hours % 24) - 6.0) / 12.0), min=0.0)
+               * (0.8 + 0.4 * torch.rand((T, n), generator=g, device="cuda", dtype=torch.float64)))
+        ch = {"pre": pre, "temp": temp, "pet": pet}
+        if world > 1:
+            for v in ch.values():
+                dist.broadcast(v, src=0)
+        host.append({k: torch.empty((T, n), dtype=torch.float64, pin_memory=True).copy_(v) for k, v in ch.items()})
+        del pre, temp, pet, wet, ch
+    torch.cuda.empty_cache()
+    firsts = list(range(1, H + 1, T))
+    nG = dom.nGaugesTotal
+    q_host = np.zeros((max(nG, 1), prob["time"]["nTimeSteps"]))
+    windows = []  # (tt_end, {(var, horizon): member-0 field at the sample cells})
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    cells = np.sort(np.random.default_rng(7).choice(n, size=2048, replace=False))
+
+    def upload(k):
+        f, cnt = firsts[k], min(T, H - firsts[k] + 1)
+        for v, t in host[k % 3].items():
+            dom.set_meteo_shared(v, t.data_ptr(), n, f, cnt)
+
+    ctx.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.time()
+    upload(0)
+    for k, f in enumerate(firsts):
+        cnt = min(T, H - f + 1)
+        dom.run_steps(f, cnt)
+        if k + 1 < len(firsts):
+            upload(k + 1)
+        if nG:
+            dom.get_runoff(f, cnt, member=0, out=q_host)
+        if outputs:
+            for w, tt_end in enumerate(dom.output_windows()):
+                fld = {}
+                for v in range(1, 22):
+                    if not DEFAULT_OUTPUTS[v - 1]:
+                        continue
+                    for h in ((1, 2) if v in (3, 4, 17, 19) else (0,)):
+                        fld[(v, h - 1 if h else -1)] = dom.get_output(w, v, h, member=0)[cells]
+                windows.append((tt_end, fld))
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.time() - t0
+    clocks = sampler.summary()
+    if world > 1:
+        t = torch.tensor([wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t[0])
+    parity = None
+    if rank == 0 and not args.no_parity:
+        import orc_run
+        import parity as P
+
+        sub = dict(prob)
+        sub["nCells"], sub["net"] = len(cells), None
+        sub["params"] = {k: (np.ascontiguousarray(v[..., cells]) if k != "rout_param" else v)
+                         for k, v in prob["params"].items()}
+        sub["states0"] = {k: np.ascontiguousarray(v[..., cells]) for k, v in prob["states0"].items()}
+        seq = [k % 3 for k in range(len(firsts))]
+        sub["forcing"] = {v: np.ascontiguousarray(np.concatenate([host[c][v].numpy()[:, cells] for c in seq])[:H])
+                          for v in ("pre", "temp", "pet")}
+        o = orc_run.OracleRun(sub, num_threads=os.cpu_count() or 1, outputs=outputs, max_windows=64)
+        o.run(1, H)
+        worst = {"state": 0.0, "output": 0.0}
+        for name in ("L1_inter", "L1_snowPack", "L1_sealSTW", "L1_unsatSTW", "L1_satSTW", "L1_soilMoist"):
+            got = dom.get_state(name, member=0)[..., cells]
+            worst["state"] = max(worst["state"], P.assert_close(got, o.S[name], "full run: " + name))
+        if outputs:
+            ref_w = o.out_windows()
+            assert [w[0] for w in ref_w] == [w[0] for w in windows], ([w[0] for w in ref_w], [w[0] for w in windows])
+            for (tt_end, got), (_, ref) in zip(windows, ref_w):
+                for key, val in got.items():
+                    worst["output"] = max(worst["output"], P.assert_close(
+                        val, ref[key], "full run: output %r of the window ending at step %d" % (key, tt_end)))
+        # gauges: the first 256 hours of the whole domain through the oracle
+        Hq = min(H, 256)
+        full = dict(prob)
+        full["forcing"] = {v: np.concatenate([host[c][v].numpy() for c in seq[: (Hq + T - 1) // T]])[:Hq]
+                           for v in ("pre", "temp", "pet")}
+        of = orc_run.OracleRun(full, num_threads=os.cpu_count() or 1)
+        of.run(1, Hq)
+        gq = P.assert_close(q_host[:, :Hq], of.mRM_runoff[:, :Hq], "full run: gauge discharge of the first hours",
+                            rtol=P.RTOL_Q)
+        parity = {"checked": True, "member": 0, "cells_sampled": int(len(cells)), "steps_checked": H,
+                  "max_rel_state": worst["state"], "max_rel_output": worst["output"],
+                  "output_windows_checked": len(windows), "gauge_hours_checked": Hq, "gauge_max_rel": gq,
+                  "max_snowpack_mm": float(np.max(o.S["L1_snowPack"]))}
+    if rank == 0:
+        idx = interface.time_indices(prob["time"], 1, 24, 1, H)
+        emit({
+            "metric": "L1 cell-timesteps/s", "value": float(n) * M * H * world / wall, "unit": "cell-timesteps/s",
+            "n_gpus": world, "steps": len(firsts), "warmup": 0, "ms_per_step": wall * 1e3 / len(firsts),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "north-star run: synthetic %d-cell domain x %d members per GPU x %d hourly steps "
+                                   "(%.1f days from 1990-05-31), forcing streamed from pinned host memory in %d-hour "
+                                   "chunks, Muskingum routing case 1, %s" % (
+                                       n, M, H, H / 24.0, T,
+                                       "default mhm_outputs.nml (22 monthly fields) accumulated on the device"
+                                       if outputs else "no gridded outputs"),
+                       "cells": n, "members_per_gpu": M, "block_hours": T, "hours": H, "math_mode": args.mode,
+                       "months_crossed": len({(s.year, s.month) for s in idx}) - 1,
+                       "land_cover_scenes": sorted({s.yId for s in idx})},
+            "wall_s": wall, "simulated_years_per_wall_hour": H / 8760.0 / (wall / 3600.0),
+            "e2e": {"value": float(n) * M * H * world / wall, "unit": "cell-timesteps/s",
+                    "h2d_bytes_per_step": int(dom.meteo_h2d_bytes() / len(firsts)),
+                    "d2h_bytes_per_step": int(max(nG, 1) * T * 8 + (len(windows) * 22 * n * 8) / len(firsts))},
+            "clocks": clocks, "parity_checked": bool(parity), "parity": parity})
+    ctx.finalize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_mpr(args):
     """MPR on the device: every transfer function and all (13 + 8 nH) nLC + 12 upscalings"""
     from mhm_b200 import interface, synth_mpr
@@ -689,6 +872,8 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.full_run:
+        run_full(a)
     elif a.mpr:
         run_mpr(a)
     elif a.shard:

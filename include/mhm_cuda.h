@@ -613,6 +613,12 @@ typedef struct mpr_l0_inputs {
   const double *slope_emp0;      /* L0_slope_emp */
   const double *y0;              /* level0%y packed: latitude */
   const double *gridded_LAI0;    /* L0_gridded_LAI (nL0, nLAI) */
+  /* A domain sharded by L1 cells (every shard holds the L0 cells under its own L1 cells): L0_soilId of
+   * the WHOLE domain's last L0 cell.  The reference's root fractions of the last horizon use the root
+   * zone depth the preceding loop left behind -- that of the last L0 cell's soil type
+   * (MPR/mo_mpr_smhorizons.f90:424-427, 453-539) -- so a shard needs this one number to reproduce the
+   * unsharded result.  0: this grid's own last cell (unsharded). */
+  int32_t lastSoilId0;
 } mpr_l0_inputs;
 int mpr_cuda_set_l0(mhm_cuda_context *ctx, int32_t iDomain, const mpr_l0_inputs *in);
 

@@ -283,6 +283,61 @@ __device__ __forceinline__ void accumulate_outputs(const uint32_t mask, double* 
   if (on(21)) add(f.v[MHM_F_MELT]);
 }
 
+// The reference's default mhm_outputs.nml (variables 1-16 and 19-21: 16 + 3 nH fields) with the open
+// window's sums in REGISTERS: the same additions in the same order, but no read-modify-write of
+// shared memory per step and field (22 fields cost 88 shared-memory wavefronts per warp-step, as much
+// as the whole cascade) and no run-time selection.  The kernel gives up occupancy for it (168
+// registers, 3 CTAs/SM).
+constexpr uint32_t kOutDefaultMask = 0xffffu << 1 | 1u << 19 | 1u << 20 | 1u << 21;  // bits 1..16, 19, 20, 21
+template <int NH>
+constexpr int out_default_slots() { return 16 + 3 * NH; }
+template <int NH>
+__device__ __forceinline__ void accumulate_outputs_default(double (&acc)[16 + 3 * NH], const FluxCapture& f,
+                                                           const CellStates<NH>& s, const double fS,
+                                                           const double* sat_o) {
+  const double fNS = 1.0 - fS;
+  int k = 0;
+  auto add = [&](double v) {
+    acc[k] = acc[k] + v;  // OutputVariable%updateVariable, mo_nc_output.f90:140-149
+    ++k;
+  };
+  add(s.inter);
+  add(s.snowpack);
+#pragma unroll
+  for (int h = 0; h < NH; ++h) add(s.sm[h]);
+#pragma unroll
+  for (int h = 0; h < NH; ++h) add(s.sm[h] / sat_o[h]);
+  {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) a = a + s.sm[h];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) b = b + sat_o[h];
+    add(a / b);
+  }
+  add(s.sealed);
+  add(s.unsat);
+  add(s.sat);
+  add(f.v[MHM_F_PET_CALC]);
+  {
+    double a = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) a = a + f.aet_soil[h];
+    const double t1 = a * fNS, t2 = f.v[MHM_F_AETSEALED] * fS;
+    add((t1 + f.v[MHM_F_AETCANOPY]) + t2);
+  }
+  add(f.v[MHM_F_TOTAL_RUNOFF]);
+  add(f.v[MHM_F_RUNOFFSEAL] * fS);
+  add(f.v[MHM_F_FASTRUNOFF] * fNS);
+  add(f.v[MHM_F_SLOWRUNOFF] * fNS);
+  add(f.v[MHM_F_BASEFLOW] * fNS);
+  add(f.v[MHM_F_PERCOL] * fNS);
+#pragma unroll
+  for (int h = 0; h < NH; ++h) add(f.aet_soil[h] * fNS);
+  add(f.v[MHM_F_PREEFFECT]);
+  add(f.v[MHM_F_MELT]);
+}
+
 // mhm_interface_run_update_optisim (mo_mhm_interface_run.f90:776-857): the step's soil-moisture
 // fraction of the first nhor_sm horizons, total evapotranspiration and total water storage are
 // added to the open dataSim column (optidata_sim%add); BFI sums (:630-636) per cell, the host
@@ -1040,8 +1095,10 @@ struct ParamStoreOf {
 // FUSED (uniform launches only): the step's runoff goes to the routing's tiled node-runoff history
 // and nowhere else (true) / to the total-runoff history row and nowhere else (false) -- a block of
 // steps always has exactly one of the two sinks
-template <int NH, int VARIANT, bool OUT, bool UNIFORM = false, bool FUSED = false>
-__global__ void __launch_bounds__(kCellThreads, ParamPlace<NH>::min_blocks)
+// OUT: 0 no gridded outputs / aggregates, 1 run-time selection with the window in shared memory,
+// 2 the reference's default output set with the window in registers (accumulate_outputs_default)
+template <int NH, int VARIANT, int OUT, bool UNIFORM = false, bool FUSED = false>
+__global__ void __launch_bounds__(kCellThreads, OUT == 2 ? 3 : ParamPlace<NH>::min_blocks)
 MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
   const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
@@ -1147,9 +1204,14 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   double* const out_acc_l = out_sh + threadIdx.x;
   int out_y = -1;
   double out_fS = 0.0, out_sat[NH];
-  if (OUT) {
+  if (OUT == 1) {
     if (a.out_mask && live)
       for (int k = 0; k < a.out_nslots; ++k) out_acc_l[k * kCellThreads] = a.out_acc[(size_t)k * hist_stride + mc];
+  }
+  double oacc[OUT == 2 ? 16 + 3 * NH : 1];
+  if (OUT == 2) {
+#pragma unroll
+    for (int k = 0; k < 16 + 3 * NH; ++k) oacc[OUT == 2 ? k : 0] = a.out_acc[(size_t)k * hist_stride + mc];
   }
   // parameters of the step's land-cover scene / LAI step, reloaded when they change (with a
   // uniform calendar: at the launch's first step only)
@@ -1337,7 +1399,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       prec_calc = raw_pre;
     }
     FluxCapture cap;
-    const FluxEmitter<EMIT, OUT> emit{a.F, mc, n, (size_t)member * NH * n + c, a.write_fluxes && live,
+    const FluxEmitter<EMIT, OUT != 0> emit{a.F, mc, n, (size_t)member * NH * n + c, a.write_fluxes && live,
                                       &cap};
     emit(MHM_F_PET_CALC, pet_calc);
     emit(MHM_F_TEMP_CALC, temp_calc);
@@ -1376,12 +1438,12 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
                                                 a.tab.inv_evap_coeff[month], warp_tasks, sh_tab, emit);
     } else {
       if constexpr (!kTasksBySource)
-        total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case,
+        total_runoff = cascade_step<NH, VARIANT, EMIT, OUT != 0>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case,
                                                             a.tab.evap_coeff[month], a.tab.inv_evap_coeff[month],
                                                             warp_tasks.xy, sh_tab, emit);
     }
 #else
-    total_runoff = cascade_step<NH, VARIANT, EMIT, OUT>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case,
+    total_runoff = cascade_step<NH, VARIANT, EMIT, OUT != 0>(p, s, pet_calc, temp_calc, prec_calc, a.soil_case,
                                                         a.tab.evap_coeff[month], emit);
 #endif
 
@@ -1395,7 +1457,8 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
           for (int h = 0; h < NH; ++h)
             out_sat[h] = a.P[MHM_P_SOILMOISTSAT][(((size_t)member * a.nLC + yo) * NH + h) * n + c];
         }
-        if (a.out_mask) accumulate_outputs<NH>(a.out_mask, out_acc_l, cap, s, out_fS, out_sat);
+        if constexpr (OUT == 2) accumulate_outputs_default<NH>(oacc, cap, s, out_fS, out_sat);
+        else if (a.out_mask) accumulate_outputs<NH>(a.out_mask, out_acc_l, cap, s, out_fS, out_sat);
         if (a.agg_mask)
           accumulate_aggregates<NH>(a.agg_mask, a.agg_nhor_sm, a.agg_col, a.bfi_acc, mc, hist_stride, cap, s,
                                     out_fS, out_sat);
@@ -1515,9 +1578,15 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   }
   step(std::true_type{}, n_last);
 
-  if (OUT) {
+  if (OUT == 1) {
     if (a.out_mask && live)
       for (int k = 0; k < a.out_nslots; ++k) a.out_acc[(size_t)k * hist_stride + mc] = out_acc_l[k * kCellThreads];
+  }
+  if (OUT == 2) {
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 16 + 3 * NH; ++k) a.out_acc[(size_t)k * hist_stride + mc] = oacc[OUT == 2 ? k : 0];
+    }
   }
   // ---- write back states ----
   if (live) {

@@ -561,7 +561,7 @@ int mpr_cuda_set_l0(mhm_cuda_context* ctx, int32_t iDomain, const mpr_l0_inputs*
     mpr_free(s);
     return 2;
   }
-  s->last_soil = in->soilId0[n0 - 1];
+  s->last_soil = in->lastSoilId0 > 0 ? in->lastSoilId0 : in->soilId0[n0 - 1];
   s->lc_max.assign((size_t)s->nLC, 0);
   for (int y = 0; y < s->nLC; ++y)
     for (size_t k = 0; k < n0; ++k) {

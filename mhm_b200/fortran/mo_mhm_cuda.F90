@@ -87,6 +87,7 @@ module mo_mhm_cuda
     integer(c_int32_t) :: nrows0, ncols0
     type(c_ptr) :: mask0, upper_bound, lower_bound, left_bound, right_bound, n_subcells, geoUnit0, soilId0, &
                    LCover0, Asp0, slope_emp0, y0, gridded_LAI0
+    integer(c_int32_t) :: lastSoilId0   !< sharded domains: L0_soilId of the whole domain's last L0 cell; 0 otherwise
   end type mpr_l0_inputs
 
   !> soilDB + geological units (MPR/mo_mpr_global_variables.f90)

@@ -185,6 +185,42 @@ def make_mpr_problem(nx0=60, ny0=40, factor=5, nLC=2, nLAI=12, nH=2, soil_case=1
     return prob
 
 
+def shard_mpr_problem(prob, cells):
+    """The MPR inputs of ONE shard of a domain cut by L1 cells (sub-catchment sharding, BASELINE
+    config 4): the L0 cells under the shard's L1 cells, cropped to their bounding box, with the
+    shard's rows of the L0 -> L1 remap.  An L1 cell's parameters depend only on the L0 cells of its
+    own rectangle (MPR/mo_mpr_eval.f90:120-154, mo_upscaling_operators.f90), so a shard's MPR needs
+    no exchange and equals the whole domain's MPR on its cells bit for bit.
+    cells: ascending 0-based L1 cell indices."""
+    cells = np.asarray(cells, dtype=np.int64)
+    g = prob["grid"]
+    ub, lb = np.asarray(g["upper_bound"])[cells], np.asarray(g["lower_bound"])[cells]   # first index (rows), 1-based
+    le, ri = np.asarray(g["left_bound"])[cells], np.asarray(g["right_bound"])[cells]    # second index (columns)
+    r0, r1, c0, c1 = int(ub.min()), int(lb.max()), int(le.min()), int(ri.max())
+    mask_full = np.asarray(prob["mask0"]) != 0          # numpy (ncols0, nrows0) == Fortran (nrows0, ncols0)
+    sel = np.zeros_like(mask_full)
+    for k in range(len(cells)):                         # union of the shard's rectangles
+        sel[le[k] - 1: ri[k], ub[k] - 1: lb[k]] = True
+    sel &= mask_full
+    packed = sel[mask_full]                             # the shard's entries of every packed L0 vector
+    sub = dict(prob)
+    sub["nrows0"], sub["ncols0"] = r1 - r0 + 1, c1 - c0 + 1
+    sub["mask0"] = np.ascontiguousarray(sel[c0 - 1: c1, r0 - 1: r1], dtype=np.int32)
+    sub["nL0"] = int(packed.sum())
+    sub["nL1"] = len(cells)
+    sub["grid"] = {"upper_bound": (ub - (r0 - 1)).astype(np.int32), "lower_bound": (lb - (r0 - 1)).astype(np.int32),
+                   "left_bound": (le - (c0 - 1)).astype(np.int32), "right_bound": (ri - (c0 - 1)).astype(np.int32),
+                   "n_subcells": np.asarray(g["n_subcells"])[cells].astype(np.int32), "nCells1": len(cells)}
+    for k in ("geoUnit0", "soilId0", "Asp0", "slope_emp0", "y0"):
+        sub[k] = np.ascontiguousarray(np.asarray(prob[k])[packed])
+    for k in ("LCover0", "LAI0"):
+        sub[k] = np.ascontiguousarray(np.asarray(prob[k])[:, packed])
+    # the one global number MPR needs: the soil type of the whole domain's last L0 cell (see
+    # mpr_l0_inputs.lastSoilId0)
+    sub["lastSoilId0"] = int(prob.get("lastSoilId0", 0)) or int(np.asarray(prob["soilId0"])[-1])
+    return sub
+
+
 def set_mpr_inputs(dom, prob):
     """mpr_cuda_set_l0 + mpr_cuda_set_soildb for an interface.Domain"""
     L, g, db = dom.L, prob["grid"], prob["soil_db"]
@@ -208,6 +244,7 @@ def set_mpr_inputs(dom, prob):
     l0.geoUnit0, l0.soilId0, l0.LCover0 = ip(prob["geoUnit0"]), ip(prob["soilId0"]), ip(prob["LCover0"])
     l0.Asp0, l0.slope_emp0, l0.y0 = dp(prob["Asp0"]), dp(prob["slope_emp0"]), dp(prob["y0"])
     l0.gridded_LAI0 = dp(prob["LAI0"])
+    l0.lastSoilId0 = int(prob.get("lastSoilId0", 0))
     check(L.mpr_cuda_set_l0(dom.h, dom.id, C.byref(l0)))
     sd = _lib.MprSoilDb()
     sd.nSoilTypes, sd.maxHorizons, sd.nGeoUnits = db["nSoil"], db["maxHor"], len(prob["GeoUnitList"])

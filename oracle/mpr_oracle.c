@@ -455,6 +455,7 @@ static void mpr_scene(const orc_mpr_in *in, orc_mpr_out *o, const orc_l0_grid *g
         FC0[k] = FC0[k] * (dpth_t - dpth_f);
         PW0[k] = PW0[k] * (dpth_t - dpth_f);
       }
+      if (h == nH - 1 && in->lastSoilId0 > 0) dpth_t = in->RZdepth[in->lastSoilId0 - 1]; /* shard of a domain */
       /* root fractions :453-539.  NOTE the reference uses dpth_t/dpth_f as the previous loop
        * left them: for the last horizon that is RZdepth of the LAST L0 cell's soil type. */
       for (k = 0; k < n0; k++) {

@@ -67,6 +67,8 @@ typedef struct orc_mpr_in {
   double fracSealed_CityArea;
   const int32_t *processMatrix;
   const double *param;
+  int32_t lastSoilId0; /* > 0: soil id whose root zone depth the last horizon's root fractions use (a shard of a
+                          domain); 0: the last L0 cell's, as the reference's loops leave it */
 } orc_mpr_in;
 
 /* L1 effective parameters, Fortran (nL1, dim2, dim3), see include/mhm_cuda.h mhm_param_id */

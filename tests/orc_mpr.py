@@ -122,6 +122,7 @@ def run_mpr(prob, param=None):
     m.fracSealed_CityArea = prob["fracSealed_CityArea"]
     m.processMatrix = ip(pm)
     m.param = dp(p)
+    m.lastSoilId0 = int(prob.get("lastSoilId0", 0))
     o = MprOut()
     out = {}
     for name, fld in _OUT_FIELD.items():

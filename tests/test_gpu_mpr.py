@@ -127,3 +127,43 @@ def test_mpr_then_cells_end_to_end(ctx):
     worst = parity.assert_close(hist, ref, "total runoff history after device MPR")
     print("max relative difference %.2e" % worst)
     assert ref.max() > 0
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_mpr_sharded_by_l1_cells_equals_whole_domain(ctx, mode):
+    """BASELINE config 4: the domain's L1 cells are dealt to shards (here three irregular sets, like
+    sub-catchments); every shard gets only the L0 cells under its own L1 cells
+    (synth_mpr.shard_mpr_problem) and evaluates MPR on them.  Its parameters equal the whole domain's
+    on the same cells bit for bit -- an L1 cell sees only its own L0 rectangle -- and the oracle
+    agrees on the shard's inputs."""
+    prob = synth_mpr.make_mpr_problem(nx0=96, ny0=70, factor=6, nH=2, soil_case=1, pet_case=-1)
+    ctx.set_math_mode(mode)
+    dom = register(ctx, prob)
+    synth_mpr.mpr_eval(dom, prob["param"])
+    names = synth_mpr.outputs_for(1, -1)
+    shape = {n: synth_mpr.MPR_OUTPUTS[n](2, prob["nLAI"], prob["nLC"]) for n in names}
+    whole = {n: dom.get_param(n, *shape[n]) for n in names}
+    rng = np.random.default_rng(5)
+    owner = rng.integers(0, 3, prob["nL1"])
+    owner[: prob["nL1"] // 4] = 0          # one contiguous stretch and scattered cells
+    seen = 0
+    for r in range(3):
+        cells = np.nonzero(owner == r)[0]
+        sub = synth_mpr.shard_mpr_problem(prob, cells)
+        assert sub["nL0"] < prob["nL0"] and sub["nL0"] == int(np.asarray(prob["grid"]["n_subcells"])[cells].sum())
+        seen += sub["nL0"]
+        sd = ctx.register_domain(10 + r, sub["nL1"], sub["nH"], sub["nLAI"], sub["nLC"], sub["processMatrix"])
+        synth_mpr.set_mpr_inputs(sd, sub)
+        synth_mpr.mpr_eval(sd, sub["param"])
+        for n in names:
+            parity.assert_bit_exact(sd.get_param(n, *shape[n]), np.ascontiguousarray(whole[n][..., cells]),
+                                    "shard %d: %s" % (r, n))
+        if mode == "strict" and r == 1:
+            ref = orc_mpr.run_mpr(sub)
+            for n in names:
+                if n == "L1_petLAIcorFactor":
+                    parity.assert_close(sd.get_param(n, *shape[n]), ref[n], n, rtol=1e-12, atol=0)
+                else:
+                    parity.assert_bit_exact(sd.get_param(n, *shape[n]), ref[n], "oracle on the shard: " + n)
+    assert seen == prob["nL0"]
+    ctx.set_math_mode("strict")

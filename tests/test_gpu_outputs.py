@@ -118,3 +118,43 @@ def test_outputs_reproduce_reference_fluxes_states_file(ctx, case):
         got = dom.get_output(0, var, hor + 1 if hor >= 0 else 0)
         worst = parity.assert_close(got, want[0], "%s variable %d horizon %d" % (case, var, hor))
         print("%s var %d h %d: max rel diff %.2e" % (case, var, hor, worst))
+
+
+@pytest.mark.parametrize("nH,soil_case", [(2, 1), (1, 4), (2, 2)])
+def test_default_output_set_in_registers_equals_shared_memory_path(ctx, monkeypatch, nH, soil_case):
+    """The reference's default mhm_outputs.nml (variables 1-16, 19-21, monthly) on hourly forcing in
+    fast mode runs the kernel that keeps the open window in registers (OUT = 2); the general kernel
+    (window in shared memory, run-time selection; MHM_CUDA_NO_OUTPUT_REGISTERS) must give the same
+    windows bit for bit, both equal the oracle, with a warming period, a year change inside the run and
+    the run issued in uneven calls."""
+    flags = np.zeros(21, dtype=np.int32)
+    flags[:16] = 1
+    flags[18:21] = 1
+    prob = synth.make_problem(nx=30, ny=17, n_days=40, nH=nH, hourly=True, soil_case=soil_case, pet_case=-1,
+                              routing=False, start=(1990, 12, 10))
+    prob["time"]["warming_days"] = 2
+    nT = prob["time"]["nTimeSteps"]
+    o = orc_run.OracleRun(prob, outputs=(flags, -2))
+    o.run(1, nT)
+    ctx.set_math_mode("fast")
+    res = {}
+    for key in ("registers", "shared"):
+        if key == "shared":
+            monkeypatch.setenv("MHM_CUDA_NO_OUTPUT_REGISTERS", "1")
+        dom = fresh(ctx, prob, nMembers=2, member_params=[prob["params"]] * 2)
+        dom.set_outputs(flags, -2)
+        got, first = {}, 0
+        for a, b in ((1, 300), (301, 331), (632, nT - 631)):
+            dom.run_steps(a, b)
+            nwin, _ = compare(dom, o, first, tol_exact=False)
+            for w, tt in enumerate(dom.output_windows()):
+                for sl, (var, hor) in enumerate(o.out_windows()[first + w][1]):
+                    got[(tt, var, hor)] = dom.get_output(w, var, hor + 1 if hor >= 0 else 0, member=1)
+            first += nwin
+        assert first == len(o.out_windows()) >= 2
+        res[key] = got
+    monkeypatch.delenv("MHM_CUDA_NO_OUTPUT_REGISTERS")
+    assert res["registers"].keys() == res["shared"].keys()
+    for k in res["registers"]:
+        parity.assert_bit_exact(res["registers"][k], res["shared"][k], "window ending %d, variable %d, horizon %d" % k)
+    ctx.set_math_mode("strict")
