@@ -877,6 +877,7 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
     // of a launch share yId / iLAI / month and read consecutive meteo rows; a launch ends where
     // the calendar turns (about once a month)
     a.uniform_calendar = 0;
+    a.forcing_tma = 0;
     // (the uniform kernels index a launch's forcing rows with 32 bits)
     if (block_mode && ctx->uniform_calendar && !a.out_mask && !a.agg_mask && a.is_hourly && a.pet_case <= 0 &&
         (uint64_t)kIdxInline * (uint64_t)a.nCells < ((uint64_t)1 << 32)) {
@@ -890,6 +891,10 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
         nb = t;
         closes = false;
         a.uniform_calendar = 1;
+        // TMA bulk copies need 16-byte aligned row stretches: an even number of cells, aligned bases
+        // (MHM_CUDA_FORCING_TMA=0 keeps the per-lane loads)
+        a.forcing_tma = ctx->forcing_tma && a.nCells % 2 == 0 &&
+                        ((uintptr_t)a.met[MHM_M_PRE] | (uintptr_t)a.met[MHM_M_TEMP] | (uintptr_t)a.met[MHM_M_PET]) % 16 == 0;
       } else {
         for (t = 1; t < nb; ++t) {  // ... that ends where the uniform stretch begins
           const StepIdx &g = idx[t0 + t], &h = idx[t0 + t - 1];
@@ -1127,6 +1132,7 @@ int mhm_cuda_run_steps(mhm_cuda_context* ctx, int32_t iDomain, int32_t tt_first,
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
   if (int rc = ensure_calendar(ctx, d)) return rc;
   ctx->uniform_calendar = getenv("MHM_CUDA_NO_UNIFORM_CALENDAR") == nullptr;
+  if (const char* e = getenv("MHM_CUDA_FORCING_TMA")) ctx->forcing_tma = atoi(e) != 0;
   MHM_REQUIRE(tt_first >= 1 && n_steps >= 1 && tt_first + n_steps - 1 <= d->axis.nTimeSteps,
               "run_steps: steps %d..%d outside 1..%d", tt_first, tt_first + n_steps - 1,
               d->axis.nTimeSteps);

@@ -1070,6 +1070,46 @@ __device__ __forceinline__ double cascade_step_sel(const PARAMS& p, CellStates<N
 }
 #endif
 
+#if MHM_FAST
+// ---- forcing through the TMA unit (cp.async.bulk + mbarrier) ------------------------------------
+// A warp's 32 cells are one contiguous 256-byte stretch of every forcing row.  Lane 0 of the warp
+// keeps kFStages rows in flight: three 1-D bulk copies per row (precipitation, temperature, PET) land
+// in the warp's slice of a shared-memory ring and complete the row's mbarrier; the lanes wait for the
+// barrier's phase, read their three values, and the slot is refilled for the row kFStages later.  A
+// warp waits only for itself (the barriers are per warp), no registers hold prefetched forcing and no
+// per-lane global address is computed.  Needs 16-byte aligned rows (an even number of cells).
+constexpr int kFStages = 4;
+struct alignas(128) ForcingRing {
+  double v[kFStages][3][kCellThreads];
+  unsigned long long full[kCellThreads / 32][kFStages];
+};
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+#endif
+
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldg(p); }
 // everything of the time loop that lives across steps besides states and parameters
 struct CellCursor {
@@ -1097,7 +1137,8 @@ struct ParamStoreOf {
 // steps always has exactly one of the two sinks
 // OUT: 0 no gridded outputs / aggregates, 1 run-time selection with the window in shared memory,
 // 2 the reference's default output set with the window in registers (accumulate_outputs_default)
-template <int NH, int VARIANT, int OUT, bool UNIFORM = false, bool FUSED = false>
+// TMA (uniform launches): the forcing rows arrive through cp.async.bulk into a shared-memory ring
+template <int NH, int VARIANT, int OUT, bool UNIFORM = false, bool FUSED = false, bool TMA = false>
 __global__ void __launch_bounds__(kCellThreads, OUT == 2 ? 3 : ParamPlace<NH>::min_blocks)
 MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
@@ -1484,19 +1525,72 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     // (opaque to the optimiser: base + 8 * index is then one IMAD.WIDE per load)
     asm volatile("" : "+l"(bpre), "+l"(btemp), "+l"(bpet));
     unsigned fi = (unsigned)c;
-    double nx_pre = ldg_stream(bpre + fi), nx_temp = ldg_stream(btemp + fi), nx_pet = ldg_stream(bpet + fi);
+    double nx_pre = 0.0, nx_temp = 0.0, nx_pet = 0.0;
+    __shared__ std::conditional_t<TMA, ForcingRing, EmptyParams> fring;
+    int f_row = 0;  // next forcing row (relative to the launch's first) to hand out
+    const int n_rows = a.nSteps;
+    // TMA: lane 0 requests row r of the warp's 32 cells (rows r - kFStages .. have been consumed)
+    auto tma_request = [&](const int r) {
+      if constexpr (TMA) {
+        const int warp = threadIdx.x >> 5, sl = r % kFStages;
+        const int cell0 = (blockIdx.x / a.nMembers) * kCellThreads + warp * 32;
+        const int cnt = min(32, max(0, a.nCells - cell0));
+        const unsigned bar = smem_addr(&fring.full[warp][sl]);
+        mbar_expect_tx(bar, (unsigned)(3 * cnt * 8));
+        if (cnt > 0) {
+          const size_t off = (size_t)r * n + (size_t)cell0;
+          tma_load_1d(smem_addr(&fring.v[sl][0][warp * 32]), bpre + off, (unsigned)(cnt * 8), bar);
+          tma_load_1d(smem_addr(&fring.v[sl][1][warp * 32]), btemp + off, (unsigned)(cnt * 8), bar);
+          tma_load_1d(smem_addr(&fring.v[sl][2][warp * 32]), bpet + off, (unsigned)(cnt * 8), bar);
+        }
+      }
+    };
+    if constexpr (TMA) {
+      if ((threadIdx.x & 31) == 0) {
+        for (int sl = 0; sl < kFStages; ++sl) mbar_init(smem_addr(&fring.full[threadIdx.x >> 5][sl]), 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int r = 0; r < kFStages && r < n_rows; ++r) tma_request(r);
+      }
+      __syncwarp();
+    } else {
+      nx_pre = ldg_stream(bpre + fi);
+      nx_temp = ldg_stream(btemp + fi);
+      nx_pet = ldg_stream(bpet + fi);
+    }
+    // the next forcing row of this cell: (pre, temp, raw pet)
+    auto next_row = [&](double& pre, double& temp, double& pet) {
+      if constexpr (TMA) {
+        const int warp = threadIdx.x >> 5, sl = f_row % kFStages;
+        mbar_wait(smem_addr(&fring.full[warp][sl]), (unsigned)((f_row / kFStages) & 1));
+        pre = fring.v[sl][0][threadIdx.x];
+        temp = fring.v[sl][1][threadIdx.x];
+        pet = fring.v[sl][2][threadIdx.x];
+        __syncwarp();  // every lane has read the slot before lane 0 lets the TMA unit overwrite it
+        if ((threadIdx.x & 31) == 0 && f_row + kFStages < n_rows) tma_request(f_row + kFStages);
+        ++f_row;
+      } else {
+        pre = nx_pre;
+        temp = nx_temp;
+        pet = nx_pet;
+        ++f_row;
+        if (f_row < n_rows) {  // the row after it is requested
+          fi += (unsigned)a.nCells;
+          nx_pre = ldg_stream(bpre + fi);
+          nx_temp = ldg_stream(btemp + fi);
+          nx_pet = ldg_stream(bpet + fi);
+        }
+      }
+    };
     if (n_last > 0) {
       const int month = a.idx_in[0].month - 1;
       const double inv_ec = a.tab.inv_evap_coeff[month];
       const FluxEmitter<false, false> noemit{a.F, mc, n, (size_t)member * NH * n + c, false, nullptr};
-      // stage A of the next step: its forcing row is consumed, the row after it requested
+      // stage A of the next step on its forcing row
       auto stage_a_next = [&]() -> StageA {
-        const double pre = nx_pre, temp = nx_temp, pet = P2(kPetTthr).x * nx_pet;
-        fi += (unsigned)a.nCells;
-        nx_pre = ldg_stream(bpre + fi);
-        nx_temp = ldg_stream(btemp + fi);
-        nx_pet = ldg_stream(bpet + fi);
-        return cascade_stage_a_sel<NH, false>(p, s, pet, temp, pre, inv_ec, noemit);
+        double pre, temp, pet;
+        next_row(pre, temp, pet);
+        return cascade_stage_a_sel<NH, false>(p, s, P2(kPetTthr).x * pet, temp, pre, inv_ec, noemit);
       };
 #if MHM_CELL_PIPE3
       // Three steps in flight.  With A = canopy / snow / sealed store, R = infiltration powers of
@@ -1565,9 +1659,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 #endif
     }
     // the launch's last step through the general path (it stores the fluxes)
-    cu.raw_pre = nx_pre;
-    cu.raw_temp = nx_temp;
-    cu.raw_pet = nx_pet;
+    next_row(cu.raw_pre, cu.raw_temp, cu.raw_pet);
   } else
 #endif
   {

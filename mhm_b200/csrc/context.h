@@ -134,6 +134,7 @@ struct mhm_cuda_context {
   size_t block_bytes = (size_t)24 << 30;  // memory budget of per-block history buffers
   int sm_count = 148;                      // streaming multiprocessors of the device
   bool uniform_calendar = true;            // MHM_CUDA_NO_UNIFORM_CALENDAR (diagnostics) switches it off
+  bool forcing_tma = false;                // forcing rows through cp.async.bulk + mbarrier (MHM_CUDA_FORCING_TMA)
   // the GPUs of one box, one process each (comm.cu): NCCL communicator owned by the library
   FILE* launch_log = nullptr;              // MHM_CUDA_LAUNCH_LOG (diagnostics)
   void* nccl_comm = nullptr;

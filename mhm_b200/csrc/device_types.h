@@ -40,6 +40,8 @@ struct CellArgs {
   // which cuts launches where the calendar turns): the specialised kernels then drop the per-step
   // calendar work
   int32_t uniform_calendar;
+  // forcing rows may go through the TMA unit (16-byte aligned rows; decided by the host)
+  int32_t forcing_tma;
   double nTstepDay_dp, c2TSTu;
   StepIdx idx_in[kIdxInline];         // calendar of the launch's steps: constant-bank loads
   const double* met[MHM_M_COUNT];     // device, [rows][nCells]

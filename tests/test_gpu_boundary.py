@@ -420,3 +420,32 @@ def test_reevaluation_with_another_celerity_changes_tsrout(ctx, mode):
     dom.set_c1c2(net["C1"], net["C2"], seen[0], member=0)
     rc = ctx.L.mhm_cuda_run_steps(ctx.h, 1, 1, 24)
     assert rc != 0 and b"share L11_TSrout" in ctx.L.mhm_cuda_last_error()
+
+
+# --------------------------------------------------------------------------- forcing through TMA
+@pytest.mark.parametrize("nx,ny", [(52, 31), (45, 29), (64, 2)])
+def test_forcing_through_tma_equals_per_lane_loads(ctx, monkeypatch, nx, ny):
+    """Uniform-calendar launches with the forcing rows staged by the TMA unit (cp.async.bulk into a
+    shared-memory ring, one mbarrier per warp and row; MHM_CUDA_FORCING_TMA=1) against the per-lane
+    __ldg path: bit-identical states, fluxes, gauge series; domains whose last tile / last warp is
+    ragged, a domain with an odd number of cells (rows are not 16-byte aligned: falls back), blocks
+    that start inside the resident chunk, three members."""
+    prob = synth.make_problem(nx=nx, ny=ny, n_days=7, hourly=True, start=(1990, 12, 28))
+    nT, M = prob["time"]["nTimeSteps"], 3
+    mp = [prob["params"]] + [dict(prob["params"], L1_kPerco=prob["params"]["L1_kPerco"] * f) for f in (0.9, 1.1)]
+    ctx.set_math_mode("fast")
+    res = {}
+    for key in ("ldg", "tma"):
+        monkeypatch.setenv("MHM_CUDA_FORCING_TMA", "1" if key == "tma" else "0")
+        clear(ctx)
+        dom = driver.setup_domain(ctx, 1, prob, nMembers=M, member_params=mp)
+        for a, b in ((1, 50), (51, 3), (54, nT - 53)):
+            dom.run_steps(a, b)
+        res[key] = [snapshot_member(dom, m) for m in range(M)]
+    monkeypatch.delenv("MHM_CUDA_FORCING_TMA")
+    for m in range(M):
+        assert_same(res["tma"][m], res["ldg"][m], "TMA forcing, member %d (%d cells)" % (m, prob["nCells"]))
+    o = orc_run.OracleRun(prob)
+    o.run(1, nT)
+    parity.assert_close(res["tma"][0]["Q"], o.mRM_runoff, "TMA forcing vs oracle", rtol=parity.RTOL_Q)
+    ctx.set_math_mode("strict")
