@@ -741,9 +741,13 @@ struct PairIds {
   static constexpr int kUnsat = NH + 6;       // unsatThr, c2TSTu / kFastFlow
   static constexpr int kSlow = NH + 7;        // c2TSTu / kSlowFlow, 1 + alpha
   static constexpr int kPerc = NH + 8;        // c2TSTu / kPerco, karstLoss
-  static constexpr int kExpWp0 = NH + 9;      // EXPN, WP                           x NH
-  static constexpr int kRoot0 = 2 * NH + 9;   // fRoots, inv_range (see above)      x NH
-  static constexpr int kCount = 3 * NH + 9;
+  static constexpr int kRoot0 = NH + 9;       // fRoots, inv_range (see above)      x NH
+  // exponents and wilting points, TWO horizons per pair (component h % 2 of pair h / 2): the horizon
+  // loop reads one pair for both horizons' wilting points, the power tasks only ever touch the exponents
+  static constexpr int kNHalf = (NH + 1) / 2;
+  static constexpr int kWp0 = 2 * NH + 9;
+  static constexpr int kExp0 = 2 * NH + 9 + kNHalf;
+  static constexpr int kCount = 2 * NH + 9 + 2 * kNHalf;
 };
 #ifndef MHM_PARAM_REG_PAIRS
 #define MHM_PARAM_REG_PAIRS 4  // pairs kept in registers when the rest is in shared memory (see ParamPlace)
@@ -765,6 +769,10 @@ struct PairStore {
   __device__ __forceinline__ double2 get(int k) const { return k < kRegPairs ? r[k] : sm->q[k - kRegPairs][threadIdx.x]; }
   // a pair of another thread's column (shared-memory pairs only)
   __device__ __forceinline__ double2 get_of(int k, unsigned tid) const { return sm->q[k - kRegPairs][tid]; }
+  // one component (0: x, 1: y) of another thread's pair: a single 8-byte load
+  __device__ __forceinline__ double get_half_of(int k, unsigned tid, unsigned half) const {
+    return reinterpret_cast<const double*>(&sm->q[k - kRegPairs][tid])[half];
+  }
   __device__ __forceinline__ void set(int k, double x, double y) {
     if (k < kRegPairs) r[k] = make_double2(x, y);
     else sm->q[k - kRegPairs][threadIdx.x] = make_double2(x, y);
@@ -792,7 +800,8 @@ struct StageA {
 template <int NH, bool EMIT, class PARAMS, class EM>
 __device__ __forceinline__ StageA cascade_stage_a_sel(const PARAMS& p, CellStates<NH>& s, const double pet,
                                                       const double temperature, const double prec,
-                                                      const double inv_evap_coeff, const EM& emit) {
+                                                      const double tthr, const double inv_evap_coeff,
+                                                      const EM& emit) {
   // ---- canopy_interc, mo_canopy_interc.f90:105-131 ----
   const double2 mi = P2(kMaxInter);
   const double aux = s.inter + prec;
@@ -806,14 +815,14 @@ __device__ __forceinline__ StageA cascade_stage_a_sel(const PARAMS& p, CellState
   emit(MHM_F_AETCANOPY, aet_canopy);
 
   // ---- snow_accum_melt, mo_snow_accum_melt.f90:117-156 ----
-  const double2 pt = P2(kPetTthr), d2 = P2(kDd);
-  const bool warm = temperature > pt.y;
+  const double2 d2 = P2(kDd);
+  const bool warm = temperature > tthr;
   const double rain = warm ? throughfall : 0.0;
   const double snow = throughfall - rain;        // exactly throughfall or 0
   // min(ddnoprec + ddinc * prec, ddmax): the reference's test prec <= (ddmax - ddnoprec) / ddinc
   // (:127) up to the rounding of that quotient
   const double dd = min_sel(d2.x + d2.y * prec, P2(kDdBase).x);
-  const double pot = dd * (temperature - pt.y);
+  const double pot = dd * (temperature - tthr);
   const double melt_w = sel_gt(pot, s.snowpack, s.snowpack, pot);  // snow_pack = 0 gives melt = 0
   const double melt = warm ? melt_w : 0.0;
   s.snowpack = s.snowpack + (snow - melt);       // one of the two terms is exactly 0
@@ -865,7 +874,7 @@ struct WarpTasks<NH, true> {
   __device__ __forceinline__ void eval(const PARAMS& p, unsigned k, const fm::Tables& tab) {
     const unsigned sc = src[k];
     const unsigned hh = (sc >> 5) < (unsigned)NH ? (sc >> 5) : 0u;  // (a stale entry must stay in range)
-    const double y = p.get_of(PID::kExpWp0 + hh, (threadIdx.x & ~31u) + (sc & 31u)).x;
+    const double y = p.get_half_of(PID::kExp0 + (int)(hh >> 1), (threadIdx.x & ~31u) + (sc & 31u), hh & 1u);
     x[k] = fm::pow_tab(tab, x[k], y);
   }
   __device__ __forceinline__ double result(unsigned k) const { return x[k]; }
@@ -876,7 +885,8 @@ struct WarpTasks<NH, false> {
   double2 xy[32 * NH];
   template <class PARAMS>
   __device__ __forceinline__ void put(const PARAMS& p, unsigned k, double base, int hh) {
-    xy[k] = make_double2(base, PH2(kExpWp0, hh).x);
+    const double2 e2 = p.get(PID::kExp0 + hh / 2);
+    xy[k] = make_double2(base, (hh & 1) ? e2.y : e2.x);
   }
   template <class PARAMS>
   __device__ __forceinline__ void eval(const PARAMS&, unsigned k, const fm::Tables& tab) {
@@ -930,7 +940,8 @@ __device__ __forceinline__ void cascade_stage_b1_sel(const PARAMS& p, const Cell
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) {
       const double2 sa = PH2(kSat0, hh);
-      const double f = fm::pow_tab(tab, s.sm[hh] * sa.y, PH2(kExpWp0, hh).x);
+      const double2 e2 = p.get(PID::kExp0 + hh / 2);
+      const double f = fm::pow_tab(tab, s.sm[hh] * sa.y, (hh & 1) ? e2.y : e2.x);
       frac_pre[hh] = (wet && !(s.sm[hh] > sa.x)) ? f : 0.0;
     }
   }
@@ -991,9 +1002,12 @@ template <int NH, class PARAMS, class EM>
 __device__ __forceinline__ double cascade_horizons_sel(const PARAMS& p, CellStates<NH>& s, const StageA& in,
                                                        const double (&frac_pre)[NH], const EM& emit) {
   double pe = in.prec_effect, aet_sum = 0.0;
+  double2 wp2 = make_double2(0.0, 0.0);
 #pragma unroll
   for (int hh = 0; hh < NH; ++hh) {
-    const double2 sa = PH2(kSat0, hh), ew = PH2(kExpWp0, hh), rt = PH2(kRoot0, hh);
+    const double2 sa = PH2(kSat0, hh), rt = PH2(kRoot0, hh);
+    if ((hh & 1) == 0) wp2 = p.get(PID::kWp0 + hh / 2);
+    const double wp = (hh & 1) ? wp2.y : wp2.x;
     const double sm0 = s.sm[hh];
     const double tmp = pe * (1.0 - frac_pre[hh]);
     const double u = sm0 + tmp;
@@ -1004,7 +1018,7 @@ __device__ __forceinline__ double cascade_horizons_sel(const PARAMS& p, CellStat
     const double inf = pe - d;                   // pe + (sm0 - SAT) bit for bit, pe - tmp, or pe
     emit(MHM_F_INFILSOIL, hh, inf);
     const double A = hh == 0 ? in.pet_left : in.pet_left - aet_sum;
-    const double w = (sm1 - ew.y) * rt.y;
+    const double w = (sm1 - wp) * rt.y;
     const double a = pos_part((A * rt.x) * sel_lt(w, 1.0, w, 1.0));  // <= 0 below the wilting point, :266 / :361
     const double a2 = sm1 > a ? a : sm1 - kEps;
     const double sm2 = sm1 - a2;                 // sm1 - a, or eps (0 for sm1 >> eps: floored next)
@@ -1063,7 +1077,7 @@ __device__ __forceinline__ double cascade_step_sel(const PARAMS& p, CellStates<N
                                                    const double temperature, const double prec,
                                                    const double inv_evap_coeff, TASKS& warp_tasks,
                                                    const fm::Tables& tab, const EM& emit) {
-  const StageA sa = cascade_stage_a_sel<NH, EMIT>(p, s, pet, temperature, prec, inv_evap_coeff, emit);
+  const StageA sa = cascade_stage_a_sel<NH, EMIT>(p, s, pet, temperature, prec, P2(kPetTthr).y, inv_evap_coeff, emit);
   double frac_pre[NH];
   cascade_stage_b1_sel<NH>(p, s, sa.prec_effect, warp_tasks, tab, frac_pre);
   return cascade_stage_b2_sel<NH, EMIT>(p, s, sa, frac_pre, tab, emit);
@@ -1147,7 +1161,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   // the warps' lists of pending infiltration powers
   // (by source: the exponents must be in shared memory)
   constexpr bool kTasksBySource = ParamStoreOf<NH, VARIANT>::paired && ParamPlace<NH>::shared &&
-                                  PairStore<NH, true>::kRegPairs <= PairIds<NH>::kExpWp0;
+                                  PairStore<NH, true>::kRegPairs <= PairIds<NH>::kExp0;
   __shared__ WarpTasks<NH, kTasksBySource> sh_tasks[kCellThreads / 32];
 #if MHM_TABLES_GLOBAL
   const fm::Tables& sh_tab = fm::d_tables;  // served from L1
@@ -1316,7 +1330,13 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
           const bool feddes = a.soil_case == 1 || a.soil_case == 4;
           const double range = feddes ? FC - WP : (SAT - WP) * a.P[MHM_P_JARVIS_C1][mc];
           p.set(PID::kSat0 + h, SAT, 1.0 / SAT);
-          p.set(PID::kExpWp0 + h, a.P[MHM_P_SOILMOISTEXP][oh], WP);
+          if (h & 1) {
+            p.sety(PID::kExp0 + h / 2, a.P[MHM_P_SOILMOISTEXP][oh]);
+            p.sety(PID::kWp0 + h / 2, WP);
+          } else {
+            p.set(PID::kExp0 + h / 2, a.P[MHM_P_SOILMOISTEXP][oh], 0.0);
+            p.set(PID::kWp0 + h / 2, WP, 0.0);
+          }
           p.set(PID::kRoot0 + h, a.P[MHM_P_FROOTS][oh], 1.0 / range);
         }
 #endif
@@ -1590,7 +1610,8 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       auto stage_a_next = [&]() -> StageA {
         double pre, temp, pet;
         next_row(pre, temp, pet);
-        return cascade_stage_a_sel<NH, false>(p, s, P2(kPetTthr).x * pet, temp, pre, inv_ec, noemit);
+        const double2 pt = P2(kPetTthr);  // petFac, tempThresh: one load
+        return cascade_stage_a_sel<NH, false>(p, s, pt.x * pet, temp, pre, pt.y, inv_ec, noemit);
       };
 #if MHM_CELL_PIPE3
       // Three steps in flight.  With A = canopy / snow / sealed store, R = infiltration powers of
