@@ -70,6 +70,81 @@ def shared_forcing(ctx, rank, world, is_f32):
             "f32" if is_f32 else "f64", world, h2d, full), flush=True)
 
 
+def domain_per_gpu(ctx, rank, world):
+    """BASELINE config 2: independent domains, one per GPU (the reference's MPI mode deals domains to
+    ranks round robin, common/mo_common_read_config.F90:416-437), with a restart in the middle: every
+    rank registers ITS domain of the module-global arrays (ld = nCellsTot, offset = s1 - 1), runs
+    half of the period, reads the states back into the globals, registers the domain anew with
+    read_states = 1 and finishes; the second half must equal the uninterrupted run bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_boundary import RSTATES, restart_problem, snapshot
+
+    probs = [synth.make_problem(nx=26 + 7 * d, ny=15 + 3 * d, n_days=8, hourly=True, seed=11 + d,
+                                start=(1990, 6, 1)) for d in range(world)]
+    ncell = [p["nCells"] for p in probs]
+    offs = np.concatenate([[0], np.cumsum(ncell)]).astype(int)
+    ntot = int(offs[-1])
+    pack = lambda key, sub: np.ascontiguousarray(np.concatenate([p[sub][key] for p in probs], axis=-1))
+    G = {"params": {k: pack(k, "params") for k in probs[0]["params"] if k in interface.PARAM_NAMES},
+         "states": {k: pack(k, "states0") for k in STATES},
+         "forcing": {k: pack(k, "forcing") for k in ("pre", "temp", "pet")}}
+    me, off = probs[rank], int(offs[rank])
+    nT, k = me["time"]["nTimeSteps"], 4 * 24
+    ctx.set_math_mode("strict")
+
+    def register(iDomain, prob, states, read_states):
+        d = ctx.register_domain(iDomain, prob["nCells"], prob["nH"], prob["nLAI"], prob["nLC"],
+                                prob["processMatrix"], timestep_h=1, read_states=read_states)
+        d.set_meteo_config(prob["pet_case"], 24, True, False, synth.FNIGHT_PREC, synth.FNIGHT_PET,
+                           synth.FNIGHT_TEMP, synth.EVAP_COEFF)
+        d.set_time(prob["time"])
+        for name, a in G["params"].items():
+            d.set_param(name, a, ld=ntot, offset=off)
+        for name, a in states.items():
+            d.set_state(name, a, ld=ntot, offset=off)
+        net = prob["net"]
+        d.set_network(net)
+        d.set_reg_rout(net["rout_param"], net["L11_length"][: net["nNodes"] - 1],
+                       net["L11_slope"][: net["nNodes"] - 1], net["L11_nLinkFracFPimp"])
+        return d
+
+    full = register(rank + 1, me, G["states"], False)
+    for name, a in G["forcing"].items():
+        full.set_meteo(name, a, ld=ntot, offset=off)
+    full.run_steps(1, nT)
+    want = snapshot(full)
+    interface.check(ctx.L.mhm_cuda_unregister_domain(ctx.h, rank + 1))
+    first = register(rank + 1, me, G["states"], False)
+    for name, a in G["forcing"].items():
+        first.set_meteo(name, a, ld=ntot, offset=off)
+    first.run_steps(1, k)
+    # "write_restart_files": the states into this domain's section of the global arrays
+    H = {name: np.array(a, copy=True) for name, a in G["states"].items()}
+    for name in STATES:
+        first.get_state(name, out=H[name], offset=off)
+    rs = {name: first.get_routing_state(name) for name in RSTATES}
+    interface.check(ctx.L.mhm_cuda_unregister_domain(ctx.h, rank + 1))
+    sub = restart_problem(me, k, {name: np.ascontiguousarray(H[name][..., off: off + me["nCells"]]) for name in STATES}, rs)
+    second = register(rank + 1, sub, H, True)
+    for name, a in G["forcing"].items():
+        second.set_meteo(name, np.ascontiguousarray(a[k:]), ld=ntot, offset=off)
+    for name in ("L11_qOUT", "L11_qTIN", "L11_qTR", "L11_qMod"):
+        second.set_routing_state(name, rs[name])
+    second.set_c1c2(rs["L11_C1"], rs["L11_C2"])
+    second.run_steps(1, nT - k)
+    got = snapshot(second)
+    for name in STATES + RSTATES:
+        parity.assert_bit_exact(got[name], want[name], "domain %d after the restart: %s" % (rank + 1, name))
+    parity.assert_bit_exact(got["Q"], np.ascontiguousarray(want["Q"][:, k:]), "domain %d: gauge series" % (rank + 1))
+    interface.check(ctx.L.mhm_cuda_unregister_domain(ctx.h, rank + 1))
+    del ctx.domains[rank + 1]
+    done = torch.tensor([1], device="cuda")
+    dist.all_reduce(done)
+    if rank == 0:
+        print("MULTI_GPU_OK %d domains (%s cells), one per GPU, restart after %d of %d steps" % (
+            world, ncell, k, nT), flush=True)
+
+
 def main():
     rank, local, world = (int(os.environ[k]) for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"))
     torch.cuda.set_device(local)
@@ -82,6 +157,7 @@ def main():
         ctx.set_math_mode(mode)
         shared_forcing(ctx, rank, world, is_f32=False)
     shared_forcing(ctx, rank, world, is_f32=True)
+    domain_per_gpu(ctx, rank, world)
     which = sys.argv[1:] or ["all"]
     if ("all" in which or "shard" in which) and os.path.exists(os.path.join(ROOT, "tests", "multi_gpu_shard.py")):
         import multi_gpu_shard
