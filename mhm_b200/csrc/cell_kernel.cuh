@@ -1578,23 +1578,26 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       nx_temp = ldg_stream(btemp + fi);
       nx_pet = ldg_stream(bpet + fi);
     }
-    // the next forcing row of this cell: (pre, temp, raw pet)
-    auto next_row = [&](double& pre, double& temp, double& pet) {
+    // the next forcing row of this cell: (pre, temp, raw pet); `last_tag`: the launch's last row
+    // (nothing is requested after it)
+    auto next_row = [&](auto last_tag, double& pre, double& temp, double& pet) {
+      constexpr bool LAST = decltype(last_tag)::value;
       if constexpr (TMA) {
         const int warp = threadIdx.x >> 5, sl = f_row % kFStages;
         mbar_wait(smem_addr(&fring.full[warp][sl]), (unsigned)((f_row / kFStages) & 1));
         pre = fring.v[sl][0][threadIdx.x];
         temp = fring.v[sl][1][threadIdx.x];
         pet = fring.v[sl][2][threadIdx.x];
-        __syncwarp();  // every lane has read the slot before lane 0 lets the TMA unit overwrite it
-        if ((threadIdx.x & 31) == 0 && f_row + kFStages < n_rows) tma_request(f_row + kFStages);
-        ++f_row;
+        if constexpr (!LAST) {
+          __syncwarp();  // every lane has read the slot before lane 0 lets the TMA unit overwrite it
+          if ((threadIdx.x & 31) == 0 && f_row + kFStages < n_rows) tma_request(f_row + kFStages);
+          ++f_row;
+        }
       } else {
         pre = nx_pre;
         temp = nx_temp;
         pet = nx_pet;
-        ++f_row;
-        if (f_row < n_rows) {  // the row after it is requested
+        if constexpr (!LAST) {  // the row after it is requested (the last row is handed out with LAST)
           fi += (unsigned)a.nCells;
           nx_pre = ldg_stream(bpre + fi);
           nx_temp = ldg_stream(btemp + fi);
@@ -1609,7 +1612,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
       // stage A of the next step on its forcing row
       auto stage_a_next = [&]() -> StageA {
         double pre, temp, pet;
-        next_row(pre, temp, pet);
+        next_row(std::false_type{}, pre, temp, pet);
         const double2 pt = P2(kPetTthr);  // petFac, tempThresh: one load
         return cascade_stage_a_sel<NH, false>(p, s, pt.x * pet, temp, pre, pt.y, inv_ec, noemit);
       };
@@ -1680,7 +1683,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 #endif
     }
     // the launch's last step through the general path (it stores the fluxes)
-    next_row(cu.raw_pre, cu.raw_temp, cu.raw_pet);
+    next_row(std::true_type{}, cu.raw_pre, cu.raw_temp, cu.raw_pet);
   } else
 #endif
   {
