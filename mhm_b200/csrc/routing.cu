@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "context.h"
 
@@ -45,13 +46,15 @@ enum : int32_t {
   kEntInflow = 16,    // node is an inflow gauge: add_inflow applies to its runoff
   kEntWriteHist = 32, // somebody reads this node's outflow series from memory
   kEntGhost = 64,     // from-node of a cut link owned by another shard: outflow is prescribed
+  kEntLeafWarp = 128, // every lane of the warp is a headwater single-node segment (position = write shift)
 };
 
 // everything a lane needs to know about its node, one 32-byte record
 struct alignas(16) LaneMeta {
   int32_t node;   // 0-based L11 node
   int32_t link;   // 0-based link (C1/C2 index)
-  int32_t flags;  // kEnt* bits | number of upstream links << 8 | position in segment << 16
+  int32_t flags;  // kEnt* bits | number of upstream links << 8 | position in segment << 16 (5 bits)
+                  // | write shift of the outflow series << 21 (3 bits), see kHistPad
   int32_t gslot;  // gauge slot or -1
   int32_t up[kMetaUps];  // first four upstream links in netPerm order: lane position of the
                          // link's from-node, or kUpShuffle
@@ -68,7 +71,19 @@ constexpr int kHistTile = 8;
 // lane: the lanes of a warp read the same aligned slots and the lean kernel fetches the kWin
 // values of a macro step with one 256-bit load per lane (with unskewed storage every 8-byte
 // load touched 32 different 64-byte runs and the L1 tag stage bounded the kernel).
+// The routed-outflow history (qtr_hist) is stored SHIFTED for its one reader from memory (the
+// lane of the downstream node, when that is not the next lane of the same segment): step r of a
+// lane sits in slot r + ws, ws = (position of the reader in its segment) & 7.  The reader works on
+// step 8 * k + j - skew in position j of its k-th tile, i.e. on slot 8 * (k - skew / 8) + j of each
+// tributary row: the same window position as its node runoff, so a half window of a tributary is
+// one aligned 32-byte piece fetched with one 256-bit load (with unshifted rows the four 8-byte
+// loads of a window touched 32 different runs each and the load/store unit bounded the levels
+// below the headwaters).  A warp that holds nothing but
+// headwater single-node segments streams whole 64-byte runs; there the position field itself
+// carries ws, so that node runoff in and routed outflow out share the shift and both stay aligned.
 constexpr int kHistPad = 48;  // slots past the last event: largest skew + window overshoot
+__host__ __device__ __forceinline__ int lane_skew(int flags) { return (flags >> 16) & 31; }
+__host__ __device__ __forceinline__ int lane_wshift(int flags) { return (flags >> 21) & 7; }
 __host__ __device__ __forceinline__ size_t hidx(int step, int M, int E, int m, int p) {
   return ((((size_t)(step >> 3) * M + m) * E + p) << 3) + (size_t)(step & 7);
 }
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(128) qout_kernel(const QoutArgs a) {
     if (lm.flags & kEntInflow) v = apply_inflow(a, node, ev, v);
     q[d] = v;
   }
-  const int skew = lm.flags >> 16;  // skewed slots: two neighbouring runs of this lane
+  const int skew = lane_skew(lm.flags);  // skewed slots: two neighbouring runs of this lane
 #pragma unroll
   for (int d = 0; d < kHistTile; ++d)
     if (tile * kHistTile + d < a.nEvents) a.qout_hist[hidx(tile * kHistTile + d + skew, a.M, a.E, m, p)] = q[d];
@@ -320,7 +335,7 @@ qout_cell_kernel(const QoutArgs a, const int32_t* __restrict__ cell_entry,
     if (lm.flags & kEntInflow) v = apply_inflow(a, lm.node, ev, v);
     q[d] = v;
   }
-  const int skew = lm.flags >> 16;
+  const int skew = lane_skew(lm.flags);
 #pragma unroll
   for (int d = 0; d < kHistTile; ++d)
     if (tile * kHistTile + d < a.nEvents) a.qout_hist[hidx(tile * kHistTile + d + skew, a.M, a.E, m, p)] = q[d];
@@ -378,7 +393,9 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
   const bool valid = lm.flags & kEntValid, is_link = lm.flags & kEntLink;
   const bool add_qout = lm.flags & kEntAddQout, zero_out = lm.flags & kEntZeroOut;
   const bool write_hist = lm.flags & kEntWriteHist, ghost = lm.flags & kEntGhost;
-  const int nup = (lm.flags >> 8) & 0xff, skew = lm.flags >> 16;
+  const int nup = (lm.flags >> 8) & 0xff, skew = lane_skew(lm.flags);
+  const int ws = lane_wshift(lm.flags);  // shift of this lane's own outflow series
+  const int ts = skew & 7;               // shift of the series this lane reads (it is their reader)
   const int rl = RL1 ? 1 : a.rl;
   const int nRS = (a.ev1 - a.ev0) * rl;  // routing sub-steps of this launch
   const int lmax = __reduce_max_sync(0xffffffffu, valid ? skew + 1 : 0);
@@ -415,7 +432,7 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
       const int ev = RL1 ? a.ev0 + r : a.ev0 + r / rl;  // its event
       const int evs = ev + skew;  // skewed slot of the node-runoff history
       const size_t oq = (size_t)(evs >> 3) * tile_stride + (size_t)(evs & 7);
-      const size_t ot = (size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7);
+      const size_t ot = (size_t)((rs + ts) >> 3) * tile_stride + (size_t)((rs + ts) & 7);
       qo[d] = (in && !ghost) ? a.qout_hist[oq + lane_off] : 0.0;
       if (MEM) {
 #pragma unroll
@@ -441,17 +458,17 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
           for (int u = 0; u < KU; ++u)
             if (u < nup) q_in = q_in + ((!MEM || lm.up[u] == kUpShuffle) ? from_prev : t[u][d]);
           for (int u = kMetaUps; u < nup; ++u)
-            q_in = q_in + a.qtr_hist[hidx(rs, a.M, a.E, m, a.up_pos[u0 + u])];
+            q_in = q_in + a.qtr_hist[hidx(rs + ts, a.M, a.E, m, a.up_pos[u0 + u])];
           if (add_qout) q_in = q_in + qout;  // :441 / :466-467
           if (is_link) {
             double q;
             if (ghost) {  // routed by the shard that owns the node, received for the whole block
-              q = a.qtr_hist[(size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7) + lane_off];
+              q = a.qtr_hist[(size_t)((rs + ws) >> 3) * tile_stride + (size_t)((rs + ws) & 7) + lane_off];
             } else {
               q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
               if (zero_out) q = 0.0;                                  // :447-452
               if (write_hist)
-                a.qtr_hist[(size_t)(rs >> 3) * tile_stride + (size_t)(rs & 7) + lane_off] = q;
+                a.qtr_hist[(size_t)((rs + ws) >> 3) * tile_stride + (size_t)((rs + ws) & 7) + lane_off] = q;
             }
             qtr1 = q;
             last_q = q;
@@ -505,7 +522,7 @@ __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain
   const LaneMeta lm = a.meta[p];
   const bool valid = lm.flags & kEntValid, is_link = lm.flags & kEntLink;
   const bool add_qout = lm.flags & kEntAddQout, write_hist = lm.flags & kEntWriteHist;
-  const int nup = (lm.flags >> 8) & 0xff, skew = lm.flags >> 16;
+  const int nup = (lm.flags >> 8) & 0xff, skew = lane_skew(lm.flags), ws = lane_wshift(lm.flags);
   const int nRS = a.ev1 - a.ev0;
   const int lmax = __reduce_max_sync(0xffffffffu, valid ? skew + 1 : 0);
   double c1 = 0.0, c2 = 0.0;
@@ -515,18 +532,19 @@ __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain
   }
   double* tin = a.qTIN + (size_t)m * 2 * a.nNodes;
   double* tr = a.qTR + (size_t)m * 2 * a.nNodes;
-  double qtin1 = 0.0, qtr1 = 0.0, qout = 0.0, last_q = 0.0, qmod = 0.0;
+  double qtin1 = 0.0, qtr1 = 0.0, qout = 0.0, qmod = 0.0;
   if (valid) {
     qtin1 = tin[lm.node];
     qtr1 = tr[lm.node];
   }
   const long long tile_bytes = (long long)a.M * a.E * kHistTile * (long long)sizeof(double);
-  if (!MEM && lmax == 1 && (a.ev0 & (kHistTile - 1)) == 0 && __all_sync(0xffffffffu, !valid || nup == 0)) {
+  if (!MEM && (a.ev0 & (kHistTile - 1)) == 0 && __all_sync(0xffffffffu, !valid || (lm.flags & kEntLeafWarp))) {
     // A warp of single-node segments (every level ends with them; on the headwater level these
     // are the leaves of the network, more than a third of all nodes): no lane waits for another
     // one, so every lane streams its own runs -- one 64-byte run of node runoff in, eight
     // Muskingum steps, one 64-byte run of routed outflow out; the next run is requested before
-    // the current one is worked on.
+    // the current one is worked on.  Slot = step + skew for both series here (skew == ws), so a
+    // lane's runs hold steps r0 .. r0 + 7 with r0 = -skew, 8 - skew, ...
     const size_t tile_elems = (size_t)(tile_bytes / (long long)sizeof(double));
     const size_t row = (size_t)(a.ev0 >> 3) * tile_elems + ((size_t)m * a.E + p) * kHistTile;
     const double* qp = a.qout_hist + row;
@@ -541,7 +559,7 @@ __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain
                    : "=d"(nx[4]), "=d"(nx[5]), "=d"(nx[6]), "=d"(nx[7]) : "l"(src + 4));
     };
     load_run(qp);
-    for (int r0 = 0; r0 < nRS; r0 += kHistTile) {
+    for (int r0 = -skew; r0 < nRS; r0 += kHistTile) {
       double v[kHistTile], o[kHistTile];
 #pragma unroll
       for (int d = 0; d < kHistTile; ++d) v[d] = nx[d];
@@ -550,7 +568,7 @@ __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain
 #pragma unroll
       for (int d = 0; d < kHistTile; ++d) {
         o[d] = 0.0;
-        if (valid && r0 + d < nRS) {
+        if (valid && (unsigned)(r0 + d) < (unsigned)nRS) {
           qout = v[d];
           double q_in = 0.0;                 // a segment head on this level has no inflowing link
           if (add_qout) q_in = q_in + qout;  // :441 / :466-467
@@ -565,13 +583,13 @@ __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain
         }
       }
       if (store) {
-        if (r0 + kHistTile <= nRS) {
+        if (r0 >= 0 && r0 + kHistTile <= nRS) {
           asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(hp), "d"(o[0]), "d"(o[1]), "d"(o[2]), "d"(o[3]) : "memory");
           asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(hp + 4), "d"(o[4]), "d"(o[5]), "d"(o[6]), "d"(o[7]) : "memory");
         } else {
 #pragma unroll
           for (int d = 0; d < kHistTile; ++d)
-            if (r0 + d < nRS) hp[d] = o[d];
+            if ((unsigned)(r0 + d) < (unsigned)nRS) hp[d] = o[d];
         }
       }
       hp += tile_elems;
@@ -588,99 +606,130 @@ __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain
     }
     return;
   }
-  // byte offset of (step e, this lane) in a tiled history; e starts before the block for the
-  // lanes that wait for their predecessors (never dereferenced there)
-  int e = a.ev0 - skew;
-  long long off = (long long)(e >> 3) * tile_bytes +
-                  (((long long)m * a.E + p) * kHistTile + (e & 7)) * (long long)sizeof(double);
-  long long up_delta[MEM ? KU : 1];  // tributary row - own row
+  // ---- pipelined segments: one iteration = one history tile (8 slots), two half windows ----
+  // qout_hist slot of (lane, step r) = ev0 + r + skew: in half h of iteration k every lane works
+  // on slots ev0 + 8k + 4h + d, i.e. on step r = 8k + 4h + d - skew (ev0 is a multiple of 8).
+  const int tile0 = a.ev0 >> 3;
+  const long long row = ((long long)m * a.E + p) * kHistTile * (long long)sizeof(double);
+  const char* const qo_b = reinterpret_cast<const char*>(a.qout_hist) + tile0 * tile_bytes + row;
+  // own outflow of step r: slot ev0 + r + ws = ev0 + 8(k + dq) + (4h + d + c); it lies in the next
+  // tile (w_hi) from window position 8 - c on
+  const int dq = (ws - skew) >> 3, c = (ws - skew) & 7;
+  char* const w_lo = reinterpret_cast<char*>(a.qtr_hist) + (tile0 + dq) * tile_bytes + row + c * (long long)sizeof(double);
+  char* const w_hi = w_lo + tile_bytes - kHistTile * (long long)sizeof(double);
+  const int wrap_at = kHistTile - c;
+  // tributary u read from memory: written with shift skew & 7 for this reader, so its step r is
+  // in slot ev0 + 8(k - skew / 8) + 4h + d: the same window position as the node runoff
+  const char* t_b[MEM ? KU : 1];
   bool up_mem[MEM ? KU : 1];
-  if (MEM) {
+  bool up_any[MEM ? KU : 1];  // some lane of the warp reads slot u from memory (warp-uniform)
+  unsigned sh_mask[KU];       // all ones when slot u is the outflow of the previous lane
 #pragma unroll
-    for (int u = 0; u < KU; ++u) {
-      up_mem[u] = u < nup && lm.up[u] != kUpShuffle;
-      up_delta[u] = up_mem[u] ? ((long long)lm.up[u] - p) * kHistTile * (long long)sizeof(double) : 0;
+  for (int u = 0; u < KU; ++u) {
+    sh_mask[u] = (valid && u < nup && lm.up[u] == kUpShuffle) ? 0xffffffffu : 0u;
+    asm volatile("" : "+r"(sh_mask[u]));  // kept as a bit mask: one LOP3 per half word and slot
+    if (MEM) {
+      up_mem[u] = valid && u < nup && lm.up[u] != kUpShuffle;
+      up_any[u] = __any_sync(0xffffffffu, up_mem[u]);
+      t_b[u] = reinterpret_cast<const char*>(a.qtr_hist) + (tile0 - (skew >> 3)) * tile_bytes +
+               ((long long)m * a.E + (up_mem[u] ? lm.up[u] : p)) * kHistTile * (long long)sizeof(double);
     }
   }
-  char* const qtr_b = reinterpret_cast<char*>(a.qtr_hist);
+  unsigned addq_mask = add_qout ? 0xffffffffu : 0u;
+  asm volatile("" : "+r"(addq_mask));
+  const bool warp_gauge = __any_sync(0xffffffffu, lm.gslot >= 0);
   double* const qg = lm.gslot >= 0 ? a.qmod_g + (size_t)m * a.nGslots + lm.gslot : nullptr;
   const size_t qg_stride = (size_t)a.M * a.nGslots;
-  const int nMacro = (nRS + lmax - 1 + kWin - 1) / kWin;
-  // node runoff: skewed slots ev0 + kWin * S + d, the same for all lanes; ev0 is a multiple of
-  // kWin (host), so the kWin slots of a macro step are one aligned 32-byte half of a run
-  static_assert(kWin == 4, "the lean kernel loads one 4-slot window per macro step");
-  int slot = a.ev0;
-  const double* qo_p = a.qout_hist + (size_t)(slot >> 3) * (size_t)(tile_bytes / (long long)sizeof(double)) +
-                       ((size_t)m * a.E + p) * kHistTile + (size_t)(slot & 7);
+  const int nRSv = valid ? nRS : 0;
+  const int nIter = (nRS + lmax - 1 + kHistTile - 1) / kHistTile;
+  static_assert(kWin == 4 && kHistTile == 8, "two 4-slot half windows per history tile");
   struct Window {
     double qo[kWin], t[MEM ? KU : 1][kWin];
-    long long wr[kWin];
   };
-  // loads of the macro step whose sub-step 0 is routing step r_ (advances the running offsets)
-  auto load_window = [&](Window& w, const int r_) {
+  // Slots nobody loads stay +0.0 for the whole launch: the inflow sum below adds every slot
+  // unconditionally (x + (+0.0) == x bit for bit for every x the sum can hold: it starts from
+  // +0.0 and can never become -0.0).
+  Window wa, wb;
+#pragma unroll
+  for (int d = 0; d < kWin; ++d) {
+    wa.qo[d] = wb.qo[d] = 0.0;
+#pragma unroll
+    for (int u = 0; u < (MEM ? KU : 1); ++u) wa.t[u][d] = wb.t[u][d] = 0.0;
+  }
+  // loads of half h of the tile at byte offset koff (one 256-bit load per row)
+  auto load_half = [&](Window& w, const long long koff, const int r0, const int h) {
     asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
                  : "=d"(w.qo[0]), "=d"(w.qo[1]), "=d"(w.qo[2]), "=d"(w.qo[3])
-                 : "l"(qo_p));
-    // (an L2 prefetch of the window four macro steps ahead was measured 4 % slower on B200)
-    qo_p += (slot & 4) ? (size_t)(tile_bytes / (long long)sizeof(double)) - 4 : (size_t)4;
-    slot += kWin;
-    long long o = off;
-    int ee = e;
+                 : "l"(qo_b + koff + h * 32));
+    if (MEM) {
+      // tributary rows were written by earlier launches; window positions outside the launch's
+      // steps hold other steps' values and never reach the state (guard below)
+      const bool some = r0 + kWin > 0 && r0 < nRSv;
 #pragma unroll
-    for (int d = 0; d < kWin; ++d) {
-      if (MEM) {
-        const bool in = valid && (unsigned)(r_ + d) < (unsigned)nRS;
-#pragma unroll
-        for (int u = 0; u < KU; ++u)
-          w.t[u][d] = (in && up_mem[u]) ? *reinterpret_cast<const double*>(qtr_b + o + up_delta[u]) : 0.0;
-      }
-      w.wr[d] = o;
-      o += ((ee & 7) == 7) ? tile_bytes - 7 * (long long)sizeof(double) : (long long)sizeof(double);
-      ++ee;
+      for (int u = 0; u < KU; ++u)
+        if (up_any[u])
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t"
+                       "@p ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];\n\t}"
+                       : "+d"(w.t[u][0]), "+d"(w.t[u][1]), "+d"(w.t[u][2]), "+d"(w.t[u][3])
+                       : "l"(t_b[u] + koff + h * 32), "r"((int)(some && up_mem[u])));
     }
-    off = o;
-    e = ee;
   };
-  auto route_window = [&](const Window& w, const int r_) {
+  // the four routing steps of a half window; GUARD: some lane is outside its steps (pipeline
+  // fill and drain), otherwise every lane is inside and nothing is predicated but the stores
+  auto route_half = [&](const Window& w, const long long koff, const int r0, const int h, auto guard_tag) {
+    constexpr bool GUARD = decltype(guard_tag)::value;
 #pragma unroll
     for (int d = 0; d < kWin; ++d) {
-      const double from_prev = __shfl_up_sync(0xffffffffu, last_q, 1);
-      if (valid && (unsigned)(r_ + d) < (unsigned)nRS) {
-        qout = w.qo[d];
-        double q_in = 0.0;  // :428, then upstream links in netPerm order :457
+      const double from_prev = __shfl_up_sync(0xffffffffu, qtr1, 1);
+      const unsigned fp_lo = (unsigned)__double2loint(from_prev), fp_hi = (unsigned)__double2hiint(from_prev);
+      const bool G = !GUARD || (unsigned)(r0 + d) < (unsigned)nRSv;
+      double q_in = 0.0;  // :428, then upstream links in netPerm order :457
 #pragma unroll
-        for (int u = 0; u < KU; ++u)
-          if (u < nup) q_in = q_in + ((!MEM || !up_mem[u]) ? from_prev : w.t[u][d]);
-        if (add_qout) q_in = q_in + qout;  // :441 / :466-467
-        if (is_link) {
-          const double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);  // :443-445
-          if (write_hist) *reinterpret_cast<double*>(qtr_b + w.wr[d]) = q;
-          qtr1 = q;
-          last_q = q;
+      for (int u = 0; u < KU; ++u) {
+        unsigned lo = fp_lo & sh_mask[u], hi = fp_hi & sh_mask[u];
+        if (MEM) {
+          lo |= (unsigned)__double2loint(w.t[u][d]);
+          hi |= (unsigned)__double2hiint(w.t[u][d]);
         }
-        qtin1 = q_in;
-        qmod = q_in;  // (0 + q) / 1, :263,:281
-        if (qg) qg[(size_t)(a.ev0 + r_ + d) * qg_stride] = qmod;
+        q_in = q_in + __hiloint2double((int)hi, (int)lo);
       }
+      q_in = q_in + __hiloint2double((int)((unsigned)__double2hiint(w.qo[d]) & addq_mask),
+                                     (int)((unsigned)__double2loint(w.qo[d]) & addq_mask));  // :441 / :466-467
+      // :443-445; lanes without a link carry c1 = c2 = 0 and never store or hand on q
+      const double q = qtr1 + c1 * (qtin1 - qtr1) + c2 * (q_in - qtin1);
+      const int idx = h * kWin + d;
+      if (G && write_hist) *reinterpret_cast<double*>((idx >= wrap_at ? w_hi : w_lo) + koff + idx * 8) = q;
+      if (warp_gauge) {
+        if (G && qg) qg[(size_t)(a.ev0 + r0 + d) * qg_stride] = q_in;  // (0 + q) / 1, :263,:281
+      }
+      qtr1 = G ? q : qtr1;
+      qtin1 = G ? q_in : qtin1;
     }
   };
-  int r = -skew;  // routing step (relative to ev0) of sub-step 0 of the macro step
+  auto route = [&](const Window& w, const long long koff, const int r0, const int h, const int base) {
+    // base = r0 + skew, the same for all lanes: the lane with the largest skew of the warp is at
+    // step base - (lmax - 1), the one with skew 0 at base
+    if (base - (lmax - 1) >= 0 && base + kWin - 1 < nRS) route_half(w, koff, r0, h, std::false_type{});
+    else route_half(w, koff, r0, h, std::true_type{});
+  };
+  long long koff = 0;
+  int r0 = -skew;
   if (PF) {
-    // narrow levels (less than one wave of CTAs): nothing hides the load latency of a macro
-    // step, so the next window is requested before the current one is routed (the tributary
-    // series were written by earlier launches)
-    Window cur, nxt;
-    load_window(nxt, r);
-    for (int S = 0; S < nMacro; ++S, r += kWin) {
-      cur = nxt;
-      if (S + 1 < nMacro) load_window(nxt, r + kWin);
-      route_window(cur, r);
+    // narrow levels (less than one wave of CTAs): nothing hides the load latency of a half
+    // window, so the next one is requested before the current one is routed
+    load_half(wa, koff, r0, 0);
+    for (int k = 0; k < nIter; ++k, koff += tile_bytes, r0 += kHistTile) {
+      load_half(wb, koff, r0 + kWin, 1);
+      route(wa, koff, r0, 0, k * kHistTile);
+      if (k + 1 < nIter) load_half(wa, koff + tile_bytes, r0 + kHistTile, 0);
+      route(wb, koff, r0 + kWin, 1, k * kHistTile + kWin);
     }
   } else {
-    for (int S = 0; S < nMacro; ++S, r += kWin) {
-      Window w;
-      load_window(w, r);
-      route_window(w, r);
+    for (int k = 0; k < nIter; ++k, koff += tile_bytes, r0 += kHistTile) {
+      load_half(wa, koff, r0, 0);
+      route(wa, koff, r0, 0, k * kHistTile);
+      load_half(wa, koff, r0 + kWin, 1);
+      route(wa, koff, r0 + kWin, 1, k * kHistTile + kWin);
     }
   }
   if (valid && nRS > 0) {
@@ -690,8 +739,8 @@ __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain
       tr[lm.node] = qtr1;
       tr[a.nNodes + lm.node] = qtr1;
     }
-    a.qMod[(size_t)m * a.nNodes + lm.node] = qmod;
-    a.qOUT[(size_t)m * a.nNodes + lm.node] = qout;
+    a.qMod[(size_t)m * a.nNodes + lm.node] = qtin1;
+    a.qOUT[(size_t)m * a.nNodes + lm.node] = a.qout_hist[hidx(a.ev0 + nRS - 1 + skew, a.M, a.E, m, p)];
   }
 }
 
@@ -857,10 +906,28 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
   std::vector<int32_t> lane_of((size_t)nNodes, -1);
   rt->lvl_ptr.assign(1, 0);
   int lane = 0;
+  // highest tributary slot (of the kMetaUps described in LaneMeta) a segment reads from memory:
+  // the lean kernel skips, per warp, the slots none of its lanes reads, so segments with the
+  // same need share warps
+  std::vector<int32_t> seg_slots((size_t)nSeg, 0);
+  for (int nd = 0; nd < nNodes; ++nd) {
+    const int s = seg_of[(size_t)nd];
+    if (s < 0) continue;
+    int u = 0;
+    for (int j : up[(size_t)nd]) {
+      if (u == kMetaUps) break;
+      const int f = net->fromN[j] - 1;
+      const bool shuffle = f == pred[(size_t)nd] && seg_of[(size_t)f] == s;
+      if (!shuffle) seg_slots[(size_t)s] = std::max(seg_slots[(size_t)s], u + 1);
+      ++u;
+    }
+  }
   for (int l = 0; l < nLv; ++l) {
     auto& v = lv_segs[(size_t)l];
     std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
-      return seg_nodes[(size_t)x].size() > seg_nodes[(size_t)y].size();
+      if (seg_nodes[(size_t)x].size() != seg_nodes[(size_t)y].size())
+        return seg_nodes[(size_t)x].size() > seg_nodes[(size_t)y].size();
+      return seg_slots[(size_t)x] > seg_slots[(size_t)y];
     });
     for (int s : v) {
       const int len = (int)seg_nodes[(size_t)s].size();
@@ -872,6 +939,21 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
   }
   const int E = lane;
   rt->E = E;
+  // write shift of every node's outflow series (see kHistPad) and the warps of headwater
+  // single-node segments, whose position field takes the shift
+  std::vector<int32_t> wshift((size_t)nNodes, 0);
+  for (int nd = 0; nd < nNodes; ++nd) {
+    const int dn = down[(size_t)nd];
+    if (dn < 0) continue;
+    const bool by_shuffle = pred[(size_t)dn] == nd && seg_of[(size_t)dn] == seg_of[(size_t)nd];
+    if (!by_shuffle) wshift[(size_t)nd] = pos_in[(size_t)dn] & 7;
+  }
+  std::vector<char> leaf_warp((size_t)E / kSegLen, 1);
+  for (int nd = 0; nd < nNodes; ++nd)
+    if (seg_nodes[(size_t)seg_of[(size_t)nd]].size() != 1 || !up[(size_t)nd].empty())
+      leaf_warp[(size_t)lane_of[(size_t)nd] / kSegLen] = 0;
+  for (int nd = 0; nd < nNodes; ++nd)
+    if (leaf_warp[(size_t)lane_of[(size_t)nd] / kSegLen]) pos_in[(size_t)nd] = wshift[(size_t)nd];
 
   std::vector<char> is_ghost((size_t)nNodes, 0), is_export((size_t)nNodes, 0);
   for (int g = 0; g < net->nGhostSources; ++g) {
@@ -900,7 +982,7 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
       continue;
     }
     const int l = link_of_node[(size_t)nd];
-    int fl = kEntValid;
+    int fl = kEntValid | (leaf_warp[(size_t)p / kSegLen] ? kEntLeafWarp : 0);
     if (l >= 0) {
       fl |= kEntLink | kEntAddQout;                 // mo_mrm_routing.f90:441
       for (int g = 0; g < net->nInflowGauges; ++g)  // :447-452
@@ -927,7 +1009,7 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
     MHM_REQUIRE(nup < 256, "set_network: node %d has %d inflowing links", nd + 1, nup);
     lm.node = nd;
     lm.link = l >= 0 ? l : 0;
-    lm.flags = fl | (nup << 8) | (pos_in[(size_t)nd] << 16);
+    lm.flags = fl | (nup << 8) | (pos_in[(size_t)nd] << 16) | (wshift[(size_t)nd] << 21);
     for (int u = 0; u < nup; ++u) {
       const int f = net->fromN[up[(size_t)nd][(size_t)u]] - 1;
       const bool shuffle = f == pred[(size_t)nd] && seg_of[(size_t)f] == seg_of[(size_t)nd];
@@ -1035,7 +1117,7 @@ static int build_topology(mhm_cuda_context* ctx, Domain* d, Routing* rt, const m
         const int nd = node_of_cell[(size_t)k];
         MHM_REQUIRE(!is_ghost[(size_t)nd], "set_network: L1 cell %d maps to a ghost node", k + 1);
         ce[(size_t)k] = lane_of[(size_t)nd];
-        cs[(size_t)k] = (int8_t)(meta[(size_t)lane_of[(size_t)nd]].flags >> 16);
+        cs[(size_t)k] = (int8_t)lane_skew(meta[(size_t)lane_of[(size_t)nd]].flags);
         ca[(size_t)k] = rt->map_flag ? net->L1_areaCell[k] : net->L11_areaCell[nd];
       }
       if (int rc = upload(&rt->d_cell_entry, ce, st)) return rc;
@@ -1121,7 +1203,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
   }
   if (int rc = ensure(&rt->d_events, &rt->ev_cap, (size_t)nEv, st)) return rc;
   if (int rc = ensure(&rt->qout_hist, &rt->qout_cap, hist_size(nEv + kHistPad, M, E), st)) return rc;
-  if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(RS, M, E), st)) return rc;
+  if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(RS + kHistPad, M, E), st)) return rc;
   if (int rc = ensure(&rt->qmod_g, &rt->qmodg_cap, (size_t)nEv * M * std::max(1, rt->nGslots), st))
     return rc;
   if (int rc = ensure(&rt->d_inflow_val, &rt->inflow_cap, std::max<size_t>(1, inflow_val.size()), st))
@@ -1236,7 +1318,7 @@ static int run_events(mhm_cuda_context* ctx, Domain* d, Routing* rt, std::vector
   else if (ku == 2) MHM_CHAIN(R, 2, true);               \
   else if (ku == 3) MHM_CHAIN(R, 3, true);               \
   else MHM_CHAIN(R, 4, true)
-      const bool lean = rl == 1 && ca.rs0 == ca.ev0 && ca.ev0 % kWin == 0 && !ca.single_node && rt->lvl_plain[l] && rt->lean_ok;
+      const bool lean = rl == 1 && ca.rs0 == ca.ev0 && ca.ev0 % kHistTile == 0 && !ca.single_node && rt->lvl_plain[l] && rt->lean_ok;
       if (lean) {
         // less than one wave of CTAs: the variant that keeps the next window's loads in flight
         const bool pf = (size_t)grid.x * grid.y <= (size_t)ctx->sm_count * MHM_LEAN_MIN_BLOCKS * rt->pf_waves;
@@ -1404,40 +1486,44 @@ extern "C" {
 
 
 // ---- sub-catchment sharding ---------------------------------------------------------------
-__global__ void export_outflow_kernel(int nList, int M, int E, int T, const int32_t* __restrict__ lanes,
+__global__ void export_outflow_kernel(int nList, int M, int E, int T, const LaneMeta* __restrict__ meta,
+    const int32_t* __restrict__ lanes,
                                       const double* __restrict__ qtr_hist, double* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = blockIdx.y, m = blockIdx.z;
   if (t >= T) return;
-  out[((size_t)m * nList + e) * T + t] = qtr_hist[hidx(t, M, E, m, lanes[e])];
+  out[((size_t)m * nList + e) * T + t] = qtr_hist[hidx(t + lane_wshift(meta[lanes[e]].flags), M, E, m, lanes[e])];
 }
-__global__ void import_outflow_kernel(int nList, int M, int E, int T, const int32_t* __restrict__ lanes,
+__global__ void import_outflow_kernel(int nList, int M, int E, int T, const LaneMeta* __restrict__ meta,
+    const int32_t* __restrict__ lanes,
                                       const double* __restrict__ in, double* __restrict__ qtr_hist) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = blockIdx.y, m = blockIdx.z;
   if (t >= T) return;
-  qtr_hist[hidx(t, M, E, m, lanes[e])] = in[((size_t)m * nList + e) * T + t];
+  qtr_hist[hidx(t + lane_wshift(meta[lanes[e]].flags), M, E, m, lanes[e])] = in[((size_t)m * nList + e) * T + t];
 }
 
 // the same for the exchange buffers of mrm_cuda_shard_run_steps: one contiguous piece
 // [member][link of the piece][step] per peer rank, pieces in rank order
-__global__ void xchg_pack_kernel(int nList, int M, int E, int T, const int32_t* __restrict__ lanes,
+__global__ void xchg_pack_kernel(int nList, int M, int E, int T, const LaneMeta* __restrict__ meta,
+    const int32_t* __restrict__ lanes,
                                  const int32_t* __restrict__ tab, const double* __restrict__ qtr_hist,
                                  double* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = blockIdx.y, m = blockIdx.z;
   if (t >= T) return;
   const size_t first = (size_t)tab[e], cnt = (size_t)tab[nList + e], loc = (size_t)tab[2 * nList + e];
-  out[(first * M + (size_t)m * cnt + loc) * T + t] = qtr_hist[hidx(t, M, E, m, lanes[e])];
+  out[(first * M + (size_t)m * cnt + loc) * T + t] = qtr_hist[hidx(t + lane_wshift(meta[lanes[e]].flags), M, E, m, lanes[e])];
 }
-__global__ void xchg_unpack_kernel(int nList, int M, int E, int T, const int32_t* __restrict__ lanes,
+__global__ void xchg_unpack_kernel(int nList, int M, int E, int T, const LaneMeta* __restrict__ meta,
+    const int32_t* __restrict__ lanes,
                                    const int32_t* __restrict__ tab, const double* __restrict__ in,
                                    double* __restrict__ qtr_hist) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = blockIdx.y, m = blockIdx.z;
   if (t >= T) return;
   const size_t first = (size_t)tab[e], cnt = (size_t)tab[nList + e], loc = (size_t)tab[2 * nList + e];
-  qtr_hist[hidx(t, M, E, m, lanes[e])] = in[(first * M + (size_t)m * cnt + loc) * T + t];
+  qtr_hist[hidx(t + lane_wshift(meta[lanes[e]].flags), M, E, m, lanes[e])] = in[(first * M + (size_t)m * cnt + loc) * T + t];
 }
 
 int mrm_partition_subcatchments(int32_t nNodes, int32_t nLinks, const int32_t* fromN,
@@ -1530,7 +1616,7 @@ int mrm_cuda_export_outflow(mhm_cuda_context* ctx, int32_t iDomain, double* dev_
   if (rt->nExport == 0) return 0;
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
   export_outflow_kernel<<<dim3((n_steps + 63) / 64, rt->nExport, rt->M), 64, 0, ctx->stream>>>(
-      rt->nExport, rt->M, rt->E, n_steps, rt->d_export_lane, rt->qtr_hist, dev_out);
+      rt->nExport, rt->M, rt->E, n_steps, rt->meta, rt->d_export_lane, rt->qtr_hist, dev_out);
   MHM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1543,9 +1629,9 @@ int mrm_cuda_import_outflow(mhm_cuda_context* ctx, int32_t iDomain, const double
               "import_outflow: the pending block has %d steps", rt ? rt->pend_n : 0);
   if (rt->nGhost == 0) return 0;
   MHM_CUDA_OK(cudaSetDevice(ctx->device));
-  if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(n_steps, rt->M, rt->E), ctx->stream)) return rc;
+  if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(n_steps + kHistPad, rt->M, rt->E), ctx->stream)) return rc;
   import_outflow_kernel<<<dim3((n_steps + 63) / 64, rt->nGhost, rt->M), 64, 0, ctx->stream>>>(
-      rt->nGhost, rt->M, rt->E, n_steps, rt->d_ghost_lane, dev_in, rt->qtr_hist);
+      rt->nGhost, rt->M, rt->E, n_steps, rt->meta, rt->d_ghost_lane, dev_in, rt->qtr_hist);
   MHM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1603,10 +1689,10 @@ static int shard_route_pending(mhm_cuda_context* ctx, Domain* d) {
   if (rt->nGhost > 0) {
     for (int r = 0; r < N; ++r) cnt[(size_t)r] = (size_t)rt->xrecv[(size_t)r] * M * n;
     if (int rc = ensure(&rt->xrecv_buf, &rt->xrecv_cap, (size_t)rt->nGhost * M * n, ctx->stream)) return rc;
-    if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(n, M, rt->E), ctx->stream)) return rc;
+    if (int rc = ensure(&rt->qtr_hist, &rt->qtr_cap, hist_size(n + kHistPad, M, rt->E), ctx->stream)) return rc;
     if (int rc = comm_send_recv(ctx, nullptr, nullptr, rt->xrecv_buf, cnt.data(), ctx->stream)) return rc;
     xchg_unpack_kernel<<<dim3((n + 63) / 64, rt->nGhost, M), 64, 0, ctx->stream>>>(
-        rt->nGhost, M, rt->E, n, rt->d_ghost_lane, rt->d_xr_tab, rt->xrecv_buf, rt->qtr_hist);
+        rt->nGhost, M, rt->E, n, rt->meta, rt->d_ghost_lane, rt->d_xr_tab, rt->xrecv_buf, rt->qtr_hist);
     MHM_CUDA_OK(cudaGetLastError());
   }
   if (int rc = routing_run_block(ctx, d, tt, n, rt->pend_fused)) return rc;
@@ -1614,7 +1700,7 @@ static int shard_route_pending(mhm_cuda_context* ctx, Domain* d) {
     for (int r = 0; r < N; ++r) cnt[(size_t)r] = (size_t)rt->xsend[(size_t)r] * M * n;
     if (int rc = ensure(&rt->xsend_buf, &rt->xsend_cap, (size_t)rt->nExport * M * n, ctx->stream)) return rc;
     xchg_pack_kernel<<<dim3((n + 63) / 64, rt->nExport, M), 64, 0, ctx->stream>>>(
-        rt->nExport, M, rt->E, n, rt->d_export_lane, rt->d_xs_tab, rt->qtr_hist, rt->xsend_buf);
+        rt->nExport, M, rt->E, n, rt->meta, rt->d_export_lane, rt->d_xs_tab, rt->qtr_hist, rt->xsend_buf);
     MHM_CUDA_OK(cudaGetLastError());
     if (int rc = comm_send_recv(ctx, rt->xsend_buf, cnt.data(), nullptr, nullptr, ctx->stream)) return rc;
   }
