@@ -657,14 +657,20 @@ __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain
     for (int u = 0; u < (MEM ? KU : 1); ++u) wa.t[u][d] = wb.t[u][d] = 0.0;
   }
   // loads of half h of the tile at byte offset koff (one 256-bit load per row)
+  // (measured on B200 and dropped: prefetch.global.L2 of the runs 1, 2 or 4 tiles ahead, 19.4 ->
+  // 23.6 / 19.8 / 20.6 ms per 128-step block; routing the headwater leaves inside their reader
+  // instead of writing and re-reading their series, 22.4 ms: the levels are bound by latency
+  // and issue, not by DRAM bytes)
   auto load_half = [&](Window& w, const long long koff, const int r0, const int h) {
-    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
-                 : "=d"(w.qo[0]), "=d"(w.qo[1]), "=d"(w.qo[2]), "=d"(w.qo[3])
-                 : "l"(qo_b + koff + h * 32));
+    // windows wholly outside the lane's steps (pipeline fill and drain) are not fetched
+    const bool some = r0 + kWin > 0 && r0 < nRSv;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t"
+                 "@p ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+d"(w.qo[0]), "+d"(w.qo[1]), "+d"(w.qo[2]), "+d"(w.qo[3])
+                 : "l"(qo_b + koff + h * 32), "r"((int)some));
     if (MEM) {
       // tributary rows were written by earlier launches; window positions outside the launch's
       // steps hold other steps' values and never reach the state (guard below)
-      const bool some = r0 + kWin > 0 && r0 < nRSv;
 #pragma unroll
       for (int u = 0; u < KU; ++u)
         if (up_any[u])
