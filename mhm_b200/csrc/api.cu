@@ -819,6 +819,7 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
   for (int32_t t0 = 0; t0 < total && rc == 0;) {
     int32_t nb = total - t0 < kIdxInline ? total - t0 : kIdxInline;
     bool closes = false;
+    int32_t out_first_l = 0, out_counted = 0;  // first accumulating step / steps counted into the open window
     a.out_mask = 0;
     a.agg_mask = 0;
     if (optisim) {
@@ -851,11 +852,13 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
       }
       if (first < nb) {
         a.out_first = first;
+        out_first_l = first;
         if (outputs) {
           a.out_mask = d->out_mask;
           a.out_acc = d->out_acc;
           a.out_nslots = d->out_nslots;
           d->out_counter += nb - first;
+          out_counted = nb - first;
         }
         if (d->bfi_on && block_mode) {
           a.agg_mask |= 8u;
@@ -879,7 +882,12 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
     a.uniform_calendar = 0;
     a.forcing_tma = 0;
     // (the uniform kernels index a launch's forcing rows with 32 bits)
-    if (block_mode && ctx->uniform_calendar && !a.out_mask && !a.agg_mask && a.is_hourly && a.pet_case <= 0 &&
+    // (with gridded outputs: only the default selection whose window the fast kernel keeps in registers)
+    const bool out_uniform_ok = !a.out_mask || (a.out_mask == kOutDefaultMask && ctx->math_mode == 1 &&
+                                                d->cfg.nHorizons <= 2 && !getenv("MHM_CUDA_NO_OUTPUT_REGISTERS") &&
+                                                !getenv("MHM_CUDA_NO_UNIFORM_OUTPUTS"));
+    const int32_t nb_before = nb;
+    if (block_mode && ctx->uniform_calendar && out_uniform_ok && !a.agg_mask && a.is_hourly && a.pet_case <= 0 &&
         (uint64_t)kIdxInline * (uint64_t)a.nCells < ((uint64_t)1 << 32)) {
       const StepIdx& f = idx[t0];
       int32_t t = 1;
@@ -888,8 +896,8 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
         if (g.yId != f.yId || g.iLAI != f.iLAI || g.month != f.month || g.iMeteoTS != f.iMeteoTS + t) break;
       }
       if (t == nb || t >= 8) {  // a change in the first steps: one short general launch instead
+        if (t < nb) closes = false;  // cut short: the output window stays open
         nb = t;
-        closes = false;
         a.uniform_calendar = 1;
         // TMA bulk copies need 16-byte aligned row stretches: an even number of cells, aligned bases
         // (MHM_CUDA_FORCING_TMA=0 keeps the per-lane loads)
@@ -905,6 +913,11 @@ static int launch_cells(mhm_cuda_context* ctx, Domain* d, CellArgs& a, const Ste
           }
         }
       }
+    }
+    if (a.out_mask && nb != nb_before) {  // the launch was cut short: fewer steps enter the open window
+      const int32_t now = nb > out_first_l ? nb - out_first_l : 0;
+      d->out_counter -= out_counted - now;
+      if (now == 0) a.out_mask = 0;
     }
     a.nSteps = nb;
     a.tt_first = tt0 + t0;

@@ -288,7 +288,6 @@ __device__ __forceinline__ void accumulate_outputs(const uint32_t mask, double* 
 // shared memory per step and field (22 fields cost 88 shared-memory wavefronts per warp-step, as much
 // as the whole cascade) and no run-time selection.  The kernel gives up occupancy for it (168
 // registers, 3 CTAs/SM).
-constexpr uint32_t kOutDefaultMask = 0xffffu << 1 | 1u << 19 | 1u << 20 | 1u << 21;  // bits 1..16, 19, 20, 21
 template <int NH>
 constexpr int out_default_slots() { return 16 + 3 * NH; }
 template <int NH>
@@ -336,6 +335,57 @@ __device__ __forceinline__ void accumulate_outputs_default(double (&acc)[16 + 3 
   for (int h = 0; h < NH; ++h) add(f.aet_soil[h] * fNS);
   add(f.v[MHM_F_PREEFFECT]);
   add(f.v[MHM_F_MELT]);
+}
+
+// The same additions split for the software-pipelined launches (stage A of step t+1 runs beside
+// stage B of step t): the slots fed by canopy / snow / sealed store are added right after stage A,
+// the others after stage B of the same step -- every slot still receives its steps in time order.
+template <int NH>
+__device__ __forceinline__ void accumulate_default_a(double (&acc)[16 + 3 * NH], const FluxCapture& f,
+                                                     const CellStates<NH>& s, const double pet_calc,
+                                                     const double fS) {
+  acc[0] = acc[0] + s.inter;
+  acc[1] = acc[1] + s.snowpack;
+  acc[3 + 2 * NH] = acc[3 + 2 * NH] + s.sealed;
+  acc[6 + 2 * NH] = acc[6 + 2 * NH] + pet_calc;
+  acc[9 + 2 * NH] = acc[9 + 2 * NH] + f.v[MHM_F_RUNOFFSEAL] * fS;
+  acc[14 + 3 * NH] = acc[14 + 3 * NH] + f.v[MHM_F_PREEFFECT];
+  acc[15 + 3 * NH] = acc[15 + 3 * NH] + f.v[MHM_F_MELT];
+}
+template <int NH>
+__device__ __forceinline__ void accumulate_default_b(double (&acc)[16 + 3 * NH], const FluxCapture& f,
+                                                     const CellStates<NH>& s, const double fS,
+                                                     const double* sat_o, const double aet_canopy,
+                                                     const double aet_sealed) {
+  const double fNS = 1.0 - fS;
+#pragma unroll
+  for (int h = 0; h < NH; ++h) acc[2 + h] = acc[2 + h] + s.sm[h];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) acc[2 + NH + h] = acc[2 + NH + h] + s.sm[h] / sat_o[h];
+  {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) a = a + s.sm[h];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) b = b + sat_o[h];
+    acc[2 + 2 * NH] = acc[2 + 2 * NH] + a / b;
+  }
+  acc[4 + 2 * NH] = acc[4 + 2 * NH] + s.unsat;
+  acc[5 + 2 * NH] = acc[5 + 2 * NH] + s.sat;
+  {
+    double a = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) a = a + f.aet_soil[h];
+    const double t1 = a * fNS, t2 = aet_sealed * fS;
+    acc[7 + 2 * NH] = acc[7 + 2 * NH] + ((t1 + aet_canopy) + t2);
+  }
+  acc[8 + 2 * NH] = acc[8 + 2 * NH] + f.v[MHM_F_TOTAL_RUNOFF];
+  acc[10 + 2 * NH] = acc[10 + 2 * NH] + f.v[MHM_F_FASTRUNOFF] * fNS;
+  acc[11 + 2 * NH] = acc[11 + 2 * NH] + f.v[MHM_F_SLOWRUNOFF] * fNS;
+  acc[12 + 2 * NH] = acc[12 + 2 * NH] + f.v[MHM_F_BASEFLOW] * fNS;
+  acc[13 + 2 * NH] = acc[13 + 2 * NH] + f.v[MHM_F_PERCOL] * fNS;
+#pragma unroll
+  for (int h = 0; h < NH; ++h) acc[14 + 2 * NH + h] = acc[14 + 2 * NH + h] + f.aet_soil[h] * fNS;
 }
 
 // mhm_interface_run_update_optisim (mo_mhm_interface_run.f90:776-857): the step's soil-moisture
@@ -796,6 +846,7 @@ struct PairStore {
 // may run beside stage B of step t (see the uniform-calendar time loop).
 struct StageA {
   double prec_effect, pet_left, runoff_sealed;  // pet_left = pet - aet_canopy
+  double aet_canopy = 0.0, aet_sealed = 0.0;    // carried to the step's output sums (OUT == 2 pipeline)
 };
 template <int NH, bool EMIT, class PARAMS, class EM>
 __device__ __forceinline__ StageA cascade_stage_a_sel(const PARAMS& p, CellStates<NH>& s, const double pet,
@@ -1149,11 +1200,14 @@ struct ParamStoreOf {
 // FUSED (uniform launches only): the step's runoff goes to the routing's tiled node-runoff history
 // and nowhere else (true) / to the total-runoff history row and nowhere else (false) -- a block of
 // steps always has exactly one of the two sinks
+#ifndef MHM_OUT2_MIN_BLOCKS
+#define MHM_OUT2_MIN_BLOCKS 3  // CTAs/SM of the launches that keep the default output window in registers
+#endif
 // OUT: 0 no gridded outputs / aggregates, 1 run-time selection with the window in shared memory,
 // 2 the reference's default output set with the window in registers (accumulate_outputs_default)
 // TMA (uniform launches): the forcing rows arrive through cp.async.bulk into a shared-memory ring
 template <int NH, int VARIANT, int OUT, bool UNIFORM = false, bool FUSED = false, bool TMA = false>
-__global__ void __launch_bounds__(kCellThreads, OUT == 2 ? 3 : ParamPlace<NH>::min_blocks)
+__global__ void __launch_bounds__(kCellThreads, OUT == 2 ? MHM_OUT2_MIN_BLOCKS : ParamPlace<NH>::min_blocks)
 MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
   const int member = blockIdx.x % a.nMembers;
   const int cell = (blockIdx.x / a.nMembers) * kCellThreads + threadIdx.x;
@@ -1530,7 +1584,7 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
 
   const int n_last = a.nSteps - 1;
 #if MHM_FAST
-  if constexpr (UNIFORM && kPaired && !OUT) {
+  if constexpr (UNIFORM && kPaired && OUT != 1) {
     // Software pipeline over the steps of a uniform-calendar launch: stage A of step t+1 (canopy,
     // snow, sealed store -- it needs only the forcing and three states stage B never touches)
     // is issued in the same basic block as stage B2 of step t (horizons, reservoirs), so the
@@ -1608,13 +1662,40 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
     if (n_last > 0) {
       const int month = a.idx_in[0].month - 1;
       const double inv_ec = a.tab.inv_evap_coeff[month];
-      const FluxEmitter<false, false> noemit{a.F, mc, n, (size_t)member * NH * n + c, false, nullptr};
+      // OUT == 2: the stages' fluxes are captured for the output sums; every step before the
+      // launch's last one shares the launch's land-cover scene also after its date increment
+      // (uniform calendar), so fSealed and the saturation depths are the parameter store's
+      FluxCapture cap_a, cap_b;
+      const FluxEmitter<false, OUT == 2> noemit{a.F, mc, n, (size_t)member * NH * n + c, false, &cap_a};
+      const FluxEmitter<false, OUT == 2> noemit_b{a.F, mc, n, (size_t)member * NH * n + c, false, &cap_b};
+      int a_step = 0;  // step of the next stage A
       // stage A of the next step on its forcing row
       auto stage_a_next = [&]() -> StageA {
         double pre, temp, pet;
         next_row(std::false_type{}, pre, temp, pet);
         const double2 pt = P2(kPetTthr);  // petFac, tempThresh: one load
-        return cascade_stage_a_sel<NH, false>(p, s, pt.x * pet, temp, pre, pt.y, inv_ec, noemit);
+        const double pet_calc = pt.x * pet;
+        StageA r = cascade_stage_a_sel<NH, false>(p, s, pet_calc, temp, pre, pt.y, inv_ec, noemit);
+        if constexpr (OUT == 2) {
+          if (a_step >= a.out_first) accumulate_default_a<NH>(oacc, cap_a, s, pet_calc, P2(kSeal2).x);
+          r.aet_canopy = cap_a.v[MHM_F_AETCANOPY];
+          r.aet_sealed = cap_a.v[MHM_F_AETSEALED];
+          ++a_step;
+        }
+        return r;
+      };
+      // stage B2 of step t (stage A result `in`), then the step's remaining output sums
+      auto stage_b2 = [&](const StageA& in, const double (&frac_pre)[NH], const int t) -> double {
+        const double r = cascade_stage_b2_sel<NH, false>(p, s, in, frac_pre, sh_tab, noemit_b);
+        if constexpr (OUT == 2) {
+          if (t >= a.out_first) {
+            double sat_o[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) sat_o[h] = PH2(kSat0, h).x;
+            accumulate_default_b<NH>(oacc, cap_b, s, P2(kSeal2).x, sat_o, in.aet_canopy, in.aet_sealed);
+          }
+        }
+        return r;
       };
 #if MHM_CELL_PIPE3
       // Three steps in flight.  With A = canopy / snow / sealed store, R = infiltration powers of
@@ -1665,21 +1746,21 @@ MHM_KERNEL_NAME(const __grid_constant__ CellArgs a) {
         double frac_pre[NH];
         cascade_stage_b1_sel<NH>(p, s, sa.prec_effect, warp_tasks, sh_tab, frac_pre);
         const StageA sb = stage_a_next();
-        put(cascade_stage_b2_sel<NH, false>(p, s, sa, frac_pre, sh_tab, noemit));
+        put(stage_b2(sa, frac_pre, t));
         cascade_stage_b1_sel<NH>(p, s, sb.prec_effect, warp_tasks, sh_tab, frac_pre);
         sa = stage_a_next();
-        put(cascade_stage_b2_sel<NH, false>(p, s, sb, frac_pre, sh_tab, noemit));
+        put(stage_b2(sb, frac_pre, t + 1));
       }
       for (; t + 1 < n_last; ++t) {
         double frac_pre[NH];
         cascade_stage_b1_sel<NH>(p, s, sa.prec_effect, warp_tasks, sh_tab, frac_pre);
         const StageA sb = stage_a_next();  // step t+1; row t+2 <= n_last requested
-        put(cascade_stage_b2_sel<NH, false>(p, s, sa, frac_pre, sh_tab, noemit));
+        put(stage_b2(sa, frac_pre, t));
         sa = sb;
       }
       double frac_pre[NH];
       cascade_stage_b1_sel<NH>(p, s, sa.prec_effect, warp_tasks, sh_tab, frac_pre);
-      put(cascade_stage_b2_sel<NH, false>(p, s, sa, frac_pre, sh_tab, noemit));  // step n_last - 1
+      put(stage_b2(sa, frac_pre, n_last - 1));  // step n_last - 1
 #endif
     }
     // the launch's last step through the general path (it stores the fluxes)

@@ -81,4 +81,7 @@ struct CellArgs {
 int launch_cell_block_strict(const CellArgs& a, int nH, void* stream);
 int launch_cell_block_fast(const CellArgs& a, int nH, void* stream);
 
+// the reference's default output selection (mhm_outputs.nml): bits 1..16, 19, 20, 21 of out_mask
+constexpr uint32_t kOutDefaultMask = 0xffffu << 1 | 1u << 19 | 1u << 20 | 1u << 21;
+
 }  // namespace mhm
