@@ -158,3 +158,51 @@ def test_default_output_set_in_registers_equals_shared_memory_path(ctx, monkeypa
     for k in res["registers"]:
         parity.assert_bit_exact(res["registers"][k], res["shared"][k], "window ending %d, variable %d, horizon %d" % k)
     ctx.set_math_mode("strict")
+
+
+@pytest.mark.parametrize("nH,soil_case,routing", [(2, 1, True), (1, 4, True), (2, 2, False)])
+def test_default_outputs_on_pipelined_uniform_launches_equal_general_launches(ctx, monkeypatch, nH, soil_case,
+                                                                               routing):
+    """Launches that accumulate the default output set are uniform-calendar launches too (fast mode):
+    they run the software-pipelined kernel with the output sums split by stage (accumulate_default_a
+    / _b), with the fused node-runoff store when the domain is routed and, with
+    mhm_cuda_keep_runoff_history, with the total-runoff history.  MHM_CUDA_NO_UNIFORM_OUTPUTS keeps
+    them on the general per-step path: the windows, the final states and the gauge series must be
+    the same bit for bit, and the windows equal the oracle's."""
+    flags = np.zeros(21, dtype=np.int32)
+    flags[:16] = 1
+    flags[18:21] = 1
+    prob = synth.make_problem(nx=30, ny=17, n_days=40, nH=nH, hourly=True, soil_case=soil_case, pet_case=-1,
+                              routing=routing, start=(1990, 12, 10))
+    prob["time"]["warming_days"] = 2
+    nT = prob["time"]["nTimeSteps"]
+    o = orc_run.OracleRun(prob, outputs=(flags, -2))
+    o.run(1, nT)
+    ctx.set_math_mode("fast")
+    res = {}
+    for key in ("pipelined", "general"):
+        if key == "general":
+            monkeypatch.setenv("MHM_CUDA_NO_UNIFORM_OUTPUTS", "1")
+        dom = fresh(ctx, prob, nMembers=2, member_params=[prob["params"]] * 2)
+        if not routing:
+            dom.keep_runoff_history(True)
+        dom.set_outputs(flags, -2)
+        got, first = {}, 0
+        for a, b in ((1, 300), (301, 331), (632, nT - 631)):
+            dom.run_steps(a, b)
+            nwin, _ = compare(dom, o, first, tol_exact=False)
+            for w, tt in enumerate(dom.output_windows()):
+                for sl, (var, hor) in enumerate(o.out_windows()[first + w][1]):
+                    got[(tt, var, hor)] = dom.get_output(w, var, hor + 1 if hor >= 0 else 0, member=1)
+            first += nwin
+        assert first == len(o.out_windows()) >= 2
+        for name in ("L1_inter", "L1_snowPack", "L1_sealSTW", "L1_unsatSTW", "L1_satSTW", "L1_soilMoist"):
+            got[("state", name, 0)] = dom.get_state(name, member=1)
+        if routing:
+            got[("gauge", 0, 0)] = dom.get_runoff(1, nT, member=1)
+        res[key] = got
+    monkeypatch.delenv("MHM_CUDA_NO_UNIFORM_OUTPUTS")
+    assert res["pipelined"].keys() == res["general"].keys()
+    for k in res["pipelined"]:
+        parity.assert_bit_exact(res["pipelined"][k], res["general"][k], "%s %s %s" % k)
+    ctx.set_math_mode("strict")
