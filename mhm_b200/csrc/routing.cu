@@ -370,10 +370,10 @@ struct ChainArgs {
 };
 
 // L11_routing (mo_mrm_routing.f90:428-478) for the segments of one level over a block of
-// routing steps.  Lane j of a segment works on routing step (8 * S + d - j) in sub-step d of
+// routing steps.  Lane j of a segment works on routing step (kWin * S + d - j) in sub-step d of
 // macro step S, so that lane j-1 finished the same routing step one sub-step earlier and its
-// outflow arrives by __shfl_up.  Every lane reads its own 8-step windows (runoff, tributary
-// outflows) with static register indexing; a window covers at most two 64-byte history runs.
+// outflow arrives by __shfl_up.  Every lane reads its own kWin-step windows (runoff, tributary
+// outflows) with static register indexing.
 // RL1: one routing step per event (the usual case) -- no index divisions in the inner loops.
 #ifndef MHM_CHAIN_WIN
 #define MHM_CHAIN_WIN 4
@@ -506,13 +506,13 @@ __global__ void __launch_bounds__(128, MHM_CHAIN_MIN_BLOCKS) route_chain_kernel(
 // Lean form of route_chain_kernel for the levels that need none of its options: one routing
 // step per event with history indices rs == ev, more than one node, no ghost sources, no zeroed
 // outflows, at most kMetaUps inflowing links per lane (Routing::lvl_plain).  Same operations in
-// the same order -> bit-identical.  The node runoff of a macro step arrives with one 256-bit
-// load per lane (skewed storage, see kHistPad); for the routed-outflow history every lane
-// carries one running byte offset (its own row; tributary rows are a constant distance away)
-// that moves by 8 bytes per routing step and by a tile at a tile end, instead of rebuilding
-// tiled addresses per step.
+// the same order -> bit-identical.  One iteration works on one history tile in two 4-slot half
+// windows: the node runoff and every tributary series read from memory arrive with one 256-bit
+// load per row and half window (skewed / reader-shifted storage, see kHistPad), all addresses
+// are a per-lane base plus the tile's byte offset, and half windows in which every lane of the
+// warp is inside its steps run unguarded.
 #ifndef MHM_LEAN_MIN_BLOCKS
-#define MHM_LEAN_MIN_BLOCKS 5  // measured on B200: 4 -> 20.9 ms, 5 -> 19.2, 6 -> 19.1 (spills), 8 -> 20.6 per 96-step block
+#define MHM_LEAN_MIN_BLOCKS 5  // measured on B200, 128-step block: 4 -> 20.3 ms, 5 -> 19.4, 6 -> 19.7 (spills)
 #endif
 template <int KU, bool MEM, bool PF>
 __global__ void __launch_bounds__(128, PF ? 2 : MHM_LEAN_MIN_BLOCKS) route_chain_lean_kernel(const ChainArgs a) {
